@@ -1,0 +1,158 @@
+/*
+ * yroots_b200 -- C ABI of the B200-native Chebyshev subdivision solver.
+ *
+ * This is the drop-in boundary for the hot path of tylerjarvis/RootFinding (YRoots):
+ *   yroots.solve -> ChebyshevApproximator.chebApproximate
+ *                -> ChebyshevSubdivisionSolver.solveChebyshevSubdivision
+ * The reference is pure Python + numba and has no FFI of its own; the functions below are
+ * what a binding for that path would call (see INTEGRATION.md for the ctypes stub a
+ * maintainer would add to yroots/ChebyshevSubdivisionSolver.py).  All pointers are DEVICE
+ * pointers unless stated otherwise; `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream).  All tensors are FP64, row-major.  No torch types cross this
+ * boundary.  Every function returns 0 on success and a negative value on failure, with
+ * yr_last_error() giving the reason.
+ *
+ * Reference interfaces replaced (file:line in /root/reference/yroots/):
+ *   yr_init_boxes          ChebyshevSubdivisionSolver.py:1423-1434 (root box of a solve) and
+ *                          :864-894 transformChebToInterval / :339-374 TransformChebInPlaceND
+ *                          (batched restriction of whole systems to sub-boxes)
+ *   yr_process_level       ChebyshevSubdivisionSolver.py:1177-1317 solvePolyRecursive, one
+ *                          frontier level: constant check :1213, quadratic_check
+ *                          (QuadraticCheck.py:25-687), trimMs :1131, zoomInOnIntervalIter :896 with
+ *                          BoundingIntervalLinearSystem :628 and the restrictions :45-337,
+ *                          getSubdivisionIntervals :1051
+ *   yr_bils_batched        ChebyshevSubdivisionSolver.py:628-753 BoundingIntervalLinearSystem
+ *   yr_quadcheck_batched   QuadraticCheck.py:25 quadratic_check
+ *   yr_dct1_axis / yr_cheb_eval_axis / yr_abs_axis_mean
+ *                          ChebyshevApproximator.py:28-89 interval_approximate_nd (grid evaluation of
+ *                          Polynomial objects polynomial.py:317-342,503-528; dctn type 1 :78-82;
+ *                          axis means of |coeff| :288)
+ */
+#ifndef YROOTS_B200_H
+#define YROOTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YR_ABI_VERSION 1
+#define YR_MAX_DIM 6
+
+/* Solver options; defaults are the reference's hard-coded constants (yr_default_params). */
+typedef struct yr_params {
+    int32_t exact;               /* SolverOptions.exact                      (ChebyshevSubdivisionSolver.py:35) */
+    int32_t constant_check;      /* SolverOptions.constant_check             (:36) */
+    int32_t low_dim_quad_check;  /* SolverOptions.low_dim_quadratic_check    (:37) */
+    int32_t all_dim_quad_check;  /* SolverOptions.all_dim_quadratic_check    (:38) */
+    int32_t max_zoom_count;      /* SolverOptions.maxZoomCount = 25          (:39) */
+    int32_t use_fma;             /* 0 = separately rounded mul/add: restrictions bit-identical to the reference */
+    int32_t trim;                /* 1 = run trimMs (:1232) */
+    int32_t reserved;
+    double  trim_rel_tol;        /* trimMs relApproxTol = 1e-3 (:1131) */
+    double  trim_abs_tol;        /* trimMs absApproxTol = 0 */
+} yr_params;
+
+/* How a kernel is launched: the host sizes shared memory from the largest box of the level. */
+typedef struct yr_launch {
+    int32_t threads;             /* threads per CTA (multiple of 32) */
+    int32_t ctas;                /* persistent CTAs */
+    int32_t ws_in_smem;          /* 1: workspace in dynamic shared memory, 0: in gws */
+    int32_t reserved;
+    uint64_t ws_doubles;         /* workspace capacity per CTA, in doubles */
+    double*  gws;                /* [ctas][gws_stride] global scratch when ws_in_smem == 0 */
+    uint64_t gws_stride;
+} yr_launch;
+
+/* One frontier level (or chunk of a level). Record layouts: yr_record_layout(). */
+typedef struct yr_level_desc {
+    int32_t dim; int32_t reserved;
+    const void*   recs_in;  const double* data_in;  uint64_t n_in;
+    void*         recs_out; double*       data_out; uint64_t cap_recs_out; uint64_t cap_data_out;
+    void*         results;  uint64_t cap_results;   /* this call appends at results[0 .. cap_results) */
+    void*         nodes;    uint64_t cap_nodes;
+    uint64_t      result_base; uint64_t node_base;  /* global indices of results[0] / nodes[0] (stored in links) */
+    void*         counters;      /* yr_counters, zeroed by the caller before the call */
+    yr_params     prm;
+    yr_launch     launch;
+} yr_level_desc;
+
+/* Level-0 boxes: one per job = (system, optional restriction). */
+typedef struct yr_init_desc {
+    int32_t dim; int32_t reserved;
+    const double*  coeffs;       /* all tensors of all systems */
+    const int64_t* coeff_off;    /* [nsys][dim] offset (in doubles) of tensor p of system s */
+    const int32_t* shapes;       /* [nsys][dim][dim] extents */
+    const double*  errs;         /* [nsys][dim] approximation errors */
+    const int32_t* job_system;   /* [njobs] */
+    const int32_t* job_restrict; /* [njobs] 0 = take the system as is, 1 = restrict by alpha/beta */
+    const double*  job_alpha;    /* [njobs][dim] */
+    const double*  job_beta;     /* [njobs][dim] */
+    const double*  job_iv;       /* [njobs][dim][2] interval of the new box in the solve's unit cube */
+    const int32_t* job_level;    /* [njobs] */
+    const double*  job_next_mid; /* [njobs][dim] */
+    const int32_t* job_parent;   /* [njobs] */
+    uint64_t       njobs;
+    void*          recs_out; double* data_out; uint64_t cap_recs_out; uint64_t cap_data_out;
+    void*          counters;
+    yr_params      prm;
+    yr_launch      launch;
+} yr_init_desc;
+
+/* Counters written by yr_process_level / yr_init_boxes (all uint64). */
+typedef struct yr_counters {
+    uint64_t next_box, n_children, data_used, n_results, n_nodes;
+    uint64_t boxes, zooms, subdivisions, discard_const, discard_quad, discard_zoom;
+    uint64_t entry_coeffs, restrict_macs, max_child_doubles, max_child_extent, max_level, overflow;
+    uint64_t max_child_tensor;
+    uint64_t reserved[2];
+} yr_counters;
+
+int         yr_abi_version(void);
+const char* yr_last_error(void);
+const char* yr_build_info(void);                 /* "cuda sm_100a ..." */
+void        yr_default_params(yr_params* out);
+
+/* Layout of the device records, so hosts do not hard-code it.  kind: 0 box, 1 result, 2 node.
+ * Writes up to cap triples (field id, byte offset, byte size) and returns the record size. */
+int64_t     yr_record_layout(int32_t dim, int32_t kind, int64_t* triples, int32_t cap);
+
+/* Workspace (doubles) a box needs: total coefficients, largest tensor, largest extent. */
+uint64_t    yr_workspace_doubles(int32_t dim, uint64_t total, uint64_t max_tensor, uint64_t max_extent, int32_t exact);
+/* Static shared memory (bytes) the solver kernels use besides the workspace, per CTA. */
+int64_t     yr_static_smem_bytes(int32_t dim);
+/* Largest dynamic shared memory a CTA may use on the current device (bytes); host pointers. */
+int         yr_device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm);
+
+int yr_init_boxes(const yr_init_desc* d, void* stream);
+int yr_process_level(const yr_level_desc* d, void* stream);
+
+/* BoundingIntervalLinearSystem on n independent dim x dim problems (thread per problem).
+ *   lin [n][dim][dim], c0 [n][dim], sumabs [n][dim], errs [n][dim], final_step [n]
+ *   -> interval [n][dim][2], flags [n][3] = (changed, should_stop, throwOut) */
+int yr_bils_batched(int32_t dim, int64_t n, const double* lin, const double* c0, const double* sumabs,
+                    const double* errs, const int32_t* final_step, double* interval, int32_t* flags, void* stream);
+
+/* quadratic_check on n tensors of identical dimension (thread per tensor).
+ *   coeffs: packed tensors, off [n], shapes [n][dim], tol [n], nd_check: force the n-D path
+ *   -> out [n] (1 = no root possible) */
+int yr_quadcheck_batched(int32_t dim, int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes,
+                         const double* tol, int32_t nd_check, int32_t* out, void* stream);
+
+/* --- approximator (ChebyshevApproximator.py) ------------------------------------------- */
+/* values [outer][n+1][inner] -> coeffs along the middle axis: DCT-I with the reference's
+ * 1/deg scaling and halved end planes (interval_approximate_nd :78-82), batched. */
+int yr_dct1_axis(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void* stream);
+/* Evaluate a Chebyshev (basis 0) or power (basis 1) coefficient tensor along one axis at npts
+ * points x: in [outer][ncoef][inner] -> out [outer][npts][inner]. */
+int yr_poly_eval_axis(const double* coef, const double* x, double* out, int64_t outer, int64_t ncoef,
+                      int64_t npts, int64_t inner, int32_t basis, void* stream);
+/* mean of |t| over all axes but one: in [outer][n][inner] -> out [n]; also max|t| -> *supnorm. */
+int yr_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YROOTS_B200_H */

@@ -1,0 +1,229 @@
+"""Drop-in for yroots.ChebyshevSubdivisionSolver on a B200.
+
+Same names, argument meaning and error behaviour as
+/root/reference/yroots/ChebyshevSubdivisionSolver.py; the work runs in the CUDA kernels
+behind include/yroots_b200.h.
+
+  solveChebyshevSubdivision   :1387-1464  one system
+  solve_batch                 the same for many independent systems in one device frontier
+                              (what the boxes/sec benchmark measures)
+  transformChebToInterval     :864-894    batched interval restriction (operator-level entry)
+  TransformChebInPlaceND      :339-374
+  BoundingIntervalLinearSystem :628-753
+  TrackedInterval             :376-576    host-side view of a reported box
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib, postpass
+from .runtime import get_engine
+
+macheps = 2.0 ** -52
+
+
+class SolverOptions:
+    """Option bag of the reference (:12-43)."""
+
+    def __init__(self):
+        self.verbose = False
+        self.exact = False
+        self.constant_check = True
+        self.low_dim_quadratic_check = True
+        self.all_dim_quadratic_check = False
+        self.maxZoomCount = 25
+        self.level = 0
+
+    def copy(self):
+        import copy
+        return copy.copy(self)
+
+
+class TrackedInterval:
+    """Host-side interval object with the reference's read API (:376-576).
+
+    Boxes returned by the solver are `postpass.ResultBox` objects (same read API); this class
+    exists for user code that builds an interval from an array, e.g.
+    tests/test_Combined_Solver.py:269 `TrackedInterval(box).__contains__(root)`.
+    """
+
+    def __init__(self, interval):
+        self.topInterval = interval
+        self.interval = interval
+        self.transforms = []
+        self.ndim = len(self.interval)
+        self.empty = False
+        self.finalStep = False
+        self.canThrowOutFinalStep = False
+        self.possibleDuplicateRoots = []
+        self.possibleExtraRoot = False
+        self.nextTransformPoints = np.array([0.0394555475981047] * self.ndim)
+
+    def size(self):
+        return np.prod(self.interval[:, 1] - self.interval[:, 0])
+
+    def dimSize(self):
+        return self.interval[:, 1] - self.interval[:, 0]
+
+    def isPoint(self):
+        return bool(np.all(np.abs(self.interval[:, 0] - self.interval[:, 1]) < 1e-32))
+
+    def copy(self):
+        twin = TrackedInterval(self.topInterval)
+        twin.interval = self.interval.copy()
+        twin.nextTransformPoints = self.nextTransformPoints.copy()
+        return twin
+
+    def __contains__(self, point):
+        return bool(np.all(point >= self.interval[:, 0]) and np.all(point <= self.interval[:, 1]))
+
+    def overlapsWith(self, other):
+        a, b = np.asarray(self.interval), np.asarray(other.interval)
+        return bool(np.all(a[:, 0] <= b[:, 1]) and np.all(b[:, 0] <= a[:, 1]))
+
+    def __repr__(self):
+        return str(self.interval)
+
+
+def _check_system(Ms, errors):
+    if np.any([np.ndim(M) != len(Ms) for M in Ms]):
+        raise ValueError("Solver Takes in N polynomials of dimension N!")
+    if len(Ms) != len(errors):
+        raise ValueError("Ms and errors must be same length!")
+
+
+def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constant_check=True,
+                low_dim_quadratic_check=True, all_dim_quadratic_check=False, use_fma=False, engine=None,
+                return_session=False):
+    """Solve many independent systems (each a list of `dim` tensors) in one device frontier.
+
+    Returns a list with one root array per system (and a list of box lists when
+    returnBoundingBoxes).  Root order within a system is depth-first, as in the reference.
+    """
+    for Ms, e in zip(systems, errors):
+        _check_system(Ms, e)
+    eng = get_engine() if engine is None else engine
+    sess = eng.session([[np.asarray(M, dtype=np.float64) for M in Ms] for Ms in systems], errors,
+                       exact=int(bool(exact)), constant_check=int(bool(constant_check)),
+                       low_dim_quad_check=int(bool(low_dim_quadratic_check)),
+                       all_dim_quad_check=int(bool(all_dim_quadratic_check)), use_fma=int(bool(use_fma)))
+    sess.run_jobs(sess.unit_jobs())
+    res, keep, dup, extra = postpass.assemble(sess)
+    if sess.stats.max_level >= 25:
+        warnings.warn("Extreme subdivision depth!\nSubdivision on the search interval has now reached"
+                      " at least depth 25, which is unusual. The solver may not finish running."
+                      "Ensure the input functions meet the requirements of being continuous, smooth,"
+                      "and having only finitely many simple roots on the search interval.")
+    elif sess.stats.max_level >= 15:
+        warnings.warn("High subdivision depth!\nSubdivision on the search interval has now reached"
+                      " at least depth 15. Runtime may be prolonged.")
+    roots, boxes = postpass.per_system_roots(res, keep, dup, extra, sess.nsys, sess.dim, want_boxes=returnBoundingBoxes)
+    out = (roots, boxes) if returnBoundingBoxes else roots
+    return (out, sess) if return_session else out
+
+
+def solveChebyshevSubdivision(Ms, errors, verbose=False, returnBoundingBoxes=False, exact=False,
+                              constant_check=True, low_dim_quadratic_check=True, all_dim_quadratic_check=False):
+    """Roots (and optionally bounding boxes) of one Chebyshev system on [-1,1]^n (:1387-1464)."""
+    _check_system(Ms, errors)
+    if verbose:
+        print("Finding roots...", end=' ')
+    out = solve_batch([Ms], [np.asarray(errors, dtype=np.float64)], True, exact, constant_check,
+                      low_dim_quadratic_check, all_dim_quadratic_check)
+    roots, boxes = out[0][0], out[1][0]
+    dim = len(Ms)
+    roots = np.array(roots).reshape(-1, dim) if len(roots) else np.array([])
+    if verbose:
+        finish_string = '\n' + f"Found {len(roots)} roots"
+        print((finish_string if len(roots) != 1 else finish_string[:-1]), end='\n\n')
+    if returnBoundingBoxes:
+        return roots, boxes
+    return roots
+
+
+# ---- operator-level entry points -----------------------------------------------------------
+def restrict_systems(systems, errors, alphas, betas, exact=False, use_fma=False, engine=None):
+    """Batched transformChebToInterval: system s restricted to x -> alphas[s]*x + betas[s].
+
+    Returns (list of lists of tensors, errors [nsys][dim]).
+    """
+    eng = get_engine() if engine is None else engine
+    sess = eng.session(systems, errors, exact=int(bool(exact)), use_fma=int(bool(use_fma)))
+    D, n = sess.dim, sess.nsys
+    jobs = sess.unit_jobs()
+    jobs["restrict"] = np.ones(n, np.int32)
+    jobs["alpha"] = np.asarray(alphas, dtype=np.float64).reshape(n, D)
+    jobs["beta"] = np.asarray(betas, dtype=np.float64).reshape(n, D)
+    recs, data, c = sess._init_boxes(jobs)
+    bdt = _lib.box_dtype(sess.lib, D)
+    boxes = sess.mem.download(recs, n * bdt.itemsize).view(bdt)
+    flat = sess.mem.download(data, int(c["data_used"]) * 8).view(np.float64)
+    out = [None] * n
+    errs = np.zeros((n, D))
+    for b in boxes:
+        s = int(b["system"])
+        off = int(b["data_off"])
+        Ms = []
+        for p in range(D):
+            shp = tuple(int(v) for v in b["shape"][p])
+            sz = int(np.prod(shp))
+            Ms.append(flat[off:off + sz].reshape(shp).copy())
+            off += sz
+        out[s] = Ms
+        errs[s] = b["err"]
+    return out, errs
+
+
+def transformChebToInterval(Ms, alphas, betas, errors, exact):
+    """:864-894 for one system."""
+    out, errs = restrict_systems([Ms], [errors], [alphas], [betas], exact)
+    return out[0], errs[0]
+
+
+def TransformChebInPlaceND(coeffs, dim, alpha, beta, exact):
+    """:339-374 -- one axis of one tensor (the tensor is embedded as polynomial 0 of a system)."""
+    coeffs = np.asarray(coeffs, dtype=np.float64)
+    if (alpha == 1.0 and beta == 0.0) or coeffs.shape[dim] == 1:
+        return coeffs
+    D = coeffs.ndim
+    al, be = np.ones(D), np.zeros(D)
+    al[dim], be[dim] = alpha, beta
+    filler = [np.zeros((1,) * D) for _ in range(D - 1)]
+    out, _ = restrict_systems([[coeffs] + filler], [np.zeros(D)], [al], [be], exact)
+    return out[0][0]
+
+
+def getLinearTerms(M):
+    """:578-605."""
+    M = np.asarray(M)
+    out = []
+    for d in range(M.ndim):
+        idx = [0] * M.ndim
+        idx[d] = 1
+        out.append(0 if M.shape[d] == 1 else M[tuple(idx)])
+    return out
+
+
+def bils_batched(systems, errors, final_steps, engine=None):
+    """BoundingIntervalLinearSystem for many systems: (intervals [n][dim][2], flags [n][3])."""
+    eng = get_engine() if engine is None else engine
+    n, D = len(systems), len(systems[0])
+    lin = np.array([[getLinearTerms(M) for M in Ms] for Ms in systems], dtype=np.float64)
+    c0 = np.array([[np.asarray(M).ravel()[0] for M in Ms] for Ms in systems], dtype=np.float64)
+    sumabs = np.array([[np.sum(np.abs(M)) for M in Ms] for Ms in systems], dtype=np.float64)
+    m = eng.mem
+    d_iv, d_fl = m.empty(n * D * 16), m.empty(n * 12)
+    bufs = [m.upload(lin), m.upload(c0), m.upload(sumabs), m.upload(np.asarray(errors, dtype=np.float64).reshape(n, D)),
+            m.upload(np.asarray(final_steps, dtype=np.int32))]
+    _lib.check(eng.lib, eng.lib.yr_bils_batched(D, n, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, bufs[4].ptr,
+                                                d_iv.ptr, d_fl.ptr, m.stream()), "yr_bils_batched")
+    iv = m.download(d_iv, n * D * 16).view(np.float64).reshape(n, D, 2)
+    fl = m.download(d_fl, n * 12).view(np.int32).reshape(n, 3).astype(bool)
+    return iv, fl
+
+
+def BoundingIntervalLinearSystem(Ms, errors, finalStep, macheps=2 ** -52):
+    """:628-753 -> (interval, changed, should_stop, throwOut)."""
+    iv, fl = bils_batched([Ms], [errors], [int(bool(finalStep))])
+    return iv[0], bool(fl[0][0]), bool(fl[0][1]), bool(fl[0][2])

@@ -1,0 +1,162 @@
+"""ctypes binding of include/yroots_b200.h.
+
+The product library is rootfinding_b200/csrc/libyroots_b200.so (hand-written sm_100a
+CUDA, built by __graft_entry__.build() / `make -C rootfinding_b200/csrc`).  There is no
+CPU fallback: if the library or a CUDA device is missing, loading raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libyroots_b200.so")
+
+u64, i64, i32 = C.c_uint64, C.c_int64, C.c_int32
+vp, dp = C.c_void_p, C.c_void_p          # device pointers travel as integers
+
+
+class YrParams(C.Structure):
+    _fields_ = [("exact", i32), ("constant_check", i32), ("low_dim_quad_check", i32), ("all_dim_quad_check", i32),
+                ("max_zoom_count", i32), ("use_fma", i32), ("trim", i32), ("reserved", i32),
+                ("trim_rel_tol", C.c_double), ("trim_abs_tol", C.c_double)]
+
+
+class YrLaunch(C.Structure):
+    _fields_ = [("threads", i32), ("ctas", i32), ("ws_in_smem", i32), ("reserved", i32),
+                ("ws_doubles", u64), ("gws", dp), ("gws_stride", u64)]
+
+
+class YrLevelDesc(C.Structure):
+    _fields_ = [("dim", i32), ("reserved", i32),
+                ("recs_in", vp), ("data_in", dp), ("n_in", u64),
+                ("recs_out", vp), ("data_out", dp), ("cap_recs_out", u64), ("cap_data_out", u64),
+                ("results", vp), ("cap_results", u64),
+                ("nodes", vp), ("cap_nodes", u64),
+                ("result_base", u64), ("node_base", u64),
+                ("counters", vp), ("prm", YrParams), ("launch", YrLaunch)]
+
+
+class YrInitDesc(C.Structure):
+    _fields_ = [("dim", i32), ("reserved", i32),
+                ("coeffs", dp), ("coeff_off", vp), ("shapes", vp), ("errs", dp),
+                ("job_system", vp), ("job_restrict", vp), ("job_alpha", dp), ("job_beta", dp), ("job_iv", dp),
+                ("job_level", vp), ("job_next_mid", dp), ("job_parent", vp), ("njobs", u64),
+                ("recs_out", vp), ("data_out", dp), ("cap_recs_out", u64), ("cap_data_out", u64),
+                ("counters", vp), ("prm", YrParams), ("launch", YrLaunch)]
+
+
+COUNTER_FIELDS = ["next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms", "subdivisions",
+                  "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "restrict_macs",
+                  "max_child_doubles", "max_child_extent", "max_level", "overflow", "max_child_tensor",
+                  "reserved0", "reserved1"]
+COUNTER_BYTES = 8 * len(COUNTER_FIELDS)
+
+# every symbol include/yroots_b200.h declares
+EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_params", "yr_record_layout",
+           "yr_workspace_doubles", "yr_static_smem_bytes", "yr_device_limits", "yr_init_boxes", "yr_process_level", "yr_bils_batched",
+           "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean"]
+
+_RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
+                  "level", "flags", "path_hi", "path_lo"]
+_NODE_FIELDS = ["iv", "next_mid", "system", "parent_node", "level", "nsplit"]
+_BOX_FIELDS = ["data_off", "shape", "err", "iv", "A", "B", "next_mid", "pf_iv", "pfA", "pfB", "flags", "system",
+               "parent_node", "collector", "level", "path_hi", "path_lo"]
+
+
+def bind(lib):
+    """Attach prototypes to a loaded library and return it."""
+    lib.yr_abi_version.restype = C.c_int
+    lib.yr_last_error.restype = C.c_char_p
+    lib.yr_build_info.restype = C.c_char_p
+    lib.yr_default_params.argtypes = [C.POINTER(YrParams)]
+    lib.yr_default_params.restype = None
+    lib.yr_record_layout.argtypes = [i32, i32, C.POINTER(i64), i32]
+    lib.yr_record_layout.restype = i64
+    lib.yr_workspace_doubles.argtypes = [i32, u64, u64, u64, i32]
+    lib.yr_workspace_doubles.restype = u64
+    lib.yr_static_smem_bytes.argtypes = [i32]
+    lib.yr_static_smem_bytes.restype = i64
+    lib.yr_device_limits.argtypes = [C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    lib.yr_device_limits.restype = C.c_int
+    lib.yr_init_boxes.argtypes = [C.POINTER(YrInitDesc), vp]
+    lib.yr_init_boxes.restype = C.c_int
+    lib.yr_process_level.argtypes = [C.POINTER(YrLevelDesc), vp]
+    lib.yr_process_level.restype = C.c_int
+    lib.yr_bils_batched.argtypes = [i32, i64, dp, dp, dp, dp, vp, dp, vp, vp]
+    lib.yr_bils_batched.restype = C.c_int
+    lib.yr_quadcheck_batched.argtypes = [i32, i64, dp, vp, vp, dp, i32, vp, vp]
+    lib.yr_quadcheck_batched.restype = C.c_int
+    lib.yr_dct1_axis.argtypes = [dp, dp, i64, i64, i64, vp]
+    lib.yr_dct1_axis.restype = C.c_int
+    lib.yr_poly_eval_axis.argtypes = [dp, dp, dp, i64, i64, i64, i64, i32, vp]
+    lib.yr_poly_eval_axis.restype = C.c_int
+    lib.yr_abs_axis_mean.argtypes = [dp, dp, dp, i64, i64, i64, vp]
+    lib.yr_abs_axis_mean.restype = C.c_int
+    if lib.yr_abi_version() != 1:
+        raise RuntimeError("yroots_b200: ABI version mismatch")
+    return lib
+
+
+def check(lib, rc, what):
+    if rc != 0:
+        raise RuntimeError(f"yroots_b200: {what} failed: {lib.yr_last_error().decode()}")
+
+
+def default_params(lib):
+    p = YrParams()
+    lib.yr_default_params(C.byref(p))
+    return p
+
+
+def _record_dtype(lib, dim, kind, names):
+    buf = (i64 * (3 * 32))()
+    size = lib.yr_record_layout(dim, kind, buf, 32)
+    fields = {}
+    for k, name in enumerate(names):
+        fid, off, nbytes = buf[3 * k], buf[3 * k + 1], buf[3 * k + 2]
+        assert fid == k
+        if name in ("system", "parent_node", "collector", "level", "nsplit"):
+            fmt = np.int32
+        elif name == "flags":
+            fmt = np.uint32
+        elif name in ("path_hi", "path_lo", "data_off"):
+            fmt = np.uint64
+        elif name == "shape":
+            fmt = (np.int32, (dim, dim))
+        elif nbytes == 8 * dim:
+            fmt = (np.float64, (dim,))
+        elif nbytes == 16 * dim:
+            fmt = (np.float64, (dim, 2))
+        else:
+            raise AssertionError((name, nbytes))
+        fields[name] = (fmt, int(off))
+    return np.dtype({"names": list(fields), "formats": [f[0] for f in fields.values()],
+                     "offsets": [f[1] for f in fields.values()], "itemsize": int(size)})
+
+
+def result_dtype(lib, dim):
+    return _record_dtype(lib, dim, 1, _RESULT_FIELDS)
+
+
+def node_dtype(lib, dim):
+    return _record_dtype(lib, dim, 2, _NODE_FIELDS)
+
+
+def box_dtype(lib, dim):
+    return _record_dtype(lib, dim, 0, _BOX_FIELDS)
+
+
+_cuda_lib = None
+
+
+def load_cuda_library():
+    """Load the CUDA library.  Raises when it has not been built -- there is no other path."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        if not os.path.exists(CUDA_LIB_PATH):
+            raise RuntimeError(
+                f"yroots_b200: CUDA library {CUDA_LIB_PATH} is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
+        _cuda_lib = bind(C.CDLL(CUDA_LIB_PATH))
+    return _cuda_lib

@@ -1,0 +1,199 @@
+// extern "C" entry points of include/yroots_b200.h, written against a handful of
+// backend hooks (namespace yr_backend) that the translation unit including this
+// file provides: yr_kernels.cu (CUDA, the product) or tests/emul/emul.cpp (pthread
+// emulator of the same kernel source, test infrastructure only).
+#pragma once
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/yroots_b200.h"
+#include "yr_box.h"
+#include "yr_items.h"
+
+// Hooks every backend defines after including this header.
+namespace yr_backend {
+const char* build_info();
+int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm);
+template <int D> int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream);
+template <int D> int launch_init(const yr::InitArgs<D>& a, const yr_launch& l, void* stream);
+template <int D> int launch_bils(int64_t n, const double* lin, const double* c0, const double* sumabs, const double* errs,
+                                 const int32_t* final_step, double* interval, int32_t* flags, void* stream);
+template <int D> int launch_quad(int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes,
+                                 const double* tol, int32_t nd_check, int32_t* out, void* stream);
+int launch_dct1(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void* stream);
+int launch_poly_eval(const double* coef, const double* x, double* out, int64_t outer, int64_t ncoef, int64_t npts,
+                     int64_t inner, int32_t basis, void* stream);
+int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream);
+}  // namespace yr_backend
+
+static_assert(sizeof(yr_params) == sizeof(yr::SolverParams), "yr_params / SolverParams mismatch");
+static_assert(sizeof(yr_counters) == sizeof(yr::LevelCounters), "yr_counters / LevelCounters mismatch");
+
+namespace yr_api {
+static thread_local char g_err[512] = "";
+inline int fail(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return -1; }
+
+inline yr::SolverParams to_params(const yr_params& p) {
+    yr::SolverParams q;
+    memcpy(&q, &p, sizeof(q));
+    return q;
+}
+
+template <int D>
+int level_impl(const yr_level_desc* d, void* stream) {
+    yr::LevelArgs<D> a;
+    a.recs_in = static_cast<const yr::BoxRec<D>*>(d->recs_in); a.data_in = d->data_in; a.n_in = d->n_in;
+    a.recs_out = static_cast<yr::BoxRec<D>*>(d->recs_out); a.data_out = d->data_out;
+    a.cap_recs_out = d->cap_recs_out; a.cap_data_out = d->cap_data_out;
+    a.results = static_cast<yr::ResultRec<D>*>(d->results); a.cap_results = d->cap_results;
+    a.nodes = static_cast<yr::NodeRec<D>*>(d->nodes); a.cap_nodes = d->cap_nodes;
+    a.result_base = d->result_base; a.node_base = d->node_base;
+    a.ctr = static_cast<yr::LevelCounters*>(d->counters);
+    a.gws = d->launch.gws; a.gws_stride = d->launch.gws_stride; a.ws_doubles = d->launch.ws_doubles;
+    a.prm = to_params(d->prm);
+    return yr_backend::launch_level<D>(a, d->launch, stream);
+}
+
+template <int D>
+int init_impl(const yr_init_desc* d, void* stream) {
+    yr::InitArgs<D> a;
+    a.coeffs = d->coeffs; a.coeff_off = reinterpret_cast<const long long*>(d->coeff_off);
+    a.shapes = d->shapes; a.errs = d->errs;
+    a.job_system = d->job_system; a.job_restrict = d->job_restrict;
+    a.job_alpha = d->job_alpha; a.job_beta = d->job_beta; a.job_iv = d->job_iv;
+    a.job_level = d->job_level; a.job_next_mid = d->job_next_mid; a.job_parent = d->job_parent;
+    a.njobs = d->njobs;
+    a.recs_out = static_cast<yr::BoxRec<D>*>(d->recs_out); a.data_out = d->data_out;
+    a.cap_recs_out = d->cap_recs_out; a.cap_data_out = d->cap_data_out;
+    a.ctr = static_cast<yr::LevelCounters*>(d->counters);
+    a.gws = d->launch.gws; a.gws_stride = d->launch.gws_stride; a.ws_doubles = d->launch.ws_doubles;
+    a.prm = to_params(d->prm);
+    return yr_backend::launch_init<D>(a, d->launch, stream);
+}
+
+template <int D>
+int64_t layout_impl(int kind, int64_t* t, int cap) {
+    int n = 0;
+    auto put = [&](int id, size_t off, size_t size) {
+        if (t && n < cap) { t[3 * n] = id; t[3 * n + 1] = (int64_t)off; t[3 * n + 2] = (int64_t)size; }
+        ++n;
+    };
+    typedef yr::BoxRec<D> B; typedef yr::ResultRec<D> R; typedef yr::NodeRec<D> N; typedef yr::IntervalState<D> S;
+    if (kind == 0) {
+        const size_t so = offsetof(B, st);
+        put(0, offsetof(B, data_off), sizeof(uint64_t)); put(1, offsetof(B, shape), sizeof(int32_t) * D * D);
+        put(2, offsetof(B, err), sizeof(double) * D);
+        put(3, so + offsetof(S, iv), sizeof(double) * D * 2); put(4, so + offsetof(S, A), sizeof(double) * D * 2);
+        put(5, so + offsetof(S, B), sizeof(double) * D * 2); put(6, so + offsetof(S, next_mid), sizeof(double) * D);
+        put(7, so + offsetof(S, pf_iv), sizeof(double) * D * 2); put(8, so + offsetof(S, pfA), sizeof(double) * D * 2);
+        put(9, so + offsetof(S, pfB), sizeof(double) * D * 2); put(10, so + offsetof(S, flags), sizeof(uint32_t));
+        put(11, offsetof(B, system), 4); put(12, offsetof(B, parent_node), 4); put(13, offsetof(B, collector), 4);
+        put(14, offsetof(B, level), 4); put(15, offsetof(B, path_hi), 8); put(16, offsetof(B, path_lo), 8);
+        return (int64_t)sizeof(B);
+    } else if (kind == 1) {
+        put(0, offsetof(R, root), sizeof(double) * D); put(1, offsetof(R, box), sizeof(double) * D * 2);
+        put(2, offsetof(R, comb_iv), sizeof(double) * D * 2); put(3, offsetof(R, iv_lo), sizeof(double) * D);
+        put(4, offsetof(R, cell_iv), sizeof(double) * D * 2); put(5, offsetof(R, next_mid), sizeof(double) * D);
+        put(6, offsetof(R, system), 4); put(7, offsetof(R, parent_node), 4); put(8, offsetof(R, collector), 4);
+        put(9, offsetof(R, level), 4); put(10, offsetof(R, flags), 4); put(11, offsetof(R, path_hi), 8);
+        put(12, offsetof(R, path_lo), 8);
+        return (int64_t)sizeof(R);
+    } else if (kind == 2) {
+        put(0, offsetof(N, iv), sizeof(double) * D * 2); put(1, offsetof(N, next_mid), sizeof(double) * D);
+        put(2, offsetof(N, system), 4); put(3, offsetof(N, parent_node), 4); put(4, offsetof(N, level), 4);
+        put(5, offsetof(N, nsplit), 4);
+        return (int64_t)sizeof(N);
+    }
+    return -1;
+}
+}  // namespace yr_api
+
+#define YR_DISPATCH_DIM(dim, CALL)                                                   \
+    switch (dim) {                                                                   \
+        case 1: return CALL(1); case 2: return CALL(2); case 3: return CALL(3);      \
+        case 4: return CALL(4); case 5: return CALL(5); case 6: return CALL(6);      \
+        default: return yr_api::fail("dimension must be 1..6");                      \
+    }
+
+extern "C" {
+
+int yr_abi_version(void) { return YR_ABI_VERSION; }
+const char* yr_last_error(void) { return yr_api::g_err; }
+const char* yr_build_info(void) { return yr_backend::build_info(); }
+
+void yr_default_params(yr_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->exact = 0; p->constant_check = 1; p->low_dim_quad_check = 1; p->all_dim_quad_check = 0;
+    p->max_zoom_count = yr::kMaxZoomCount; p->use_fma = 0; p->trim = 1;
+    p->trim_rel_tol = 1e-3; p->trim_abs_tol = 0.0;
+}
+
+int64_t yr_record_layout(int32_t dim, int32_t kind, int64_t* triples, int32_t cap) {
+#define YR_CALL(D) yr_api::layout_impl<D>(kind, triples, cap)
+    YR_DISPATCH_DIM(dim, YR_CALL)
+#undef YR_CALL
+}
+
+uint64_t yr_workspace_doubles(int32_t dim, uint64_t total, uint64_t max_tensor, uint64_t max_extent, int32_t exact) {
+    return yr::workspace_doubles(dim, total, max_tensor, max_extent, exact);
+}
+
+int64_t yr_static_smem_bytes(int32_t dim) {
+    switch (dim) {
+        case 1: return sizeof(yr::BoxShared<1>) + 512; case 2: return sizeof(yr::BoxShared<2>) + 512;
+        case 3: return sizeof(yr::BoxShared<3>) + 512; case 4: return sizeof(yr::BoxShared<4>) + 512;
+        case 5: return sizeof(yr::BoxShared<5>) + 512; case 6: return sizeof(yr::BoxShared<6>) + 512;
+        default: return -1;
+    }
+}
+
+int yr_device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm) {
+    return yr_backend::device_limits(sm_count, max_smem_per_cta, smem_per_sm);
+}
+
+int yr_process_level(const yr_level_desc* d, void* stream) {
+    if (!d) return yr_api::fail("null descriptor");
+    if (d->launch.threads <= 0 || d->launch.threads % 32 != 0 || d->launch.ctas <= 0) return yr_api::fail("bad launch configuration");
+#define YR_CALL(D) yr_api::level_impl<D>(d, stream)
+    YR_DISPATCH_DIM(d->dim, YR_CALL)
+#undef YR_CALL
+}
+
+int yr_init_boxes(const yr_init_desc* d, void* stream) {
+    if (!d) return yr_api::fail("null descriptor");
+    if (d->launch.threads <= 0 || d->launch.threads % 32 != 0 || d->launch.ctas <= 0) return yr_api::fail("bad launch configuration");
+#define YR_CALL(D) yr_api::init_impl<D>(d, stream)
+    YR_DISPATCH_DIM(d->dim, YR_CALL)
+#undef YR_CALL
+}
+
+int yr_bils_batched(int32_t dim, int64_t n, const double* lin, const double* c0, const double* sumabs,
+                    const double* errs, const int32_t* final_step, double* interval, int32_t* flags, void* stream) {
+#define YR_CALL(D) yr_backend::launch_bils<D>(n, lin, c0, sumabs, errs, final_step, interval, flags, stream)
+    YR_DISPATCH_DIM(dim, YR_CALL)
+#undef YR_CALL
+}
+
+int yr_quadcheck_batched(int32_t dim, int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes,
+                         const double* tol, int32_t nd_check, int32_t* out, void* stream) {
+#define YR_CALL(D) yr_backend::launch_quad<D>(n, coeffs, off, shapes, tol, nd_check, out, stream)
+    YR_DISPATCH_DIM(dim, YR_CALL)
+#undef YR_CALL
+}
+
+int yr_dct1_axis(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void* stream) {
+    if (npts < 2) return yr_api::fail("DCT-I needs at least two points");
+    return yr_backend::launch_dct1(values, coeffs, outer, npts, inner, stream);
+}
+
+int yr_poly_eval_axis(const double* coef, const double* x, double* out, int64_t outer, int64_t ncoef,
+                      int64_t npts, int64_t inner, int32_t basis, void* stream) {
+    return yr_backend::launch_poly_eval(coef, x, out, outer, ncoef, npts, inner, basis, stream);
+}
+
+int yr_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream) {
+    return yr_backend::launch_abs_axis_mean(t, out, supnorm, outer, n, inner, stream);
+}
+
+}  // extern "C"
+

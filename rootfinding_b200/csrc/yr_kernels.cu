@@ -1,0 +1,278 @@
+// CUDA backend (sm_100a) of include/yroots_b200.h.
+//
+// Kernels are persistent: a launch has at most (SM count x resident CTAs per SM) CTAs, each
+// pulling boxes from an atomic cursor, so grids are sized to the 148 SMs of a B200 rather than
+// to the number of boxes.  A box's tensors are contiguous in the level pool and are staged
+// into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); all FP64
+// work on them (reductions, restriction-matrix recurrences, triangular contractions) then runs
+// out of shared memory, and only the children go back to HBM.  Compiled with -fmad=false:
+// products and sums are rounded separately (like the reference's numba code) except where
+// fma() is written explicitly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "yr_api_impl.h"
+#include "yr_approx.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "YR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra YR_DONE;\n"
+        "bra YR_WAIT;\n"
+        "YR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct DeviceCtx {
+    int tid, nthreads, lane, lanes, warp, nwarps;
+    double* red;          // [32] shared scratch for block reductions
+    uint64_t* mbar;       // shared mbarrier for TMA staging
+    uint32_t phase;       // its current parity (uniform across the CTA)
+    int ws_is_smem;
+
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ double warp_tree(double v) {
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        return v;
+    }
+    __device__ __forceinline__ double block_sum(double v) {
+        v = warp_tree(v);
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += red[w];
+        __syncthreads();
+        return t;
+    }
+    __device__ __forceinline__ double block_max(double v) {
+        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        double t = red[0];
+        for (int w = 1; w < nwarps; ++w) t = fmax(t, red[w]);
+        __syncthreads();
+        return t;
+    }
+    __device__ __forceinline__ double warp_sum(double v) {
+        v = warp_tree(v);
+        return __shfl_sync(0xffffffffu, v, 0);
+    }
+    __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+    __device__ __forceinline__ void atomic_max(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
+
+    // Stage n doubles (global -> workspace).  Collective.  With the workspace in shared memory and
+    // 16-byte aligned endpoints the copy is a TMA bulk transfer tracked by an mbarrier.
+    __device__ __forceinline__ void copy_in(double* dst, const double* src, long long n) {
+        const bool tma_ok = ws_is_smem && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && n >= 2;
+        if (tma_ok) {
+            const long long nbulk = n & ~1ll;                    // multiple of 16 bytes
+            if (tid == 0) {
+                const unsigned long long bytes = (unsigned long long)nbulk * 8ull;
+                fence_proxy_async();       // earlier generic-proxy accesses to this workspace are ordered before the bulk write
+                mbar_arrive_expect_tx(mbar, (uint32_t)bytes);
+                unsigned long long done = 0;
+                while (done < bytes) {
+                    const uint32_t chunk = (uint32_t)((bytes - done) > 65536ull ? 65536ull : (bytes - done));
+                    tma_bulk_g2s(reinterpret_cast<char*>(dst) + done, reinterpret_cast<const char*>(src) + done, chunk, mbar);
+                    done += chunk;
+                }
+            }
+            if (tid == 32 % nthreads && (n & 1)) dst[n - 1] = src[n - 1];
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+        } else {
+            for (long long i = tid; i < n; i += nthreads) dst[i] = src[i];
+        }
+    }
+    __device__ __forceinline__ double cospi_ratio(long long m, long long N) const { return cospi((double)m / (double)N); }
+};
+
+__device__ __forceinline__ DeviceCtx make_ctx(double* red, uint64_t* mbar, int ws_is_smem) {
+    DeviceCtx cx;
+    cx.tid = threadIdx.x; cx.nthreads = blockDim.x; cx.lane = threadIdx.x & 31; cx.lanes = 32;
+    cx.warp = threadIdx.x >> 5; cx.nwarps = blockDim.x >> 5;
+    cx.red = red; cx.mbar = mbar; cx.phase = 0; cx.ws_is_smem = ws_is_smem;
+    if (threadIdx.x == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncthreads();
+    return cx;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) level_kernel(const yr::LevelArgs<D> args, int ws_in_smem) {
+    extern __shared__ __align__(16) double dyn_ws[];
+    __shared__ yr::BoxShared<D> sh;
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, ws_in_smem);
+    double* ws = ws_in_smem ? dyn_ws : args.gws + (size_t)blockIdx.x * args.gws_stride;
+    yr::level_worker<D>(cx, args, sh, ws);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) init_kernel(const yr::InitArgs<D> args, int ws_in_smem) {
+    extern __shared__ __align__(16) double dyn_ws[];
+    __shared__ yr::BoxShared<D> sh;
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, ws_in_smem);
+    double* ws = ws_in_smem ? dyn_ws : args.gws + (size_t)blockIdx.x * args.gws_stride;
+    yr::init_worker<D>(cx, args, sh, ws);
+}
+
+template <int D>
+__global__ void bils_kernel(long long n, const double* lin, const double* c0, const double* sumabs, const double* errs,
+                            const int* final_step, double* interval, int* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) yr::bils_item<D>(i, lin, c0, sumabs, errs, final_step, interval, flags);
+}
+
+template <int D>
+__global__ void quad_kernel(long long n, const double* coeffs, const long long* off, const int* shapes, const double* tol,
+                            int nd_check, int* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) yr::quad_item<D>(i, coeffs, off, shapes, tol, nd_check, out);
+}
+
+__global__ void dct1_kernel(yr::Dct1Args a) {
+    extern __shared__ __align__(16) double table[];
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::dct1_worker(cx, a, table, blockIdx.x, gridDim.x);
+}
+
+__global__ void poly_eval_kernel(yr::PolyEvalArgs a) {
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::poly_eval_worker(cx, a, blockIdx.x, gridDim.x);
+}
+
+__global__ void abs_mean_kernel(yr::AbsMeanArgs a) {
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::abs_mean_worker(cx, a, blockIdx.x);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    char buf[400];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    return yr_api::fail(buf);
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+}
+
+}  // namespace
+
+namespace yr_backend {
+
+const char* build_info() { return "cuda sm_100a (nvcc " __VERSION__ ", -fmad=false)"; }
+
+int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm) {
+    int dev = 0, v = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (sm_count) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); *sm_count = v; }
+    if (max_smem_per_cta) { cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); *max_smem_per_cta = v; }
+    if (smem_per_sm) { cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev); *smem_per_sm = v; }
+    return 0;
+}
+
+template <int D>
+int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream) {
+    const size_t smem = l.ws_in_smem ? (size_t)l.ws_doubles * 8 : 0;
+    if (!l.ws_in_smem && !l.gws) return yr_api::fail("global workspace missing");
+    if (smem > 48 * 1024 && set_smem(level_kernel<D>, smem)) return -1;
+    if (a.n_in == 0) return 0;
+    level_kernel<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, l.ws_in_smem);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "level_kernel launch");
+}
+
+template <int D>
+int launch_init(const yr::InitArgs<D>& a, const yr_launch& l, void* stream) {
+    const size_t smem = l.ws_in_smem ? (size_t)l.ws_doubles * 8 : 0;
+    if (!l.ws_in_smem && !l.gws) return yr_api::fail("global workspace missing");
+    if (smem > 48 * 1024 && set_smem(init_kernel<D>, smem)) return -1;
+    if (a.njobs == 0) return 0;
+    init_kernel<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, l.ws_in_smem);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "init_kernel launch");
+}
+
+template <int D>
+int launch_bils(int64_t n, const double* lin, const double* c0, const double* sumabs, const double* errs,
+                const int32_t* final_step, double* interval, int32_t* flags, void* stream) {
+    if (n == 0) return 0;
+    bils_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, lin, c0, sumabs, errs, final_step, interval, flags);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "bils_kernel launch");
+}
+
+template <int D>
+int launch_quad(int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes, const double* tol,
+                int32_t nd_check, int32_t* out, void* stream) {
+    if (n == 0) return 0;
+    quad_kernel<D><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        n, coeffs, reinterpret_cast<const long long*>(off), shapes, tol, nd_check, out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "quad_kernel launch");
+}
+
+static unsigned grid_for(long long total, int threads) {
+    long long g = (total + threads - 1) / threads;
+    const long long cap = 148ll * 8;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int launch_dct1(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void* stream) {
+    yr::Dct1Args a{values, coeffs, outer, npts, inner};
+    const size_t smem = (size_t)(2 * (npts - 1)) * 8;
+    if (smem > 200 * 1024) return yr_api::fail("DCT axis too long for the shared-memory cosine table");
+    if (smem > 48 * 1024 && set_smem(dct1_kernel, smem)) return -1;
+    dct1_kernel<<<grid_for(outer * npts * inner, 256), 256, smem, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "dct1_kernel launch");
+}
+
+int launch_poly_eval(const double* coef, const double* x, double* out, int64_t outer, int64_t ncoef, int64_t npts,
+                     int64_t inner, int32_t basis, void* stream) {
+    yr::PolyEvalArgs a{coef, x, out, outer, ncoef, npts, inner, basis};
+    poly_eval_kernel<<<grid_for(outer * npts * inner, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "poly_eval_kernel launch");
+}
+
+int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream) {
+    yr::AbsMeanArgs a{t, out, supnorm, outer, n, inner};
+    abs_mean_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "abs_mean_kernel launch");
+}
+
+}  // namespace yr_backend

@@ -1,0 +1,342 @@
+"""Host driver of the device-resident subdivision frontier.
+
+A solve is a sequence of level launches (include/yroots_b200.h: yr_init_boxes, then
+yr_process_level until the frontier is empty).  Boxes, their coefficient tensors, the
+result records and the node table live in device memory for the whole solve; the host
+only reads one small counter block per level to size the next launch.  PyTorch supplies
+device memory (caching allocator), the stream and pinned staging buffers -- plumbing; all
+arithmetic happens in the hand-written CUDA kernels behind the C ABI.
+
+Reference: this replaces the recursion of
+/root/reference/yroots/ChebyshevSubdivisionSolver.py:1177-1317 (solvePolyRecursive) and the
+entry point :1387-1464; the tree-structured bookkeeping that the recursion does on its way
+back up (:1266-1298 final-step de-duplication, :1318-1385 merging of touching exterior boxes)
+is rootfinding_b200/postpass.py.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+FIRST_SPLIT = 0.0394555475981047      # TrackedInterval.nextTransformPoints, ChebyshevSubdivisionSolver.py:414
+
+
+class _Buf:
+    __slots__ = ("ptr", "nbytes", "owner")
+
+    def __init__(self, ptr, nbytes, owner):
+        self.ptr, self.nbytes, self.owner = ptr, nbytes, owner
+
+
+class CudaMemory:
+    """Device memory, stream and host staging through torch (cuda only)."""
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("yroots_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def empty(self, nbytes):
+        n8 = max(1, (int(nbytes) + 7) // 8)
+        t = self.torch.empty(n8, dtype=self.torch.int64, device=self.device)
+        return _Buf(t.data_ptr(), n8 * 8, t)
+
+    def zeros(self, nbytes):
+        b = self.empty(nbytes)
+        b.owner.zero_()
+        return b
+
+    def zero_(self, buf):
+        buf.owner.zero_()
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        b = self.empty(arr.nbytes)
+        if arr.nbytes:
+            src = self.torch.from_numpy(arr.view(np.uint8).reshape(-1))
+            b.owner.view(self.torch.uint8)[:arr.nbytes].copy_(src, non_blocking=False)
+            self.h2d_bytes += arr.nbytes
+        return b
+
+    def download(self, buf, nbytes, offset=0):
+        if nbytes == 0:
+            return np.empty(0, dtype=np.uint8)
+        t = buf.owner.view(self.torch.uint8)[offset:offset + nbytes]
+        self.d2h_bytes += nbytes
+        return t.cpu().numpy()
+
+    def copy(self, dst, src, nbytes):
+        dst.owner.view(self.torch.uint8)[:nbytes].copy_(src.owner.view(self.torch.uint8)[:nbytes])
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def synchronize(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+
+@dataclass
+class SolveStats:
+    boxes: int = 0
+    zooms: int = 0
+    subdivisions: int = 0
+    discard_const: int = 0
+    discard_quad: int = 0
+    discard_zoom: int = 0
+    entry_coeffs: int = 0
+    restrict_macs: int = 0
+    max_level: int = 0
+    levels: int = 0
+    launches: int = 0
+    retries: int = 0
+    per_level: list = field(default_factory=list)     # (boxes in, children out, results, smem?, ctas, threads)
+
+    def add(self, c):
+        for k in ("boxes", "zooms", "subdivisions", "discard_const", "discard_quad", "discard_zoom",
+                  "entry_coeffs", "restrict_macs"):
+            setattr(self, k, getattr(self, k) + int(c[k]))
+        self.max_level = max(self.max_level, int(c["max_level"]))
+
+    @property
+    def algorithmic_bytes(self):
+        """every box's tensors are written once and read once."""
+        return 16 * self.entry_coeffs
+
+
+class SubdivisionEngine:
+    """Owns the library handle and launch heuristics; create sessions to solve batches."""
+
+    def __init__(self, lib=None, mem=None, threads=None, max_ctas_per_sm=None):
+        self.lib = _lib.load_cuda_library() if lib is None else lib
+        self.mem = CudaMemory() if mem is None else mem
+        sm, smem_cta, smem_sm = C.c_int32(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib, self.lib.yr_device_limits(C.byref(sm), C.byref(smem_cta), C.byref(smem_sm)), "yr_device_limits")
+        self.sm_count, self.max_smem_cta, self.smem_per_sm = sm.value, smem_cta.value, smem_sm.value
+        self.threads = threads
+        self.max_ctas_per_sm = max_ctas_per_sm
+        self.worst_case_budget = 1 << 28              # below this many bytes, just allocate the worst case
+
+    def params(self, **kw):
+        p = _lib.default_params(self.lib)
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown solver parameter {k}")
+            setattr(p, k, type(getattr(p, k))(v))
+        return p
+
+    def launch_config(self, dim, n_items, total, max_tensor, max_extent, exact):
+        """threads / persistent CTAs / workspace placement for boxes of at most this size."""
+        ws = int(self.lib.yr_workspace_doubles(dim, int(total), int(max_tensor), int(max_extent), int(exact)))
+        threads = self.threads or (128 if total >= 768 else 64)
+        static = int(self.lib.yr_static_smem_bytes(dim))
+        in_smem = ws * 8 + static <= self.max_smem_cta
+        if in_smem:
+            per_sm = max(1, min(32, 2048 // threads, self.smem_per_sm // (ws * 8 + static + 1024)))
+        else:
+            per_sm = 2
+        if self.max_ctas_per_sm:
+            per_sm = min(per_sm, self.max_ctas_per_sm)
+        ctas = int(max(1, min(n_items, self.sm_count * per_sm)))
+        return threads, ctas, in_smem, ws
+
+    def session(self, systems, errors, **params):
+        return SolveSession(self, systems, errors, self.params(**params))
+
+
+class SolveSession:
+    """One batch of systems resident on the device, plus everything solves on it produce."""
+
+    def __init__(self, engine, systems, errors, prm):
+        self.eng, self.lib, self.mem, self.prm = engine, engine.lib, engine.mem, prm
+        self.dim = D = len(systems[0])
+        if not 1 <= D <= 6:
+            raise ValueError("yroots_b200 supports systems of dimension 1..6")
+        self.nsys = len(systems)
+        shapes = np.ones((self.nsys, D, D), dtype=np.int32)
+        offs = np.zeros((self.nsys, D), dtype=np.int64)
+        chunks, pos = [], 0
+        for s, Ms in enumerate(systems):
+            for p, M in enumerate(Ms):
+                M = np.asarray(M, dtype=np.float64)
+                if M.ndim != D:
+                    raise ValueError("Solver Takes in N polynomials of dimension N!")
+                shapes[s, p] = M.shape
+                offs[s, p] = pos
+                chunks.append(np.ascontiguousarray(M).reshape(-1))
+                pos += M.size
+        self.shapes_h, self.total_coeffs = shapes, pos
+        self.sys_total = shapes.prod(axis=2).sum(axis=1)          # coefficients per system
+        self.sys_max_tensor = shapes.prod(axis=2).max(axis=1)
+        self.sys_max_extent = shapes.reshape(self.nsys, -1).max(axis=1)
+        errs = np.ascontiguousarray(np.asarray(errors, dtype=np.float64).reshape(self.nsys, D))
+        m = self.mem
+        self.d_coeffs = m.upload(np.concatenate(chunks) if chunks else np.zeros(0))
+        self.d_off = m.upload(offs)
+        self.d_shapes = m.upload(shapes)
+        self.d_errs = m.upload(errs)
+        self.rdt = _lib.result_dtype(self.lib, D)
+        self.ndt = _lib.node_dtype(self.lib, D)
+        self.box_bytes = int(self.lib.yr_record_layout(D, 0, None, 0))
+        self.d_counters = m.zeros(_lib.COUNTER_BYTES)
+        self.cap_results = 0
+        self.n_results = 0
+        self.d_results = None
+        self.cap_nodes = 0
+        self.n_nodes = 0
+        self.d_nodes = None
+        self._results_host = np.empty(0, dtype=self.rdt)
+        self._nodes_host = np.empty(0, dtype=self.ndt)
+        self.stats = SolveStats()
+        self._reserve("results", max(256, 4 * self.nsys))
+        self._reserve("nodes", max(256, 4 * self.nsys))
+
+    # -- growable append-only device arrays ------------------------------------------------
+    def _reserve(self, which, want):
+        cap = getattr(self, "cap_" + which)
+        if want <= cap:
+            return
+        new_cap = max(want, 2 * cap)
+        item = (self.rdt if which == "results" else self.ndt).itemsize
+        buf = self.mem.empty(new_cap * item)
+        old = getattr(self, "d_" + which)
+        used = getattr(self, "n_" + which)
+        if old is not None and used:
+            self.mem.copy(buf, old, used * item)
+        setattr(self, "d_" + which, buf)
+        setattr(self, "cap_" + which, new_cap)
+
+    def _read_counters(self):
+        raw = self.mem.download(self.d_counters, _lib.COUNTER_BYTES).view(np.uint64)
+        return dict(zip(_lib.COUNTER_FIELDS, (int(v) for v in raw)))
+
+    def _launch(self, threads, ctas, in_smem, ws):
+        L = _lib.YrLaunch()
+        L.threads, L.ctas, L.ws_in_smem, L.ws_doubles = threads, ctas, int(in_smem), ws
+        gws = None
+        if not in_smem:
+            gws = self.mem.empty(ctas * ws * 8)
+            L.gws, L.gws_stride = gws.ptr, ws
+        return L, gws
+
+    # -- level 0 -----------------------------------------------------------------------------
+    def _init_boxes(self, jobs):
+        D, m = self.dim, self.mem
+        sysidx = np.ascontiguousarray(jobs["system"], dtype=np.int32)
+        nj = len(sysidx)
+        total = int(self.sys_total[sysidx].sum())
+        keep = [m.upload(sysidx), m.upload(np.ascontiguousarray(jobs["restrict"], dtype=np.int32)),
+                m.upload(np.ascontiguousarray(jobs["alpha"], dtype=np.float64)),
+                m.upload(np.ascontiguousarray(jobs["beta"], dtype=np.float64)),
+                m.upload(np.ascontiguousarray(jobs["iv"], dtype=np.float64)),
+                m.upload(np.ascontiguousarray(jobs["level"], dtype=np.int32)),
+                m.upload(np.ascontiguousarray(jobs["next_mid"], dtype=np.float64)),
+                m.upload(np.ascontiguousarray(jobs["parent"], dtype=np.int32))]
+        recs = m.empty(nj * self.box_bytes)
+        data = m.empty((total + 2 * nj + 2) * 8)
+        threads, ctas, in_smem, ws = self.eng.launch_config(
+            D, nj, int(self.sys_total[sysidx].max()), int(self.sys_max_tensor[sysidx].max()),
+            int(self.sys_max_extent[sysidx].max()), self.prm.exact)
+        L, gws = self._launch(threads, ctas, in_smem, ws)
+        d = _lib.YrInitDesc()
+        d.dim = D
+        d.coeffs, d.coeff_off, d.shapes, d.errs = self.d_coeffs.ptr, self.d_off.ptr, self.d_shapes.ptr, self.d_errs.ptr
+        (d.job_system, d.job_restrict, d.job_alpha, d.job_beta, d.job_iv, d.job_level, d.job_next_mid,
+         d.job_parent) = [b.ptr for b in keep]
+        d.njobs = nj
+        d.recs_out, d.data_out, d.cap_recs_out, d.cap_data_out = recs.ptr, data.ptr, nj, total + 2 * nj
+        d.counters, d.prm, d.launch = self.d_counters.ptr, self.prm, L
+        m.zero_(self.d_counters)
+        _lib.check(self.lib, self.lib.yr_init_boxes(C.byref(d), m.stream()), "yr_init_boxes")
+        c = self._read_counters()
+        self.stats.launches += 1
+        self.stats.restrict_macs += c["restrict_macs"]
+        if c["overflow"]:
+            raise RuntimeError("yroots_b200: level-0 buffers too small (internal error)")
+        del keep, gws
+        return recs, data, c
+
+    # -- the level loop ------------------------------------------------------------------------
+    def run_jobs(self, jobs):
+        """Solve the given level-0 jobs to completion. Returns (first new result index, count)."""
+        D, m, eng = self.dim, self.mem, self.eng
+        first_result = self.n_results
+        recs, data, c = self._init_boxes(jobs)
+        n_in, data_used = c["n_children"], c["data_used"]
+        big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
+        fan = 1 << D
+        while n_in > 0:
+            threads, ctas, in_smem, ws = eng.launch_config(D, n_in, big_box, big_tensor, big_extent, self.prm.exact)
+            worst_recs, worst_data = n_in * fan, data_used * fan + 2 * n_in * fan
+            if worst_recs * self.box_bytes + worst_data * 8 <= eng.worst_case_budget:
+                cap_recs, cap_data = worst_recs, worst_data
+            else:
+                cap_recs = min(worst_recs, max(4096, int(1.6 * n_in)))
+                cap_data = min(worst_data, max(1 << 16, int(1.6 * data_used)))
+            while True:
+                self._reserve("results", self.n_results + n_in)            # a box emits at most one record
+                self._reserve("nodes", self.n_nodes + n_in)
+                out_recs = m.empty(max(1, cap_recs) * self.box_bytes)
+                out_data = m.empty(max(1, cap_data) * 8)
+                L, gws = self._launch(threads, ctas, in_smem, ws)
+                d = _lib.YrLevelDesc()
+                d.dim = D
+                d.recs_in, d.data_in, d.n_in = recs.ptr, data.ptr, n_in
+                d.recs_out, d.data_out, d.cap_recs_out, d.cap_data_out = out_recs.ptr, out_data.ptr, cap_recs, cap_data
+                d.results = self.d_results.ptr + self.n_results * self.rdt.itemsize
+                d.cap_results = self.cap_results - self.n_results
+                d.nodes = self.d_nodes.ptr + self.n_nodes * self.ndt.itemsize
+                d.cap_nodes = self.cap_nodes - self.n_nodes
+                d.result_base, d.node_base = self.n_results, self.n_nodes
+                d.counters, d.prm, d.launch = self.d_counters.ptr, self.prm, L
+                m.zero_(self.d_counters)
+                _lib.check(self.lib, self.lib.yr_process_level(C.byref(d), m.stream()), "yr_process_level")
+                c = self._read_counters()
+                self.stats.launches += 1
+                del gws
+                if not c["overflow"]:
+                    break
+                self.stats.retries += 1                                      # optimistic buffers were too small
+                cap_recs, cap_data = worst_recs, worst_data
+            self.stats.add(c)
+            self.stats.levels += 1
+            self.stats.per_level.append((n_in, c["n_children"], c["n_results"], bool(in_smem), ctas, threads, ws))
+            self.n_results += c["n_results"]
+            self.n_nodes += c["n_nodes"]
+            recs, data = out_recs, out_data
+            n_in, data_used = c["n_children"], c["data_used"]
+            big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
+        return first_result, self.n_results - first_result
+
+    def unit_jobs(self, systems=None):
+        """One job per system: the whole unit cube (ChebyshevSubdivisionSolver.py:1423)."""
+        D = self.dim
+        idx = np.arange(self.nsys, dtype=np.int32) if systems is None else np.asarray(systems, dtype=np.int32)
+        n = len(idx)
+        iv = np.empty((n, D, 2))
+        iv[:, :, 0], iv[:, :, 1] = -1.0, 1.0
+        return dict(system=idx, restrict=np.zeros(n, np.int32), alpha=np.ones((n, D)), beta=np.zeros((n, D)), iv=iv,
+                    level=np.zeros(n, np.int32), next_mid=np.full((n, D), FIRST_SPLIT), parent=np.full(n, -1, np.int32))
+
+    # -- results -----------------------------------------------------------------------------
+    def results(self):
+        """All result records so far as a numpy structured array (downloads only what is new)."""
+        have = len(self._results_host)
+        if self.n_results > have:
+            item = self.rdt.itemsize
+            raw = self.mem.download(self.d_results, (self.n_results - have) * item, have * item)
+            self._results_host = np.concatenate([self._results_host, raw.view(self.rdt)])
+        return self._results_host
+
+    def nodes(self):
+        have = len(self._nodes_host)
+        if self.n_nodes > have:
+            item = self.ndt.itemsize
+            raw = self.mem.download(self.d_nodes, (self.n_nodes - have) * item, have * item)
+            self._nodes_host = np.concatenate([self._nodes_host, raw.view(self.ndt)])
+        return self._nodes_host

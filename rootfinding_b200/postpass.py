@@ -1,0 +1,226 @@
+"""Tree-structured bookkeeping the reference does while its recursion unwinds.
+
+The device frontier is breadth first and emits flat result records; two pieces of
+solvePolyRecursive are defined on the recursion tree and act only on the (small) set of
+result boxes, so they run here on the host:
+
+ A. final-step subdivision (ChebyshevSubdivisionSolver.py:1266-1298): a box that has to be
+    subdivided *inside* its final step reports itself; the boxes found below it are
+    de-duplicated by the exact lower corner of their interval and become its
+    `possibleDuplicateRoots`; if nothing is found it is kept with `possibleExtraRoot`.
+ B. merging of exterior boxes (:1318-1385): result boxes of different children that touch or
+    overlap are replaced by the solve of their bounding box, started from the lowest common
+    ancestor's level.  The re-solve restricts the *top-level* tensors of the system to the
+    merged interval on the device (yr_init_boxes with job_restrict=1).
+
+Both are rare (2 of the 27 Chebfun2 systems); everything is vectorised so that
+batches with millions of ordinary results pay only a few numpy passes.
+"""
+import warnings
+
+import numpy as np
+
+RES_FINAL, RES_EXTRA, RES_COLLECTOR, RES_TOUCH, RES_POINT = 1, 2, 4, 8, 16
+
+
+class ResultBox:
+    """What the reference returns per root box (a TrackedInterval, :376-576), read-only."""
+
+    def __init__(self, rec, dup_roots=None, extra=False):
+        self.finalInterval = np.array(rec["box"])
+        self.interval = np.array(rec["comb_iv"])
+        self.topInterval = np.array([[-1., 1.]] * len(self.interval))
+        self.root = np.array(rec["root"])
+        self.possibleDuplicateRoots = [] if dup_roots is None else dup_roots
+        self.possibleExtraRoot = bool(extra)
+        self.finalStep = bool(rec["flags"] & RES_FINAL)
+        self.ndim = len(self.interval)
+        self.system = int(rec["system"])
+        self.level = int(rec["level"])
+
+    def getFinalInterval(self):
+        return self.finalInterval
+
+    def getFinalPoint(self):
+        return self.root
+
+    def finalDimSize(self):
+        return self.finalInterval[:, 1] - self.finalInterval[:, 0]
+
+    def dimSize(self):
+        return self.interval[:, 1] - self.interval[:, 0]
+
+    def getIntervalForCombining(self):
+        return self.interval
+
+    def __contains__(self, point):
+        return bool(np.all(point >= self.interval[:, 0]) and np.all(point <= self.interval[:, 1]))
+
+    def __repr__(self):
+        return str(self.finalInterval)
+
+
+def _path_order(res, idx):
+    return idx[np.lexsort((res["path_lo"][idx], res["path_hi"][idx], res["system"][idx]))]
+
+
+def resolve_collectors(res):
+    """Step A.  Returns (alive mask over records, {record index: list of roots}, set of extra-root records)."""
+    n = len(res)
+    alive = np.ones(n, dtype=bool)
+    dup = {}
+    extra = set()
+    coll = np.nonzero(res["flags"] & RES_COLLECTOR)[0]
+    member = np.nonzero(res["collector"] >= 0)[0]
+    if len(coll) == 0 and len(member) == 0:
+        return alive, dup, extra
+    alive[member] = False                      # everything below a collector is absorbed by it
+    kids = {}
+    for i in _path_order(res, member):         # depth-first order == the reference's visiting order
+        kids.setdefault(int(res["collector"][i]), []).append(int(i))
+    for c in coll[np.argsort(-res["level"][coll], kind="stable")]:     # deepest collectors first
+        c = int(c)
+        seen, roots = set(), []
+        for i in kids.get(c, []):
+            key = tuple(res["iv_lo"][i])
+            if key in seen:
+                continue
+            seen.add(key)
+            if dup.get(i):
+                roots += dup[i]
+            else:
+                roots.append(np.array(res["root"][i]))
+        if roots:
+            dup[c] = roots
+        else:
+            extra.add(c)
+    return alive, dup, extra
+
+
+def _overlap(a, b):
+    """TrackedInterval.overlapsWith :548-556 (closed intervals: touching counts)."""
+    return bool(np.all(a[:, 0] <= b[:, 1]) and np.all(b[:, 0] <= a[:, 1]))
+
+
+def _ancestors(nodes, start):
+    chain = []
+    k = int(start)
+    while k >= 0:
+        chain.append(k)
+        k = int(nodes["parent_node"][k])
+    return chain
+
+
+def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
+    """Step B.  May run more device jobs through `session`; returns the updated (res, alive, dup, extra)."""
+    rounds = 0
+    while rounds < max_rounds:
+        rounds += 1
+        cand = np.nonzero(alive & ((res["flags"] & RES_TOUCH) != 0))[0]
+        if len(cand) < 2:
+            break
+        pairs = []
+        order = cand[np.argsort(res["system"][cand], kind="stable")]
+        sysv = res["system"][order]
+        starts = np.nonzero(np.r_[True, sysv[1:] != sysv[:-1], True])[0]
+        for s, e in zip(starts[:-1], starts[1:]):
+            grp = order[s:e]
+            if len(grp) < 2:
+                continue
+            iv = res["comb_iv"][grp]
+            for x in range(len(grp)):
+                for y in range(x + 1, len(grp)):
+                    if _overlap(iv[x], iv[y]):
+                        pairs.append((int(grp[x]), int(grp[y])))
+        if not pairs:
+            break
+        nodes = session.nodes()
+        best = None
+        for i, j in pairs:                      # deepest common ancestor first, like the unwinding recursion
+            ai = _ancestors(nodes, res["parent_node"][i])
+            aj = set(_ancestors(nodes, res["parent_node"][j]))
+            lca = next((k for k in ai if k in aj), -1)
+            lvl = int(nodes["level"][lca]) if lca >= 0 else 0
+            if best is None or lvl > best[0]:
+                best = (lvl, i, j, lca)
+        lvl, i, j, lca = best
+        dim = res["comb_iv"].shape[1]
+        lo = np.minimum(res["comb_iv"][i][:, 0], res["comb_iv"][j][:, 0])
+        hi = np.maximum(res["comb_iv"][i][:, 1], res["comb_iv"][j][:, 1])
+        if lca >= 0:
+            anc_iv, anc_mid, anc_level = nodes["iv"][lca], nodes["next_mid"][lca], int(nodes["level"][lca])
+        else:                                   # the two boxes come from different level-0 jobs of one system
+            anc_iv = np.array([[-1., 1.]] * dim)
+            anc_mid, anc_level = np.full(dim, 0.0394555475981047), 0
+        alive[i] = alive[j] = False
+        session.stats_merges = getattr(session, "stats_merges", 0) + 1
+        if np.array_equal(lo, anc_iv[:, 0]) and np.array_equal(hi, anc_iv[:, 1]):
+            # :1370-1371 the merged box is the ancestor's whole box: keep it, do not re-solve
+            keep = i
+            res["comb_iv"][keep][:, 0], res["comb_iv"][keep][:, 1] = lo, hi
+            res["box"][keep][:, 0] = np.minimum(res["box"][i][:, 0], res["box"][j][:, 0])
+            res["box"][keep][:, 1] = np.maximum(res["box"][i][:, 1], res["box"][j][:, 1])
+            res["root"][keep] = (res["box"][keep][:, 0] + res["box"][keep][:, 1]) / 2
+            res["flags"][keep] &= ~np.uint32(RES_TOUCH)
+            alive[keep] = True
+            continue
+        iv = np.stack([lo, hi], axis=1)[None]
+        job = dict(system=np.array([res["system"][i]], np.int32), restrict=np.ones(1, np.int32),
+                   alpha=((hi - lo) / 2)[None], beta=((hi + lo) / 2)[None], iv=iv,
+                   level=np.array([anc_level], np.int32), next_mid=np.array(anc_mid)[None],
+                   parent=np.array([lca], np.int32))
+        first, count = session.run_jobs(job)
+        res = session.results()
+        grow = len(res) - len(alive)
+        alive = np.r_[alive, np.ones(grow, dtype=bool)]
+        sub_alive, sub_dup, sub_extra = resolve_collectors(res[first:first + count])
+        alive[first:first + count] = sub_alive
+        for k, v in sub_dup.items():
+            dup[first + k] = v
+        extra |= {first + k for k in sub_extra}
+    return res, alive, dup, extra
+
+
+def assemble(session, first=0, count=None, merge=True):
+    """Turn the session's result records into per-system (roots, boxes) in depth-first order."""
+    res = session.results()
+    if count is None:
+        count = len(res) - first
+    res = res[first:first + count] if (first or count != len(res)) else res
+    alive, dup, extra = resolve_collectors(res)
+    if merge and first == 0:
+        res, alive, dup, extra = merge_exterior(session, res, alive, dup, extra)
+    keep = _path_order(res, np.nonzero(alive)[0])
+    return res, keep, dup, extra
+
+
+def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False):
+    """Vectorised gathering of roots per system; special records are patched in afterwards."""
+    sysv = res["system"][keep]
+    bounds = np.searchsorted(sysv, np.arange(nsys + 1))
+    roots_all = res["root"][keep]
+    out_roots, out_boxes, has_dup, has_extra = [], [], False, False
+    special = {int(k) for k in dup} | {int(k) for k in extra}
+    for s in range(nsys):
+        idx = keep[bounds[s]:bounds[s + 1]]
+        if special and not special.isdisjoint(idx.tolist()):
+            rows = []
+            for i in idx:
+                if int(i) in dup:
+                    rows += dup[int(i)]
+                    has_dup = True
+                else:
+                    rows.append(res["root"][i])
+                if int(i) in extra:
+                    has_extra = True
+            r = np.array(rows).reshape(-1, dim)
+        else:
+            r = roots_all[bounds[s]:bounds[s + 1]]
+        out_roots.append(r)
+        if want_boxes:
+            out_boxes.append([ResultBox(res[i], dup.get(int(i)), int(i) in extra) for i in idx])
+    if has_extra:
+        warnings.warn("Might Have Extra Roots! See Bounding Boxes for details!")
+    if has_dup:
+        warnings.warn("Might Have Duplicate Roots! See Bounding Boxes for details!")
+    return out_roots, out_boxes

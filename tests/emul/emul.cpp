@@ -1,0 +1,163 @@
+// TEST INFRASTRUCTURE ONLY -- SPMD emulator of the CUDA kernel source.
+//
+// Compiles rootfinding_b200/csrc/yr_box.h (the per-box pipeline the CUDA kernels run)
+// for the CPU and executes each "CTA" as a team of pthreads with a spin barrier, warp
+// and block reductions performed in the same order as on the device.  It exports the
+// same C ABI as the product library so tests can drive the real host code against it
+// on a machine without a GPU.  The product package never loads this library.
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../rootfinding_b200/csrc/yr_api_impl.h"
+#include "../../rootfinding_b200/csrc/yr_approx.h"
+
+namespace {
+
+struct SpinBarrier {
+    std::atomic<int> count{0};
+    std::atomic<int> sense{0};
+    int n = 1;
+    void wait() {
+        const int s = sense.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(1 - s, std::memory_order_release);
+        } else {
+            int spins = 0;
+            while (sense.load(std::memory_order_acquire) == s) { if (++spins > 2000) { std::this_thread::yield(); spins = 0; } }
+        }
+    }
+};
+
+struct Team {
+    int T, lanes;
+    SpinBarrier bar;
+    std::vector<double> scratch;
+};
+
+struct HostCtx {
+    int tid, nthreads, lane, lanes, warp, nwarps;
+    Team* team;
+    void sync() { team->bar.wait(); }
+    double tree(int w) const {
+        double a[64];
+        for (int l = 0; l < lanes; ++l) a[l] = team->scratch[w * lanes + l];
+        for (int off = lanes / 2; off >= 1; off /= 2) for (int l = 0; l < off; ++l) a[l] += a[l + off];
+        return a[0];
+    }
+    double block_sum(double v) {
+        team->scratch[tid] = v; sync();
+        double tot = 0; for (int w = 0; w < nwarps; ++w) tot += tree(w);
+        sync(); return tot;
+    }
+    double block_max(double v) {
+        team->scratch[tid] = v; sync();
+        double m = team->scratch[0]; for (int t = 1; t < nthreads; ++t) m = team->scratch[t] > m ? team->scratch[t] : m;
+        sync(); return m;
+    }
+    double warp_sum(double v) {
+        team->scratch[tid] = v; sync();
+        const double r = tree(warp);
+        sync(); return r;
+    }
+    unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+    void atomic_max(unsigned long long* p, unsigned long long v) {
+        unsigned long long cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+        while (cur < v && !__atomic_compare_exchange_n(p, &cur, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    }
+    void copy_in(double* dst, const double* src, long long n) { for (long long i = tid; i < n; i += nthreads) dst[i] = src[i]; }
+    double cospi_ratio(long long m, long long N) const { return cos(M_PI * (double)m / (double)N); }
+};
+
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+
+template <class Body>
+void run_team(int T, int lanes, Body body) {
+    Team team; team.T = T; team.lanes = lanes; team.bar.n = T; team.scratch.assign(T, 0.0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+            HostCtx cx; cx.tid = t; cx.nthreads = T; cx.lanes = lanes; cx.lane = t % lanes; cx.warp = t / lanes;
+            cx.nwarps = T / lanes; cx.team = &team;
+            body(cx);
+        });
+    for (auto& x : th) x.join();
+}
+
+}  // namespace
+
+namespace yr_backend {
+
+const char* build_info() { return "emulator (pthreads; tests only)"; }
+
+int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm) {
+    if (sm_count) *sm_count = 2;
+    if (max_smem_per_cta) *max_smem_per_cta = 227 * 1024;
+    if (smem_per_sm) *smem_per_sm = 228 * 1024;
+    return 0;
+}
+
+template <int D>
+int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void*) {
+    const int T = env_int("YR_EMUL_THREADS", 8), lanes = env_int("YR_EMUL_LANES", 4);
+    std::vector<double> ws;
+    double* wsp;
+    if (l.ws_in_smem) { ws.assign(l.ws_doubles + 8, 0.0); wsp = ws.data(); } else wsp = l.gws;
+    yr::BoxShared<D>* sh = new yr::BoxShared<D>();
+    run_team(T, lanes, [&](HostCtx& cx) { yr::level_worker<D>(cx, a, *sh, wsp); });
+    delete sh;
+    return 0;
+}
+
+template <int D>
+int launch_init(const yr::InitArgs<D>& a, const yr_launch& l, void*) {
+    const int T = env_int("YR_EMUL_THREADS", 8), lanes = env_int("YR_EMUL_LANES", 4);
+    std::vector<double> ws;
+    double* wsp;
+    if (l.ws_in_smem) { ws.assign(l.ws_doubles + 8, 0.0); wsp = ws.data(); } else wsp = l.gws;
+    yr::BoxShared<D>* sh = new yr::BoxShared<D>();
+    run_team(T, lanes, [&](HostCtx& cx) { yr::init_worker<D>(cx, a, *sh, wsp); });
+    delete sh;
+    return 0;
+}
+
+template <int D>
+int launch_bils(int64_t n, const double* lin, const double* c0, const double* sumabs, const double* errs,
+                const int32_t* final_step, double* interval, int32_t* flags, void*) {
+    for (int64_t i = 0; i < n; ++i) yr::bils_item<D>(i, lin, c0, sumabs, errs, final_step, interval, flags);
+    return 0;
+}
+
+template <int D>
+int launch_quad(int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes, const double* tol,
+                int32_t nd_check, int32_t* out, void*) {
+    for (int64_t i = 0; i < n; ++i)
+        yr::quad_item<D>(i, coeffs, reinterpret_cast<const long long*>(off), shapes, tol, nd_check, out);
+    return 0;
+}
+
+int launch_dct1(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void*) {
+    yr::Dct1Args a{values, coeffs, outer, npts, inner};
+    std::vector<double> table(2 * npts);
+    run_team(4, 4, [&](HostCtx& cx) { yr::dct1_worker(cx, a, table.data(), 0, 1); });
+    return 0;
+}
+
+int launch_poly_eval(const double* coef, const double* x, double* out, int64_t outer, int64_t ncoef, int64_t npts,
+                     int64_t inner, int32_t basis, void*) {
+    yr::PolyEvalArgs a{coef, x, out, outer, ncoef, npts, inner, basis};
+    run_team(4, 4, [&](HostCtx& cx) { yr::poly_eval_worker(cx, a, 0, 1); });
+    return 0;
+}
+
+int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void*) {
+    yr::AbsMeanArgs a{t, out, supnorm, outer, n, inner};
+    run_team(4, 4, [&](HostCtx& cx) { for (int64_t j = 0; j < n; ++j) yr::abs_mean_worker(cx, a, j); });
+    return 0;
+}
+
+}  // namespace yr_backend
