@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py -- subdivision boxes/sec on batched random dense 2-D degree-50 Chebyshev systems.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl own|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path (device frontier solve) over one batch of B synthetic systems per
+GPU: `rand_coeffs(dim=2, deg=50, B, 'randn')` of the reference's tests/random_tests.py:5-19, solved as
+solveChebyshevSubdivision(Ms, errors=2^-52).  Weak scaling: every rank owns its own B systems.
+
+  value      boxes/s (boxes = invocations of the reference's solvePolyRecursive, counted on the
+             device), inputs resident in HBM, CUDA events around the level loop, max over ranks
+  e2e        the same metric through the public API rootfinding_b200.solve_batch with HOST buffers:
+             pack + pinned H2D + solve + D2H of the result records + host post-pass, per step
+  roofline   for the dominant kernel (level_kernel<2>): algorithmic bytes (16 B per coefficient of
+             every box at entry) / summed kernel time from CUDA events around every launch
+  cpu_baseline  the oracle port of the reference solver on the host cores (one process per core)
+`--impl reference` times that CPU arm alone on the same workload (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+DIM, DEG = 2, 50
+METRIC = "subdivision boxes/sec"
+UNIT = "boxes/s"
+
+
+def workload(batch, seed):
+    from oracle.gen_golden import rand_coeffs           # generator only (restates tests/random_tests.py:5-19)
+    np.random.seed(seed)
+    arr = rand_coeffs(DIM, DEG, batch, "randn")
+    systems = [[np.ascontiguousarray(m) for m in arr[s]] for s in range(batch)]
+    return systems, [np.full(DIM, 2.0 ** -52)] * batch
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_arm(steps, warmup, cores=None):
+    from oracle.cpu_bench import CpuArm
+    arm = CpuArm(DIM, DEG, cores=cores, per_worker=1)
+    for _ in range(warmup):
+        arm.step()
+    boxes = roots = 0
+    wall = 0.0
+    for _ in range(steps):
+        b, r, w = arm.step()
+        boxes, roots, wall = boxes + b, roots + r, wall + w
+    arm.close()
+    return {"value": boxes / wall, "unit": UNIT, "cores": arm.cores, "kind": "port",
+            "sample": f"{steps} x {arm.cores} random 2-D degree-{DEG} systems (one per core per step), "
+                      f"{boxes} boxes in {wall:.1f} s; oracle/ port of the reference solver, pinned bit-for-bit to it"}, wall, steps
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    base, wall, steps = cpu_arm(args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, base["cores"]), "cpu_baseline": base, "gpu_launches": 0,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, systems_per_step):
+    return {"workload": f"batched random dense 2-D Chebyshev systems, degree {DEG} (BASELINE.json configs[2], headline deg 50): "
+                        f"rand_coeffs(2,{DEG},B,'randn'), errors 2^-52",
+            "systems_per_gpu_per_step": systems_per_step, "dim": DIM, "degree": DEG,
+            "l2": "frontier traffic per step >> 126 MB L2; 256 MB scratch written between steps",
+            "arithmetic": "fma" if args.fma else "separately rounded mul/add (restrictions bit-identical to the reference)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("YR_BENCH_BATCH", "1024")))
+    ap.add_argument("--fma", type=int, default=int(os.environ.get("YR_BENCH_FMA", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warnings.simplefilter("ignore")
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    base = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        base, _, _ = cpu_arm(steps=2, warmup=0)            # bounded sample, before CUDA is touched
+
+    import torch
+    import torch.distributed as dist
+    from rootfinding_b200 import ChebyshevSubdivisionSolver as S, postpass
+    from rootfinding_b200.runtime import get_engine
+    from rootfinding_b200.distributed import all_gather_roots
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = get_engine()
+    systems, errs = workload(args.batch, seed=2 + rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(timed):
+        """Inputs resident in HBM; timed region = level-0 box creation + every level launch."""
+        sess = eng.session(systems, errs, use_fma=args.fma)
+        sess.time_kernels = timed
+        flush.fill_(1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sess.run_jobs(sess.unit_jobs())
+        e1.record()
+        barrier()
+        return sess, e0.elapsed_time(e1)
+
+    def api_step():
+        """Public API with host buffers: pack, pinned H2D, solve, D2H, post-pass, root all-gather."""
+        flush.fill_(1)
+        barrier()
+        h0, d0 = eng.mem.h2d_bytes, eng.mem.d2h_bytes
+        t0 = time.perf_counter()
+        roots, sess = S.solve_batch(systems, errs, use_fma=bool(args.fma), return_session=True)
+        if world > 1:
+            all_gather_roots(roots, np.arange(rank, world * len(systems), world), world * len(systems), DIM)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return sess, dt, eng.mem.h2d_bytes - h0, eng.mem.d2h_bytes - d0, sum(len(r) for r in roots)
+
+    for _ in range(args.warmup):
+        device_step(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, boxes, launches, kernel_ms, kernel_bytes = 0.0, 0, 0, 0.0, 0
+    for _ in range(args.steps):
+        sess, ms = device_step(True)
+        total_ms += ms
+        boxes += sess.stats.boxes
+        launches += sess.stats.launches
+        kernel_ms += sum(k[0] for k in sess.kernel_ms)
+        kernel_bytes += sum(k[1] for k in sess.kernel_ms)
+        stats = sess.stats
+    e2e_s, e2e_boxes, h2d, d2h, nroots = 0.0, 0, 0, 0, 0
+    api_step()                                                 # warm the API path once
+    for _ in range(args.steps):
+        sess, dt, hb, db, nroots = api_step()
+        e2e_s += dt
+        e2e_boxes += sess.stats.boxes
+        h2d, d2h = hb, db
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([boxes, e2e_boxes, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)               # slowest rank defines the step
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    boxes_all, e2e_boxes_all, launches_all = float(cnt[0]), float(cnt[1]), int(cnt[2])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        line = {"metric": METRIC, "value": boxes_all / (total_ms_max * 1e-3), "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, args.batch),
+                "e2e": {"value": e2e_boxes_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "solves_per_s": args.batch * world * args.steps / e2e_s_max, "roots_per_step_rank0": int(nroots)},
+                "gpu_launches": launches_all,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "level_kernel<2> (all level launches of the timed steps, rank 0)",
+                             "peak_source": peak_src,
+                             "bytes_per_box": 16.0 * stats.entry_coeffs / max(stats.boxes, 1),
+                             "kernel_share_of_step": kernel_ms / max(total_ms, 1e-9)},
+                "clocks": sampler.summary(),
+                "detail": {"boxes_per_step_rank0": stats.boxes, "levels": stats.levels, "retries": stats.retries,
+                           "zooms": stats.zooms, "subdivisions": stats.subdivisions,
+                           "restrict_gflops_per_s": 2.0 * stats.restrict_macs / 1e9 / (total_ms / args.steps * 1e-3),
+                           "build": eng.lib.yr_build_info().decode()}}
+        if base is not None:
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,248 @@
+"""Drop-in for yroots.ChebyshevApproximator on a B200.
+
+Same functions and results as /root/reference/yroots/ChebyshevApproximator.py; the heavy parts run
+on the device through include/yroots_b200.h:
+  * grid samples of MultiCheb / MultiPower objects     -> yr_poly_eval_axis, axis by axis (Clenshaw / Horner)
+  * values -> Chebyshev coefficients (dctn type 1, :78-82) -> yr_dct1_axis, axis by axis
+  * axis means of |coeff| for the decay tests (:288) and max|values| (:72) -> yr_abs_axis_mean
+Opaque Python callables are sampled point by point on the host exactly as the reference does (:69) --
+an upstream input that bench.py times separately -- and uploaded once.
+"""
+import itertools
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .polynomial import MultiCheb, MultiPower
+from .runtime import get_engine
+
+macheps = 2.0 ** -52
+
+
+def transform(x, a, b):
+    """[-1,1] -> [a,b] (:8-26)."""
+    return ((b - a) * x + (b + a)) / 2
+
+
+def _is_poly(f):
+    return isinstance(f, (MultiCheb, MultiPower))
+
+
+class _DeviceGrid:
+    """Values of one function on a Chebyshev-Lobatto grid, resident on the device."""
+
+    def __init__(self, eng, f, degs, a, b):
+        self.eng, m, lib = eng, eng.mem, eng.lib
+        self.npts = [int(d) + 1 for d in degs]
+        dim = len(degs)
+        axes = [transform(np.cos(np.arange(n + 1) * np.pi / n), lo, hi) for n, lo, hi in zip(degs, a, b)]
+        if _is_poly(f):
+            # tensor-product evaluation: one axis at a time, same recurrences as Polynomial.__call__
+            cur = m.upload(np.ascontiguousarray(f.coeff, dtype=np.float64))
+            shape = list(f.coeff.shape)
+            for d in range(dim):
+                outer = int(np.prod(self.npts[:d], dtype=np.int64))
+                inner = int(np.prod(shape[d + 1:], dtype=np.int64))
+                x = m.upload(np.ascontiguousarray(axes[d], dtype=np.float64))
+                out = m.empty(outer * self.npts[d] * inner * 8)
+                _lib.check(lib, lib.yr_poly_eval_axis(cur.ptr, x.ptr, out.ptr, outer, shape[d], self.npts[d], inner,
+                                                      f.basis_id, m.stream()), "yr_poly_eval_axis")
+                cur = out
+            self.values = cur
+        else:
+            grid = np.meshgrid(*axes, indexing='ij')
+            pts = np.column_stack(tuple(g.flatten() for g in grid))
+            vals = np.array([f(*p) for p in pts], dtype=np.float64)             # host sampling, as the reference
+            self.values = m.upload(vals)
+        self.size = int(np.prod(self.npts, dtype=np.int64))
+
+    def sup_norm(self):
+        m, lib = self.eng.mem, self.eng.lib
+        n0 = self.npts[0]
+        mean, mx = m.empty(n0 * 8), m.empty(n0 * 8)
+        _lib.check(lib, lib.yr_abs_axis_mean(self.values.ptr, mean.ptr, mx.ptr, 1, n0, self.size // n0, m.stream()),
+                   "yr_abs_axis_mean")
+        return float(np.max(m.download(mx, n0 * 8).view(np.float64)))
+
+    def coefficients(self):
+        """DCT-I along every axis; returns the device buffer of the full (deg+1)^dim coefficient tensor."""
+        m, lib = self.eng.mem, self.eng.lib
+        cur = self.values
+        for d, n in enumerate(self.npts):
+            outer = int(np.prod(self.npts[:d], dtype=np.int64))
+            inner = int(np.prod(self.npts[d + 1:], dtype=np.int64))
+            out = m.empty(self.size * 8)
+            _lib.check(lib, lib.yr_dct1_axis(cur.ptr, out.ptr, outer, n, inner, m.stream()), "yr_dct1_axis")
+            cur = out
+        return cur
+
+    def axis_mean_abs(self, coeff_buf, axis):
+        m, lib = self.eng.mem, self.eng.lib
+        n = self.npts[axis]
+        outer = int(np.prod(self.npts[:axis], dtype=np.int64))
+        inner = int(np.prod(self.npts[axis + 1:], dtype=np.int64))
+        mean = m.empty(n * 8)
+        _lib.check(lib, lib.yr_abs_axis_mean(coeff_buf.ptr, mean.ptr, None, outer, n, inner, m.stream()), "yr_abs_axis_mean")
+        return m.download(mean, n * 8).view(np.float64).copy()
+
+
+def interval_approximate_nd(f, degs, a, b, retSupNorm=False, engine=None, _want_chunk_axis=None):
+    """Chebyshev interpolant of f on [a,b] with the given degrees (:28-89)."""
+    eng = get_engine() if engine is None else engine
+    originalDegs = degs.copy()
+    degs[degs == 0] = 1                                # like the reference, this edits the caller's array
+    grid = _DeviceGrid(eng, f, degs, a, b)
+    supNorm = grid.sup_norm() if retSupNorm else None
+    buf = grid.coefficients()
+    chunk = None
+    if _want_chunk_axis is not None and np.all(originalDegs >= 1):
+        chunk = grid.axis_mean_abs(buf, _want_chunk_axis)
+    full = eng.mem.download(buf, grid.size * 8).view(np.float64).reshape(grid.npts)
+    coeffs = full[tuple(slice(0, d + 1) for d in originalDegs)]
+    if _want_chunk_axis is not None:
+        return coeffs, supNorm, chunk
+    return (coeffs, supNorm) if retSupNorm else coeffs
+
+
+def startedConverging(coeffList, tol):
+    """:91-106."""
+    return np.all(coeffList[-5:] < tol)
+
+
+def hasConverged(coeff, coeff2, tol):
+    """:108-129."""
+    diff = coeff2.copy()
+    diff[tuple(slice(0, d) for d in coeff.shape)] -= coeff
+    return np.max(np.abs(diff)) < tol
+
+
+def getFinalDegree(coeff, tol, macheps=2 ** -52):
+    """:131-172 -> (degree, epsVal, rho)."""
+    settled = int(3 * (len(coeff) - 1) / 4)
+    epsVal = 2 * max(macheps, np.max(coeff[settled:]))
+    big = np.where(coeff > epsVal)[0]
+    degree = 1 if len(big) == 0 else max(1, big[-1])
+    if np.all(coeff[1:] < tol):
+        degree = 0
+    peak = np.argmax(coeff)
+    if epsVal == 0:
+        epsVal = coeff[peak] * 1e-24
+    rho = (coeff[peak] / epsVal) ** (1 / ((degree - peak) + 1))
+    return degree, epsVal, rho
+
+
+_PROBES_1 = [-0.7996847717584993, 0.18546110255464776, -0.13975937255055182, 0., 1., -1.]
+_PROBES_2 = [-0.17223860129797386, 0.10828286380141305, -0.5333148248321931, 0.46471703497219596]
+
+
+def checkConstantInDimension(f, a, b, currDim, relApproxTol, absApproxTol=0):
+    """:174-226 -- a dozen point evaluations; stays on the host."""
+    call = (lambda p: f(p)) if _is_poly(f) else (lambda p: f(*p))
+    dim = len(a)
+    for base, probes in ((np.array([0.8984743990614998 ** (k + 1) for k in range(dim)]), _PROBES_1),
+                         (np.array([(-0.2598647169391334 * (k + 1) / dim) ** 2 for k in range(dim)]), _PROBES_2)):
+        x = transform(base, a, b)
+        ref = call(x)
+        if np.isclose(ref, 0, rtol=relApproxTol, atol=absApproxTol):
+            return False
+        for v in transform(np.array(probes), a[currDim], b[currDim]):
+            x[currDim] = v
+            if not np.allclose(ref, call(x), rtol=relApproxTol, atol=absApproxTol):
+                return False
+    return True
+
+
+def getChebyshevDegrees(f, a, b, relApproxTol, absApproxTol=0, engine=None):
+    """Degree search per axis by doubling (:228-311) -> (degrees, epsilons, rhos)."""
+    dim = len(a)
+    chebDegrees = [np.inf] * dim
+    epsilons, rhos = [], []
+    for currDim in range(dim):
+        if checkConstantInDimension(f, a, b, currDim, relApproxTol, absApproxTol):
+            chebDegrees[currDim] = 0
+    for currDim in range(dim):
+        if chebDegrees[currDim] == 0:
+            epsilons.append(0)
+            rhos.append(np.inf)
+            continue
+        degs = np.array([5] * dim if dim <= 5 else [2] * dim)
+        for i in range(dim):
+            if chebDegrees[i] < degs[i]:
+                degs[i] = chebDegrees[i]
+        currGuess = 8
+        while True:
+            if currGuess > 1e5:
+                warnings.warn(f"Approximation bound exceeded!\n\nApproximation degree in dimension {currDim} "
+                              "has exceeded 1e5, so the process may not finish.\n\nConsider interrupting "
+                              "and restarting the process after ensuring that the function(s) inputted are "
+                              "continuous and smooth on the approximation interval.\n\n")
+            degs[currDim] = currGuess
+            coeff, supNorm, chunk = interval_approximate_nd(f, degs, a, b, True, engine, _want_chunk_axis=currDim)
+            chunk = _sliced_chunk(coeff, chunk, currDim)
+            tol = absApproxTol + supNorm * relApproxTol
+            currGuess *= 2
+            if not startedConverging(chunk, tol):
+                continue
+            degs[currDim] = currGuess + 1
+            coeff2, supNorm2, chunk2 = interval_approximate_nd(f, degs, a, b, True, engine, _want_chunk_axis=currDim)
+            tol = absApproxTol + max(supNorm, supNorm2) * relApproxTol
+            if not hasConverged(coeff, coeff2, tol):
+                continue
+            chunk2 = _sliced_chunk(coeff2, chunk2, currDim)
+            deg, eps, rho = getFinalDegree(chunk2, tol)
+            chebDegrees[currDim] = deg
+            epsilons.append(eps)
+            rhos.append(rho)
+            break
+    return np.array(chebDegrees), np.array(epsilons), np.array(rhos)
+
+
+def _sliced_chunk(coeff, device_chunk, axis):
+    """Axis means of |coeff| (:288): the device's when it covers exactly the returned tensor, else
+    (degree-0 axes are sampled as degree 1 and sliced away, :57,:85) recomputed on the sliced tensor."""
+    if device_chunk is not None:
+        return device_chunk
+    return np.average(np.abs(coeff), axis=tuple(i for i in range(coeff.ndim) if i != axis))
+
+
+def getApproxError(degs, epsilons, rhos):
+    """Geometric-tail bound over the 2^dim - 1 truncated index classes (:313-356)."""
+    total = 0
+    for mask in itertools.product(range(2), repeat=len(degs)):
+        if np.sum(mask) == 0:
+            continue
+        weight, eps = 1, 0
+        for i, beyond in enumerate(mask):
+            if beyond:
+                weight /= (rhos[i] - 1)
+                eps = max(eps, epsilons[i])
+            else:
+                weight *= (degs[i] + 1)
+        total += weight * eps
+    return total
+
+
+def chebApproximate(f, a, b, relApproxTol=1e-10, engine=None):
+    """(coefficient tensor, error bound) of f on [a,b] (:358-450)."""
+    if not hasattr(f, '__call__'):
+        raise ValueError("Invalid input: input function is not callable")
+    if type(a) == list:
+        a = np.array(a)
+    if type(b) == list:
+        b = np.array(b)
+    if type(a) != np.ndarray:
+        a = np.array([a])
+    if type(b) != np.ndarray:
+        b = np.array([b])
+    if len(a) != len(b):
+        raise ValueError(f"Invalid input: {len(a)} lower bounds were given but {len(b)} upper bounds were given")
+    if (b < a).any():
+        raise ValueError("Invalid input: at least one lower bound is greater than the corresponding upper bound.")
+    mid = [(u + l) / 2 for l, u in zip(a, b)]
+    try:
+        f(mid) if _is_poly(f) else f(*mid)
+    except TypeError:
+        raise ValueError("Invalid input: length of the upper/lower bound lists must match the dimension of the function")
+    degs, epsilons, rhos = getChebyshevDegrees(f, a, b, relApproxTol, engine=engine)
+    return interval_approximate_nd(f, degs, a, b, engine=engine), getApproxError(degs, epsilons, rhos)

@@ -592,9 +592,17 @@ YR_DEV void subdivide_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, d
         out.parent_node = final_step_split ? sh.rec.parent_node : sh.node_index;
         out.collector = final_step_split ? sh.result_index : sh.rec.collector;
         out.level = sh.level;
-        // append k bits of child slot to the DFS path key
+        // append the k-bit child slot below the bits already used (left aligned 128-bit key)
         unsigned long long hi = sh.rec.path_hi, lo = sh.rec.path_lo;
-        hi = (hi << k) | (lo >> (64 - k)); lo = (lo << k) | (unsigned long long)c;
+        const int used = sh.rec.path_bits;
+        const int shift = 128 - used - k;
+        if (shift >= 64) hi |= (unsigned long long)c << (shift - 64);
+        else if (shift >= 0) {
+            lo |= (unsigned long long)c << shift;
+            if (shift + k > 64) hi |= (unsigned long long)c >> (64 - shift);
+        }
+        out.path_bits = (shift >= 0) ? used + k : used;
+        out.pad0 = 0;
         out.path_hi = hi; out.path_lo = lo;
     }
     // tensors: per polynomial, halve along its own axis order (largest extent first), depth first,
@@ -933,7 +941,7 @@ YR_DEV void init_worker(Ctx& cx, const InitArgs<D>& args, BoxShared<D>& sh, doub
                 for (int p = 0; p < D; ++p) { for (int a = 0; a < D; ++a) out.shape[p][a] = sh.shape[p][a]; out.err[p] = sh.err[p]; }
                 out.st = sh.rec.st;
                 out.system = sys; out.parent_node = args.job_parent[j]; out.collector = -1;
-                out.level = args.job_level[j]; out.path_hi = 0; out.path_lo = (unsigned long long)j;
+                out.level = args.job_level[j]; out.path_hi = 0; out.path_lo = 0; out.path_bits = 0; out.pad0 = 0;
             }
         }
         cx.sync();

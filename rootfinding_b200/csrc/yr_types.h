@@ -36,7 +36,9 @@ struct BoxRec {
     int32_t  parent_node;          // NodeRec index of the subdividing parent (-1: top)
     int32_t  collector;            // ResultRec index of the enclosing final-step subdivision (-1: none)
     int32_t  level;                // solverOptions.level of the parent invocation
-    uint64_t path_hi, path_lo;     // child slots from the top, D bits per subdivision (DFS order key)
+    int32_t  path_bits;            // bits of path_hi:path_lo in use
+    int32_t  pad0;
+    uint64_t path_hi, path_lo;     // child slots from the top, left aligned (MSB first): integer order == depth-first order
 };
 
 enum : uint32_t {

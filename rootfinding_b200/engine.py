@@ -41,6 +41,7 @@ class CudaMemory:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._staging = []
 
     def empty(self, nbytes):
         n8 = max(1, (int(nbytes) + 7) // 8)
@@ -56,20 +57,30 @@ class CudaMemory:
         buf.owner.zero_()
 
     def upload(self, arr):
+        """Host -> device through a pinned staging buffer (asynchronous on the current stream)."""
         arr = np.ascontiguousarray(arr)
         b = self.empty(arr.nbytes)
         if arr.nbytes:
-            src = self.torch.from_numpy(arr.view(np.uint8).reshape(-1))
-            b.owner.view(self.torch.uint8)[:arr.nbytes].copy_(src, non_blocking=False)
+            pinned = self.torch.empty(arr.nbytes, dtype=self.torch.uint8, pin_memory=True)
+            pinned.numpy()[:] = arr.view(np.uint8).reshape(-1)
+            b.owner.view(self.torch.uint8)[:arr.nbytes].copy_(pinned, non_blocking=True)
+            self._staging.append(pinned)                       # keep alive until the next synchronize
             self.h2d_bytes += arr.nbytes
         return b
+
+    def timer(self):
+        """CUDA event pair helper: returns (record_start, record_stop, elapsed_ms) bound to the current stream."""
+        ev = self.torch.cuda.Event
+        return ev(enable_timing=True), ev(enable_timing=True)
 
     def download(self, buf, nbytes, offset=0):
         if nbytes == 0:
             return np.empty(0, dtype=np.uint8)
         t = buf.owner.view(self.torch.uint8)[offset:offset + nbytes]
         self.d2h_bytes += nbytes
-        return t.cpu().numpy()
+        out = t.cpu().numpy()                                  # synchronises the stream
+        self._staging.clear()
+        return out
 
     def copy(self, dst, src, nbytes):
         dst.owner.view(self.torch.uint8)[:nbytes].copy_(src.owner.view(self.torch.uint8)[:nbytes])
@@ -79,6 +90,7 @@ class CudaMemory:
 
     def synchronize(self):
         self.torch.cuda.current_stream(self.device).synchronize()
+        self._staging.clear()
 
 
 @dataclass
@@ -193,6 +205,8 @@ class SolveSession:
         self._results_host = np.empty(0, dtype=self.rdt)
         self._nodes_host = np.empty(0, dtype=self.ndt)
         self.stats = SolveStats()
+        self.time_kernels = False        # bench.py: CUDA events around every level launch
+        self.kernel_ms = []              # (ms, algorithmic bytes, boxes) per level launch
         self._reserve("results", max(256, 4 * self.nsys))
         self._reserve("nodes", max(256, 4 * self.nsys))
 
@@ -295,8 +309,15 @@ class SolveSession:
                 d.result_base, d.node_base = self.n_results, self.n_nodes
                 d.counters, d.prm, d.launch = self.d_counters.ptr, self.prm, L
                 m.zero_(self.d_counters)
+                ev = m.timer() if (self.time_kernels and hasattr(m, "timer")) else None
+                if ev:
+                    ev[0].record()
                 _lib.check(self.lib, self.lib.yr_process_level(C.byref(d), m.stream()), "yr_process_level")
+                if ev:
+                    ev[1].record()
                 c = self._read_counters()
+                if ev:
+                    self.kernel_ms.append((ev[0].elapsed_time(ev[1]), 16 * c["entry_coeffs"], c["boxes"]))
                 self.stats.launches += 1
                 del gws
                 if not c["overflow"]:

@@ -64,17 +64,21 @@ def _path_order(res, idx):
     return idx[np.lexsort((res["path_lo"][idx], res["path_hi"][idx], res["system"][idx]))]
 
 
-def resolve_collectors(res):
-    """Step A.  Returns (alive mask over records, {record index: list of roots}, set of extra-root records)."""
-    n = len(res)
-    alive = np.ones(n, dtype=bool)
+def resolve_collectors(res, start=0, stop=None):
+    """Step A on records [start, stop).  Record links (`collector`) are global indices into `res`.
+
+    Returns (alive mask for that range, {global record index: list of roots}, set of extra-root records).
+    """
+    stop = len(res) if stop is None else stop
+    alive = np.ones(stop - start, dtype=bool)
     dup = {}
     extra = set()
-    coll = np.nonzero(res["flags"] & RES_COLLECTOR)[0]
-    member = np.nonzero(res["collector"] >= 0)[0]
+    rng = np.arange(start, stop)
+    coll = rng[(res["flags"][start:stop] & RES_COLLECTOR) != 0]
+    member = rng[res["collector"][start:stop] >= 0]
     if len(coll) == 0 and len(member) == 0:
         return alive, dup, extra
-    alive[member] = False                      # everything below a collector is absorbed by it
+    alive[member - start] = False              # everything below a collector is absorbed by it
     kids = {}
     for i in _path_order(res, member):         # depth-first order == the reference's visiting order
         kids.setdefault(int(res["collector"][i]), []).append(int(i))
@@ -173,22 +177,18 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
         res = session.results()
         grow = len(res) - len(alive)
         alive = np.r_[alive, np.ones(grow, dtype=bool)]
-        sub_alive, sub_dup, sub_extra = resolve_collectors(res[first:first + count])
+        sub_alive, sub_dup, sub_extra = resolve_collectors(res, first, first + count)
         alive[first:first + count] = sub_alive
-        for k, v in sub_dup.items():
-            dup[first + k] = v
-        extra |= {first + k for k in sub_extra}
+        dup.update(sub_dup)
+        extra |= sub_extra
     return res, alive, dup, extra
 
 
-def assemble(session, first=0, count=None, merge=True):
+def assemble(session, merge=True):
     """Turn the session's result records into per-system (roots, boxes) in depth-first order."""
     res = session.results()
-    if count is None:
-        count = len(res) - first
-    res = res[first:first + count] if (first or count != len(res)) else res
     alive, dup, extra = resolve_collectors(res)
-    if merge and first == 0:
+    if merge:
         res, alive, dup, extra = merge_exterior(session, res, alive, dup, extra)
     keep = _path_order(res, np.nonzero(alive)[0])
     return res, keep, dup, extra

@@ -1,0 +1,67 @@
+"""Shared helpers for the parity tests (CPU emulator tier and GPU tier use the same checks)."""
+import os
+import warnings
+
+import numpy as np
+
+from oracle import subdivision as osub
+from oracle.gen_golden import rand_coeffs
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT_TOL = 1e-10          # BASELINE.json north_star: roots within 1e-10 (max-norm) of the reference's output
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def unpack(z, prefix):
+    return [z[f"{prefix}_{i}"] for i in range(int(z[prefix + "_n"]))]
+
+
+def seeded_systems(dim, deg, N, kind="randn"):
+    np.random.seed(2)                                   # /root/reference/tests/gen_random_tests.py:3
+    batch = rand_coeffs(dim, deg, N, kind)
+    return [[np.ascontiguousarray(m) for m in batch[s]] for s in range(N)]
+
+
+def match_points(A, B, tol):
+    """assert_same_points of the reference's tests/test_Combined_Solver.py:12-29 (max-norm)."""
+    A = np.asarray(A, float).reshape(len(A), -1)
+    B = np.asarray(B, float).reshape(len(B), -1)
+    assert A.shape == B.shape, (A.shape, B.shape)
+    used = np.zeros(len(B), dtype=bool)
+    worst = 0.0
+    for a in A:
+        d = np.max(np.abs(B - a), axis=1)
+        j = int(np.argmin(d))
+        assert d[j] < tol, f"point {a} not matched, best distance {d[j]}"
+        assert not used[j], "matched the same point twice"
+        used[j] = True
+        worst = max(worst, d[j])
+    return worst
+
+
+def oracle_solve(Ms, errs, **kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        trace = osub.Trace()
+        roots = osub.solve_chebyshev_subdivision([m.copy() for m in Ms], np.array(errs, dtype=float), trace=trace, **kw)
+    return np.asarray(roots, dtype=float).reshape(-1, len(Ms)), trace
+
+
+def check_batch_against_oracle(solve_batch, systems, errs, engine=None, **kw):
+    """Runs `solve_batch` and the oracle on the same systems; identical counts, roots within ROOT_TOL."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, sess = solve_batch(systems, errs, engine=engine, return_session=True, **kw)
+    boxes = 0
+    worst = 0.0
+    okw = {k: v for k, v in kw.items() if k in ("exact", "constant_check", "low_dim_quadratic_check", "all_dim_quadratic_check")}
+    for Ms, e, g in zip(systems, errs, got):
+        want, trace = oracle_solve(Ms, e, **okw)
+        boxes += trace.boxes
+        assert len(g) == len(want), (len(g), len(want))
+        if len(want):
+            worst = max(worst, match_points(want, g, ROOT_TOL))
+    return sess, boxes, worst

@@ -1,0 +1,200 @@
+"""CPU tier: the C ABI library loads and exports what include/*.h declares, the product refuses to
+run without CUDA, and the kernel-source emulator reproduces the oracle through the real host code."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import kernels as okern
+from oracle import quadratic as oquad
+from oracle import subdivision as osub
+from rootfinding_b200 import ChebyshevSubdivisionSolver as S
+from rootfinding_b200 import QuadraticCheck as Q
+from rootfinding_b200 import _lib, engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emul.backend import emulated_engine
+    return emulated_engine(threads=8, lanes=4)
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "yroots_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(yr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_match_binding():
+    assert _declared_symbols() == sorted(_lib.EXPORTS)
+
+
+def test_cuda_library_exports_every_symbol():
+    """No compute calls: only dlopen + dlsym + the pure-host helpers."""
+    if not os.path.exists(_lib.CUDA_LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(_lib.CUDA_LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    _lib.bind(lib)
+    assert lib.yr_abi_version() == 1
+    assert b"sm_100a" in lib.yr_build_info()
+    p = _lib.default_params(lib)
+    assert (p.max_zoom_count, p.constant_check, p.low_dim_quad_check, p.all_dim_quad_check, p.exact) == (25, 1, 1, 0, 0)
+    assert p.trim_rel_tol == 1e-3
+    for dim in range(1, 7):
+        for kind in (0, 1, 2):
+            assert lib.yr_record_layout(dim, kind, None, 0) > 0
+        rd = _lib.result_dtype(lib, dim)
+        assert rd["root"].shape == (dim,) and rd["box"].shape == (dim, 2)
+    assert lib.yr_workspace_doubles(2, 5202, 2601, 51, 0) > 5202
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.CudaMemory()
+    with pytest.raises(RuntimeError):
+        E.SubdivisionEngine()
+
+
+@pytest.mark.parametrize("dim,deg,N,kind,exact", [
+    (1, 10, 3, "randn", False), (2, 3, 4, "randn", False), (2, 5, 4, "randint", False), (2, 10, 3, "randn", False),
+    (2, 10, 2, "randn", True), (3, 3, 2, "randn", False), (3, 6, 1, "randn", False), (4, 2, 2, "randn", False),
+    (2, 20, 2, "randn", False)])
+def test_emulated_solver_matches_oracle(emu, dim, deg, N, kind, exact):
+    systems = H.seeded_systems(dim, deg, N, kind)
+    errs = [np.full(dim, 2. ** -52)] * N
+    sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu, exact=exact)
+    assert sess.stats.boxes == boxes          # same search tree as the reference, box for box
+    assert worst < 1e-14
+
+
+def test_emulated_solver_golden_roots(emu):
+    """Against roots the unmodified reference produced (tests/golden/solves_random.npz)."""
+    z = H.load("solves_random.npz")
+    cache = {}
+    for i in range(int(z["n"])):
+        dim, deg, s, randint, exact, nbox = (int(v) for v in z[f"meta_{i}"])
+        if deg > 10 or dim > 3:
+            continue
+        key = (dim, deg, randint)
+        if key not in cache:
+            N = {(1, 10): 3, (2, 3): 4, (2, 5): 4, (2, 10): 3, (3, 3): 2, (3, 6): 2}[(dim, deg)]
+            cache[key] = H.seeded_systems(dim, deg, N, "randint" if randint else "randn")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got, sess = S.solve_batch([cache[key][s]], [np.full(dim, 2. ** -52)], exact=bool(exact), engine=emu,
+                                      return_session=True)
+        want = z[f"roots_{i}"]
+        assert len(got[0]) == len(want)
+        if len(want):
+            H.match_points(want, got[0], H.ROOT_TOL)
+        assert sess.stats.boxes == nbox
+
+
+def test_emulated_restriction_bit_exact(emu):
+    """TransformChebInPlaceND through yr_init_boxes == the reference, bit for bit (plain and exact)."""
+    z = H.load("restrict_axis.npz")
+    groups = {}
+    for i in range(int(z["n"])):
+        axis, al, be, exact = z[f"par_{i}"]
+        M = z[f"in_{i}"]
+        if M.size > 700:
+            continue
+        groups.setdefault((M.ndim, bool(exact)), []).append((i, int(axis), al, be, M))
+    checked = 0
+    for (D, exact), items in groups.items():
+        systems, alphas, betas = [], [], []
+        for (i, axis, al, be, M) in items:
+            systems.append([M] + [np.zeros((1,) * D)] * (D - 1))
+            a, b = np.ones(D), np.zeros(D)
+            a[axis], b[axis] = al, be
+            alphas.append(a)
+            betas.append(b)
+        out, errs = S.restrict_systems(systems, [np.zeros(D)] * len(items), alphas, betas, exact=exact, engine=emu)
+        for (i, axis, al, be, M), Ms in zip(items, out):
+            want = z[f"out_{i}"]
+            assert Ms[0].shape == want.shape, (i, Ms[0].shape, want.shape)
+            assert np.array_equal(Ms[0], want), i
+            checked += 1
+    assert checked > 100
+
+
+def test_emulated_restrict_system_errors(emu):
+    """transformChebToInterval: tensors bit-exact, error bound to rounding of the |M| sums."""
+    rng = np.random.RandomState(5)
+    for D, shp in [(2, (9, 7)), (3, (5, 6, 4))]:
+        Ms = [rng.randn(*shp) * np.exp(-0.4 * np.indices(shp).sum(0)) for _ in range(D)]
+        errs = np.abs(rng.randn(D)) * 1e-12
+        al, be = rng.uniform(0.05, 0.6, D), rng.uniform(-0.3, 0.3, D)
+        want_M, want_E = osub.restrict_system([m.copy() for m in Ms], al, be, errs.copy(), False)
+        got_M, got_E = S.transformChebToInterval(Ms, al, be, errs, False) if False else S.restrict_systems(
+            [Ms], [errs], [al], [be], engine=emu)
+        for a, b in zip(want_M, got_M[0]):
+            assert np.array_equal(np.ascontiguousarray(a), b)
+        assert np.allclose(want_E, got_E[0], rtol=1e-12, atol=0)
+
+
+def test_emulated_bils_matches_reference(emu):
+    z = H.load("bils.npz")
+    by_dim = {}
+    for i in range(int(z["n"])):
+        Ms = H.unpack(z, f"Ms_{i}")
+        by_dim.setdefault(len(Ms), []).append((i, Ms))
+    for D, items in by_dim.items():
+        iv, fl = S.bils_batched([Ms for _, Ms in items], [z[f"errs_{i}"] for i, _ in items],
+                                [int(z[f"final_{i}"]) for i, _ in items], engine=emu)
+        for k, (i, Ms) in enumerate(items):
+            want_iv, want_fl = z[f"iv_{i}"], z[f"flags_{i}"]
+            assert list(fl[k]) == list(want_fl), (i, fl[k], want_fl)
+            if np.all(np.isfinite(want_iv)):
+                # different SVD (one-sided Jacobi vs LAPACK) and summation order: a few ulp
+                assert np.allclose(iv[k], want_iv, rtol=1e-11, atol=1e-13), (i, iv[k], want_iv)
+            else:
+                assert np.array_equal(np.isnan(iv[k]), np.isnan(want_iv))
+
+
+def test_emulated_quadratic_check_matches_reference(emu):
+    z = H.load("quadcheck.npz")
+    by_dim = {}
+    for i in range(int(z["n"])):
+        by_dim.setdefault(z[f"M_{i}"].ndim, []).append(i)
+    for D, idx in by_dim.items():
+        Ms, tols = [z[f"M_{i}"] for i in idx], [float(z[f"tol_{i}"]) for i in idx]
+        got = Q.quadratic_check_batched(Ms, tols, engine=emu)
+        got_nd = Q.quadratic_check_batched(Ms, tols, nd_check=True, engine=emu)
+        want = np.array([z[f"res_{i}"] for i in idx])
+        assert np.array_equal(got, want[:, 0]), D
+        assert np.array_equal(got_nd, want[:, 1]), D
+
+
+def test_engine_overflow_retry_and_global_workspace(emu):
+    """Force the optimistic-capacity retry and the global-memory workspace path."""
+    systems = H.seeded_systems(2, 10, 2)
+    errs = [np.full(2, 2. ** -52)] * 2
+    old = (emu.worst_case_budget, emu.max_smem_cta)
+    try:
+        emu.worst_case_budget = 0               # never allocate the worst case up front
+        emu.max_smem_cta = 1024                 # nothing fits "shared memory"
+        sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
+        assert sess.stats.boxes == boxes
+        assert not any(lvl[3] for lvl in sess.stats.per_level)       # every level ran from the global workspace
+    finally:
+        emu.worst_case_budget, emu.max_smem_cta = old
+
+
+def test_argument_errors():
+    with pytest.raises(ValueError, match="Solver Takes in N polynomials of dimension N!"):
+        S.solveChebyshevSubdivision([np.zeros((2, 2)), np.zeros(3)], np.zeros(2))
+    with pytest.raises(ValueError, match="Ms and errors must be same length!"):
+        S.solveChebyshevSubdivision([np.zeros((2, 2)), np.zeros((2, 2))], np.zeros(3))

