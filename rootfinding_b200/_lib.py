@@ -23,7 +23,7 @@ class YrParams(C.Structure):
 
 
 class YrLaunch(C.Structure):
-    _fields_ = [("threads", i32), ("ctas", i32), ("ws_in_smem", i32), ("reserved", i32),
+    _fields_ = [("threads", i32), ("ctas", i32), ("ws_in_smem", i32), ("warp_per_box", i32),
                 ("ws_doubles", u64), ("gws", dp), ("gws_stride", u64)]
 
 

@@ -111,32 +111,87 @@ YR_HD void fiber_offsets(int f, int axis, const int* shape, const int* sstride, 
     }
 }
 
+// Rows of a tensor view = all index combinations of axes 0..D-2; the last axis is contiguous (stride 1
+// survives every in-place restriction).  One division chain per row, none per element.
+template <int D>
+YR_HD int row_offset(int r, const int* shape, const int* stride) {
+    int off = 0;
+    for (int a = D - 2; a > 0; --a) { const int q = r / shape[a]; off += (r - q * shape[a]) * stride[a]; r = q; }
+    return (D >= 2) ? off + r * stride[0] : 0;
+}
+
 template <int D, class Ctx>
 YR_DEV double tensor_abs_sum(Ctx& cx, const double* base, const int* shape, const int* stride) {
-    const int n = tensor_size<D>(shape);
+    int nrows = 1;
+    for (int a = 0; a < D - 1; ++a) nrows *= shape[a];
+    const int len = shape[D - 1];
     double s = 0;
-    for (int e = cx.tid; e < n; e += cx.nthreads) s += fabs(base[view_offset<D>(e, shape, stride)]);
+    if (len >= 16 || D == 1) {            // lanes along the contiguous axis, warps over rows
+        for (int r = cx.warp; r < nrows; r += cx.nwarps) {
+            const double* row = base + row_offset<D>(r, shape, stride);
+            for (int j = cx.lane; j < len; j += cx.lanes) s += fabs(row[j]);
+        }
+    } else {                              // short rows: threads over rows
+        for (int r = cx.tid; r < nrows; r += cx.nthreads) {
+            const double* row = base + row_offset<D>(r, shape, stride);
+            for (int j = 0; j < len; ++j) s += fabs(row[j]);
+        }
+    }
     return cx.block_sum(s);
 }
 
+// Restriction matrices are stored row-major packed upper triangular: row i holds C[i][k], k = i..ncol-1.
+YR_HD int crow_start(int i, int ncol) { return i * ncol - i * (i - 1) / 2; }
+
 template <bool FMA>
-YR_HD double tri_dot(const double* C, int i, int n, const double* src, int stride) {
-    // sum_{k=i}^{n-1} C[k(k+1)/2 + i] * src[k*stride], accumulated in ascending k like the reference (:84-112)
+YR_HD double tri_dot(const double* crow, int len, const double* s, int stride) {
+    // sum_{j<len} crow[j] * s[j*stride], accumulated in ascending order like the reference (:84-112)
     double acc = 0.0;
-    int idx = i * (i + 1) / 2 + i;
-    const double* s = src + (long long)i * stride;
-    for (int k = i; k < n; ++k) {
-        if (FMA) acc = fma(C[idx], *s, acc); else acc = acc + C[idx] * *s;
-        idx += k + 1; s += stride;
+    for (int j = 0; j < len; ++j) {
+        if (FMA) acc = fma(crow[j], *s, acc); else acc = acc + crow[j] * *s;
+        s += stride;
     }
     return acc;
+}
+
+// One fiber, all output rows, two rows per pass (they share the source loads).  Safe in place:
+// rows i, i+1 are stored after everything they read (source rows >= i) has been read, and later
+// rows never read them.
+template <bool FMA>
+YR_HD double fiber_restrict(const double* C, int ncol, int n, int rows_out, const double* src, int sa, double* dst, int da) {
+    double asum = 0.0;
+    int i = 0;
+    for (; i + 1 < rows_out; i += 2) {
+        const double* c0 = C + crow_start(i, ncol);
+        const double* c1 = C + crow_start(i + 1, ncol);
+        const double* s = src + (long long)i * sa;
+        double a0 = 0.0, a1 = 0.0;
+        if (FMA) a0 = fma(c0[0], *s, a0); else a0 = a0 + c0[0] * *s;
+        s += sa;
+        const int len = n - i - 1;
+#pragma unroll 4
+        for (int j = 0; j < len; ++j) {
+            const double x = *s;
+            if (FMA) { a0 = fma(c0[j + 1], x, a0); a1 = fma(c1[j], x, a1); }
+            else { a0 = a0 + c0[j + 1] * x; a1 = a1 + c1[j] * x; }
+            s += sa;
+        }
+        dst[(long long)i * da] = a0; dst[(long long)(i + 1) * da] = a1;
+        asum += fabs(a0) + fabs(a1);
+    }
+    if (i < rows_out) {
+        const double v = tri_dot<FMA>(C + crow_start(i, ncol), n - i, src + (long long)i * sa, sa);
+        dst[(long long)i * da] = v;
+        asum += fabs(v);
+    }
+    return asum;
 }
 
 // dst = C applied along `axis` of src (rows_out output rows).  dst may be src (inplace).
 // Returns sum|dst| to every thread.  Collective: all threads of the CTA must call it.
 template <int D, class Ctx>
 YR_DEV double transform_axis(Ctx& cx, const double* src, const int* sshape, const int* sstride, int axis,
-                             const double* C, int rows_out, double* dst, const int* dstride,
+                             const double* C, int ncol, int rows_out, double* dst, const int* dstride,
                              bool inplace, bool use_fma) {
     const int n = sshape[axis];
     int F = 1;
@@ -145,45 +200,52 @@ YR_DEV double transform_axis(Ctx& cx, const double* src, const int* sshape, cons
     const int sa = sstride[axis], da = dstride[axis];
     double asum = 0;
     const long long items = (long long)rows_out * F;
-    if (!inplace) {
+    if (T <= 32 || F >= T || (inplace && rows_out > T * kStage)) {
+        // a thread owns whole fibers: no barriers, no per-element index arithmetic
+        for (int f = cx.tid; f < F; f += T) {
+            int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
+            asum += use_fma ? fiber_restrict<true>(C, ncol, n, rows_out, src + so, sa, dst + dofs, da)
+                            : fiber_restrict<false>(C, ncol, n, rows_out, src + so, sa, dst + dofs, da);
+        }
+    } else if (!inplace) {
         for (long long id = cx.tid; id < items; id += T) {
             const int i = (int)(id / F), f = (int)(id - (long long)i * F);
             int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
-            const double v = use_fma ? tri_dot<true>(C, i, n, src + so, sa) : tri_dot<false>(C, i, n, src + so, sa);
+            const double* crow = C + crow_start(i, ncol);
+            const double* s0 = src + so + (long long)i * sa;
+            const double v = use_fma ? tri_dot<true>(crow, n - i, s0, sa) : tri_dot<false>(crow, n - i, s0, sa);
             dst[dofs + (long long)i * da] = v;
             asum += fabs(v);
         }
-    } else if (F >= T || rows_out > T * kStage) {
-        // enough fibers: a thread owns whole fibers; ascending rows make in-place safe
-        for (int f = cx.tid; f < F; f += T) {
-            int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
-            for (int i = 0; i < rows_out; ++i) {
-                const double v = use_fma ? tri_dot<true>(C, i, n, src + so, sa) : tri_dot<false>(C, i, n, src + so, sa);
-                dst[dofs + (long long)i * da] = v;
-                asum += fabs(v);
-            }
-        }
     } else {
-        // few fibers: spread (row, fiber) pairs over the CTA, stage results in registers,
+        // few fibers, many threads: spread (row, fiber) pairs over the CTA, stage results in registers,
         // barrier, then overwrite.  Fibers are taken in groups that fit the staging budget.
         int gf = (T * kStage) / rows_out; if (gf > F) gf = F; if (gf < 1) gf = 1;
         for (int f0 = 0; f0 < F; f0 += gf) {
             const int nf = (F - f0 < gf) ? (F - f0) : gf;
             const int cnt = rows_out * nf;
             double stage[kStage];
-            int slot = 0;
-            for (int id = cx.tid; id < cnt; id += T, ++slot) {
-                const int i = id / nf, f = f0 + (id - i * nf);
-                int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
-                stage[slot] = use_fma ? tri_dot<true>(C, i, n, src + so, sa) : tri_dot<false>(C, i, n, src + so, sa);
+#pragma unroll
+            for (int slot = 0; slot < kStage; ++slot) {
+                const int id = cx.tid + slot * T;
+                if (id < cnt) {
+                    const int i = id / nf, f = f0 + (id - i * nf);
+                    int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
+                    const double* crow = C + crow_start(i, ncol);
+                    const double* s0 = src + so + (long long)i * sa;
+                    stage[slot] = use_fma ? tri_dot<true>(crow, n - i, s0, sa) : tri_dot<false>(crow, n - i, s0, sa);
+                }
             }
             cx.sync();
-            slot = 0;
-            for (int id = cx.tid; id < cnt; id += T, ++slot) {
-                const int i = id / nf, f = f0 + (id - i * nf);
-                int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
-                dst[dofs + (long long)i * da] = stage[slot];
-                asum += fabs(stage[slot]);
+#pragma unroll
+            for (int slot = 0; slot < kStage; ++slot) {
+                const int id = cx.tid + slot * T;
+                if (id < cnt) {
+                    const int i = id / nf, f = f0 + (id - i * nf);
+                    int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
+                    dst[dofs + (long long)i * da] = stage[slot];
+                    asum += fabs(stage[slot]);
+                }
             }
             cx.sync();
         }
@@ -277,14 +339,14 @@ YR_DEV void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
     int kmax = 0;
     for (int m = 0; m < nmat; ++m) kmax = sh.mat_n[m] > kmax ? sh.mat_n[m] : kmax;
     const int xs = L.nmax + 2;
-    if (cx.tid < nmat) {
-        const int m = cx.tid;
+    for (int m = cx.tid; m < nmat; m += cx.nthreads) {
         double* C = ws + L.cmat[m];
-        C[0] = 1.0;
+        const int nc = sh.mat_n[m];
+        C[0] = 1.0;                                              // C[0][0]
         rows_after[m * L.nmax + 0] = 1;
         sh.rows_buf[0][m] = 1;
-        if (sh.mat_n[m] >= 2) {
-            C[1] = sh.beta[m]; C[2] = sh.alpha[m];
+        if (nc >= 2) {
+            C[1] = sh.beta[m]; C[crow_start(1, nc)] = sh.alpha[m];   // C[0][1], C[1][1]
             rows_after[m * L.nmax + 1] = 2;
         }
         sh.rows_buf[1][m] = 2;
@@ -292,8 +354,7 @@ YR_DEV void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
     if (exact) {
         for (int id = cx.tid; id < nmat * 6 * xs; id += cx.nthreads) ws[L.xscratch + id] = 0.0;
         cx.sync();
-        if (cx.tid < nmat) {
-            const int m = cx.tid;
+        for (int m = cx.tid; m < nmat; m += cx.nthreads) {
             double* X = ws + L.xscratch + m * 6 * xs;
             const bool split = (sh.alpha[m] == 0.5 && fabs(sh.beta[m]) == 0.5);
             X[0 * xs + 0] = 1.0;                                   // column 0 values
@@ -304,21 +365,21 @@ YR_DEV void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
     cx.sync();
     for (int k = 2; k < kmax; ++k) {
         const int per = k + 1;
-        const int o0 = k * (k + 1) / 2, o1 = (k - 1) * k / 2, o2 = (k - 2) * (k - 1) / 2;
         for (int id = cx.tid; id < nmat * per; id += cx.nthreads) {
             const int m = id / per, i = id - m * per;
             if (k >= sh.mat_n[m]) continue;
+            const int nc = sh.mat_n[m];
             const int rows = sh.rows_buf[(k - 1) & 1][m];
             double* C = ws + L.cmat[m];
             const double alpha = sh.alpha[m], beta = sh.beta[m];
             double val = 0.0;
             if (!exact) {
                 if (i <= rows) {
-                    // zero padding beyond a column's length reproduces the reference's edge formulas exactly
-                    const double cm1 = (i >= 1) ? C[o1 + i - 1] : 0.0;
-                    const double ci = (i <= k - 1) ? C[o1 + i] : 0.0;
-                    const double cp1 = (i + 1 <= k - 1) ? C[o1 + i + 1] : 0.0;
-                    const double pi = (i <= k - 2) ? C[o2 + i] : 0.0;
+                    // entries beyond a column's length are zero, which reproduces the reference's edge formulas exactly
+                    const double cm1 = (i >= 1) ? C[crow_start(i - 1, nc) + (k - 1) - (i - 1)] : 0.0;
+                    const double ci = (i <= k - 1) ? C[crow_start(i, nc) + (k - 1) - i] : 0.0;
+                    const double cp1 = (i + 1 <= k - 1) ? C[crow_start(i + 1, nc) + (k - 1) - (i + 1)] : 0.0;
+                    const double pi = (i <= k - 2) ? C[crow_start(i, nc) + (k - 2) - i] : 0.0;
                     double t;
                     if (i == 0) t = alpha * cp1;
                     else if (i == 1) t = alpha * (2 * cm1 + cp1);
@@ -351,7 +412,7 @@ YR_DEV void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
                     }
                 }
             }
-            C[o0 + i] = val;
+            C[crow_start(i, nc) + k - i] = val;
         }
         cx.sync();
     }
@@ -399,9 +460,21 @@ YR_DEV void trim_box(Ctx& cx, BoxShared<D>& sh, double* ws, const SolverParams& 
                     int shp[D];
                     for (int a = 0; a < D; ++a) shp[a] = sh.shape[p][a];
                     shp[axis] = 1;
-                    const int cnt = tensor_size<D>(shp);
                     const double* plane = base + (long long)(n - 1 - cx.warp) * sh.stride[p][axis];
-                    for (int e = cx.lane; e < cnt; e += cx.lanes) s += fabs(plane[view_offset<D>(e, shp, sh.stride[p])]);
+                    int nrows = 1;
+                    for (int a = 0; a < D - 1; ++a) nrows *= shp[a];
+                    const int len = shp[D - 1];
+                    if (len >= 16 || D == 1) {
+                        for (int r = 0; r < nrows; ++r) {
+                            const double* row = plane + row_offset<D>(r, shp, sh.stride[p]);
+                            for (int j = cx.lane; j < len; j += cx.lanes) s += fabs(row[j]);
+                        }
+                    } else {
+                        for (int r = cx.lane; r < nrows; r += cx.lanes) {
+                            const double* row = plane + row_offset<D>(r, shp, sh.stride[p]);
+                            for (int j = 0; j < len; ++j) s += fabs(row[j]);
+                        }
+                    }
                 }
                 s = cx.warp_sum(s);
                 if (cx.warp < nb && cx.lane == 0) sh.plane[cx.warp] = s;
@@ -642,7 +715,7 @@ YR_DEV void subdivide_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, d
                 int st = 1;
                 for (int a = D - 1; a >= 0; --a) { tstride[s + 1][a] = st; st *= tshape[s + 1][a]; }
                 if (n > 1) {
-                    tsum[s + 1] = transform_axis<D>(cx, src, tshape[s], tstride[s], axis, ws + sh.lay.cmat[m], rows,
+                    tsum[s + 1] = transform_axis<D>(cx, src, tshape[s], tstride[s], axis, ws + sh.lay.cmat[m], sh.mat_n[m], rows,
                                                     dst, tstride[s + 1], false, prm.use_fma != 0);
                     if (cx.tid == 0) sh.c_macs += (unsigned long long)(tensor_size<D>(tshape[s]) / n) *
                                                   ((unsigned long long)rows * n - (unsigned long long)rows * (rows - 1) / 2);
@@ -675,7 +748,7 @@ YR_DEV void restrict_system_inplace(Ctx& cx, BoxShared<D>& sh, double* ws, const
             if (!identity) {
                 const int rows = rows_for<D>(sh, ws, axis, n);
                 double* M = ws + sh.lay.base[p];
-                s = transform_axis<D>(cx, M, sh.shape[p], sh.stride[p], axis, ws + sh.lay.cmat[axis], rows,
+                s = transform_axis<D>(cx, M, sh.shape[p], sh.stride[p], axis, ws + sh.lay.cmat[axis], sh.mat_n[axis], rows,
                                       M, sh.stride[p], true, prm.use_fma != 0);
                 if (cx.tid == 0) {
                     sh.c_macs += (unsigned long long)(tensor_size<D>(sh.shape[p]) / n) *

@@ -128,6 +128,70 @@ __global__ void __launch_bounds__(256) level_kernel(const yr::LevelArgs<D> args,
     yr::level_worker<D>(cx, args, sh, ws);
 }
 
+// Warp-per-box variant of the execution context: one warp is a whole "CTA" of the pipeline.
+// Barriers become __syncwarp, block reductions one shuffle tree; a serial section (BILS, checks)
+// stalls only its own warp while the other warps of the SM work on their own boxes.
+struct WarpCtx {
+    int tid, nthreads, lane, lanes, warp, nwarps;
+    uint64_t* mbar;
+    uint32_t phase;
+
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+    __device__ __forceinline__ double block_sum(double v) {
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        return __shfl_sync(0xffffffffu, v, 0);
+    }
+    __device__ __forceinline__ double block_max(double v) {
+        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
+        return __shfl_sync(0xffffffffu, v, 0);
+    }
+    __device__ __forceinline__ double warp_sum(double v) { return block_sum(v); }
+    __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+    __device__ __forceinline__ void atomic_max(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
+    __device__ __forceinline__ void copy_in(double* dst, const double* src, long long n) {
+        const bool tma_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && n >= 2;
+        if (tma_ok) {
+            const long long nbulk = n & ~1ll;
+            if (lane == 0) {
+                const unsigned long long bytes = (unsigned long long)nbulk * 8ull;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(mbar, (uint32_t)bytes);
+                unsigned long long done = 0;
+                while (done < bytes) {
+                    const uint32_t chunk = (uint32_t)((bytes - done) > 65536ull ? 65536ull : (bytes - done));
+                    tma_bulk_g2s(reinterpret_cast<char*>(dst) + done, reinterpret_cast<const char*>(src) + done, chunk, mbar);
+                    done += chunk;
+                }
+            }
+            if (lane == 1 && (n & 1)) dst[n - 1] = src[n - 1];
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+        } else {
+            for (long long i = lane; i < n; i += 32) dst[i] = src[i];
+        }
+    }
+    __device__ __forceinline__ double cospi_ratio(long long m, long long N) const { return cospi((double)m / (double)N); }
+};
+
+__host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// dynamic shared memory per warp: [BoxShared<D> | mbarrier (16 B) | workspace doubles]
+template <int D>
+__global__ void __launch_bounds__(128, 4) level_kernel_warp(const yr::LevelArgs<D> args, unsigned warp_stride_bytes) {
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    const int w = threadIdx.x >> 5;
+    unsigned char* base = dyn_raw + (size_t)w * warp_stride_bytes;
+    yr::BoxShared<D>* sh = reinterpret_cast<yr::BoxShared<D>*>(base);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(base + align16(sizeof(yr::BoxShared<D>)));
+    double* ws = reinterpret_cast<double*>(base + align16(sizeof(yr::BoxShared<D>)) + 16);
+    WarpCtx cx;
+    cx.tid = cx.lane = threadIdx.x & 31; cx.nthreads = cx.lanes = 32; cx.warp = 0; cx.nwarps = 1;
+    cx.mbar = mbar; cx.phase = 0;
+    if (cx.lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncwarp();
+    yr::level_worker<D>(cx, args, *sh, ws);
+}
+
 template <int D>
 __global__ void __launch_bounds__(256) init_kernel(const yr::InitArgs<D> args, int ws_in_smem) {
     extern __shared__ __align__(16) double dyn_ws[];
@@ -205,10 +269,19 @@ int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_pe
 
 template <int D>
 int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream) {
+    if (a.n_in == 0) return 0;
+    if (l.warp_per_box) {
+        if (!l.ws_in_smem) return yr_api::fail("warp-per-box mode needs the workspace in shared memory");
+        const size_t stride = align16(sizeof(yr::BoxShared<D>)) + 16 + align16((size_t)l.ws_doubles * 8);
+        const size_t smem = stride * (size_t)(l.threads / 32);
+        if (smem > 48 * 1024 && set_smem(level_kernel_warp<D>, smem)) return -1;
+        level_kernel_warp<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, (unsigned)stride);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : cuda_fail(e, "level_kernel_warp launch");
+    }
     const size_t smem = l.ws_in_smem ? (size_t)l.ws_doubles * 8 : 0;
     if (!l.ws_in_smem && !l.gws) return yr_api::fail("global workspace missing");
     if (smem > 48 * 1024 && set_smem(level_kernel<D>, smem)) return -1;
-    if (a.n_in == 0) return 0;
     level_kernel<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, l.ws_in_smem);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "level_kernel launch");

@@ -167,7 +167,7 @@ YR_HDN void jacobi_svd(const double A[D][D], double W[D][D], double V[D][D], dou
             for (int q = p + 1; q < D; ++q) {
                 double app = 0, aqq = 0, apq = 0;
                 for (int i = 0; i < D; ++i) { app += W[i][p] * W[i][p]; aqq += W[i][q] * W[i][q]; apq += W[i][p] * W[i][q]; }
-                if (apq == 0.0 || fabs(apq) <= 1e-17 * sqrt(app * aqq)) continue;
+                if (apq == 0.0 || fabs(apq) <= 4e-16 * sqrt(app * aqq)) continue;   // columns orthogonal to ~2 ulp
                 rotated = true;
                 double zeta = (aqq - app) / (2.0 * apq);
                 double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

@@ -14,6 +14,7 @@ back up (:1266-1298 final-step de-duplication, :1318-1385 merging of touching ex
 is rootfinding_b200/postpass.py.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -133,6 +134,8 @@ class SubdivisionEngine:
         self.threads = threads
         self.max_ctas_per_sm = max_ctas_per_sm
         self.worst_case_budget = 1 << 28              # below this many bytes, just allocate the worst case
+        self.warp_max_ws = int(os.environ.get("YR_WARP_MAX_WS", "3072"))      # doubles; larger boxes run CTA-per-box
+        self.warp_ctas_per_sm = int(os.environ.get("YR_WARP_CTAS_PER_SM", "4"))   # 128-thread CTAs (register bound)
 
     def params(self, **kw):
         p = _lib.default_params(self.lib)
@@ -142,11 +145,23 @@ class SubdivisionEngine:
             setattr(p, k, type(getattr(p, k))(v))
         return p
 
-    def launch_config(self, dim, n_items, total, max_tensor, max_extent, exact):
-        """threads / persistent CTAs / workspace placement for boxes of at most this size."""
+    def launch_config(self, dim, n_items, total, max_tensor, max_extent, exact, allow_warp=True):
+        """threads / persistent CTAs / workspace placement / box granularity for boxes of at most this size.
+
+        Small boxes run warp-per-box (every warp of a 128-thread CTA owns its own box: no block barriers,
+        a serial section stalls one warp only); larger ones CTA-per-box; boxes that do not fit shared
+        memory run CTA-per-box from a global workspace.
+        """
         ws = int(self.lib.yr_workspace_doubles(dim, int(total), int(max_tensor), int(max_extent), int(exact)))
-        threads = self.threads or (128 if total >= 768 else 64)
         static = int(self.lib.yr_static_smem_bytes(dim))
+        warps = 4
+        per_warp = static + 16 + ((ws * 8 + 15) & ~15)
+        per_cta = warps * per_warp + 1024
+        if allow_warp and ws <= self.warp_max_ws and per_cta <= self.max_smem_cta:
+            per_sm = max(1, min(self.warp_ctas_per_sm, self.smem_per_sm // per_cta))
+            ctas = int(max(1, min((n_items + warps - 1) // warps, self.sm_count * per_sm)))
+            return 32 * warps, ctas, True, ws, True
+        threads = self.threads or (128 if total >= 768 else 64)
         in_smem = ws * 8 + static <= self.max_smem_cta
         if in_smem:
             per_sm = max(1, min(32, 2048 // threads, self.smem_per_sm // (ws * 8 + static + 1024)))
@@ -155,7 +170,7 @@ class SubdivisionEngine:
         if self.max_ctas_per_sm:
             per_sm = min(per_sm, self.max_ctas_per_sm)
         ctas = int(max(1, min(n_items, self.sm_count * per_sm)))
-        return threads, ctas, in_smem, ws
+        return threads, ctas, in_smem, ws, False
 
     def session(self, systems, errors, **params):
         return SolveSession(self, systems, errors, self.params(**params))
@@ -207,6 +222,7 @@ class SolveSession:
         self.stats = SolveStats()
         self.time_kernels = False        # bench.py: CUDA events around every level launch
         self.kernel_ms = []              # (ms, algorithmic bytes, boxes) per level launch
+        self.retry_ms = 0.0              # time of launches that overflowed their optimistic buffers
         self._reserve("results", max(256, 4 * self.nsys))
         self._reserve("nodes", max(256, 4 * self.nsys))
 
@@ -229,9 +245,9 @@ class SolveSession:
         raw = self.mem.download(self.d_counters, _lib.COUNTER_BYTES).view(np.uint64)
         return dict(zip(_lib.COUNTER_FIELDS, (int(v) for v in raw)))
 
-    def _launch(self, threads, ctas, in_smem, ws):
+    def _launch(self, threads, ctas, in_smem, ws, warp=False):
         L = _lib.YrLaunch()
-        L.threads, L.ctas, L.ws_in_smem, L.ws_doubles = threads, ctas, int(in_smem), ws
+        L.threads, L.ctas, L.ws_in_smem, L.ws_doubles, L.warp_per_box = threads, ctas, int(in_smem), ws, int(warp)
         gws = None
         if not in_smem:
             gws = self.mem.empty(ctas * ws * 8)
@@ -253,9 +269,9 @@ class SolveSession:
                 m.upload(np.ascontiguousarray(jobs["parent"], dtype=np.int32))]
         recs = m.empty(nj * self.box_bytes)
         data = m.empty((total + 2 * nj + 2) * 8)
-        threads, ctas, in_smem, ws = self.eng.launch_config(
+        threads, ctas, in_smem, ws, _ = self.eng.launch_config(
             D, nj, int(self.sys_total[sysidx].max()), int(self.sys_max_tensor[sysidx].max()),
-            int(self.sys_max_extent[sysidx].max()), self.prm.exact)
+            int(self.sys_max_extent[sysidx].max()), self.prm.exact, allow_warp=False)
         L, gws = self._launch(threads, ctas, in_smem, ws)
         d = _lib.YrInitDesc()
         d.dim = D
@@ -284,20 +300,22 @@ class SolveSession:
         n_in, data_used = c["n_children"], c["data_used"]
         big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
         fan = 1 << D
+        growth = [float(fan), float(fan)]                     # children per box / child data per parent data, last level
         while n_in > 0:
-            threads, ctas, in_smem, ws = eng.launch_config(D, n_in, big_box, big_tensor, big_extent, self.prm.exact)
+            threads, ctas, in_smem, ws, warp = eng.launch_config(D, n_in, big_box, big_tensor, big_extent, self.prm.exact)
             worst_recs, worst_data = n_in * fan, data_used * fan + 2 * n_in * fan
             if worst_recs * self.box_bytes + worst_data * 8 <= eng.worst_case_budget:
                 cap_recs, cap_data = worst_recs, worst_data
             else:
-                cap_recs = min(worst_recs, max(4096, int(1.6 * n_in)))
-                cap_data = min(worst_data, max(1 << 16, int(1.6 * data_used)))
+                # the frontier's growth factor changes slowly from level to level: last factor + 30 %
+                cap_recs = min(worst_recs, max(4096, int(1.3 * growth[0] * n_in) + 1024))
+                cap_data = min(worst_data, max(1 << 16, int(1.3 * growth[1] * data_used) + (1 << 16)))
             while True:
                 self._reserve("results", self.n_results + n_in)            # a box emits at most one record
                 self._reserve("nodes", self.n_nodes + n_in)
                 out_recs = m.empty(max(1, cap_recs) * self.box_bytes)
                 out_data = m.empty(max(1, cap_data) * 8)
-                L, gws = self._launch(threads, ctas, in_smem, ws)
+                L, gws = self._launch(threads, ctas, in_smem, ws, warp)
                 d = _lib.YrLevelDesc()
                 d.dim = D
                 d.recs_in, d.data_in, d.n_in = recs.ptr, data.ptr, n_in
@@ -316,8 +334,10 @@ class SolveSession:
                 if ev:
                     ev[1].record()
                 c = self._read_counters()
-                if ev:
+                if ev and not c["overflow"]:
                     self.kernel_ms.append((ev[0].elapsed_time(ev[1]), 16 * c["entry_coeffs"], c["boxes"]))
+                elif ev:
+                    self.retry_ms += ev[0].elapsed_time(ev[1])
                 self.stats.launches += 1
                 del gws
                 if not c["overflow"]:
@@ -326,9 +346,10 @@ class SolveSession:
                 cap_recs, cap_data = worst_recs, worst_data
             self.stats.add(c)
             self.stats.levels += 1
-            self.stats.per_level.append((n_in, c["n_children"], c["n_results"], bool(in_smem), ctas, threads, ws))
+            self.stats.per_level.append((n_in, c["n_children"], c["n_results"], bool(in_smem), ctas, threads, ws, bool(warp)))
             self.n_results += c["n_results"]
             self.n_nodes += c["n_nodes"]
+            growth = [max(0.25, c["n_children"] / n_in), max(0.25, c["data_used"] / max(data_used, 1))]
             recs, data = out_recs, out_data
             n_in, data_used = c["n_children"], c["data_used"]
             big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]

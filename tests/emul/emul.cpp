@@ -103,7 +103,8 @@ int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_pe
 
 template <int D>
 int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void*) {
-    const int T = env_int("YR_EMUL_THREADS", 8), lanes = env_int("YR_EMUL_LANES", 4);
+    const int lanes = env_int("YR_EMUL_LANES", 4);
+    const int T = l.warp_per_box ? lanes : env_int("YR_EMUL_THREADS", 8);     // warp-per-box: a one-warp team
     std::vector<double> ws;
     double* wsp;
     if (l.ws_in_smem) { ws.assign(l.ws_doubles + 8, 0.0); wsp = ws.data(); } else wsp = l.gws;
