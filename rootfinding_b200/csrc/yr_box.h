@@ -29,8 +29,10 @@
 #ifndef YR_DEV
 #if defined(__CUDACC__)
 #define YR_DEV __device__
+#define YR_DEVN __device__ __noinline__     /* large helpers exist once: the kernel is instruction-cache bound */
 #else
 #define YR_DEV
+#define YR_DEVN
 #endif
 #endif
 
@@ -121,7 +123,7 @@ YR_HD int row_offset(int r, const int* shape, const int* stride) {
 }
 
 template <int D, class Ctx>
-YR_DEV double tensor_abs_sum(Ctx& cx, const double* base, const int* shape, const int* stride) {
+YR_DEVN double tensor_abs_sum(Ctx& cx, const double* base, const int* shape, const int* stride) {
     int nrows = 1;
     for (int a = 0; a < D - 1; ++a) nrows *= shape[a];
     const int len = shape[D - 1];
@@ -158,7 +160,7 @@ YR_HD double tri_dot(const double* crow, int len, const double* s, int stride) {
 // rows i, i+1 are stored after everything they read (source rows >= i) has been read, and later
 // rows never read them.
 template <bool FMA>
-YR_HD double fiber_restrict(const double* C, int ncol, int n, int rows_out, const double* src, int sa, double* dst, int da) {
+YR_HDN double fiber_restrict(const double* C, int ncol, int n, int rows_out, const double* src, int sa, double* dst, int da) {
     double asum = 0.0;
     int i = 0;
     for (; i + 1 < rows_out; i += 2) {
@@ -190,7 +192,7 @@ YR_HD double fiber_restrict(const double* C, int ncol, int n, int rows_out, cons
 // dst = C applied along `axis` of src (rows_out output rows).  dst may be src (inplace).
 // Returns sum|dst| to every thread.  Collective: all threads of the CTA must call it.
 template <int D, class Ctx>
-YR_DEV double transform_axis(Ctx& cx, const double* src, const int* sshape, const int* sstride, int axis,
+YR_DEVN double transform_axis(Ctx& cx, const double* src, const int* sshape, const int* sstride, int axis,
                              const double* C, int ncol, int rows_out, double* dst, const int* dstride,
                              bool inplace, bool use_fma) {
     const int n = sshape[axis];
@@ -200,13 +202,15 @@ YR_DEV double transform_axis(Ctx& cx, const double* src, const int* sshape, cons
     const int sa = sstride[axis], da = dstride[axis];
     double asum = 0;
     const long long items = (long long)rows_out * F;
-    if (T <= 32 || F >= T || (inplace && rows_out > T * kStage)) {
+    if (Ctx::kWarpPerBox || T <= 32 || F >= T || (inplace && rows_out > T * kStage)) {
         // a thread owns whole fibers: no barriers, no per-element index arithmetic
         for (int f = cx.tid; f < F; f += T) {
             int so, dofs; fiber_offsets<D>(f, axis, sshape, sstride, dstride, so, dofs);
             asum += use_fma ? fiber_restrict<true>(C, ncol, n, rows_out, src + so, sa, dst + dofs, da)
                             : fiber_restrict<false>(C, ncol, n, rows_out, src + so, sa, dst + dofs, da);
         }
+    } else if (Ctx::kWarpPerBox) {
+        // unreachable: lets the compiler drop the CTA-only paths from the warp-per-box kernel
     } else if (!inplace) {
         for (long long id = cx.tid; id < items; id += T) {
             const int i = (int)(id / F), f = (int)(id - (long long)i * F);
@@ -332,7 +336,7 @@ YR_HD void exact_entry_split(const ExactCols& b, int i, int rows, double sgn, do
 // column (the three-term recurrence couples neighbouring rows, so columns are sequential and rows
 // parallel), together with rows_after[m][k] = the reference's `maxRow` after column k.
 template <int D, class Ctx>
-YR_DEV void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
+YR_DEVN void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
     const Layout<D>& L = sh.lay;
     int* rows_after = reinterpret_cast<int*>(ws + L.rows_after);
     const int nmat = sh.nmat;
@@ -444,7 +448,7 @@ YR_HD void compute_layout(BoxShared<D>& sh, bool exact) {
 
 // ---------------------------------------------------------------------------------------------
 template <int D, class Ctx>
-YR_DEV void trim_box(Ctx& cx, BoxShared<D>& sh, double* ws, const SolverParams& prm) {
+YR_DEVN void trim_box(Ctx& cx, BoxShared<D>& sh, double* ws, const SolverParams& prm) {
     for (int p = 0; p < D; ++p) {
         if (cx.tid == 0) sh.budget = prm.trim_abs_tol + sh.err[p] * prm.trim_rel_tol;
         cx.sync();
@@ -529,7 +533,7 @@ YR_HD void fill_result(const BoxShared<D>& sh, ResultRec<D>& r, uint32_t extra_f
 }
 
 template <int D, class Ctx>
-YR_DEV void emit_result(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, uint32_t extra_flags) {
+YR_DEVN void emit_result(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, uint32_t extra_flags) {
     if (cx.tid == 0) {
         const unsigned long long idx = cx.atomic_add(&args.ctr->n_results, 1ull);
         sh.result_index = (int)(idx + args.result_base);
@@ -576,7 +580,7 @@ YR_HDN bool quadratic_check_box(const BoxShared<D>& sh, const double* ws, int p,
 // ---------------------------------------------------------------------------------------------
 // Subdivision: 2^k children written straight to the next level's pool.
 template <int D, class Ctx>
-YR_DEV void subdivide_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws, bool final_step_split) {
+YR_DEVN void subdivide_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws, bool final_step_split) {
     const SolverParams& prm = args.prm;
     if (cx.tid == 0) {
         const int k = subdivision_axes<D>(sh.shape, sh.rec.st.iv, sh.level, sh.order);
@@ -717,8 +721,11 @@ YR_DEV void subdivide_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, d
                 if (n > 1) {
                     tsum[s + 1] = transform_axis<D>(cx, src, tshape[s], tstride[s], axis, ws + sh.lay.cmat[m], sh.mat_n[m], rows,
                                                     dst, tstride[s + 1], false, prm.use_fma != 0);
-                    if (cx.tid == 0) sh.c_macs += (unsigned long long)(tensor_size<D>(tshape[s]) / n) *
-                                                  ((unsigned long long)rows * n - (unsigned long long)rows * (rows - 1) / 2);
+                    if (cx.tid == 0) {
+                        unsigned long long fibers = 1;
+                        for (int a = 0; a < D; ++a) if (a != axis) fibers *= (unsigned long long)tshape[s][a];
+                        sh.c_macs += fibers * ((unsigned long long)rows * n - (unsigned long long)rows * (rows - 1) / 2);
+                    }
                 } else {
                     // extent-1 axis: TransformChebInPlaceND returns the tensor unchanged (:363)
                     const int cnt = tensor_size<D>(tshape[s]);
@@ -737,7 +744,7 @@ YR_DEV void subdivide_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, d
 // transformChebToInterval :864-894 on the staged box: sh.alpha/beta[axis] hold the restriction,
 // every tensor is restricted in place along every axis, errors are charged before each axis.
 template <int D, class Ctx>
-YR_DEV void restrict_system_inplace(Ctx& cx, BoxShared<D>& sh, double* ws, const SolverParams& prm) {
+YR_DEVN void restrict_system_inplace(Ctx& cx, BoxShared<D>& sh, double* ws, const SolverParams& prm) {
     build_matrices<D>(cx, sh, ws, prm.exact != 0);
     for (int p = 0; p < D; ++p) {
         double s = sh.sumabs[p];
@@ -751,8 +758,9 @@ YR_DEV void restrict_system_inplace(Ctx& cx, BoxShared<D>& sh, double* ws, const
                 s = transform_axis<D>(cx, M, sh.shape[p], sh.stride[p], axis, ws + sh.lay.cmat[axis], sh.mat_n[axis], rows,
                                       M, sh.stride[p], true, prm.use_fma != 0);
                 if (cx.tid == 0) {
-                    sh.c_macs += (unsigned long long)(tensor_size<D>(sh.shape[p]) / n) *
-                                 ((unsigned long long)rows * n - (unsigned long long)rows * (rows - 1) / 2);
+                    unsigned long long fibers = 1;
+                    for (int a = 0; a < D; ++a) if (a != axis) fibers *= (unsigned long long)sh.shape[p][a];
+                    sh.c_macs += fibers * ((unsigned long long)rows * n - (unsigned long long)rows * (rows - 1) / 2);
                     sh.shape[p][axis] = rows;
                 }
                 cx.sync();
@@ -768,8 +776,13 @@ template <int D, class Ctx>
 YR_DEV void process_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws, unsigned long long box_index) {
     const SolverParams& prm = args.prm;
     // ---- stage the box: record, then its tensors (contiguous in the pool) ----
+    {   // the record is a few hundred bytes: all threads copy it, 8 bytes each
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&args.recs_in[box_index]);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.rec);
+        for (int w = cx.tid; w < (int)(sizeof(BoxRec<D>) / 8); w += cx.nthreads) dst[w] = src[w];
+    }
+    cx.sync();
     if (cx.tid == 0) {
-        sh.rec = args.recs_in[box_index];
         for (int p = 0; p < D; ++p) {
             int st = 1;
             for (int a = D - 1; a >= 0; --a) { sh.shape[p][a] = sh.rec.shape[p][a]; sh.stride[p][a] = st; st *= sh.rec.shape[p][a]; }

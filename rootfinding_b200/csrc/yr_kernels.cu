@@ -43,6 +43,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 struct DeviceCtx {
+    static constexpr bool kWarpPerBox = false;
     int tid, nthreads, lane, lanes, warp, nwarps;
     double* red;          // [32] shared scratch for block reductions
     uint64_t* mbar;       // shared mbarrier for TMA staging
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) level_kernel(const yr::LevelArgs<D> args,
 // Barriers become __syncwarp, block reductions one shuffle tree; a serial section (BILS, checks)
 // stalls only its own warp while the other warps of the SM work on their own boxes.
 struct WarpCtx {
+    static constexpr bool kWarpPerBox = true;
     int tid, nthreads, lane, lanes, warp, nwarps;
     uint64_t* mbar;
     uint32_t phase;

@@ -17,10 +17,11 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define YR_HD __host__ __device__ __forceinline__
-#define YR_HDN __host__ __device__
+#define YR_HDN __host__ __device__ __noinline__      /* one copy: instruction-cache footprint matters (profiles/) */
 #else
 #define YR_HD inline
 #define YR_HDN inline
@@ -36,6 +37,11 @@ constexpr int kMaxZoomCount = 25;                        // SolverOptions.maxZoo
 // error-free transformations / double-double
 // ---------------------------------------------------------------------------
 struct dd { double hi, lo; };
+
+// IEEE division / square root kept out of line on the device: every inline expansion is ~15-25
+// instructions, and the scalar per-box code has dozens of them.
+YR_HDN double yr_div(double a, double b) { return a / b; }
+YR_HDN double yr_sqrt(double a) { return sqrt(a); }
 
 YR_HD dd two_sum(double a, double b) {
     dd r; r.hi = a + b;
@@ -167,11 +173,11 @@ YR_HDN void jacobi_svd(const double A[D][D], double W[D][D], double V[D][D], dou
             for (int q = p + 1; q < D; ++q) {
                 double app = 0, aqq = 0, apq = 0;
                 for (int i = 0; i < D; ++i) { app += W[i][p] * W[i][p]; aqq += W[i][q] * W[i][q]; apq += W[i][p] * W[i][q]; }
-                if (apq == 0.0 || fabs(apq) <= 4e-16 * sqrt(app * aqq)) continue;   // columns orthogonal to ~2 ulp
+                if (apq == 0.0 || fabs(apq) <= 4e-16 * yr_sqrt(app * aqq)) continue;   // columns orthogonal to ~2 ulp
                 rotated = true;
-                double zeta = (aqq - app) / (2.0 * apq);
-                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                double zeta = yr_div(aqq - app, 2.0 * apq);
+                double t = yr_div(zeta >= 0 ? 1.0 : -1.0, fabs(zeta) + yr_sqrt(1.0 + zeta * zeta));
+                double c = yr_div(1.0, yr_sqrt(1.0 + t * t)), s = c * t;
                 for (int i = 0; i < D; ++i) {
                     double wp = W[i][p], wq = W[i][q];
                     W[i][p] = c * wp - s * wq; W[i][q] = s * wp + c * wq;
@@ -184,7 +190,7 @@ YR_HDN void jacobi_svd(const double A[D][D], double W[D][D], double V[D][D], dou
     for (int j = 0; j < D; ++j) {
         double s2 = 0;
         for (int i = 0; i < D; ++i) s2 += W[i][j] * W[i][j];
-        sig[j] = sqrt(s2);
+        sig[j] = yr_sqrt(s2);
     }
 }
 
@@ -197,8 +203,8 @@ YR_HD void linear_check(const double total[D], const double A[D][D], const doubl
         for (int j = 0; j < D; ++j) {
             const double a = A[r][j];
             if (a == 0.0) continue;
-            const double v1 = total[r] / fabs(a) - 1;
-            const double v2 = 2 * consts[r] / a;
+            const double v1 = yr_div(total[r], fabs(a)) - 1;
+            const double v2 = yr_div(2 * consts[r], a);
             double l, h;
             if (v2 >= 0) { l = -v1; h = v1 - v2; } else { l = -v2 - v1; h = v1; }
             lo[j] = fmax(lo[j], l);
@@ -207,7 +213,21 @@ YR_HD void linear_check(const double total[D], const double A[D][D], const doubl
 }
 
 YR_HD double pow2_floor_log2(double x) {   // 2^floor(log2(x)), x > 0 finite
-    return ldexp(1.0, ilogb(x));
+    unsigned long long bits;
+#if defined(__CUDA_ARCH__)
+    bits = (unsigned long long)__double_as_longlong(x);
+#else
+    memcpy(&bits, &x, 8);
+#endif
+    if (bits & 0x7FF0000000000000ull) {                      // normal number: keep the exponent field only
+        bits &= 0x7FF0000000000000ull;
+#if defined(__CUDA_ARCH__)
+        return __longlong_as_double((long long)bits);
+#else
+        double r; memcpy(&r, &bits, 8); return r;
+#endif
+    }
+    return ldexp(1.0, ilogb(x));                             // subnormal
 }
 
 struct BilsOut { bool changed, should_stop, throw_out; };
@@ -236,9 +256,9 @@ YR_HDN BilsOut bounding_interval(const double lin[D][D], const double c0[D], con
         double big = 0;
         for (int d = 0; d < D; ++d) big = fmax(big, fabs(A[p][d]));
         if (big > 0) {
-            const double s = pow2_floor_log2(big);
-            for (int d = 0; d < D; ++d) A[p][d] /= s;
-            consts[p] /= s; total[p] /= s; lsum[p] /= s; err[p] /= s; errors[p] /= s;
+            const double inv = yr_div(1.0, pow2_floor_log2(big));   // power of two: x * inv == x / s exactly
+            for (int d = 0; d < D; ++d) A[p][d] *= inv;
+            consts[p] *= inv; total[p] *= inv; lsum[p] *= inv; err[p] *= inv; errors[p] *= inv;
         }
     }
     double col_scale[D];
@@ -247,7 +267,7 @@ YR_HDN BilsOut bounding_interval(const double lin[D][D], const double c0[D], con
         double big = 0;
         for (int p = 0; p < D; ++p) big = fmax(big, fabs(A[p][d]));
         if (big > 0) {
-            const double s = 1.0 / pow2_floor_log2(big);
+            const double s = yr_div(1.0, pow2_floor_log2(big));
             col_scale[d] = s;
             for (int p = 0; p < D; ++p) { total[p] += fabs(A[p][d]) * (s - 1); A[p][d] *= s; }
         }
@@ -265,15 +285,17 @@ YR_HDN BilsOut bounding_interval(const double lin[D][D], const double c0[D], con
         r.changed = false; r.throw_out = false; r.should_stop = final_step;
         return r;
     }
-    const double cond = smin / smax;
+    const double cond = yr_div(smin, smax);
     const bool well = cond > 1e-10;
     const double pad = fmax(cond, 2.0) * kMachEps;             // :696 (always 2^-51)
     double Ainv[D][D], center[D];
     if (well) {
+        double inv_s2[D];
+        for (int k = 0; k < D; ++k) inv_s2[k] = yr_div(1.0, sig[k] * sig[k]);
         for (int i = 0; i < D; ++i)
             for (int j = 0; j < D; ++j) {
                 double s = 0;
-                for (int k = 0; k < D; ++k) s += V[i][k] / (sig[k] * sig[k]) * W[j][k];
+                for (int k = 0; k < D; ++k) s += V[i][k] * inv_s2[k] * W[j][k];
                 Ainv[i][j] = s;
             }
         for (int i = 0; i < D; ++i) {
@@ -357,7 +379,7 @@ YR_HDN int subdivision_axes(const int shape[D][D], const double iv[D][2], int le
         for (int j = 0; j < nc; ++j) widest = fmax(widest, iv[cand[j]][1] - iv[cand[j]][0]);
         int m = 0;
         for (int j = 0; j < nc; ++j)
-            if ((iv[cand[j]][1] - iv[cand[j]][0]) > widest / 5) cand[m++] = cand[j];
+            if ((iv[cand[j]][1] - iv[cand[j]][0]) > yr_div(widest, 5.0)) cand[m++] = cand[j];
         nc = m;
         if (nc > 1) {
             int per_axis[D]; int total = 0;
@@ -406,7 +428,7 @@ YR_HDN bool quad_check_2d(const double c[6], double sumabs, double tol) {
     auto q = [&](double x, double y) { return k0 + (c[1] + k3 * x + c[4] * y) * x + (c[2] + k5 * y) * y; };
     const double det = 16 * c[3] * c[5] - c[4] * c[4];
     double ix = INFINITY, iy = INFINITY;
-    if (det != 0) { ix = (c[2] * c[4] - 4 * c[1] * c[5]) / det; iy = (c[1] * c[4] - 4 * c[2] * c[3]) / det; }
+    if (det != 0) { ix = yr_div(c[2] * c[4] - 4 * c[1] * c[5], det); iy = yr_div(c[1] * c[4] - 4 * c[2] * c[3], det); }
     if (r.feed(q(-1, -1))) return false;
     if (r.feed(q(1, -1))) return false;
     if (r.feed(q(-1, 1))) return false;
@@ -414,14 +436,14 @@ YR_HDN bool quad_check_2d(const double c[6], double sumabs, double tol) {
     if (c[5] != 0) {
         const double cc5 = 4 * c[5];
         for (int sx = -1; sx <= 1; sx += 2) {
-            const double x = sx, y = -(c[2] + c[4] * x) / cc5;
+            const double x = sx, y = yr_div(-(c[2] + c[4] * x), cc5);
             if (-1 < y && y < 1 && r.feed(q(x, y))) return false;
         }
     }
     if (c[3] != 0) {
         const double cc3 = 4 * c[3];
         for (int sy = -1; sy <= 1; sy += 2) {
-            const double y = sy, x = -(c[1] + c[4] * y) / cc3;
+            const double y = sy, x = yr_div(-(c[1] + c[4] * y), cc3);
             if (-1 < x && x < 1 && r.feed(q(x, y))) return false;
         }
     }
@@ -443,9 +465,9 @@ YR_HDN bool quad_check_3d(const double c[10], double sumabs, double tol) {
     const double det = 4 * c[7] * dx - c[4] * m12 + c[5] * m13;
     double ix = INFINITY, iy = INFINITY, iz = INFINITY;
     if (det != 0) {
-        ix = (c[1] * -dx + c[2] * m12 + c[3] * -m13) / det;
-        iy = (c[1] * m12 + c[2] * -dy + c[3] * m23) / det;
-        iz = (c[1] * -m13 + c[2] * m23 + c[3] * -dz) / det;
+        ix = yr_div((c[1] * -dx + c[2] * m12 + c[3] * -m13), det);
+        iy = yr_div((c[1] * m12 + c[2] * -dy + c[3] * m23), det);
+        iz = yr_div((c[1] * -m13 + c[2] * m23 + c[3] * -dz), det);
     }
     auto in = [](double v) { return -1 < v && v < 1; };
     const double L = -1, H = 1;
@@ -459,27 +481,27 @@ YR_HDN bool quad_check_3d(const double c[10], double sumabs, double tol) {
     if (r.feed(q(H, H, H))) return false;
     if (c[9] != 0)
         for (int a = 0; a < 2; ++a) { const double x = a ? H : L, t = c[5] * x + c[3];
-            for (int b = 0; b < 2; ++b) { const double y = b ? H : L, z = -(t + c[6] * y) / kk9;
+            for (int b = 0; b < 2; ++b) { const double y = b ? H : L, z = yr_div(-(t + c[6] * y), kk9);
                 if (in(z) && r.feed(q(x, y, z))) return false; } }
     if (c[8] != 0)
         for (int a = 0; a < 2; ++a) { const double x = a ? H : L, t = c[2] + c[4] * x;
-            for (int b = 0; b < 2; ++b) { const double z = b ? H : L, y = -(t + c[6] * z) / kk8;
+            for (int b = 0; b < 2; ++b) { const double z = b ? H : L, y = yr_div(-(t + c[6] * z), kk8);
                 if (in(y) && r.feed(q(x, y, z))) return false; } }
     if (c[7] != 0)
         for (int a = 0; a < 2; ++a) { const double y = a ? H : L, t = c[1] + c[4] * y;
-            for (int b = 0; b < 2; ++b) { const double z = b ? H : L, x = -(t + c[5] * z) / kk7;
+            for (int b = 0; b < 2; ++b) { const double z = b ? H : L, x = yr_div(-(t + c[5] * z), kk7);
                 if (in(x) && r.feed(q(x, y, z))) return false; } }
     if (dx != 0)
         for (int a = 0; a < 2; ++a) { const double x = a ? H : L, u = c[2] + c[4] * x, v = c[3] + c[5] * x;
-            const double y = (-kk9 * u + c[6] * v) / dx, z = (c[6] * u - kk8 * v) / dx;
+            const double y = yr_div((-kk9 * u + c[6] * v), dx), z = yr_div((c[6] * u - kk8 * v), dx);
             if (in(y) && in(z) && r.feed(q(x, y, z))) return false; }
     if (dy != 0)
         for (int a = 0; a < 2; ++a) { const double y = a ? H : L, u = c[1] + c[4] * y, v = c[3] + c[6] * y;
-            const double x = (-kk9 * u + c[5] * v) / dy, z = (c[5] * u - kk7 * v) / dy;
+            const double x = yr_div((-kk9 * u + c[5] * v), dy), z = yr_div((c[5] * u - kk7 * v), dy);
             if (in(x) && in(z) && r.feed(q(x, y, z))) return false; }
     if (dz != 0)
         for (int a = 0; a < 2; ++a) { const double z = a ? H : L, u = c[1] + c[5] * z, v = c[2] + c[6] * z;
-            const double x = (-kk8 * u + c[4] * v) / dz, y = (c[4] * u - kk7 * v) / dz;
+            const double x = yr_div((-kk8 * u + c[4] * v), dz), y = yr_div((c[4] * u - kk7 * v), dz);
             if (in(x) && in(y) && r.feed(q(x, y, z))) return false; }
     if (in(ix) && in(iy) && in(iz) && r.feed(q(ix, iy, iz))) return false;
     return true;
@@ -503,7 +525,7 @@ YR_HDN bool small_solve(int m, double H[D][D], double rhs[D], double x[D]) {
             double t = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = t;
         }
         for (int i = k + 1; i < m; ++i) {
-            const double f = H[i][k] / H[k][k];
+            const double f = yr_div(H[i][k], H[k][k]);
             for (int j = k; j < m; ++j) H[i][j] -= f * H[k][j];
             rhs[i] -= f * rhs[k];
         }
@@ -511,7 +533,7 @@ YR_HDN bool small_solve(int m, double H[D][D], double rhs[D], double x[D]) {
     for (int i = m - 1; i >= 0; --i) {
         double s = rhs[i];
         for (int j = i + 1; j < m; ++j) s -= H[i][j] * x[j];
-        x[i] = s / H[i][i];
+        x[i] = yr_div(s, H[i][i]);
     }
     return true;
 }

@@ -134,7 +134,8 @@ class SubdivisionEngine:
         self.threads = threads
         self.max_ctas_per_sm = max_ctas_per_sm
         self.worst_case_budget = 1 << 28              # below this many bytes, just allocate the worst case
-        self.warp_max_ws = int(os.environ.get("YR_WARP_MAX_WS", "3072"))      # doubles; larger boxes run CTA-per-box
+        self.warp_max_ws = int(os.environ.get("YR_WARP_MAX_WS", "28000"))     # doubles; larger boxes run CTA-per-box
+        self.warp_min_items = int(os.environ.get("YR_WARP_MIN_ITEMS", "1024"))  # fewer boxes than this: CTA-per-box (latency)
         self.warp_ctas_per_sm = int(os.environ.get("YR_WARP_CTAS_PER_SM", "4"))   # 128-thread CTAs (register bound)
 
     def params(self, **kw):
@@ -154,13 +155,14 @@ class SubdivisionEngine:
         """
         ws = int(self.lib.yr_workspace_doubles(dim, int(total), int(max_tensor), int(max_extent), int(exact)))
         static = int(self.lib.yr_static_smem_bytes(dim))
-        warps = 4
         per_warp = static + 16 + ((ws * 8 + 15) & ~15)
-        per_cta = warps * per_warp + 1024
-        if allow_warp and ws <= self.warp_max_ws and per_cta <= self.max_smem_cta:
-            per_sm = max(1, min(self.warp_ctas_per_sm, self.smem_per_sm // per_cta))
-            ctas = int(max(1, min((n_items + warps - 1) // warps, self.sm_count * per_sm)))
-            return 32 * warps, ctas, True, ws, True
+        if allow_warp and ws <= self.warp_max_ws and n_items >= self.warp_min_items:
+            for warps in (4, 2, 1):
+                per_cta = warps * per_warp + 1024
+                if per_cta <= self.max_smem_cta:
+                    per_sm = max(1, min((4 * self.warp_ctas_per_sm) // warps, self.smem_per_sm // per_cta))
+                    ctas = int(max(1, min((n_items + warps - 1) // warps, self.sm_count * per_sm)))
+                    return 32 * warps, ctas, True, ws, True
         threads = self.threads or (128 if total >= 768 else 64)
         in_smem = ws * 8 + static <= self.max_smem_cta
         if in_smem:

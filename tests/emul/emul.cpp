@@ -40,6 +40,7 @@ struct Team {
 };
 
 struct HostCtx {
+    static constexpr bool kWarpPerBox = false;
     int tid, nthreads, lane, lanes, warp, nwarps;
     Team* team;
     void sync() { team->bar.wait(); }
