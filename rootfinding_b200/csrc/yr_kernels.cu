@@ -139,6 +139,8 @@ struct WarpCtx {
     uint32_t phase;
 
     __device__ __forceinline__ void sync() { __syncwarp(); }
+    __device__ __forceinline__ void cta_sync() { __syncthreads(); }
+    __device__ __forceinline__ bool cta_all(bool pred) { return __syncthreads_and(pred ? 1 : 0) != 0; }
     __device__ __forceinline__ double block_sum(double v) {
         for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
         return __shfl_sync(0xffffffffu, v, 0);
@@ -179,7 +181,7 @@ __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(siz
 
 // dynamic shared memory per warp: [BoxShared<D> | mbarrier (16 B) | workspace doubles]
 template <int D>
-__global__ void __launch_bounds__(128, 4) level_kernel_warp(const yr::LevelArgs<D> args, unsigned warp_stride_bytes) {
+__global__ void __launch_bounds__(512, 1) level_kernel_warp(const yr::LevelArgs<D> args, unsigned warp_stride_bytes) {
     extern __shared__ __align__(16) unsigned char dyn_raw[];
     const int w = threadIdx.x >> 5;
     unsigned char* base = dyn_raw + (size_t)w * warp_stride_bytes;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(128, 4) level_kernel_warp(const yr::LevelArgs<
     cx.mbar = mbar; cx.phase = 0;
     if (cx.lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     __syncwarp();
-    yr::level_worker<D>(cx, args, *sh, ws);
+    yr::lockstep_worker<D>(cx, args, *sh, ws);
 }
 
 template <int D>

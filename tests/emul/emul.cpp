@@ -39,11 +39,30 @@ struct Team {
     std::vector<double> scratch;
 };
 
+struct CtaShared {          // what the warp-teams of one emulated CTA share
+    SpinBarrier bar;
+    std::atomic<int> vote{1};
+};
+
 struct HostCtx {
     static constexpr bool kWarpPerBox = false;
     int tid, nthreads, lane, lanes, warp, nwarps;
     Team* team;
+    CtaShared* cta = nullptr;
+    int cta_tid = 0;
     void sync() { team->bar.wait(); }
+    void cta_sync() { if (cta) cta->bar.wait(); else team->bar.wait(); }
+    bool cta_all(bool pred) {
+        if (!cta) return pred;
+        cta->bar.wait();
+        if (cta_tid == 0) cta->vote.store(1);
+        cta->bar.wait();
+        if (!pred) cta->vote.store(0);
+        cta->bar.wait();
+        const bool r = cta->vote.load() != 0;
+        cta->bar.wait();
+        return r;
+    }
     double tree(int w) const {
         double a[64];
         for (int l = 0; l < lanes; ++l) a[l] = team->scratch[w * lanes + l];
@@ -105,7 +124,31 @@ int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_pe
 template <int D>
 int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void*) {
     const int lanes = env_int("YR_EMUL_LANES", 4);
-    const int T = l.warp_per_box ? lanes : env_int("YR_EMUL_THREADS", 8);     // warp-per-box: a one-warp team
+    if (l.warp_per_box) {
+        // one emulated CTA of W warp-teams walking the phases in lock step (lockstep_worker)
+        const int W = env_int("YR_EMUL_WARPS", 2);
+        CtaShared cta; cta.bar.n = W * lanes;
+        std::vector<Team> teams(W);
+        std::vector<std::vector<double>> wss(W);
+        std::vector<yr::BoxShared<D>*> shs(W);
+        for (int w = 0; w < W; ++w) {
+            teams[w].T = lanes; teams[w].lanes = lanes; teams[w].bar.n = lanes; teams[w].scratch.assign(lanes, 0.0);
+            wss[w].assign(l.ws_doubles + 8, 0.0);
+            shs[w] = new yr::BoxShared<D>();
+        }
+        std::vector<std::thread> th;
+        for (int w = 0; w < W; ++w)
+            for (int t = 0; t < lanes; ++t)
+                th.emplace_back([&, w, t]() {
+                    HostCtx cx; cx.tid = t; cx.nthreads = lanes; cx.lanes = lanes; cx.lane = t; cx.warp = 0; cx.nwarps = 1;
+                    cx.team = &teams[w]; cx.cta = &cta; cx.cta_tid = w * lanes + t;
+                    yr::lockstep_worker<D>(cx, a, *shs[w], wss[w].data());
+                });
+        for (auto& x : th) x.join();
+        for (auto p : shs) delete p;
+        return 0;
+    }
+    const int T = env_int("YR_EMUL_THREADS", 8);
     std::vector<double> ws;
     double* wsp;
     if (l.ws_in_smem) { ws.assign(l.ws_doubles + 8, 0.0); wsp = ws.data(); } else wsp = l.gws;

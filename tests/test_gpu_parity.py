@@ -271,9 +271,11 @@ def test_full_size_properties(yr):
     idx = [i for i in range(int(z["n"])) if int(z[f"meta_{i}"][1]) == 50][0]
     assert len(roots[0]) == len(z[f"roots_{idx}"])
     H.match_points(z[f"roots_{idx}"], roots[0], H.ROOT_TOL)
-    assert np.array_equal(alone, roots[3])                      # bit-identical regardless of batch composition
+    # the launch shape (CTA- vs warp-per-box) depends on how many boxes a level holds, and the two differ in
+    # the order of the |M| reductions: same roots to rounding, not necessarily the same bits
+    assert len(alone) == len(roots[3]) and H.match_points(alone, roots[3], 1e-13) < 1e-13
     for r1, r2 in zip(roots, rev):
-        assert np.array_equal(r1, r2)
+        assert np.array_equal(r1, r2)                           # same batch, other order: identical
     for Ms, r in zip(systems, roots):
         assert 500 < len(r) < 900 and np.all(np.abs(r) <= 1)
         for M in Ms:
