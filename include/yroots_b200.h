@@ -60,7 +60,8 @@ typedef struct yr_launch {
     int32_t threads;             /* threads per CTA (multiple of 32) */
     int32_t ctas;                /* persistent CTAs */
     int32_t ws_in_smem;          /* 1: workspace in dynamic shared memory, 0: in gws */
-    int32_t warp_per_box;        /* 1: every warp of a CTA owns a box of its own (small boxes); 0: CTA per box */
+    int32_t warp_per_box;        /* 0: CTA per box; 1: every warp of a CTA owns a box of its own (small boxes);
+                                    2: same, and the warps of a CTA walk the pipeline phases in lock step */
     uint64_t ws_doubles;         /* workspace capacity per CTA, in doubles */
     double*  gws;                /* [ctas][gws_stride] global scratch when ws_in_smem == 0 */
     uint64_t gws_stride;

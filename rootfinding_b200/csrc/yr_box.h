@@ -106,6 +106,8 @@ YR_HD int view_offset(int e, const int* shape, const int* stride) {
 // fiber f (all axes except `axis`, row-major) -> offsets in source and destination
 template <int D>
 YR_HD void fiber_offsets(int f, int axis, const int* shape, const int* sstride, const int* dstride, int& so, int& dofs) {
+    if (D == 1) { so = 0; dofs = 0; return; }
+    if (D == 2) { so = f * sstride[1 - axis]; dofs = f * dstride[1 - axis]; return; }     // no integer division
     so = 0; dofs = 0;
     for (int a = D - 1; a >= 0; --a) {
         if (a == axis) continue;
@@ -369,9 +371,8 @@ YR_DEVN void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
     }
     cx.sync();
     for (int k = 2; k < kmax; ++k) {
-        const int per = k + 1;
-        for (int id = cx.tid; id < nmat * per; id += cx.nthreads) {
-            const int m = id / per, i = id - m * per;
+        for (int m = 0; m < nmat; ++m)
+        for (int i = cx.tid; i <= k; i += cx.nthreads) {
             if (k >= sh.mat_n[m]) continue;
             const int nc = sh.mat_n[m];
             const int rows = sh.rows_buf[(k - 1) & 1][m];

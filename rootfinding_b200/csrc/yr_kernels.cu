@@ -181,7 +181,7 @@ __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(siz
 
 // dynamic shared memory per warp: [BoxShared<D> | mbarrier (16 B) | workspace doubles]
 template <int D>
-__global__ void __launch_bounds__(512, 1) level_kernel_warp(const yr::LevelArgs<D> args, unsigned warp_stride_bytes) {
+__global__ void __launch_bounds__(512, 1) level_kernel_warp(const yr::LevelArgs<D> args, unsigned warp_stride_bytes, int lockstep) {
     extern __shared__ __align__(16) unsigned char dyn_raw[];
     const int w = threadIdx.x >> 5;
     unsigned char* base = dyn_raw + (size_t)w * warp_stride_bytes;
@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(512, 1) level_kernel_warp(const yr::LevelArgs<
     cx.mbar = mbar; cx.phase = 0;
     if (cx.lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
     __syncwarp();
-    yr::lockstep_worker<D>(cx, args, *sh, ws);
+    if (lockstep) yr::lockstep_worker<D>(cx, args, *sh, ws);
+    else yr::level_worker<D>(cx, args, *sh, ws);
 }
 
 template <int D>
@@ -279,7 +280,7 @@ int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream) {
         const size_t stride = align16(sizeof(yr::BoxShared<D>)) + 16 + align16((size_t)l.ws_doubles * 8);
         const size_t smem = stride * (size_t)(l.threads / 32);
         if (smem > 48 * 1024 && set_smem(level_kernel_warp<D>, smem)) return -1;
-        level_kernel_warp<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, (unsigned)stride);
+        level_kernel_warp<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, (unsigned)stride, l.warp_per_box == 2);
         cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : cuda_fail(e, "level_kernel_warp launch");
     }

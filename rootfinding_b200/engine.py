@@ -136,7 +136,8 @@ class SubdivisionEngine:
         self.worst_case_budget = 1 << 28              # below this many bytes, just allocate the worst case
         self.warp_max_ws = int(os.environ.get("YR_WARP_MAX_WS", "28000"))     # doubles; larger boxes run CTA-per-box
         self.warp_min_items = int(os.environ.get("YR_WARP_MIN_ITEMS", "1024"))  # fewer boxes than this: CTA-per-box (latency)
-        self.warp_teams = int(os.environ.get("YR_WARP_TEAMS", "16"))          # warp-teams per lock-step CTA
+        self.warp_teams = int(os.environ.get("YR_WARP_TEAMS", "16"))          # warp-teams per SM (register bound: 16 x 32 x 128)
+        self.warp_mode = int(os.environ.get("YR_WARP_MODE", "1"))             # 1: independent warp-teams, 2: lock-step CTA
 
     def params(self, **kw):
         p = _lib.default_params(self.lib)
@@ -157,12 +158,18 @@ class SubdivisionEngine:
         static = int(self.lib.yr_static_smem_bytes(dim))
         per_warp = static + 16 + ((ws * 8 + 15) & ~15)
         if allow_warp and ws <= self.warp_max_ws and n_items >= self.warp_min_items and per_warp + 1024 <= self.max_smem_cta:
-            # lock-step CTA of up to 16 warp-teams (512 threads x 128 registers fill an SM's register file)
-            warps = int(max(1, min(self.warp_teams, (self.max_smem_cta - 1024) // per_warp)))
-            per_cta = warps * per_warp + 1024
-            per_sm = max(1, min(16 // warps, self.smem_per_sm // per_cta))
+            if self.warp_mode == 2:
+                # lock-step CTA of up to 16 warp-teams (512 threads x 128 registers fill an SM's register file)
+                warps = int(max(1, min(self.warp_teams, (self.max_smem_cta - 1024) // per_warp)))
+                per_cta = warps * per_warp + 1024
+                per_sm = max(1, min(16 // warps, self.smem_per_sm // per_cta))
+            else:
+                # independent warp-teams, 4 per CTA (fewer when a box is large)
+                warps = int(max(1, min(4, (self.max_smem_cta - 1024) // per_warp)))
+                per_cta = warps * per_warp + 1024
+                per_sm = max(1, min(self.warp_teams // warps, self.smem_per_sm // per_cta))
             ctas = int(max(1, min((n_items + warps - 1) // warps, self.sm_count * per_sm)))
-            return 32 * warps, ctas, True, ws, True
+            return 32 * warps, ctas, True, ws, self.warp_mode
         threads = self.threads or (128 if total >= 768 else 64)
         in_smem = ws * 8 + static <= self.max_smem_cta
         if in_smem:

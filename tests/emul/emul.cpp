@@ -142,7 +142,8 @@ int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void*) {
                 th.emplace_back([&, w, t]() {
                     HostCtx cx; cx.tid = t; cx.nthreads = lanes; cx.lanes = lanes; cx.lane = t; cx.warp = 0; cx.nwarps = 1;
                     cx.team = &teams[w]; cx.cta = &cta; cx.cta_tid = w * lanes + t;
-                    yr::lockstep_worker<D>(cx, a, *shs[w], wss[w].data());
+                    if (l.warp_per_box == 2) yr::lockstep_worker<D>(cx, a, *shs[w], wss[w].data());
+                    else yr::level_worker<D>(cx, a, *shs[w], wss[w].data());
                 });
         for (auto& x : th) x.join();
         for (auto p : shs) delete p;

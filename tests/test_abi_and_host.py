@@ -200,16 +200,19 @@ def test_argument_errors():
         S.solveChebyshevSubdivision([np.zeros((2, 2)), np.zeros((2, 2))], np.zeros(3))
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("dim,deg,N", [(1, 10, 2), (2, 10, 3), (3, 4, 2), (4, 2, 1)])
-def test_emulated_lockstep_warp_per_box(emu, dim, deg, N):
-    """The warp-per-box kernel path (lock-step CTA of warp-teams) gives the same search tree and roots."""
+def test_emulated_warp_per_box(emu, dim, deg, N, mode):
+    """The warp-per-box kernel paths (independent warp-teams / lock-step CTA) give the same search tree and roots."""
     systems = H.seeded_systems(dim, deg, N)
     errs = [np.full(dim, 2. ** -52)] * N
     old = emu.warp_min_items
     try:
         emu.warp_min_items = 1                  # every level runs warp-per-box
+        emu.warp_mode = mode
         sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
         assert sess.stats.boxes == boxes and worst < 1e-14
         assert all(lvl[7] for lvl in sess.stats.per_level)
     finally:
         emu.warp_min_items = old
+        emu.warp_mode = 1
