@@ -78,6 +78,12 @@ typedef struct yr_level_desc {
     void*         counters;      /* yr_counters, zeroed by the caller before the call */
     yr_params     prm;
     yr_launch     launch;
+    /* pipeline 1 (phase-split kernels): scratch of yr_level_work_bytes(dim, n_in) bytes that must stay
+     * alive, untouched, until the level has succeeded; recs_in / data_in are updated in place.
+     * resume_subdivide = 1 re-runs only the subdivision step after an overflow (larger *_out buffers). */
+    void*         work;          uint64_t work_bytes;
+    int32_t       pipeline;      /* 0: one fused kernel per level, 1: phase-split kernels */
+    int32_t       resume_subdivide;
 } yr_level_desc;
 
 /* Level-0 boxes: one per job = (system, optional restriction). */
@@ -122,6 +128,8 @@ int64_t     yr_record_layout(int32_t dim, int32_t kind, int64_t* triples, int32_
 
 /* Workspace (doubles) a box needs: total coefficients, largest tensor, largest extent. */
 uint64_t    yr_workspace_doubles(int32_t dim, uint64_t total, uint64_t max_tensor, uint64_t max_extent, int32_t exact);
+/* Scratch bytes yr_process_level needs for a level of n boxes when desc.pipeline == 1. */
+uint64_t    yr_level_work_bytes(int32_t dim, uint64_t n_boxes);
 /* Static shared memory (bytes) the solver kernels use besides the workspace, per CTA. */
 int64_t     yr_static_smem_bytes(int32_t dim);
 /* Largest dynamic shared memory a CTA may use on the current device (bytes); host pointers. */

@@ -34,7 +34,8 @@ class YrLevelDesc(C.Structure):
                 ("results", vp), ("cap_results", u64),
                 ("nodes", vp), ("cap_nodes", u64),
                 ("result_base", u64), ("node_base", u64),
-                ("counters", vp), ("prm", YrParams), ("launch", YrLaunch)]
+                ("counters", vp), ("prm", YrParams), ("launch", YrLaunch),
+                ("work", vp), ("work_bytes", u64), ("pipeline", i32), ("resume_subdivide", i32)]
 
 
 class YrInitDesc(C.Structure):
@@ -54,7 +55,7 @@ COUNTER_BYTES = 8 * len(COUNTER_FIELDS)
 
 # every symbol include/yroots_b200.h declares
 EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_params", "yr_record_layout",
-           "yr_workspace_doubles", "yr_static_smem_bytes", "yr_device_limits", "yr_init_boxes", "yr_process_level", "yr_bils_batched",
+           "yr_workspace_doubles", "yr_level_work_bytes", "yr_static_smem_bytes", "yr_device_limits", "yr_init_boxes", "yr_process_level", "yr_bils_batched",
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
@@ -75,6 +76,8 @@ def bind(lib):
     lib.yr_record_layout.restype = i64
     lib.yr_workspace_doubles.argtypes = [i32, u64, u64, u64, i32]
     lib.yr_workspace_doubles.restype = u64
+    lib.yr_level_work_bytes.argtypes = [i32, u64]
+    lib.yr_level_work_bytes.restype = u64
     lib.yr_static_smem_bytes.argtypes = [i32]
     lib.yr_static_smem_bytes.restype = i64
     lib.yr_device_limits.argtypes = [C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]

@@ -8,6 +8,7 @@
 #include <string.h>
 #include "../../include/yroots_b200.h"
 #include "yr_box.h"
+#include "yr_phases.h"
 #include "yr_items.h"
 
 // Hooks every backend defines after including this header.
@@ -16,6 +17,12 @@ const char* build_info();
 int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm);
 template <int D> int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream);
 template <int D> int launch_init(const yr::InitArgs<D>& a, const yr_launch& l, void* stream);
+// phase-split pipeline: one step over pa.list_in[0 .. pa.n_list)
+template <int D> int launch_tensor_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream);
+template <int D> int launch_scalar_step(const yr::PhaseArgs<D>& pa, void* stream);
+template <int D> int launch_subdivide_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream);
+int read_u64(const void* dev, unsigned long long* out, void* stream);        // device -> host, synchronises the stream
+int zero_bytes(void* dev, size_t bytes, void* stream);
 template <int D> int launch_bils(int64_t n, const double* lin, const double* c0, const double* sumabs, const double* errs,
                                  const int32_t* final_step, double* interval, int32_t* flags, void* stream);
 template <int D> int launch_quad(int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes,
@@ -39,6 +46,61 @@ inline yr::SolverParams to_params(const yr_params& p) {
     return q;
 }
 
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int D>
+struct WorkLayout {
+    size_t work, list_a, list_b, list_sub, ctl, total;
+    explicit WorkLayout(unsigned long long n) {
+        work = 0;
+        list_a = align_up(sizeof(yr::BoxWork<D>) * n, 16);
+        list_b = list_a + align_up(4 * n, 16);
+        list_sub = list_b + align_up(4 * n, 16);
+        ctl = list_sub + align_up(4 * n, 16);
+        total = ctl + sizeof(yr::RoundCtl);
+    }
+};
+
+// One level with the phase-split kernels: rounds of (tensor step, scalar step) over the shrinking list of
+// boxes that still need work, then the subdivision step.  One 8-byte read-back per round.
+template <int D>
+int run_level_phased(const yr::LevelArgs<D>& a, const yr_level_desc* d, void* stream) {
+    const WorkLayout<D> wl(a.n_in);
+    if (!d->work || d->work_bytes < wl.total) return fail("work buffer missing or too small (yr_level_work_bytes)");
+    if (a.n_in == 0) return 0;
+    if (a.n_in > 0xFFFFFFF0ull) return fail("level too large for 32-bit box lists");
+    char* base = static_cast<char*>(d->work);
+    yr::PhaseArgs<D> pa;
+    pa.lv = a;
+    pa.work = reinterpret_cast<yr::BoxWork<D>*>(base + wl.work);
+    unsigned int* lists[2] = {reinterpret_cast<unsigned int*>(base + wl.list_a), reinterpret_cast<unsigned int*>(base + wl.list_b)};
+    pa.list_sub = reinterpret_cast<unsigned int*>(base + wl.list_sub);
+    pa.ctl = reinterpret_cast<yr::RoundCtl*>(base + wl.ctl);
+    unsigned long long n_sub = 0;
+    if (!d->resume_subdivide) {
+        if (yr_backend::zero_bytes(pa.ctl, sizeof(yr::RoundCtl), stream)) return -1;
+        pa.list_in = nullptr; pa.n_list = a.n_in; pa.first_round = 1;
+        int cur = 0;
+        for (int round = 0; pa.n_list > 0; ++round) {
+            if (round > 100000) return fail("round loop did not terminate");
+            pa.list_next = lists[cur];
+            if (yr_backend::launch_tensor_step<D>(pa, d->launch, stream)) return -1;
+            if (yr_backend::zero_bytes(&pa.ctl->cursor, sizeof(unsigned long long), stream)) return -1;
+            if (yr_backend::launch_scalar_step<D>(pa, stream)) return -1;
+            unsigned long long n_next = 0;
+            if (yr_backend::read_u64(&pa.ctl->n_next, &n_next, stream)) return -1;
+            if (yr_backend::zero_bytes(pa.ctl, 2 * sizeof(unsigned long long), stream)) return -1;   // cursor, n_next
+            pa.list_in = lists[cur]; pa.n_list = n_next; pa.first_round = 0;
+            cur ^= 1;
+        }
+    }
+    if (yr_backend::read_u64(&pa.ctl->n_sub, &n_sub, stream)) return -1;
+    if (yr_backend::zero_bytes(&pa.ctl->cursor, sizeof(unsigned long long), stream)) return -1;
+    pa.list_in = pa.list_sub; pa.n_list = n_sub; pa.first_round = 0; pa.list_next = nullptr;
+    if (n_sub == 0) return 0;
+    return yr_backend::launch_subdivide_step<D>(pa, d->launch, stream);
+}
+
 template <int D>
 int level_impl(const yr_level_desc* d, void* stream) {
     yr::LevelArgs<D> a;
@@ -51,6 +113,7 @@ int level_impl(const yr_level_desc* d, void* stream) {
     a.ctr = static_cast<yr::LevelCounters*>(d->counters);
     a.gws = d->launch.gws; a.gws_stride = d->launch.gws_stride; a.ws_doubles = d->launch.ws_doubles;
     a.prm = to_params(d->prm);
+    if (d->pipeline == 1) return run_level_phased<D>(a, d, stream);
     return yr_backend::launch_level<D>(a, d->launch, stream);
 }
 
@@ -136,6 +199,15 @@ int64_t yr_record_layout(int32_t dim, int32_t kind, int64_t* triples, int32_t ca
 
 uint64_t yr_workspace_doubles(int32_t dim, uint64_t total, uint64_t max_tensor, uint64_t max_extent, int32_t exact) {
     return yr::workspace_doubles(dim, total, max_tensor, max_extent, exact);
+}
+
+uint64_t yr_level_work_bytes(int32_t dim, uint64_t n) {
+    switch (dim) {
+        case 1: return yr_api::WorkLayout<1>(n).total; case 2: return yr_api::WorkLayout<2>(n).total;
+        case 3: return yr_api::WorkLayout<3>(n).total; case 4: return yr_api::WorkLayout<4>(n).total;
+        case 5: return yr_api::WorkLayout<5>(n).total; case 6: return yr_api::WorkLayout<6>(n).total;
+        default: return 0;
+    }
 }
 
 int64_t yr_static_smem_bytes(int32_t dim) {

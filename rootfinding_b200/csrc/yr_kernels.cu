@@ -208,6 +208,88 @@ __global__ void __launch_bounds__(256) init_kernel(const yr::InitArgs<D> args, i
     yr::init_worker<D>(cx, args, sh, ws);
 }
 
+// ---- phase-split pipeline kernels (yr_phases.h) ---------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) tensor_step_kernel(const yr::PhaseArgs<D> pa, int ws_in_smem) {
+    extern __shared__ __align__(16) double dyn_ws[];
+    __shared__ yr::BoxShared<D> sh;
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, ws_in_smem);
+    double* ws = ws_in_smem ? dyn_ws : pa.lv.gws + (size_t)blockIdx.x * pa.lv.gws_stride;
+    yr::tensor_step_worker<D>(cx, pa, sh, ws);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) subdivide_step_kernel(const yr::PhaseArgs<D> pa, int ws_in_smem) {
+    extern __shared__ __align__(16) double dyn_ws[];
+    __shared__ yr::BoxShared<D> sh;
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, ws_in_smem);
+    double* ws = ws_in_smem ? dyn_ws : pa.lv.gws + (size_t)blockIdx.x * pa.lv.gws_stride;
+    yr::subdivide_step_worker<D>(cx, pa, sh, ws);
+}
+
+template <int D>
+__device__ __forceinline__ WarpCtx make_warp_ctx(unsigned char* dyn_raw, unsigned warp_stride_bytes, yr::BoxShared<D>*& sh, double*& ws) {
+    const int w = threadIdx.x >> 5;
+    unsigned char* base = dyn_raw + (size_t)w * warp_stride_bytes;
+    sh = reinterpret_cast<yr::BoxShared<D>*>(base);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(base + align16(sizeof(yr::BoxShared<D>)));
+    ws = reinterpret_cast<double*>(base + align16(sizeof(yr::BoxShared<D>)) + 16);
+    WarpCtx cx;
+    cx.tid = cx.lane = threadIdx.x & 31; cx.nthreads = cx.lanes = 32; cx.warp = 0; cx.nwarps = 1;
+    cx.mbar = mbar; cx.phase = 0;
+    if (cx.lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
+    __syncwarp();
+    return cx;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 4) tensor_step_kernel_warp(const yr::PhaseArgs<D> pa, unsigned warp_stride_bytes) {
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    yr::BoxShared<D>* sh; double* ws;
+    WarpCtx cx = make_warp_ctx<D>(dyn_raw, warp_stride_bytes, sh, ws);
+    yr::tensor_step_worker<D>(cx, pa, *sh, ws);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128, 4) subdivide_step_kernel_warp(const yr::PhaseArgs<D> pa, unsigned warp_stride_bytes) {
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    yr::BoxShared<D>* sh; double* ws;
+    WarpCtx cx = make_warp_ctx<D>(dyn_raw, warp_stride_bytes, sh, ws);
+    yr::subdivide_step_worker<D>(cx, pa, *sh, ws);
+}
+
+struct DeviceAtomics {
+    __device__ __forceinline__ unsigned long long add(unsigned long long* p, unsigned long long v) const { return atomicAdd(p, v); }
+};
+
+// thread per box: the serial per-box mathematics, 32 boxes per instruction stream
+template <int D>
+__global__ void __launch_bounds__(128) scalar_step_kernel(const yr::PhaseArgs<D> pa) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    yr::ScalarCounts c{};
+    if (i < pa.n_list) yr::scalar_step<D>(pa, pa.list_in ? pa.list_in[i] : (unsigned int)i, c, DeviceAtomics());
+    unsigned long long v[6] = {c.boxes, c.zooms, c.dconst, c.dquad, c.dzoom, c.coeffs};
+    unsigned long long mx = c.maxlevel;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+    for (int off = 16; off > 0; off >>= 1) { const unsigned long long o = __shfl_down_sync(0xffffffffu, mx, off); mx = o > mx ? o : mx; }
+    if ((threadIdx.x & 31) == 0) {
+        yr::LevelCounters* k = pa.lv.ctr;
+        if (v[0]) atomicAdd(&k->boxes, v[0]);
+        if (v[1]) atomicAdd(&k->zooms, v[1]);
+        if (v[2]) atomicAdd(&k->discard_const, v[2]);
+        if (v[3]) atomicAdd(&k->discard_quad, v[3]);
+        if (v[4]) atomicAdd(&k->discard_zoom, v[4]);
+        if (v[5]) atomicAdd(&k->entry_coeffs, v[5]);
+        if (mx) atomicMax(&k->max_level, mx);
+    }
+}
+
 template <int D>
 __global__ void bils_kernel(long long n, const double* lin, const double* c0, const double* sumabs, const double* errs,
                             const int* final_step, double* interval, int* flags) {
@@ -290,6 +372,67 @@ int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream) {
     level_kernel<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, l.ws_in_smem);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "level_kernel launch");
+}
+
+template <int D, class KC, class KW>
+int launch_box_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream, KC cta_kernel, KW warp_kernel, const char* what) {
+    if (pa.n_list == 0) return 0;
+    // never more workers than boxes of this step
+    cudaError_t e;
+    if (l.warp_per_box) {
+        if (!l.ws_in_smem) return yr_api::fail("warp-per-box mode needs the workspace in shared memory");
+        const int warps = l.threads / 32;
+        const size_t stride = align16(sizeof(yr::BoxShared<D>)) + 16 + align16((size_t)l.ws_doubles * 8);
+        const size_t smem = stride * (size_t)warps;
+        if (smem > 48 * 1024 && set_smem(warp_kernel, smem)) return -1;
+        unsigned long long want = (pa.n_list + warps - 1) / warps;
+        const unsigned ctas = (unsigned)(want < (unsigned long long)l.ctas ? want : (unsigned long long)l.ctas);
+        warp_kernel<<<ctas, l.threads, smem, (cudaStream_t)stream>>>(pa, (unsigned)stride);
+    } else {
+        const size_t smem = l.ws_in_smem ? (size_t)l.ws_doubles * 8 : 0;
+        if (!l.ws_in_smem && !l.gws) return yr_api::fail("global workspace missing");
+        if (smem > 48 * 1024 && set_smem(cta_kernel, smem)) return -1;
+        const unsigned ctas = (unsigned)(pa.n_list < (unsigned long long)l.ctas ? pa.n_list : (unsigned long long)l.ctas);
+        cta_kernel<<<ctas, l.threads, smem, (cudaStream_t)stream>>>(pa, l.ws_in_smem);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, what);
+}
+
+template <int D>
+int launch_tensor_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream) {
+    return launch_box_step<D>(pa, l, stream, tensor_step_kernel<D>, tensor_step_kernel_warp<D>, "tensor_step launch");
+}
+
+template <int D>
+int launch_subdivide_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream) {
+    return launch_box_step<D>(pa, l, stream, subdivide_step_kernel<D>, subdivide_step_kernel_warp<D>, "subdivide_step launch");
+}
+
+template <int D>
+int launch_scalar_step(const yr::PhaseArgs<D>& pa, void* stream) {
+    if (pa.n_list == 0) return 0;
+    scalar_step_kernel<D><<<(unsigned)((pa.n_list + 127) / 128), 128, 0, (cudaStream_t)stream>>>(pa);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "scalar_step launch");
+}
+
+int read_u64(const void* dev, unsigned long long* out, void* stream) {
+    static unsigned long long* pinned = nullptr;
+    if (!pinned) {
+        cudaError_t e0 = cudaHostAlloc(reinterpret_cast<void**>(&pinned), 64, cudaHostAllocDefault);
+        if (e0 != cudaSuccess) return cuda_fail(e0, "cudaHostAlloc");
+    }
+    cudaError_t e = cudaMemcpyAsync(pinned, dev, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "counter read-back");
+    *out = *pinned;
+    return 0;
+}
+
+int zero_bytes(void* dev, size_t bytes, void* stream) {
+    cudaError_t e = cudaMemsetAsync(dev, 0, bytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaMemsetAsync");
 }
 
 template <int D>

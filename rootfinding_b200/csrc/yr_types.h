@@ -105,6 +105,53 @@ struct LevelArgs {
     SolverParams prm;
 };
 
+// ---- phase-split pipeline (yr_phases.h) ------------------------------------------------------
+// Per-box working state of one level.  It lives in HBM only while the level is being processed:
+// the scalar kernel (thread per box) and the tensor kernels (warp / CTA per box) hand a box back
+// and forth through it.
+constexpr int low_count(int D) { return (D + 1) * (D + 2) / 2; }   // coefficients of total degree <= 2
+
+enum BoxPhase : int32_t {
+    kPhNew = 0,        // sums + low-order coefficients are ready: node entry checks come next
+    kPhTrimmed,        // trimMs done: initialise the zoom loop, first BILS
+    kPhZoomed,         // a restriction was applied: zoom-loop bookkeeping, next BILS or finish
+    kPhDone            // discarded, emitted, or queued for subdivision
+};
+enum TensorOp : int32_t { kOpNone = 0, kOpPrep, kOpTrim, kOpRestrict };
+
+template <int D>
+struct BoxWork {
+    double sumabs[D];                 // sum|M_p| of the current tensors
+    double low[D][low_count(D)];      // [c0 | linear[D] | pure T2[D] | cross pairs (a<b)] per polynomial
+    double entry_iv[D][2];            // originalInterval.getIntervalForCombining() of the current invocation
+    double cell_iv[D][2];             // tracked interval when the box entered the level
+    double last_size[D];
+    double alpha[D], beta[D];         // pending restriction (kOpRestrict)
+    int32_t phase, op;
+    int32_t zoom_count, changed, should_stop, final_split;
+    int32_t node_level, result_index;
+};
+
+// Cursors and list lengths of one level's round loop (device memory, 16 x uint64).
+struct RoundCtl {
+    unsigned long long cursor;        // work-distribution cursor of the running kernel
+    unsigned long long n_next;        // boxes queued for the next tensor step
+    unsigned long long n_sub;         // boxes queued for subdivision
+    unsigned long long reserved[13];
+};
+
+template <int D>
+struct PhaseArgs {
+    LevelArgs<D> lv;                  // NB this pipeline updates lv.recs_in in place while a level is processed
+    BoxWork<D>* work;                 // [lv.n_in]
+    const unsigned int* list_in;      // boxes of the current step (nullptr: 0 .. n_list-1)
+    unsigned long long n_list;
+    unsigned int* list_next;          // boxes that need another tensor step
+    unsigned int* list_sub;           // boxes to subdivide once the round loop is over
+    RoundCtl* ctl;
+    int first_round;                  // 1: every box of the level gets kOpPrep and a fresh BoxWork
+};
+
 // Workspace need (doubles) of a box whose largest tensor has `max_size` coefficients,
 // `total` coefficients overall and largest extent `nmax` -- the host sizes launches with it.
 YR_HD unsigned long long workspace_doubles(int D, unsigned long long total, unsigned long long max_size,

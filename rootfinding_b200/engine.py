@@ -138,6 +138,7 @@ class SubdivisionEngine:
         self.warp_min_items = int(os.environ.get("YR_WARP_MIN_ITEMS", "1024"))  # fewer boxes than this: CTA-per-box (latency)
         self.warp_teams = int(os.environ.get("YR_WARP_TEAMS", "16"))          # warp-teams per SM (register bound: 16 x 32 x 128)
         self.warp_mode = int(os.environ.get("YR_WARP_MODE", "1"))             # 1: independent warp-teams, 2: lock-step CTA
+        self.pipeline = int(os.environ.get("YR_PIPELINE", "1"))               # 0: fused kernel per level, 1: phase-split kernels
 
     def params(self, **kw):
         p = _lib.default_params(self.lib)
@@ -319,6 +320,11 @@ class SolveSession:
                 # the frontier's growth factor changes slowly from level to level: last factor + 30 %
                 cap_recs = min(worst_recs, max(4096, int(1.3 * growth[0] * n_in) + 1024))
                 cap_data = min(worst_data, max(1 << 16, int(1.3 * growth[1] * data_used) + (1 << 16)))
+            pipeline = eng.pipeline
+            if pipeline == 1 and warp == 2:
+                warp = 1                                                 # lock-step exists for the fused kernel only
+            work = m.empty(int(self.lib.yr_level_work_bytes(D, n_in))) if pipeline == 1 else None
+            first_c = None
             while True:
                 self._reserve("results", self.n_results + n_in)            # a box emits at most one record
                 self._reserve("nodes", self.n_nodes + n_in)
@@ -335,6 +341,10 @@ class SolveSession:
                 d.cap_nodes = self.cap_nodes - self.n_nodes
                 d.result_base, d.node_base = self.n_results, self.n_nodes
                 d.counters, d.prm, d.launch = self.d_counters.ptr, self.prm, L
+                d.pipeline = pipeline
+                if work is not None:
+                    d.work, d.work_bytes = work.ptr, work.nbytes
+                    d.resume_subdivide = int(first_c is not None)       # after an overflow only the subdivision is redone
                 m.zero_(self.d_counters)
                 ev = m.timer() if (self.time_kernels and hasattr(m, "timer")) else None
                 if ev:
@@ -344,15 +354,24 @@ class SolveSession:
                     ev[1].record()
                 c = self._read_counters()
                 if ev and not c["overflow"]:
-                    self.kernel_ms.append((ev[0].elapsed_time(ev[1]), 16 * c["entry_coeffs"], c["boxes"]))
+                    self.kernel_ms.append((ev[0].elapsed_time(ev[1]), 16 * (first_c or c)["entry_coeffs"], (first_c or c)["boxes"]))
                 elif ev:
                     self.retry_ms += ev[0].elapsed_time(ev[1])
                 self.stats.launches += 1
                 del gws
+                if pipeline == 1 and first_c is not None:
+                    # the retry only re-ran the subdivision: box statistics and results come from the first pass
+                    for k in ("boxes", "zooms", "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "max_level", "n_results"):
+                        c[k] = first_c[k]
+                    c["restrict_macs"] += first_c["restrict_macs"]
                 if not c["overflow"]:
                     break
                 self.stats.retries += 1                                      # optimistic buffers were too small
+                if pipeline == 1 and first_c is None:
+                    first_c = dict(c)
+                    first_c["restrict_macs"] = 0                             # (counted again by the re-run's subdivision only partly; keep it simple)
                 cap_recs, cap_data = worst_recs, worst_data
+            del work
             self.stats.add(c)
             self.stats.levels += 1
             self.stats.per_level.append((n_in, c["n_children"], c["n_results"], bool(in_smem), ctas, threads, ws, bool(warp)))

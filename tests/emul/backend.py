@@ -23,7 +23,7 @@ def build():
     srcs = [os.path.join(HERE, "emul.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
     srcs.append(os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "yroots_b200.h"))
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared", "-pthread",
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared", "-pthread", "-Wno-subobject-linkage",
                                "-o", SO, os.path.join(HERE, "emul.cpp")])
     return SO
 

@@ -159,6 +159,64 @@ int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void*) {
     return 0;
 }
 
+struct HostAtomics {
+    unsigned long long add(unsigned long long* p, unsigned long long v) const { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+};
+
+template <int D, class Body>
+void run_box_teams(const yr_launch& l, Body body) {
+    // tensor-type steps: CTA-per-box -> one team of YR_EMUL_THREADS; warp-per-box -> YR_EMUL_WARPS independent one-warp teams
+    const int lanes = env_int("YR_EMUL_LANES", 4);
+    const int W = l.warp_per_box ? env_int("YR_EMUL_WARPS", 2) : 1;
+    const int T = l.warp_per_box ? lanes : env_int("YR_EMUL_THREADS", 8);
+    std::vector<Team> teams(W);
+    std::vector<std::vector<double>> wss(W);
+    std::vector<yr::BoxShared<D>*> shs(W);
+    for (int w = 0; w < W; ++w) {
+        teams[w].T = T; teams[w].lanes = lanes; teams[w].bar.n = T; teams[w].scratch.assign(T, 0.0);
+        if (l.ws_in_smem || l.warp_per_box) wss[w].assign(l.ws_doubles + 8, 0.0);
+        shs[w] = new yr::BoxShared<D>();
+    }
+    std::vector<std::thread> th;
+    for (int w = 0; w < W; ++w)
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, w, t]() {
+                HostCtx cx; cx.tid = t; cx.nthreads = T; cx.lanes = lanes; cx.lane = t % lanes; cx.warp = t / lanes;
+                cx.nwarps = T / lanes; cx.team = &teams[w];
+                double* ws = wss[w].empty() ? l.gws + (size_t)w * l.gws_stride : wss[w].data();
+                body(cx, *shs[w], ws);
+            });
+    for (auto& x : th) x.join();
+    for (auto p : shs) delete p;
+}
+
+template <int D>
+int launch_tensor_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void*) {
+    run_box_teams<D>(l, [&](HostCtx& cx, yr::BoxShared<D>& sh, double* ws) { yr::tensor_step_worker<D>(cx, pa, sh, ws); });
+    return 0;
+}
+
+template <int D>
+int launch_subdivide_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void*) {
+    run_box_teams<D>(l, [&](HostCtx& cx, yr::BoxShared<D>& sh, double* ws) { yr::subdivide_step_worker<D>(cx, pa, sh, ws); });
+    return 0;
+}
+
+template <int D>
+int launch_scalar_step(const yr::PhaseArgs<D>& pa, void*) {
+    yr::ScalarCounts c{};
+    for (unsigned long long i = 0; i < pa.n_list; ++i)
+        yr::scalar_step<D>(pa, pa.list_in ? pa.list_in[i] : (unsigned int)i, c, HostAtomics());
+    yr::LevelCounters* k = pa.lv.ctr;
+    k->boxes += c.boxes; k->zooms += c.zooms; k->discard_const += c.dconst; k->discard_quad += c.dquad;
+    k->discard_zoom += c.dzoom; k->entry_coeffs += c.coeffs;
+    if (c.maxlevel > k->max_level) k->max_level = c.maxlevel;
+    return 0;
+}
+
+int read_u64(const void* dev, unsigned long long* out, void*) { *out = *static_cast<const unsigned long long*>(dev); return 0; }
+int zero_bytes(void* dev, size_t bytes, void*) { memset(dev, 0, bytes); return 0; }
+
 template <int D>
 int launch_init(const yr::InitArgs<D>& a, const yr_launch& l, void*) {
     const int T = env_int("YR_EMUL_THREADS", 8), lanes = env_int("YR_EMUL_LANES", 4);
