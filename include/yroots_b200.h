@@ -84,6 +84,8 @@ typedef struct yr_level_desc {
     void*         work;          uint64_t work_bytes;
     int32_t       pipeline;      /* 0: one fused kernel per level, 1: phase-split kernels */
     int32_t       resume_subdivide;
+    /* pipeline 1 plans its own launches from the size of the largest box of the level: */
+    uint64_t      max_box_doubles; uint64_t max_tensor_doubles; uint64_t max_extent;
 } yr_level_desc;
 
 /* Level-0 boxes: one per job = (system, optional restriction). */

@@ -35,7 +35,8 @@ class YrLevelDesc(C.Structure):
                 ("nodes", vp), ("cap_nodes", u64),
                 ("result_base", u64), ("node_base", u64),
                 ("counters", vp), ("prm", YrParams), ("launch", YrLaunch),
-                ("work", vp), ("work_bytes", u64), ("pipeline", i32), ("resume_subdivide", i32)]
+                ("work", vp), ("work_bytes", u64), ("pipeline", i32), ("resume_subdivide", i32),
+                ("max_box_doubles", u64), ("max_tensor_doubles", u64), ("max_extent", u64)]
 
 
 class YrInitDesc(C.Structure):

@@ -21,7 +21,10 @@ template <int D> int launch_init(const yr::InitArgs<D>& a, const yr_launch& l, v
 template <int D> int launch_tensor_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream);
 template <int D> int launch_scalar_step(const yr::PhaseArgs<D>& pa, void* stream);
 template <int D> int launch_subdivide_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream);
-int read_u64(const void* dev, unsigned long long* out, void* stream);        // device -> host, synchronises the stream
+int read_words(const void* dev, unsigned long long* out, int count, void* stream);   // device -> host, synchronises the stream
+// launch shape of one step of the phase-split pipeline for boxes of at most the given size
+template <int D> int plan_step(int subdivide, unsigned long long n_items, unsigned long long total, unsigned long long tensor,
+                               unsigned long long extent, int exact, const yr_launch& base, yr_launch* out);
 int zero_bytes(void* dev, size_t bytes, void* stream);
 template <int D> int launch_bils(int64_t n, const double* lin, const double* c0, const double* sumabs, const double* errs,
                                  const int32_t* final_step, double* interval, int32_t* flags, void* stream);
@@ -76,7 +79,8 @@ int run_level_phased(const yr::LevelArgs<D>& a, const yr_level_desc* d, void* st
     unsigned int* lists[2] = {reinterpret_cast<unsigned int*>(base + wl.list_a), reinterpret_cast<unsigned int*>(base + wl.list_b)};
     pa.list_sub = reinterpret_cast<unsigned int*>(base + wl.list_sub);
     pa.ctl = reinterpret_cast<yr::RoundCtl*>(base + wl.ctl);
-    unsigned long long n_sub = 0;
+    unsigned long long sizes[3] = {d->max_box_doubles, d->max_tensor_doubles, d->max_extent};
+    yr_launch L;
     if (!d->resume_subdivide) {
         if (yr_backend::zero_bytes(pa.ctl, sizeof(yr::RoundCtl), stream)) return -1;
         pa.list_in = nullptr; pa.n_list = a.n_in; pa.first_round = 1;
@@ -84,21 +88,28 @@ int run_level_phased(const yr::LevelArgs<D>& a, const yr_level_desc* d, void* st
         for (int round = 0; pa.n_list > 0; ++round) {
             if (round > 100000) return fail("round loop did not terminate");
             pa.list_next = lists[cur];
-            if (yr_backend::launch_tensor_step<D>(pa, d->launch, stream)) return -1;
-            if (yr_backend::zero_bytes(&pa.ctl->cursor, sizeof(unsigned long long), stream)) return -1;
+            if (yr_backend::plan_step<D>(0, pa.n_list, sizes[0], sizes[1], sizes[2], a.prm.exact, d->launch, &L)) return -1;
+            pa.lv.gws = L.gws; pa.lv.gws_stride = L.gws_stride; pa.lv.ws_doubles = L.ws_doubles;
+            if (yr_backend::launch_tensor_step<D>(pa, L, stream)) return -1;
             if (yr_backend::launch_scalar_step<D>(pa, stream)) return -1;
-            unsigned long long n_next = 0;
-            if (yr_backend::read_u64(&pa.ctl->n_next, &n_next, stream)) return -1;
-            if (yr_backend::zero_bytes(pa.ctl, 2 * sizeof(unsigned long long), stream)) return -1;   // cursor, n_next
-            pa.list_in = lists[cur]; pa.n_list = n_next; pa.first_round = 0;
+            unsigned long long w[6];                        // cursor, n_next, n_sub, max_total, max_tensor, max_extent
+            if (yr_backend::read_words(pa.ctl, w, 6, stream)) return -1;
+            if (yr_backend::zero_bytes(pa.ctl, 2 * sizeof(unsigned long long), stream)) return -1;            // cursor, n_next
+            if (yr_backend::zero_bytes(&pa.ctl->max_total, 3 * sizeof(unsigned long long), stream)) return -1;
+            pa.list_in = lists[cur]; pa.n_list = w[1]; pa.first_round = 0;
+            sizes[0] = w[3]; sizes[1] = w[4]; sizes[2] = w[5];
             cur ^= 1;
         }
     }
-    if (yr_backend::read_u64(&pa.ctl->n_sub, &n_sub, stream)) return -1;
+    unsigned long long w[9];
+    if (yr_backend::read_words(pa.ctl, w, 9, stream)) return -1;
     if (yr_backend::zero_bytes(&pa.ctl->cursor, sizeof(unsigned long long), stream)) return -1;
+    const unsigned long long n_sub = w[2];
     pa.list_in = pa.list_sub; pa.n_list = n_sub; pa.first_round = 0; pa.list_next = nullptr;
     if (n_sub == 0) return 0;
-    return yr_backend::launch_subdivide_step<D>(pa, d->launch, stream);
+    if (yr_backend::plan_step<D>(1, n_sub, w[6], w[7], w[8], a.prm.exact, d->launch, &L)) return -1;
+    pa.lv.gws = L.gws; pa.lv.gws_stride = L.gws_stride; pa.lv.ws_doubles = L.ws_doubles;
+    return yr_backend::launch_subdivide_step<D>(pa, L, stream);
 }
 
 template <int D>

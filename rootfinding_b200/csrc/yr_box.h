@@ -432,7 +432,7 @@ YR_HD int rows_for(const BoxShared<D>& sh, const double* ws, int m, int n) {
 }
 
 template <int D>
-YR_HD void compute_layout(BoxShared<D>& sh, bool exact) {
+YR_HD void compute_layout(BoxShared<D>& sh, bool exact, bool subdivide = true) {
     Layout<D>& L = sh.lay;
     int off = 0, mx = 0, nmax = 1;
     for (int p = 0; p < D; ++p) {
@@ -441,11 +441,12 @@ YR_HD void compute_layout(BoxShared<D>& sh, bool exact) {
         for (int a = 0; a < D; ++a) nmax = sh.shape[p][a] > nmax ? sh.shape[p][a] : nmax;
     }
     L.total = off; L.max_size = mx; L.nmax = nmax; L.tri = nmax * (nmax + 1) / 2;
-    for (int j = 0; j < D; ++j) { L.tmp[j] = off; if (j < D - 1) off += mx; }
-    for (int m = 0; m < 2 * D; ++m) { L.cmat[m] = off; off += L.tri; }
+    const int nmat = subdivide ? 2 * D : D;
+    for (int j = 0; j < D; ++j) { L.tmp[j] = off; if (subdivide && j < D - 1) off += mx; }
+    for (int m = 0; m < 2 * D; ++m) { L.cmat[m] = off; if (m < nmat) off += L.tri; }
     L.rows_after = off; off += (2 * D * nmax + 1) / 2 + 1;
     L.xscratch = off;
-    if (exact) off += 2 * D * 6 * (nmax + 2);
+    if (exact) off += nmat * 6 * (nmax + 2);
 }
 
 // ---------------------------------------------------------------------------------------------

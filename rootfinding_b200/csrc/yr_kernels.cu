@@ -10,6 +10,7 @@
 // fma() is written explicitly.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "yr_api_impl.h"
 #include "yr_approx.h"
@@ -288,6 +289,15 @@ __global__ void __launch_bounds__(128) scalar_step_kernel(const yr::PhaseArgs<D>
         if (v[5]) atomicAdd(&k->entry_coeffs, v[5]);
         if (mx) atomicMax(&k->max_level, mx);
     }
+    unsigned long long m6[6] = {c.t_total, c.t_tensor, c.t_extent, c.s_total, c.s_tensor, c.s_extent};
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        for (int off = 16; off > 0; off >>= 1) { const unsigned long long o = __shfl_down_sync(0xffffffffu, m6[k], off); m6[k] = o > m6[k] ? o : m6[k]; }
+    if ((threadIdx.x & 31) == 0) {
+        yr::RoundCtl* r = pa.ctl;
+        if (m6[0]) { atomicMax(&r->max_total, m6[0]); atomicMax(&r->max_tensor, m6[1]); atomicMax(&r->max_extent, m6[2]); }
+        if (m6[3]) { atomicMax(&r->sub_max_total, m6[3]); atomicMax(&r->sub_max_tensor, m6[4]); atomicMax(&r->sub_max_extent, m6[5]); }
+    }
 }
 
 template <int D>
@@ -417,16 +427,63 @@ int launch_scalar_step(const yr::PhaseArgs<D>& pa, void* stream) {
     return e == cudaSuccess ? 0 : cuda_fail(e, "scalar_step launch");
 }
 
-int read_u64(const void* dev, unsigned long long* out, void* stream) {
+int read_words(const void* dev, unsigned long long* out, int count, void* stream) {
     static unsigned long long* pinned = nullptr;
     if (!pinned) {
-        cudaError_t e0 = cudaHostAlloc(reinterpret_cast<void**>(&pinned), 64, cudaHostAllocDefault);
+        cudaError_t e0 = cudaHostAlloc(reinterpret_cast<void**>(&pinned), 256, cudaHostAllocDefault);
         if (e0 != cudaSuccess) return cuda_fail(e0, "cudaHostAlloc");
     }
-    cudaError_t e = cudaMemcpyAsync(pinned, dev, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (count > 32) return yr_api::fail("read_words: too many words");
+    cudaError_t e = cudaMemcpyAsync(pinned, dev, 8 * (size_t)count, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "counter read-back");
-    *out = *pinned;
+    for (int i = 0; i < count; ++i) out[i] = pinned[i];
+    return 0;
+}
+
+static long env_long(const char* name, long dflt) { const char* v = getenv(name); return v ? atol(v) : dflt; }
+
+// Launch shape of one step: warp-per-box (4 independent warp-teams per CTA, up to 16 per SM) while a
+// box fits a warp's slice of shared memory and there are enough boxes to fill the machine; CTA-per-box
+// otherwise; the caller's global workspace when a box does not fit shared memory at all.
+template <int D>
+int plan_step(int subdivide, unsigned long long n_items, unsigned long long total, unsigned long long tensor,
+              unsigned long long extent, int exact, const yr_launch& base, yr_launch* out) {
+    static int sm = 0, smem_cta = 0, smem_sm = 0;
+    if (!sm) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_cta, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    }
+    static const long warp_min_items = env_long("YR_WARP_MIN_ITEMS", 1024), warps_per_sm = env_long("YR_WARP_TEAMS", 16);
+    if (total < 1) total = 1;
+    if (tensor < 1) tensor = 1;
+    if (extent < 1) extent = 1;
+    const unsigned long long ws = yr::workspace_doubles(D, total, tensor, extent, exact, subdivide);
+    *out = base;
+    out->ws_doubles = ws; out->gws = nullptr; out->gws_stride = 0;
+    const size_t per_warp = align16(sizeof(yr::BoxShared<D>)) + 16 + align16((size_t)ws * 8);
+    if ((long)n_items >= warp_min_items && per_warp + 1024 <= (size_t)smem_cta) {
+        int warps = (int)(((size_t)smem_cta - 1024) / per_warp); if (warps > 4) warps = 4;
+        const size_t per_cta = (size_t)warps * per_warp + 1024;
+        long per_sm = (long)((size_t)smem_sm / per_cta); if (per_sm > warps_per_sm / warps) per_sm = warps_per_sm / warps; if (per_sm < 1) per_sm = 1;
+        unsigned long long want = (n_items + warps - 1) / warps, cap = (unsigned long long)sm * per_sm;
+        out->threads = 32 * warps; out->ctas = (int)(want < cap ? want : cap); out->ws_in_smem = 1; out->warp_per_box = 1;
+        return 0;
+    }
+    out->warp_per_box = 0;
+    out->threads = total >= 768 ? 128 : 64;
+    const size_t need = (size_t)ws * 8 + sizeof(yr::BoxShared<D>) + 512;
+    if (need <= (size_t)smem_cta) {
+        long per_sm = (long)((size_t)smem_sm / (need + 1024)); if (per_sm > 2048 / out->threads) per_sm = 2048 / out->threads; if (per_sm > 32) per_sm = 32; if (per_sm < 1) per_sm = 1;
+        unsigned long long cap = (unsigned long long)sm * per_sm;
+        out->ctas = (int)(n_items < cap ? n_items : cap); out->ws_in_smem = 1;
+        return 0;
+    }
+    if (!base.gws || base.gws_stride < ws) return yr_api::fail("box does not fit shared memory and no global workspace was provided");
+    out->ws_in_smem = 0; out->gws = base.gws; out->gws_stride = base.gws_stride;
+    out->ctas = (int)(n_items < (unsigned long long)base.ctas ? n_items : (unsigned long long)base.ctas);
     return 0;
 }
 

@@ -70,7 +70,7 @@ YR_HD bool quadratic_check_low(const double* l, double sumabs, double tol) {
 // ---- tensor step ------------------------------------------------------------------------------
 // stage a box of the level into the team's shared memory (record, layout, tensors)
 template <int D, class Ctx>
-YR_DEVN void stage_for_step(Ctx& cx, const PhaseArgs<D>& pa, BoxShared<D>& sh, double* ws, unsigned int b) {
+YR_DEVN void stage_for_step(Ctx& cx, const PhaseArgs<D>& pa, BoxShared<D>& sh, double* ws, unsigned int b, bool subdivide) {
     const SolverParams& prm = pa.lv.prm;
     {
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&pa.lv.recs_in[b]);
@@ -84,7 +84,7 @@ YR_DEVN void stage_for_step(Ctx& cx, const PhaseArgs<D>& pa, BoxShared<D>& sh, d
             for (int a = D - 1; a >= 0; --a) { sh.shape[p][a] = sh.rec.shape[p][a]; sh.stride[p][a] = st; st *= sh.rec.shape[p][a]; }
             sh.err[p] = sh.rec.err[p];
         }
-        compute_layout<D>(sh, prm.exact != 0);
+        compute_layout<D>(sh, prm.exact != 0, subdivide);
         sh.action = kActNone;
         sh.trimmed_any = 0;
     }
@@ -131,7 +131,7 @@ YR_DEV void tensor_step_worker(Ctx& cx, const PhaseArgs<D>& pa, BoxShared<D>& sh
         const unsigned int b = pa.list_in ? pa.list_in[i] : (unsigned int)i;
         BoxWork<D>& wk = pa.work[b];
         const int op = pa.first_round ? (int)kOpPrep : wk.op;
-        stage_for_step<D>(cx, pa, sh, ws, b);
+        stage_for_step<D>(cx, pa, sh, ws, b, false);
         if (op == kOpPrep) {
             for (int p = 0; p < D; ++p) {
                 const double s = tensor_abs_sum<D>(cx, ws + sh.lay.base[p], sh.shape[p], sh.stride[p]);
@@ -187,6 +187,8 @@ YR_DEV void tensor_step_worker(Ctx& cx, const PhaseArgs<D>& pa, BoxShared<D>& sh
 // ---- scalar step (thread per box) -----------------------------------------------------------------
 struct ScalarCounts {
     unsigned long long boxes, zooms, dconst, dquad, dzoom, coeffs, maxlevel;
+    unsigned long long t_total, t_tensor, t_extent;      // largest box queued for a tensor step by this thread
+    unsigned long long s_total, s_tensor, s_extent;      // ... for subdivision
 };
 
 // The atomics differ between backends; they are passed in as a tiny policy object `At` with
@@ -230,8 +232,18 @@ YR_HDN void scalar_step(const PhaseArgs<D>& pa, unsigned int b, ScalarCounts& cn
             r.path_hi = rec.path_hi; r.path_lo = rec.path_lo;
         } else at.add(&pa.lv.ctr->overflow, 1ull);
     };
+    auto box_size = [&](unsigned long long& total, unsigned long long& tensor, unsigned long long& extent) {
+        unsigned long long t = 0;
+        for (int p = 0; p < D; ++p) {
+            unsigned long long sz = 1;
+            for (int a = 0; a < D; ++a) { sz *= (unsigned long long)rec.shape[p][a]; if ((unsigned long long)rec.shape[p][a] > extent) extent = rec.shape[p][a]; }
+            t += sz; if (sz > tensor) tensor = sz;
+        }
+        if (t > total) total = t;
+    };
     auto queue_tensor = [&](int op, int next_phase) {
         wk.op = op; wk.phase = next_phase;
+        box_size(cnt.t_total, cnt.t_tensor, cnt.t_extent);
         const unsigned long long pos = at.add(&pa.ctl->n_next, 1ull);
         pa.list_next[pos] = b;
     };
@@ -322,6 +334,7 @@ YR_HDN void scalar_step(const PhaseArgs<D>& pa, unsigned int b, ScalarCounts& cn
         {
             const unsigned long long pos = at.add(&pa.ctl->n_sub, 1ull);
             pa.list_sub[pos] = b;
+            box_size(cnt.s_total, cnt.s_tensor, cnt.s_extent);
         }
         finish_box();
         break;
@@ -341,7 +354,7 @@ YR_DEV void subdivide_step_worker(Ctx& cx, const PhaseArgs<D>& pa, BoxShared<D>&
         if (i >= pa.n_list) break;
         const unsigned int b = pa.list_in[i];
         const BoxWork<D>& wk = pa.work[b];
-        stage_for_step<D>(cx, pa, sh, ws, b);
+        stage_for_step<D>(cx, pa, sh, ws, b, true);
         if (cx.tid == 0) {
             for (int d = 0; d < D; ++d) {
                 sh.sumabs[d] = wk.sumabs[d];

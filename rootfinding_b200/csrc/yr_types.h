@@ -137,7 +137,9 @@ struct RoundCtl {
     unsigned long long cursor;        // work-distribution cursor of the running kernel
     unsigned long long n_next;        // boxes queued for the next tensor step
     unsigned long long n_sub;         // boxes queued for subdivision
-    unsigned long long reserved[13];
+    unsigned long long max_total, max_tensor, max_extent;          // largest box queued for the next tensor step
+    unsigned long long sub_max_total, sub_max_tensor, sub_max_extent;   // largest box queued for subdivision
+    unsigned long long reserved[7];
 };
 
 template <int D>
@@ -155,11 +157,14 @@ struct PhaseArgs {
 // Workspace need (doubles) of a box whose largest tensor has `max_size` coefficients,
 // `total` coefficients overall and largest extent `nmax` -- the host sizes launches with it.
 YR_HD unsigned long long workspace_doubles(int D, unsigned long long total, unsigned long long max_size,
-                                           unsigned long long nmax, int exact) {
+                                           unsigned long long nmax, int exact, int subdivide = 1) {
+    // subdivide = 0: a tensor step (prep / trim / restrict) needs neither the subdivision temporaries nor
+    // the upper-half matrices
     unsigned long long tri = nmax * (nmax + 1) / 2;
-    unsigned long long w = total + (unsigned long long)(D > 1 ? D - 1 : 0) * max_size + 2ull * D * tri;
+    const unsigned long long nmat = subdivide ? 2ull * D : (unsigned long long)D;
+    unsigned long long w = total + (subdivide ? (unsigned long long)(D > 1 ? D - 1 : 0) * max_size : 0ull) + nmat * tri;
     w += (2ull * D * nmax + 1) / 2 + 1;                       // rowsAfter (ints)
-    if (exact) w += 2ull * D * 6 * (nmax + 2);
+    if (exact) w += nmat * 6 * (nmax + 2);
     return w + 8;
 }
 

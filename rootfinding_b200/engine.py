@@ -342,6 +342,7 @@ class SolveSession:
                 d.result_base, d.node_base = self.n_results, self.n_nodes
                 d.counters, d.prm, d.launch = self.d_counters.ptr, self.prm, L
                 d.pipeline = pipeline
+                d.max_box_doubles, d.max_tensor_doubles, d.max_extent = int(big_box), int(big_tensor), int(big_extent)
                 if work is not None:
                     d.work, d.work_bytes = work.ptr, work.nbytes
                     d.resume_subdivide = int(first_c is not None)       # after an overflow only the subdivision is redone

@@ -211,10 +211,27 @@ int launch_scalar_step(const yr::PhaseArgs<D>& pa, void*) {
     k->boxes += c.boxes; k->zooms += c.zooms; k->discard_const += c.dconst; k->discard_quad += c.dquad;
     k->discard_zoom += c.dzoom; k->entry_coeffs += c.coeffs;
     if (c.maxlevel > k->max_level) k->max_level = c.maxlevel;
+    yr::RoundCtl* r = pa.ctl;
+    if (c.t_total > r->max_total) r->max_total = c.t_total;
+    if (c.t_tensor > r->max_tensor) r->max_tensor = c.t_tensor;
+    if (c.t_extent > r->max_extent) r->max_extent = c.t_extent;
+    if (c.s_total > r->sub_max_total) r->sub_max_total = c.s_total;
+    if (c.s_tensor > r->sub_max_tensor) r->sub_max_tensor = c.s_tensor;
+    if (c.s_extent > r->sub_max_extent) r->sub_max_extent = c.s_extent;
     return 0;
 }
 
-int read_u64(const void* dev, unsigned long long* out, void*) { *out = *static_cast<const unsigned long long*>(dev); return 0; }
+int read_words(const void* dev, unsigned long long* out, int count, void*) { memcpy(out, dev, 8 * (size_t)count); return 0; }
+
+template <int D>
+int plan_step(int subdivide, unsigned long long n_items, unsigned long long total, unsigned long long tensor,
+              unsigned long long extent, int exact, const yr_launch& base, yr_launch* out) {
+    *out = base;                                         // box granularity / placement as the test asked for
+    out->ws_doubles = yr::workspace_doubles(D, total, tensor, extent, exact, subdivide);
+    if (!base.ws_in_smem && !base.warp_per_box && out->ws_doubles > base.gws_stride) return yr_api::fail("global workspace too small");
+    (void)n_items;
+    return 0;
+}
 int zero_bytes(void* dev, size_t bytes, void*) { memset(dev, 0, bytes); return 0; }
 
 template <int D>
