@@ -159,32 +159,47 @@ YR_HD double tri_dot(const double* crow, int len, const double* s, int stride) {
     return acc;
 }
 
-// One fiber, all output rows, two rows per pass (they share the source loads).  Safe in place:
-// rows i, i+1 are stored after everything they read (source rows >= i) has been read, and later
-// rows never read them.
+// One fiber, all output rows, four rows per pass (they share the source loads; the matrix entries are
+// the same for every lane of a warp, i.e. broadcast loads).  Safe in place: rows i..i+3 are stored after
+// everything they read (source rows >= i) has been read, and later rows never read them.  Every row is
+// accumulated in ascending source order starting from 0, exactly like tri_dot.
 template <bool FMA>
 YR_HDN double fiber_restrict(const double* C, int ncol, int n, int rows_out, const double* src, int sa, double* dst, int da) {
     double asum = 0.0;
     int i = 0;
-    for (; i + 1 < rows_out; i += 2) {
-        const double* c0 = C + crow_start(i, ncol);
-        const double* c1 = C + crow_start(i + 1, ncol);
+    for (; i + 3 < rows_out; i += 4) {
+        const double* c0 = C + crow_start(i, ncol);          // c0[j] = C[i][i+j]
+        const double* c1 = C + crow_start(i + 1, ncol);      // c1[j] = C[i+1][i+1+j]
+        const double* c2 = C + crow_start(i + 2, ncol);
+        const double* c3 = C + crow_start(i + 3, ncol);
         const double* s = src + (long long)i * sa;
-        double a0 = 0.0, a1 = 0.0;
-        if (FMA) a0 = fma(c0[0], *s, a0); else a0 = a0 + c0[0] * *s;
-        s += sa;
-        const int len = n - i - 1;
-#pragma unroll 4
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        {   // the triangular head: source rows i, i+1, i+2
+            const double x0 = s[0], x1 = s[sa], x2 = s[2 * sa];
+            if (FMA) {
+                a0 = fma(c0[0], x0, a0); a0 = fma(c0[1], x1, a0); a0 = fma(c0[2], x2, a0);
+                a1 = fma(c1[0], x1, a1); a1 = fma(c1[1], x2, a1);
+                a2 = fma(c2[0], x2, a2);
+            } else {
+                a0 = a0 + c0[0] * x0; a0 = a0 + c0[1] * x1; a0 = a0 + c0[2] * x2;
+                a1 = a1 + c1[0] * x1; a1 = a1 + c1[1] * x2;
+                a2 = a2 + c2[0] * x2;
+            }
+        }
+        s += 3 * sa;
+        const int len = n - i - 3;                            // source rows i+3 .. n-1 feed all four
+#pragma unroll 2
         for (int j = 0; j < len; ++j) {
             const double x = *s;
-            if (FMA) { a0 = fma(c0[j + 1], x, a0); a1 = fma(c1[j], x, a1); }
-            else { a0 = a0 + c0[j + 1] * x; a1 = a1 + c1[j] * x; }
+            if (FMA) { a0 = fma(c0[j + 3], x, a0); a1 = fma(c1[j + 2], x, a1); a2 = fma(c2[j + 1], x, a2); a3 = fma(c3[j], x, a3); }
+            else { a0 = a0 + c0[j + 3] * x; a1 = a1 + c1[j + 2] * x; a2 = a2 + c2[j + 1] * x; a3 = a3 + c3[j] * x; }
             s += sa;
         }
         dst[(long long)i * da] = a0; dst[(long long)(i + 1) * da] = a1;
-        asum += fabs(a0) + fabs(a1);
+        dst[(long long)(i + 2) * da] = a2; dst[(long long)(i + 3) * da] = a3;
+        asum += fabs(a0) + fabs(a1) + fabs(a2) + fabs(a3);
     }
-    if (i < rows_out) {
+    for (; i < rows_out; ++i) {
         const double v = tri_dot<FMA>(C + crow_start(i, ncol), n - i, src + (long long)i * sa, sa);
         dst[(long long)i * da] = v;
         asum += fabs(v);
@@ -335,6 +350,9 @@ YR_HD void exact_entry_split(const ExactCols& b, int i, int rows, double sgn, do
     }
 }
 
+template <int D, class Ctx>
+YR_DEVN void build_matrices_warp(Ctx& cx, BoxShared<D>& sh, double* ws);
+
 // Builds sh.nmat restriction matrices C(alpha_m, beta_m) with mat_n[m] columns each, column by
 // column (the three-term recurrence couples neighbouring rows, so columns are sequential and rows
 // parallel), together with rows_after[m][k] = the reference's `maxRow` after column k.
@@ -345,6 +363,9 @@ YR_DEVN void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
     const int nmat = sh.nmat;
     int kmax = 0;
     for (int m = 0; m < nmat; ++m) kmax = sh.mat_n[m] > kmax ? sh.mat_n[m] : kmax;
+    if constexpr (Ctx::kWarpPerBox) {
+        if (!exact && kmax <= cx.lanes) { build_matrices_warp<D>(cx, sh, ws); return; }
+    }
     const int xs = L.nmax + 2;
     for (int m = cx.tid; m < nmat; m += cx.nthreads) {
         double* C = ws + L.cmat[m];
@@ -422,6 +443,51 @@ YR_DEVN void build_matrices(Ctx& cx, BoxShared<D>& sh, double* ws, bool exact) {
         }
         cx.sync();
     }
+}
+
+// Warp-per-box variant of build_matrices (plain arithmetic, extents <= warp width): lane i keeps row i of
+// the two live columns in registers, neighbours come from shuffles, no shared-memory reads and no barriers.
+// Same expressions, same order, same truncation rule -> bit-identical matrices.
+template <int D, class Ctx>
+YR_DEVN void build_matrices_warp(Ctx& cx, BoxShared<D>& sh, double* ws) {
+    const Layout<D>& L = sh.lay;
+    int* rows_after = reinterpret_cast<int*>(ws + L.rows_after);
+    const int i = cx.lane;
+    for (int m = 0; m < sh.nmat; ++m) {
+        const int nc = sh.mat_n[m];
+        double* C = ws + L.cmat[m];
+        const double alpha = sh.alpha[m], beta = sh.beta[m];
+        double* row = C + crow_start(i, nc) - i;                 // row[k] == C[i][k] for k >= i
+        double prev2 = (i == 0) ? 1.0 : 0.0;                      // column 0
+        double prev = (i == 0) ? beta : (i == 1 ? alpha : 0.0);   // column 1
+        if (i == 0) { row[0] = 1.0; rows_after[m * L.nmax] = 1; if (nc >= 2) { row[1] = beta; rows_after[m * L.nmax + 1] = 2; } }
+        if (i == 1 && nc >= 2) row[1] = alpha;
+        int rows = 2;
+        for (int k = 2; k < nc; ++k) {
+            double cm1 = cx.shfl_up(prev, 1), cp1 = cx.shfl_down(prev, 1);
+            if (i == 0) cm1 = 0.0;
+            if (i + 1 > k - 1) cp1 = 0.0;
+            double val = 0.0;
+            int grow = 0;
+            if (i <= rows) {
+                double t;
+                if (i == 0) t = alpha * cp1;
+                else if (i == 1) t = alpha * (2 * cm1 + cp1);
+                else t = alpha * (cm1 + cp1);
+                val = (-prev2 + t) + (2 * beta) * prev;
+                if (i == rows) {                                  // the reference's finalVal, :106-112
+                    val = alpha * cm1;
+                    if (fabs(val) > 1e-16) grow = 1; else val = 0.0;
+                }
+            }
+            grow = cx.shfl_idx_int(grow, rows);
+            if (i <= k) row[k] = val;
+            prev2 = prev; prev = val;
+            rows += grow;
+            if (i == 0) rows_after[m * L.nmax + k] = rows;
+        }
+    }
+    cx.sync();
 }
 
 // rows the reference returns for a tensor of extent n along the axis of matrix m

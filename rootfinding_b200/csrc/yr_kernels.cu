@@ -151,6 +151,9 @@ struct WarpCtx {
         return __shfl_sync(0xffffffffu, v, 0);
     }
     __device__ __forceinline__ double warp_sum(double v) { return block_sum(v); }
+    __device__ __forceinline__ double shfl_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+    __device__ __forceinline__ double shfl_down(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+    __device__ __forceinline__ int shfl_idx_int(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
     __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
     __device__ __forceinline__ void atomic_max(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
     __device__ __forceinline__ void copy_in(double* dst, const double* src, long long n) {

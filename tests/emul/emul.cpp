@@ -44,8 +44,9 @@ struct CtaShared {          // what the warp-teams of one emulated CTA share
     std::atomic<int> vote{1};
 };
 
-struct HostCtx {
-    static constexpr bool kWarpPerBox = false;
+template <bool WARP>
+struct HostCtxT {
+    static constexpr bool kWarpPerBox = WARP;
     int tid, nthreads, lane, lanes, warp, nwarps;
     Team* team;
     CtaShared* cta = nullptr;
@@ -84,6 +85,22 @@ struct HostCtx {
         const double r = tree(warp);
         sync(); return r;
     }
+    // warp shuffles (collective over the team, which is one warp when WARP)
+    double shfl_up(double v, int d) {
+        team->scratch[tid] = v; sync();
+        const double r = (lane >= d) ? team->scratch[tid - d] : v;
+        sync(); return r;
+    }
+    double shfl_down(double v, int d) {
+        team->scratch[tid] = v; sync();
+        const double r = (lane + d < lanes) ? team->scratch[tid + d] : v;
+        sync(); return r;
+    }
+    int shfl_idx_int(int v, int src) {
+        team->scratch[tid] = (double)v; sync();
+        const int r = (int)team->scratch[warp * lanes + src];
+        sync(); return r;
+    }
     unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
     void atomic_max(unsigned long long* p, unsigned long long v) {
         unsigned long long cur = __atomic_load_n(p, __ATOMIC_RELAXED);
@@ -92,6 +109,8 @@ struct HostCtx {
     void copy_in(double* dst, const double* src, long long n) { for (long long i = tid; i < n; i += nthreads) dst[i] = src[i]; }
     double cospi_ratio(long long m, long long N) const { return cos(M_PI * (double)m / (double)N); }
 };
+typedef HostCtxT<false> HostCtx;
+typedef HostCtxT<true> HostWarpCtx;
 
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 
@@ -181,10 +200,15 @@ void run_box_teams(const yr_launch& l, Body body) {
     for (int w = 0; w < W; ++w)
         for (int t = 0; t < T; ++t)
             th.emplace_back([&, w, t]() {
-                HostCtx cx; cx.tid = t; cx.nthreads = T; cx.lanes = lanes; cx.lane = t % lanes; cx.warp = t / lanes;
-                cx.nwarps = T / lanes; cx.team = &teams[w];
                 double* ws = wss[w].empty() ? l.gws + (size_t)w * l.gws_stride : wss[w].data();
-                body(cx, *shs[w], ws);
+                if (l.warp_per_box) {
+                    HostWarpCtx cx; cx.tid = t; cx.nthreads = T; cx.lanes = lanes; cx.lane = t; cx.warp = 0; cx.nwarps = 1; cx.team = &teams[w];
+                    body(cx, *shs[w], ws);
+                } else {
+                    HostCtx cx; cx.tid = t; cx.nthreads = T; cx.lanes = lanes; cx.lane = t % lanes; cx.warp = t / lanes;
+                    cx.nwarps = T / lanes; cx.team = &teams[w];
+                    body(cx, *shs[w], ws);
+                }
             });
     for (auto& x : th) x.join();
     for (auto p : shs) delete p;
@@ -192,13 +216,13 @@ void run_box_teams(const yr_launch& l, Body body) {
 
 template <int D>
 int launch_tensor_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void*) {
-    run_box_teams<D>(l, [&](HostCtx& cx, yr::BoxShared<D>& sh, double* ws) { yr::tensor_step_worker<D>(cx, pa, sh, ws); });
+    run_box_teams<D>(l, [&](auto& cx, yr::BoxShared<D>& sh, double* ws) { yr::tensor_step_worker<D>(cx, pa, sh, ws); });
     return 0;
 }
 
 template <int D>
 int launch_subdivide_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void*) {
-    run_box_teams<D>(l, [&](HostCtx& cx, yr::BoxShared<D>& sh, double* ws) { yr::subdivide_step_worker<D>(cx, pa, sh, ws); });
+    run_box_teams<D>(l, [&](auto& cx, yr::BoxShared<D>& sh, double* ws) { yr::subdivide_step_worker<D>(cx, pa, sh, ws); });
     return 0;
 }
 

@@ -216,3 +216,22 @@ def test_emulated_warp_per_box(emu, dim, deg, N, mode):
     finally:
         emu.warp_min_items = old
         emu.warp_mode = 1
+
+
+def test_emulated_warp_shuffle_matrix_build(emu):
+    """32-lane warp-teams exercise the shuffle-based restriction-matrix build (extents <= warp width);
+    the search tree and roots must not change, and restrictions stay bit-exact."""
+    old = (emu.warp_min_items, os.environ.get("YR_EMUL_LANES"), os.environ.get("YR_EMUL_THREADS"))
+    try:
+        emu.warp_min_items = 1
+        os.environ["YR_EMUL_LANES"] = "32"
+        os.environ["YR_EMUL_THREADS"] = "32"
+        systems = H.seeded_systems(2, 7, 2)
+        errs = [np.full(2, 2. ** -52)] * 2
+        sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
+        assert sess.stats.boxes == boxes and worst < 1e-14
+        assert all(lvl[7] for lvl in sess.stats.per_level)
+    finally:
+        emu.warp_min_items = old[0]
+        os.environ["YR_EMUL_LANES"] = old[1] or "4"
+        os.environ["YR_EMUL_THREADS"] = old[2] or "8"
