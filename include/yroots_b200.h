@@ -140,6 +140,39 @@ int         yr_device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64
 int yr_init_boxes(const yr_init_desc* d, void* stream);
 int yr_process_level(const yr_level_desc* d, void* stream);
 
+/* --- 2-D frontier pipeline ------------------------------------------------------------------
+ * yr_frontier_solve runs the whole of solveChebyshevSubdivision's search
+ * (ChebyshevSubdivisionSolver.py:1177-1317 for every box of every system) for systems of two
+ * polynomials in two variables, starting from the level-0 boxes yr_init_boxes wrote: rounds of
+ * (tensor ops: restriction :864-894 / subdivision :1051-1129, a team per box) and (scalar step:
+ * checks :1213-1224, trimMs :1131 adoption, BoundingIntervalLinearSystem :628, zoom bookkeeping
+ * :1243-1252, thread per box) over one device-resident frontier that is not level-synchronous.
+ * The library owns every buffer of the solve; result and node records (yr_record_layout kinds 1, 2)
+ * stay on the device until yr_frontier_release and are read with yr_fetch.  exact = 0 only. */
+typedef struct yr_frontier_desc {
+    int32_t dim;                 /* must be 2 */
+    int32_t time_kernels;        /* 1: CUDA-event timing of the tensor / scalar launches (out->tensor_ms, scalar_ms) */
+    const void*   recs_in;  const double* data_in;  uint64_t n_in;   /* level-0 boxes (yr_init_boxes) */
+    uint64_t      max_extent;    /* largest extent of any of their tensors */
+    uint64_t      result_base; uint64_t node_base;  /* global indices of the first record this solve appends */
+    yr_params     prm;
+} yr_frontier_desc;
+
+typedef struct yr_frontier_out {
+    void*    results; uint64_t n_results;   /* device arrays owned by the library */
+    void*    nodes;   uint64_t n_nodes;
+    yr_counters counters;                   /* totals of the solve (boxes, zooms, subdivisions, discards, ...) */
+    uint64_t rounds, launches, slots;
+    double   tensor_ms, scalar_ms;          /* summed device time of the two kernel families (time_kernels = 1) */
+} yr_frontier_out;
+
+int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream);
+/* 1 when 2-D boxes with extents up to max_extent fit the pipeline's shared-memory budget (else use yr_process_level) */
+int yr_frontier_fits(uint64_t max_extent);
+int yr_frontier_release(yr_frontier_out* out, void* stream);
+/* device -> host copy of `bytes` bytes on `stream`, synchronous (host_dst is a HOST pointer) */
+int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void* stream);
+
 /* BoundingIntervalLinearSystem on n independent dim x dim problems (thread per problem).
  *   lin [n][dim][dim], c0 [n][dim], sumabs [n][dim], errs [n][dim], final_step [n]
  *   -> interval [n][dim][2], flags [n][3] = (changed, should_stop, throwOut) */

@@ -48,6 +48,23 @@ class YrInitDesc(C.Structure):
                 ("counters", vp), ("prm", YrParams), ("launch", YrLaunch)]
 
 
+class YrCounters(C.Structure):
+    _fields_ = [(n, u64) for n in ("next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms",
+                                   "subdivisions", "discard_const", "discard_quad", "discard_zoom", "entry_coeffs",
+                                   "restrict_macs", "max_child_doubles", "max_child_extent", "max_level", "overflow",
+                                   "max_child_tensor", "reserved0", "reserved1")]
+
+
+class YrFrontierDesc(C.Structure):
+    _fields_ = [("dim", i32), ("time_kernels", i32), ("recs_in", vp), ("data_in", dp), ("n_in", u64),
+                ("max_extent", u64), ("result_base", u64), ("node_base", u64), ("prm", YrParams)]
+
+
+class YrFrontierOut(C.Structure):
+    _fields_ = [("results", vp), ("n_results", u64), ("nodes", vp), ("n_nodes", u64), ("counters", YrCounters),
+                ("rounds", u64), ("launches", u64), ("slots", u64), ("tensor_ms", C.c_double), ("scalar_ms", C.c_double)]
+
+
 COUNTER_FIELDS = ["next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms", "subdivisions",
                   "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "restrict_macs",
                   "max_child_doubles", "max_child_extent", "max_level", "overflow", "max_child_tensor",
@@ -57,7 +74,8 @@ COUNTER_BYTES = 8 * len(COUNTER_FIELDS)
 # every symbol include/yroots_b200.h declares
 EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_params", "yr_record_layout",
            "yr_workspace_doubles", "yr_level_work_bytes", "yr_static_smem_bytes", "yr_device_limits", "yr_init_boxes", "yr_process_level", "yr_bils_batched",
-           "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean"]
+           "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
+           "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_fetch"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -97,6 +115,14 @@ def bind(lib):
     lib.yr_poly_eval_axis.restype = C.c_int
     lib.yr_abs_axis_mean.argtypes = [dp, dp, dp, i64, i64, i64, vp]
     lib.yr_abs_axis_mean.restype = C.c_int
+    lib.yr_frontier_solve.argtypes = [C.POINTER(YrFrontierDesc), C.POINTER(YrFrontierOut), vp]
+    lib.yr_frontier_solve.restype = C.c_int
+    lib.yr_frontier_release.argtypes = [C.POINTER(YrFrontierOut), vp]
+    lib.yr_frontier_release.restype = C.c_int
+    lib.yr_frontier_fits.argtypes = [u64]
+    lib.yr_frontier_fits.restype = C.c_int
+    lib.yr_fetch.argtypes = [vp, vp, u64, vp]
+    lib.yr_fetch.restype = C.c_int
     if lib.yr_abi_version() != 1:
         raise RuntimeError("yroots_b200: ABI version mismatch")
     return lib

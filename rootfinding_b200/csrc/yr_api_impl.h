@@ -193,6 +193,7 @@ extern "C" {
 
 int yr_abi_version(void) { return YR_ABI_VERSION; }
 const char* yr_last_error(void) { return yr_api::g_err; }
+void yr_set_error(const char* msg) { yr_api::fail(msg); }          /* used by the other translation units of the library */
 const char* yr_build_info(void) { return yr_backend::build_info(); }
 
 void yr_default_params(yr_params* p) {

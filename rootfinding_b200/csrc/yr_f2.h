@@ -1,0 +1,753 @@
+// 2-D frontier pipeline ("f2"): the Chebyshev subdivision solver for systems of two polynomials in two
+// variables, organised for throughput on a B200.
+//
+// The whole search (every solvePolyRecursive invocation of every system of a batch) runs as a sequence of
+// ROUNDS over one device-resident frontier.  A round is
+//
+//   tensor ops   team (warp, or CTA of 4 / 8 warps) per box, one launch per (op, size class):
+//                  RESTRICT   transformChebToInterval (:864-894): build C(alpha,beta) per axis, restrict both
+//                             tensors along both axes
+//                  SUBDIVIDE  getSubdivisionIntervals (:1051-1129): halve both tensors along the split axes with
+//                             the level-independent matrices C(1/2 +- m/2, ...) kept in a global table
+//                every produced tensor leaves the team with its sum|M|, its coefficients of total degree <= 2
+//                and the outcome trimMs (:1131-1171) would have on it, so that ...
+//   scalar step  thread per box: ... isPoint, constant check (:1213), quadratic check (QuadraticCheck.py:34-182),
+//                trimMs adoption, BoundingIntervalLinearSystem (:628-753), addTransform (:420-454), the zoom-loop
+//                bookkeeping (:1243-1252), final-step re-entry (:1264), result / node records, and the choice of
+//                the box's next tensor op never touch a tensor.
+//
+// Boxes are not level-synchronous: a box that needs another zoom simply appears in the next round's RESTRICT
+// list next to boxes of other levels and other systems, so the number of rounds is the length of the longest
+// dependency chain, not (levels x longest zoom loop).  Tensors ping-pong between two arenas (every live box is
+// rewritten by exactly one tensor op per round); box records live in stable slots.
+//
+// Layout of a tensor in an arena and in shared memory: row-major with an ODD row stride ld >= n1, so that both
+// restriction passes read shared memory without bank conflicts and global <-> shared copies are flat.
+// Restriction matrices are stored in 4-row panels: panel b holds C[4b..4b+3][k], k = 4b..n-1, as [k][4] -- one
+// item (fiber f, row block b) loads a source element once and feeds four accumulators from two 16-byte loads.
+//
+// Arithmetic: compiled with -fmad=false; every matrix entry is generated with the reference's expression order
+// (:87-112) and every output accumulates its sources in ascending order, so restricted tensors are bit-identical
+// to TransformChebInPlace1D (use_fma = 1 fuses the contraction's multiply-add).
+//
+// Written against a small `Team` interface (tid, nthreads, sync, sum, bcast) and backend hooks so that
+// tests/emul can run the same source on pthreads.  The emulator is test infrastructure only.
+#pragma once
+#include "yr_types.h"
+
+#ifndef YR_DEV
+#if defined(__CUDACC__)
+#define YR_DEV __device__
+#define YR_DEVN __device__ __noinline__
+#else
+#define YR_DEV
+#define YR_DEVN
+#endif
+#endif
+
+namespace yr {
+namespace f2 {
+
+#if defined(__CUDACC__)
+typedef double2 pair_t;
+#else
+struct alignas(16) pair_t { double x, y; };
+#endif
+
+constexpr int kClasses = 4;                 // 0,1: warp per box   2: CTA of 128   3: CTA of 256
+constexpr int kOps = 2;
+enum Op : int32_t { kTNone = 0, kTRestrict = 1, kTSubdivide = 2 };
+YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
+
+YR_HD int class_threads(int cls) { return cls <= 1 ? 32 : (cls == 2 ? 128 : 256); }
+YR_HD int class_of(unsigned long long need) {         // need = per-team shared-memory doubles
+    return need <= 768ull ? 0 : (need <= 2048ull ? 1 : (need <= 6144ull ? 2 : 3));
+}
+constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
+
+YR_HD int odd_ld(int n1) { return n1 | 1; }
+YR_HD int even_up(int x) { return (x + 1) & ~1; }
+YR_HD int tensor_doubles(int n0, int ld) { return even_up(n0 * ld); }
+
+// ---- 4-row panels ------------------------------------------------------------------------------
+YR_HD int panel_off(int b, int nt) { return 4 * b * nt - 8 * b * (b - 1); }
+YR_HD int panel_doubles(int nt) { const int B = (nt + 3) >> 2; return panel_off(B, nt); }
+YR_HD int panel_index(int i, int k, int nt) { const int b = i >> 2; return panel_off(b, nt) + ((k - 4 * b) << 2) + (i & 3); }
+
+YR_HD unsigned long long need_restrict(int T, int n0max, int n1max) {
+    return 2ull * T + panel_doubles(n0max) + panel_doubles(n1max) + (unsigned)((n0max + n1max + 1) / 2) + 2;
+}
+YR_HD unsigned long long need_subdivide(int T) { return 4ull * T; }
+
+// Per-box state next to BoxRec<2> (same slot index).
+struct Work {
+    unsigned long long off[2];   // first double of tensor p in the arena the box currently lives in
+    int32_t ld[2];               // its row stride (odd once the box has been through a tensor op)
+    int32_t tshape[2][2];        // extents trimMs would leave              } valid for the tensors as the last
+    double  tsumabs[2], terr[2]; // sum|M_p| and error after that trim      } tensor op wrote them (trim_valid)
+    double  sumabs[2];           // sum|M_p| of the current view
+    double  low[2][6];           // M00, M10, M01, M20, M11, M02 (0 beyond the extents): quad_check_2d order
+    double  alpha[2], beta[2];   // pending restriction
+    double  entry_iv[2][2];      // originalInterval.getIntervalForCombining() of the current invocation
+    double  cell_iv[2][2];       // tracked interval when the box was created
+    double  last_size[2];
+    int32_t op, fresh, copy_only, trim_valid;
+    int32_t zoom_count, changed, should_stop, final_split;
+    int32_t node_level, result_index, node_index, nsplit;
+    int32_t order[2][2];         // per polynomial: axes to halve, in order
+};
+
+// Device control block; the host reads it once per round.
+struct Ctl {
+    unsigned long long n_list[kOps][kClasses];      // boxes queued for the next round
+    unsigned long long need_max[kOps][kClasses];    // largest per-team need (doubles) among them
+    unsigned long long ext_max[kClasses];           // largest extent among queued subdivisions
+    unsigned long long out_bound;                   // doubles the next round's tensor ops may write
+    unsigned long long data_used;                   // doubles written to the current output arena
+    unsigned long long n_boxes, n_results, n_nodes; // slots in use
+    unsigned long long overflow, bad_mid;
+    unsigned long long boxes, zooms, subdivisions, dconst, dquad, dzoom, entry_coeffs, restrict_macs, max_level;
+    unsigned long long reserved[4];
+};
+constexpr int kCtlWords = sizeof(Ctl) / 8;
+
+struct Tables {                // level-independent subdivision matrices, panels for extent `nt`
+    const double* mat[2][2];   // [mid: 0 -> m = 0, 1 -> m = kFirstSplit][half: 0 lower, 1 upper]
+    const int* rows_after[2][2];
+    int nt;
+};
+
+struct Args {
+    BoxRec<2>* recs; Work* work;
+    const double* data_in; double* data_out; unsigned long long cap_data_out;
+    ResultRec<2>* results; unsigned long long cap_results, result_base;
+    NodeRec<2>* nodes; unsigned long long cap_nodes, node_base;
+    unsigned int* lists[kOps][kClasses];            // queues being filled for the next round
+    unsigned long long cap_boxes;
+    Ctl* ctl;
+    Tables tab;
+    SolverParams prm;
+};
+
+// ---- restriction matrix C(alpha, beta) in panel form ---------------------------------------------
+// Column by column (the three-term recurrence couples neighbouring rows: columns sequential, rows parallel),
+// with rows_after[k] = the reference's `maxRow` after column k (:106-112).  Collective over the team.
+template <class Team>
+YR_DEV void build_panels(Team& tm, double* Cp, int* rows_after, int nt, double alpha, double beta) {
+    const int P = panel_doubles(nt);
+    for (int e = tm.tid; e < P; e += tm.nthreads) Cp[e] = 0.0;
+    tm.sync();
+    if (tm.tid == 0) {
+        Cp[panel_index(0, 0, nt)] = 1.0; rows_after[0] = 1;
+        if (nt >= 2) { Cp[panel_index(0, 1, nt)] = beta; Cp[panel_index(1, 1, nt)] = alpha; rows_after[1] = 2; }
+    }
+    tm.sync();
+    const double beta2 = 2 * beta;
+    for (int k = 2; k < nt; ++k) {
+        const int rows = rows_after[k - 1];
+        for (int i = tm.tid; i <= rows; i += tm.nthreads) {
+            // entries beyond a column's length are zero, which reproduces the reference's edge formulas exactly
+            const double cm1 = (i >= 1) ? Cp[panel_index(i - 1, k - 1, nt)] : 0.0;
+            const double ci = (i <= k - 1) ? Cp[panel_index(i, k - 1, nt)] : 0.0;
+            const double cp1 = (i + 1 <= k - 1) ? Cp[panel_index(i + 1, k - 1, nt)] : 0.0;
+            const double pi = (i <= k - 2) ? Cp[panel_index(i, k - 2, nt)] : 0.0;
+            double t;
+            if (i == 0) t = alpha * cp1;
+            else if (i == 1) t = alpha * (2 * cm1 + cp1);
+            else t = alpha * (cm1 + cp1);
+            double val = (-pi + t) + beta2 * ci;
+            if (i == rows) {                                  // the reference's finalVal
+                val = alpha * cm1;
+                int nr = rows;
+                if (fabs(val) > 1e-16) nr = rows + 1; else val = 0.0;
+                rows_after[k] = nr;
+            }
+            Cp[panel_index(i, k, nt)] = val;
+        }
+        tm.sync();
+    }
+}
+
+// ---- one restriction pass ---------------------------------------------------------------------------
+// src element (k, f) at src[k*sk + f*sf], k < n;  dst element (i, f) at dst[i*dk + f*df], i < r;  f < F.
+// An item is (row block b, fiber f): four output rows from one sweep over source rows 4b .. n-1.
+// Returns the team-wide sum|dst|.  src and dst must not overlap.
+template <bool FMA, class Team>
+YR_DEV double restrict_pass(Team& tm, const double* src, int sk, int sf, double* dst, int dk, int df,
+                            int n, int r, int F, const double* Cp, int nt) {
+    const int B = (r + 3) >> 2;
+    double asum = 0.0;
+    int b = 0, f = tm.tid;
+    while (f >= F) { f -= F; ++b; }
+    while (b < B) {
+        const int i0 = b << 2;
+        const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));      // 16-byte aligned: two loads per k
+        const double* s = src + i0 * sk + f * sf;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+        for (int k = i0; k < n; ++k) {
+            const double x = *s; s += sk;
+            const pair_t c01 = cp[0], c23 = cp[1]; cp += 2;
+            const double c0 = c01.x, c1 = c01.y, c2 = c23.x, c3 = c23.y;
+            if (FMA) { a0 = fma(c0, x, a0); a1 = fma(c1, x, a1); a2 = fma(c2, x, a2); a3 = fma(c3, x, a3); }
+            else { a0 = a0 + c0 * x; a1 = a1 + c1 * x; a2 = a2 + c2 * x; a3 = a3 + c3 * x; }
+        }
+        double* d = dst + i0 * dk + f * df;
+        const int rem = r - i0;
+        d[0] = a0; asum += fabs(a0);
+        if (rem > 1) { d[dk] = a1; asum += fabs(a1); }
+        if (rem > 2) { d[2 * dk] = a2; asum += fabs(a2); }
+        if (rem > 3) { d[3 * dk] = a3; asum += fabs(a3); }
+        f += tm.nthreads;
+        while (f >= F) { f -= F; ++b; }
+    }
+    return tm.sum(asum);
+}
+
+template <class Team>
+YR_DEV void copy_flat(Team& tm, double* dst, const double* src, int n_even) {
+    // both 16-byte aligned, n_even even
+    const pair_t* s = reinterpret_cast<const pair_t*>(src);
+    pair_t* d = reinterpret_cast<pair_t*>(dst);
+    for (int e = tm.tid; e < (n_even >> 1); e += tm.nthreads) d[e] = s[e];
+}
+
+template <class Team>
+YR_DEV double view_abs_sum(Team& tm, const double* M, int n0, int n1, int ld) {
+    double s = 0.0;
+    if (n1 >= 12) {
+        // lanes along rows
+        const int per = tm.nthreads;
+        for (int e = tm.tid; e < n0 * n1; e += per) { const int i = e / n1; s += fabs(M[i * ld + (e - i * n1)]); }
+    } else {
+        for (int i = tm.tid; i < n0; i += tm.nthreads) { const double* row = M + i * ld; for (int j = 0; j < n1; ++j) s += fabs(row[j]); }
+    }
+    return tm.sum(s);
+}
+
+// What every produced tensor leaves behind: low-order coefficients and the outcome of trimMs (:1131-1171)
+// for error `err` -- collective; thread 0 holds the results.
+struct Epilogue { double low[6]; int t0, t1; double tsum, terr; };
+
+template <class Team>
+YR_DEV void tensor_epilogue(Team& tm, const double* M, int n0, int n1, int ld, double sumabs, double err,
+                            const SolverParams& prm, Epilogue& ep) {
+    ep.low[0] = M[0];
+    ep.low[1] = n0 > 1 ? M[ld] : 0.0;
+    ep.low[2] = n1 > 1 ? M[1] : 0.0;
+    ep.low[3] = n0 > 2 ? M[2 * ld] : 0.0;
+    ep.low[4] = (n0 > 1 && n1 > 1) ? M[ld + 1] : 0.0;
+    ep.low[5] = n1 > 2 ? M[2] : 0.0;
+    int t0 = n0, t1 = n1;
+    double budget = prm.trim_abs_tol + err * prm.trim_rel_tol;
+    bool trimmed = false;
+    if (prm.trim) {
+        while (t0 > 3) {                                      // axis 0: trailing rows
+            double s = 0.0;
+            const double* row = M + (t0 - 1) * ld;
+            for (int j = tm.tid; j < t1; j += tm.nthreads) s += fabs(row[j]);
+            s = tm.sum(s);
+            if (s < budget) { t0 -= 1; budget -= s; err += s; trimmed = true; } else break;
+        }
+        while (t1 > 3) {                                      // axis 1: trailing columns of the remaining rows
+            double s = 0.0;
+            const double* col = M + (t1 - 1);
+            for (int i = tm.tid; i < t0; i += tm.nthreads) s += fabs(col[i * ld]);
+            s = tm.sum(s);
+            if (s < budget) { t1 -= 1; budget -= s; err += s; trimmed = true; } else break;
+        }
+    }
+    ep.t0 = t0; ep.t1 = t1; ep.terr = err;
+    ep.tsum = trimmed ? view_abs_sum(tm, M, t0, t1, ld) : sumabs;
+}
+
+YR_HD void store_epilogue(Work& w, int p, const Epilogue& ep, double sumabs) {
+    w.sumabs[p] = sumabs;
+    for (int q = 0; q < 6; ++q) w.low[p][q] = ep.low[q];
+    w.tshape[p][0] = ep.t0; w.tshape[p][1] = ep.t1; w.tsumabs[p] = ep.tsum; w.terr[p] = ep.terr;
+}
+
+// ---- RESTRICT ------------------------------------------------------------------------------------------
+// slice: [A: T][B: T][C0 panels][C1 panels][rows_after ints]
+template <bool FMA, class Team>
+YR_DEV void restrict_box(Team& tm, const Args& a, unsigned int b, double* slice, unsigned long long& macs) {
+    BoxRec<2>& rec = a.recs[b];
+    Work& wk = a.work[b];
+    const SolverParams& prm = a.prm;
+    const int copy_only = wk.copy_only;
+    int shp[2][2], ldg[2];
+    for (int p = 0; p < 2; ++p) { shp[p][0] = rec.shape[p][0]; shp[p][1] = rec.shape[p][1]; ldg[p] = wk.ld[p]; }
+    const int lds0 = odd_ld(shp[0][1]), lds1 = odd_ld(shp[1][1]);
+    const int sz0 = tensor_doubles(shp[0][0], lds0), sz1 = tensor_doubles(shp[1][0], lds1);
+    const int T = sz0 > sz1 ? sz0 : sz1;
+    const int n0max = shp[0][0] > shp[1][0] ? shp[0][0] : shp[1][0];
+    const int n1max = shp[0][1] > shp[1][1] ? shp[0][1] : shp[1][1];
+    double* A = slice; double* Bf = slice + T;
+    double* C0 = slice + 2 * T; double* C1 = C0 + panel_doubles(n0max);
+    int* rows0 = reinterpret_cast<int*>(C1 + panel_doubles(n1max)); int* rows1 = rows0 + n0max;
+    const double al0 = wk.alpha[0], be0 = wk.beta[0], al1 = wk.alpha[1], be1 = wk.beta[1];
+    const bool id0 = copy_only || (al0 == 1.0 && be0 == 0.0), id1 = copy_only || (al1 == 1.0 && be1 == 0.0);
+    // output space: never larger than the input (rows only shrink)
+    unsigned long long base = 0;
+    if (tm.tid == 0) base = tm.atomic_add(&a.ctl->data_used, (unsigned long long)(sz0 + sz1));
+    base = tm.bcast(base);
+    if (base + (unsigned long long)(sz0 + sz1) > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
+    tm.sync();                                                   // previous box's reads of the slice are over
+    if (!id0 && n0max > 1) build_panels(tm, C0, rows0, n0max, al0, be0);
+    if (!id1 && n1max > 1) build_panels(tm, C1, rows1, n1max, al1, be1);
+    unsigned long long out_off = base;
+    for (int p = 0; p < 2; ++p) {
+        const int n0 = shp[p][0], n1 = shp[p][1];
+        const int lds = p ? lds1 : lds0;
+        const double* src = a.data_in + wk.off[p];
+        tm.sync();
+        if (ldg[p] == lds && (wk.off[p] & 1ull) == 0) copy_flat(tm, A, src, tensor_doubles(n0, lds));
+        else for (int e = tm.tid; e < n0 * n1; e += tm.nthreads) { const int i = e / n1, j = e - i * n1; A[i * lds + j] = src[(long long)i * ldg[p] + j]; }
+        tm.sync();
+        double s = copy_only ? view_abs_sum(tm, A, n0, n1, lds) : wk.sumabs[p];
+        double err = rec.err[p];
+        double* cur = A; double* oth = Bf;
+        int r0 = n0, r1 = n1, ld = lds;
+        if (!copy_only) err += n0 * kMachEps * s;                    // charged before the axis (:860)
+        if (!id0 && n0 > 1) {
+            r0 = rows0[n0 - 1];
+            s = restrict_pass<FMA>(tm, cur, ld, 1, oth, ld, 1, n0, r0, n1, C0, n0max);
+            if (tm.tid == 0) macs += (unsigned long long)n1 * ((unsigned long long)r0 * n0 - (unsigned long long)r0 * (r0 - 1) / 2);
+            double* t = cur; cur = oth; oth = t;
+            tm.sync();
+        }
+        if (!copy_only) err += n1 * kMachEps * s;
+        if (!id1 && n1 > 1) {
+            r1 = rows1[n1 - 1];
+            const int ld2 = odd_ld(r1);
+            s = restrict_pass<FMA>(tm, cur, 1, ld, oth, 1, ld2, n1, r1, r0, C1, n1max);
+            if (tm.tid == 0) macs += (unsigned long long)r0 * ((unsigned long long)r1 * n1 - (unsigned long long)r1 * (r1 - 1) / 2);
+            double* t = cur; cur = oth; oth = t;
+            ld = ld2;
+            tm.sync();
+        }
+        Epilogue ep;
+        tensor_epilogue(tm, cur, r0, r1, ld, s, err, prm, ep);
+        const int osz = tensor_doubles(r0, ld);
+        copy_flat(tm, a.data_out + out_off, cur, osz);
+        if (tm.tid == 0) {
+            store_epilogue(wk, p, ep, s);
+            rec.shape[p][0] = r0; rec.shape[p][1] = r1; rec.err[p] = err;
+            wk.off[p] = out_off; wk.ld[p] = ld;
+        }
+        out_off += (unsigned long long)osz;
+    }
+    if (tm.tid == 0) { wk.op = kTNone; wk.copy_only = 0; wk.trim_valid = 1; }
+}
+
+// ---- SUBDIVIDE -----------------------------------------------------------------------------------------
+// slice: [S][L][U][X], each T doubles.  Matrices come from the level-independent tables (shared-memory copy
+// `smat` for m = 0 when the launch staged one, else the global table).
+struct SubMats { const double* lo; const double* hi; const int* rlo; const int* rhi; int nt; };
+
+template <class Team>
+YR_DEV void child_record(Team& tm, const Args& a, const BoxRec<2>& rec, const Work& wk, unsigned int child, int c, int k,
+                         const int split_axes[2]) {
+    // :1111-1128 -- thread-serial
+    BoxRec<2>& out = a.recs[child];
+    Work& ow = a.work[child];
+    IntervalState<2> st = rec.st;
+    for (int j = 0; j < k; ++j) {
+        const int ax = split_axes[j];
+        const int half = (c >> (k - 1 - j)) & 1;
+        const double mid = st.next_mid[ax];
+        double sub[2][2], al[2], be[2];
+        for (int d = 0; d < 2; ++d) { sub[d][0] = -1.0; sub[d][1] = 1.0; }
+        if (half) sub[ax][0] = mid; else sub[ax][1] = mid;
+        add_transform<2>(st, sub, al, be);
+    }
+    for (int j = 0; j < k; ++j) st.next_mid[split_axes[j]] = 0.0;
+    out.st = st;
+    out.data_off = 0;
+    out.system = rec.system;
+    const bool fsplit = wk.final_split != 0;
+    out.parent_node = fsplit ? rec.parent_node : wk.node_index;
+    out.collector = fsplit ? wk.result_index : rec.collector;
+    out.level = wk.node_level;
+    unsigned long long hi = rec.path_hi, lo = rec.path_lo;
+    const int used = rec.path_bits;
+    const int shift = 128 - used - k;
+    if (shift >= 64) hi |= (unsigned long long)c << (shift - 64);
+    else if (shift >= 0) {
+        lo |= (unsigned long long)c << shift;
+        if (shift + k > 64) hi |= (unsigned long long)c >> (64 - shift);
+    }
+    out.path_bits = (shift >= 0) ? used + k : used;
+    out.pad0 = 0;
+    out.path_hi = hi; out.path_lo = lo;
+    for (int d = 0; d < 2; ++d) { ow.cell_iv[d][0] = st.iv[d][0]; ow.cell_iv[d][1] = st.iv[d][1]; }
+    ow.op = kTNone; ow.fresh = 1; ow.copy_only = 0; ow.trim_valid = 1;
+    ow.zoom_count = 0; ow.changed = 1; ow.should_stop = 0; ow.final_split = 0;
+    ow.node_level = wk.node_level; ow.result_index = -1; ow.node_index = -1; ow.nsplit = 0;
+    (void)tm;
+}
+
+template <bool FMA, class Team>
+YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice, const double* smat_lo, const double* smat_hi,
+                          int smat_nt, unsigned long long& macs) {
+    const BoxRec<2>& rec = a.recs[b];
+    const Work& wk = a.work[b];
+    const SolverParams& prm = a.prm;
+    const int k = wk.nsplit, nchild = 1 << k;
+    int shp[2][2];
+    for (int p = 0; p < 2; ++p) { shp[p][0] = rec.shape[p][0]; shp[p][1] = rec.shape[p][1]; }
+    const int sz0 = tensor_doubles(shp[0][0], wk.ld[0]), sz1 = tensor_doubles(shp[1][0], wk.ld[1]);
+    const int T = sz0 > sz1 ? sz0 : sz1;
+    int split_axes[2]; { bool used[2] = {false, false}; for (int j = 0; j < k; ++j) used[wk.order[0][j]] = true; int j = 0; for (int ax = 0; ax < 2; ++ax) if (used[ax]) split_axes[j++] = ax; if (j < 2) split_axes[1] = split_axes[0]; }
+    // which table: m = 0 (every split after an axis' first) or m = kFirstSplit
+    int midsel[2];
+    for (int ax = 0; ax < 2; ++ax) midsel[ax] = (rec.st.next_mid[ax] == 0.0) ? 0 : 1;
+    // slots and output space: children are never larger than their parent
+    unsigned long long cbase = 0, dbase = 0;
+    const unsigned long long per_child = (unsigned long long)(sz0 + sz1);
+    if (tm.tid == 0) {
+        cbase = tm.atomic_add(&a.ctl->n_boxes, (unsigned long long)nchild);
+        dbase = tm.atomic_add(&a.ctl->data_used, per_child * nchild);
+        for (int j = 0; j < k; ++j) { const double m = rec.st.next_mid[split_axes[j]]; if (m != 0.0 && m != kFirstSplit) tm.atomic_add(&a.ctl->bad_mid, 1ull); }
+    }
+    cbase = tm.bcast(cbase); dbase = tm.bcast(dbase);
+    if (cbase + nchild > a.cap_boxes || dbase + per_child * nchild > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
+    if (tm.tid < nchild) child_record(tm, a, rec, wk, (unsigned int)(cbase + tm.tid), tm.tid, k, split_axes);
+    double* S = slice; double* L = slice + T; double* U = slice + 2 * T; double* X = slice + 3 * T;
+    for (int p = 0; p < 2; ++p) {
+        const int n0 = shp[p][0], n1 = shp[p][1], ld = wk.ld[p];
+        tm.sync();
+        if ((wk.off[p] & 1ull) == 0) copy_flat(tm, S, a.data_in + wk.off[p], tensor_doubles(n0, ld));
+        else for (int e = tm.tid; e < n0 * ld; e += tm.nthreads) S[e] = a.data_in[wk.off[p] + e];
+        tm.sync();
+        // stage 1 along a1 = order[p][0]: S -> L (lower half), U (upper half)
+        const int a1 = wk.order[p][0];
+        const int n_a1 = a1 == 0 ? n0 : n1;
+        SubMats m1;
+        {
+            const int ms = midsel[a1];
+            const bool sm = (ms == 0 && smat_lo != nullptr);
+            m1.lo = sm ? smat_lo : a.tab.mat[ms][0]; m1.hi = sm ? smat_hi : a.tab.mat[ms][1];
+            m1.rlo = a.tab.rows_after[ms][0]; m1.rhi = a.tab.rows_after[ms][1]; m1.nt = sm ? smat_nt : a.tab.nt;
+        }
+        const double e1 = n_a1 * kMachEps * wk.sumabs[p];
+        const double terr1 = e1 + rec.err[p];
+        int shL[2] = {n0, n1}, shU[2] = {n0, n1}; int ldL = ld, ldU = ld;
+        double sumL, sumU;
+        if (n_a1 > 1) {
+            const int rl = m1.rlo[n_a1 - 1], ru = m1.rhi[n_a1 - 1];
+            if (a1 == 0) {
+                shL[0] = rl; shU[0] = ru;
+                sumL = restrict_pass<FMA>(tm, S, ld, 1, L, ld, 1, n0, rl, n1, m1.lo, m1.nt);
+                sumU = restrict_pass<FMA>(tm, S, ld, 1, U, ld, 1, n0, ru, n1, m1.hi, m1.nt);
+                if (tm.tid == 0) macs += (unsigned long long)n1 * (((unsigned long long)rl * n0 - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * n0 - (unsigned long long)ru * (ru - 1) / 2));
+            } else {
+                shL[1] = rl; shU[1] = ru; ldL = odd_ld(rl); ldU = odd_ld(ru);
+                sumL = restrict_pass<FMA>(tm, S, 1, ld, L, 1, ldL, n1, rl, n0, m1.lo, m1.nt);
+                sumU = restrict_pass<FMA>(tm, S, 1, ld, U, 1, ldU, n1, ru, n0, m1.hi, m1.nt);
+                if (tm.tid == 0) macs += (unsigned long long)n0 * (((unsigned long long)rl * n1 - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * n1 - (unsigned long long)ru * (ru - 1) / 2));
+            }
+        } else {
+            // extent-1 axis: TransformChebInPlaceND returns the tensor unchanged (:363)
+            copy_flat(tm, L, S, tensor_doubles(n0, ld)); copy_flat(tm, U, S, tensor_doubles(n0, ld));
+            sumL = sumU = wk.sumabs[p];
+        }
+        tm.sync();
+        const int rank0 = (split_axes[0] == a1) ? 0 : 1;      // position of a1 in the ascending set of split axes
+        for (int h1 = 0; h1 < 2; ++h1) {
+            const double* H = h1 ? U : L;
+            const int* shH = h1 ? shU : shL; const int ldH = h1 ? ldU : ldL; const double sumH = h1 ? sumU : sumL;
+            if (k == 1) {
+                const int c = h1;
+                Epilogue ep;
+                tensor_epilogue(tm, H, shH[0], shH[1], ldH, sumH, terr1, prm, ep);
+                const int osz = tensor_doubles(shH[0], ldH);
+                const unsigned long long off = dbase + per_child * c + (p ? (unsigned long long)sz0 : 0ull);
+                copy_flat(tm, a.data_out + off, H, osz);
+                if (tm.tid == 0) {
+                    const unsigned int child = (unsigned int)(cbase + c);
+                    Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
+                    store_epilogue(ow, p, ep, sumH);
+                    orec.shape[p][0] = shH[0]; orec.shape[p][1] = shH[1]; orec.err[p] = terr1;
+                    ow.off[p] = off; ow.ld[p] = ldH;
+                }
+                continue;
+            }
+            // stage 2 along a2 = order[p][1]: H -> (lower -> S, upper -> X)
+            const int a2 = wk.order[p][1];
+            const int n_a2 = shH[a2];
+            SubMats m2;
+            {
+                const int ms = midsel[a2];
+                const bool sm = (ms == 0 && smat_lo != nullptr);
+                m2.lo = sm ? smat_lo : a.tab.mat[ms][0]; m2.hi = sm ? smat_hi : a.tab.mat[ms][1];
+                m2.rlo = a.tab.rows_after[ms][0]; m2.rhi = a.tab.rows_after[ms][1]; m2.nt = sm ? smat_nt : a.tab.nt;
+            }
+            const double e2 = n_a2 * kMachEps * sumH;
+            const double terr2 = e2 + terr1;
+            int shA[2] = {shH[0], shH[1]}, shB[2] = {shH[0], shH[1]}; int ldA = ldH, ldB = ldH;
+            double sumA, sumB;
+            tm.sync();                                         // S / X are free (previous epilogue copies are done)
+            if (n_a2 > 1) {
+                const int rl = m2.rlo[n_a2 - 1], ru = m2.rhi[n_a2 - 1];
+                if (a2 == 0) {
+                    shA[0] = rl; shB[0] = ru;
+                    sumA = restrict_pass<FMA>(tm, H, ldH, 1, S, ldH, 1, shH[0], rl, shH[1], m2.lo, m2.nt);
+                    sumB = restrict_pass<FMA>(tm, H, ldH, 1, X, ldH, 1, shH[0], ru, shH[1], m2.hi, m2.nt);
+                    if (tm.tid == 0) macs += (unsigned long long)shH[1] * (((unsigned long long)rl * shH[0] - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * shH[0] - (unsigned long long)ru * (ru - 1) / 2));
+                } else {
+                    shA[1] = rl; shB[1] = ru; ldA = odd_ld(rl); ldB = odd_ld(ru);
+                    sumA = restrict_pass<FMA>(tm, H, 1, ldH, S, 1, ldA, shH[1], rl, shH[0], m2.lo, m2.nt);
+                    sumB = restrict_pass<FMA>(tm, H, 1, ldH, X, 1, ldB, shH[1], ru, shH[0], m2.hi, m2.nt);
+                    if (tm.tid == 0) macs += (unsigned long long)shH[0] * (((unsigned long long)rl * shH[1] - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * shH[1] - (unsigned long long)ru * (ru - 1) / 2));
+                }
+            } else {
+                copy_flat(tm, S, H, tensor_doubles(shH[0], ldH)); copy_flat(tm, X, H, tensor_doubles(shH[0], ldH));
+                sumA = sumB = sumH;
+            }
+            tm.sync();
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const double* O = h2 ? X : S;
+                const int* shO = h2 ? shB : shA; const int ldO = h2 ? ldB : ldA; const double sumO = h2 ? sumB : sumA;
+                // canonical child: split axes ascending, smallest axis most significant
+                const int c = (rank0 == 0) ? ((h1 << 1) | h2) : ((h2 << 1) | h1);
+                Epilogue ep;
+                tensor_epilogue(tm, O, shO[0], shO[1], ldO, sumO, terr2, prm, ep);
+                const int osz = tensor_doubles(shO[0], ldO);
+                const unsigned long long off = dbase + per_child * c + (p ? (unsigned long long)sz0 : 0ull);
+                copy_flat(tm, a.data_out + off, O, osz);
+                if (tm.tid == 0) {
+                    const unsigned int child = (unsigned int)(cbase + c);
+                    Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
+                    store_epilogue(ow, p, ep, sumO);
+                    orec.shape[p][0] = shO[0]; orec.shape[p][1] = shO[1]; orec.err[p] = terr2;
+                    ow.off[p] = off; ow.ld[p] = ldO;
+                }
+            }
+        }
+    }
+}
+
+// ---- scalar step (thread per box) -------------------------------------------------------------------
+YR_HD void box_sizes(const BoxRec<2>& rec, const Work& wk, int& T, int& n0max, int& n1max, unsigned long long& total) {
+    const int l0 = odd_ld(rec.shape[0][1]) > wk.ld[0] ? odd_ld(rec.shape[0][1]) : wk.ld[0];
+    const int l1 = odd_ld(rec.shape[1][1]) > wk.ld[1] ? odd_ld(rec.shape[1][1]) : wk.ld[1];
+    const int s0 = tensor_doubles(rec.shape[0][0], l0), s1 = tensor_doubles(rec.shape[1][0], l1);
+    T = s0 > s1 ? s0 : s1; total = (unsigned long long)s0 + s1;
+    n0max = rec.shape[0][0] > rec.shape[1][0] ? rec.shape[0][0] : rec.shape[1][0];
+    n1max = rec.shape[0][1] > rec.shape[1][1] ? rec.shape[0][1] : rec.shape[1][1];
+}
+
+struct Decision {
+    int op, cls;                                // next tensor op (kTNone: the box is finished)
+    unsigned long long need, bound, ext;        // its shared-memory need, output bound, largest extent
+    unsigned long long boxes, zooms, dconst, dquad, dzoom, coeffs, maxlevel, subdiv;
+};
+
+template <class At>
+YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
+    const SolverParams& prm = a.prm;
+    BoxRec<2>& rec = a.recs[b];
+    Work& wk = a.work[b];
+    IntervalState<2> st = rec.st;
+
+    auto emit = [&](uint32_t extra_flags) {
+        const unsigned long long idx = at.add(&a.ctl->n_results, 1ull);
+        wk.result_index = (int)(idx + a.result_base);
+        if (idx < a.cap_results) {
+            ResultRec<2>& r = a.results[idx];
+            const bool fin = st.final_step();
+            bool touch = false;
+            for (int d = 0; d < 2; ++d) {
+                const dd A = fin ? st.pfA[d] : st.A[d], B = fin ? st.pfB[d] : st.B[d];
+                dd nA; nA.hi = -A.hi; nA.lo = -A.lo;
+                r.box[d][0] = dd_to_double(dd_add(B, nA));
+                r.box[d][1] = dd_to_double(dd_add(B, A));
+                dd nA2; nA2.hi = -st.A[d].hi; nA2.lo = -st.A[d].lo;
+                const double lo = dd_to_double(dd_add(st.B[d], nA2));
+                const double hi = dd_to_double(dd_add(st.B[d], st.A[d]));
+                r.root[d] = fin ? (lo + hi) / 2 : (r.box[d][0] + r.box[d][1]) / 2;
+                r.comb_iv[d][0] = fin ? st.pf_iv[d][0] : st.iv[d][0];
+                r.comb_iv[d][1] = fin ? st.pf_iv[d][1] : st.iv[d][1];
+                r.iv_lo[d] = st.iv[d][0];
+                r.cell_iv[d][0] = wk.cell_iv[d][0]; r.cell_iv[d][1] = wk.cell_iv[d][1];
+                r.next_mid[d] = st.next_mid[d];
+                touch = touch || r.comb_iv[d][0] == wk.cell_iv[d][0] || r.comb_iv[d][1] == wk.cell_iv[d][1];
+            }
+            r.system = rec.system; r.parent_node = rec.parent_node; r.collector = rec.collector;
+            r.level = wk.node_level;
+            r.flags = extra_flags | (fin ? kResFinalStep : 0u) | (touch ? kResTouchesCell : 0u);
+            r.pad = 0;
+            r.path_hi = rec.path_hi; r.path_lo = rec.path_lo;
+        } else at.add(&a.ctl->overflow, 1ull);
+    };
+    auto sizes = [&](int& T, int& n0max, int& n1max, unsigned long long& total) { box_sizes(rec, wk, T, n0max, n1max, total); };
+    auto queue_restrict = [&]() {
+        int T, n0m, n1m; unsigned long long total;
+        sizes(T, n0m, n1m, total);
+        wk.op = kTRestrict;
+        dc.op = kTRestrict; dc.need = need_restrict(T, n0m, n1m); dc.cls = class_of(dc.need); dc.bound = total;
+        dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
+    };
+
+    for (;;) {
+        if (wk.fresh) {
+            // ---- entry of one solvePolyRecursive invocation :1202-1241
+            dc.boxes += 1;
+            if (st.is_point()) { emit(kResPointAtEntry); break; }
+            wk.node_level += 1;
+            if ((unsigned long long)wk.node_level > dc.maxlevel) dc.maxlevel = wk.node_level;
+            dc.coeffs += (unsigned long long)rec.shape[0][0] * rec.shape[0][1] + (unsigned long long)rec.shape[1][0] * rec.shape[1][1];
+            bool discard = false;
+            if (prm.constant_check)
+                for (int p = 0; p < 2 && !discard; ++p) {
+                    const double c0 = wk.low[p][0];
+                    if (fabs(c0) > wk.sumabs[p] - fabs(c0) + rec.err[p]) { discard = true; dc.dconst += 1; }
+                }
+            if (!discard && (prm.low_dim_quad_check || prm.all_dim_quad_check))
+                for (int p = 0; p < 2 && !discard; ++p)
+                    if (quad_check_2d(wk.low[p], wk.sumabs[p], rec.err[p])) { discard = true; dc.dquad += 1; }
+            if (discard) break;
+            if (prm.trim) {                                          // trimMs :1232, computed by the producing tensor op
+                bool any = false;
+                for (int p = 0; p < 2; ++p) {
+                    any = any || wk.tshape[p][0] != rec.shape[p][0] || wk.tshape[p][1] != rec.shape[p][1];
+                    rec.shape[p][0] = wk.tshape[p][0]; rec.shape[p][1] = wk.tshape[p][1];
+                    wk.sumabs[p] = wk.tsumabs[p]; rec.err[p] = wk.terr[p];
+                }
+                if (any) wk.trim_valid = 0;                         // a second trimMs of these tensors would start from here
+            }
+            for (int d = 0; d < 2; ++d) {
+                wk.entry_iv[d][0] = st.final_step() ? st.pf_iv[d][0] : st.iv[d][0];
+                wk.entry_iv[d][1] = st.final_step() ? st.pf_iv[d][1] : st.iv[d][1];
+                wk.last_size[d] = st.iv[d][1] - st.iv[d][0];
+            }
+            wk.zoom_count = 0; wk.changed = 1; wk.should_stop = 0; wk.fresh = 0;
+        } else {
+            // after a restriction :952-954, :1249-1252
+            if (st.final_step() && st.is_point()) { wk.should_stop = 1; wk.changed = 0; }
+            bool all_big = true;
+            for (int d = 0; d < 2; ++d) {
+                const double now = st.iv[d][1] - st.iv[d][0];
+                all_big = all_big && (now >= wk.last_size[d] / 2);
+                wk.last_size[d] = now;
+            }
+            if (all_big) wk.zoom_count += 1;
+        }
+        // ---- zoom loop :1243-1252
+        bool queued = false, dead = false;
+        while (wk.changed && wk.zoom_count <= prm.max_zoom_count) {
+            dc.zooms += 1;
+            double lin[2][2], c0[2];
+            for (int p = 0; p < 2; ++p) {
+                c0[p] = wk.low[p][0];
+                lin[p][0] = (rec.shape[p][0] == 1) ? 0.0 : wk.low[p][1];
+                lin[p][1] = (rec.shape[p][1] == 1) ? 0.0 : wk.low[p][2];
+            }
+            double sub[2][2];
+            BilsOut bo = bounding_interval<2>(lin, c0, wk.sumabs, rec.err, st.final_step(), sub);
+            for (int d = 0; d < 2; ++d)                                       // frozen axes :932-935
+                if (st.iv[d][0] == st.iv[d][1]) { sub[d][0] = -1.0; sub[d][1] = 1.0; }
+            bool changed = bo.changed, should_stop = bo.should_stop, thr = bo.throw_out;
+            if (thr && !st.can_throw_out()) { thr = false; should_stop = true; changed = true; }   // :937-940
+            wk.changed = changed ? 1 : 0; wk.should_stop = should_stop ? 1 : 0;
+            if (thr) { dc.dzoom += 1; dead = true; break; }
+            if (changed) {
+                double al[2], be[2];
+                if (!add_transform<2>(st, sub, al, be)) { dc.dzoom += 1; dead = true; break; }
+                for (int d = 0; d < 2; ++d) { wk.alpha[d] = al[d]; wk.beta[d] = be[d]; }
+                queue_restrict();
+                queued = true;
+                break;
+            }
+            wk.zoom_count += 1;                                                // nothing changed: counts towards maxZoomCount (:1250)
+        }
+        if (queued || dead) break;
+        // ---- what next? :1254-1317
+        if (wk.should_stop) {
+            if (st.final_step()) { emit(0u); break; }
+            st.start_final_step();                                          // :1264 re-enter on the same tensors
+            wk.fresh = 1;
+            if (prm.trim && !wk.trim_valid) {
+                // these tensors were trimmed at entry and not rewritten since: let a copy-only pass recompute
+                // what a second trimMs does to them
+                wk.alpha[0] = wk.alpha[1] = 1.0; wk.beta[0] = wk.beta[1] = 0.0; wk.copy_only = 1;
+                queue_restrict();
+                break;
+            }
+            continue;
+        }
+        if (st.final_step()) {
+            st.flags |= kFlagCanThrowFinal;
+            emit(kResCollector);                                            // the parent reports; its subtree supplies the points
+            wk.final_split = 1;
+        } else wk.final_split = 0;
+        {
+            int shape[2][2] = {{rec.shape[0][0], rec.shape[0][1]}, {rec.shape[1][0], rec.shape[1][1]}};
+            int order[2][2];
+            const int k = subdivision_axes<2>(shape, st.iv, wk.node_level, order);
+            wk.nsplit = k;
+            for (int p = 0; p < 2; ++p) { wk.order[p][0] = order[p][0]; wk.order[p][1] = (k > 1) ? order[p][1] : order[p][0]; }
+            wk.node_index = -1;
+            if (!wk.final_split) {
+                const unsigned long long ni = at.add(&a.ctl->n_nodes, 1ull);
+                if (ni < a.cap_nodes) {
+                    NodeRec<2>& nd = a.nodes[ni];
+                    for (int d = 0; d < 2; ++d) { nd.iv[d][0] = wk.entry_iv[d][0]; nd.iv[d][1] = wk.entry_iv[d][1]; nd.next_mid[d] = st.next_mid[d]; }
+                    nd.system = rec.system; nd.parent_node = rec.parent_node; nd.level = wk.node_level; nd.nsplit = k;
+                    wk.node_index = (int)(ni + a.node_base);
+                } else at.add(&a.ctl->overflow, 1ull);
+            }
+            int T, n0m, n1m; unsigned long long total;
+            sizes(T, n0m, n1m, total);
+            wk.op = kTSubdivide;
+            dc.op = kTSubdivide; dc.need = need_subdivide(T); dc.cls = class_of(dc.need); dc.bound = total << k;
+            dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
+            dc.subdiv += 1;
+        }
+        break;
+    }
+    rec.st = st;
+}
+
+// Level-0 boxes arrive packed from yr_init_boxes: give them their Work state and queue a copy-only pass that
+// re-lays the tensors out (odd row stride) and computes sums / low-order coefficients / trim outcome.
+template <class At>
+YR_HD void import_box(const Args& a, unsigned int b, Decision& dc, At at) {
+    const BoxRec<2>& rec = a.recs[b];
+    Work& w = a.work[b];
+    w.off[0] = rec.data_off; w.off[1] = rec.data_off + (unsigned long long)rec.shape[0][0] * rec.shape[0][1];
+    for (int p = 0; p < 2; ++p) {
+        w.ld[p] = rec.shape[p][1];
+        w.tshape[p][0] = rec.shape[p][0]; w.tshape[p][1] = rec.shape[p][1]; w.tsumabs[p] = 0.0; w.terr[p] = rec.err[p];
+        w.sumabs[p] = 0.0;
+        for (int q = 0; q < 6; ++q) w.low[p][q] = 0.0;
+        w.alpha[p] = 1.0; w.beta[p] = 0.0; w.last_size[p] = 0.0;
+        w.entry_iv[p][0] = w.entry_iv[p][1] = 0.0;
+        w.cell_iv[p][0] = rec.st.iv[p][0]; w.cell_iv[p][1] = rec.st.iv[p][1];
+        w.order[p][0] = w.order[p][1] = 0;
+    }
+    w.op = kTRestrict; w.fresh = 1; w.copy_only = 1; w.trim_valid = 0;
+    w.zoom_count = 0; w.changed = 1; w.should_stop = 0; w.final_split = 0;
+    w.node_level = rec.level; w.result_index = -1; w.node_index = -1; w.nsplit = 0;
+    int T, n0m, n1m; unsigned long long total;
+    box_sizes(rec, w, T, n0m, n1m, total);
+    dc.op = kTRestrict; dc.need = need_restrict(T, n0m, n1m); dc.cls = class_of(dc.need); dc.bound = total;
+    dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
+    at.add(&a.ctl->n_boxes, 1ull);
+}
+
+// queue the box for its next tensor op (plain per-thread atomics; the CUDA backend aggregates per warp)
+template <class At>
+YR_HD void commit_decision(const Args& a, unsigned int b, const Decision& dc, At at) {
+    if (dc.op == kTNone) return;
+    const int slot = op_slot(dc.op);
+    const unsigned long long pos = at.add(&a.ctl->n_list[slot][dc.cls], 1ull);
+    a.lists[slot][dc.cls][pos] = b;
+    at.max(&a.ctl->need_max[slot][dc.cls], dc.need);
+    if (slot == 1) at.max(&a.ctl->ext_max[dc.cls], dc.ext);
+    at.add(&a.ctl->out_bound, dc.bound);
+}
+
+}  // namespace f2
+}  // namespace yr

@@ -1,0 +1,212 @@
+// Host side of the 2-D frontier pipeline (yr_f2.h): the round loop behind yr_frontier_solve, written against
+// backend hooks (namespace yr_f2_backend) that yr_f2_kernels.cu (CUDA, the product) and tests/emul (pthreads,
+// test infrastructure) provide.
+#pragma once
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/yroots_b200.h"
+#include "yr_f2.h"
+
+extern "C" void yr_set_error(const char* msg);       // defined next to yr_last_error (yr_api_impl.h)
+
+namespace yr_f2_backend {
+void* dev_alloc(size_t bytes, void* stream);
+void dev_free(void* p, void* stream);
+int dev_copy(void* dst, const void* src, size_t bytes, void* stream);          // device -> device
+int dev_zero(void* p, size_t bytes, void* stream);
+int to_host(void* dst, const void* src, size_t bytes, void* stream);           // synchronises the stream
+int launch_tables(double* mats, int* rows, int nt, void* stream);              // 4 matrices / 4 rows_after arrays
+int launch_import(const yr::f2::Args& a, unsigned long long n, void* stream);
+// boxes list[0 .. n): tensor op `op` with `need` doubles of shared memory per team, extents <= ext
+int launch_tensor(const yr::f2::Args& a, int op, int cls, const unsigned int* list, unsigned long long n,
+                  unsigned long long need, int ext, void* stream);
+struct Segments { const unsigned int* list[yr::f2::kClasses]; unsigned long long n[yr::f2::kClasses];
+                  unsigned long long child_lo, child_bound; };
+int launch_scalar(const yr::f2::Args& a, const Segments& s, void* stream);
+// optional CUDA-event timing of the tensor / scalar launches of a solve
+void timer_reset(int enable);
+void timer_mark(int which, int begin, void* stream);      // which: 0 tensor, 1 scalar
+void timer_collect(double* tensor_ms, double* scalar_ms);
+}  // namespace yr_f2_backend
+
+namespace yr_f2_host {
+using namespace yr;
+using namespace yr::f2;
+
+inline int fail(const char* msg) { yr_set_error(msg); return -1; }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    // grow to at least `bytes`, keeping the first `keep` bytes
+    int reserve(size_t bytes, size_t keep, void* stream, double slack = 1.5) {
+        if (bytes <= cap) return 0;
+        size_t want = (size_t)(bytes * slack) + 256;
+        void* q = yr_f2_backend::dev_alloc(want, stream);
+        if (!q) return fail("device allocation failed (frontier buffers)");
+        if (p && keep) { if (yr_f2_backend::dev_copy(q, p, keep, stream)) return -1; }
+        if (p) yr_f2_backend::dev_free(p, stream);
+        p = q; cap = want;
+        return 0;
+    }
+    void release(void* stream) { if (p) yr_f2_backend::dev_free(p, stream); p = nullptr; cap = 0; }
+};
+
+inline int fits(unsigned long long max_extent) {
+    const int n = (int)(max_extent < 4 ? 4 : max_extent);
+    if (max_extent > 4096) return 0;
+    const int T = even_up(n * odd_ld(n));
+    return need_subdivide(T) + 2ull * panel_doubles(n) <= kMaxNeed && need_restrict(T, n, n) <= kMaxNeed;
+}
+
+inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) {
+    namespace be = yr_f2_backend;
+    memset(out, 0, sizeof(*out));
+    if (d->dim != 2) return fail("yr_frontier_solve: dim must be 2");
+    if (d->prm.exact) return fail("yr_frontier_solve: exact mode is served by yr_process_level");
+    const unsigned long long n0 = d->n_in;
+    if (n0 == 0) return 0;
+    if (n0 > 0x3FFFFFFFull) return fail("yr_frontier_solve: too many level-0 boxes");
+    const int nt = (int)(d->max_extent < 4 ? 4 : d->max_extent);
+    if (!fits(d->max_extent)) return fail("yr_frontier_solve: tensors too large for the shared-memory pipeline");
+    be::timer_reset(d->time_kernels);
+
+    DevBuf recs, work, results, nodes, arena[2], lists[2], tabs, ctlbuf;
+    auto cleanup = [&](bool keep_out) {
+        recs.release(stream); work.release(stream); arena[0].release(stream); arena[1].release(stream);
+        lists[0].release(stream); lists[1].release(stream); tabs.release(stream); ctlbuf.release(stream);
+        if (!keep_out) { results.release(stream); nodes.release(stream); }
+    };
+#define F2_TRY(expr) do { if (expr) { cleanup(false); return -1; } } while (0)
+
+    // level-independent subdivision matrices
+    const size_t P = (size_t)panel_doubles(nt);
+    F2_TRY(tabs.reserve(4 * P * 8 + 4 * (size_t)nt * 4 + 64, 0, stream, 1.0));
+    double* mats = static_cast<double*>(tabs.p);
+    int* rows = reinterpret_cast<int*>(mats + 4 * P);
+    F2_TRY(be::launch_tables(mats, rows, nt, stream));
+
+    F2_TRY(ctlbuf.reserve(sizeof(Ctl), 0, stream, 1.0));
+    F2_TRY(be::dev_zero(ctlbuf.p, sizeof(Ctl), stream));
+    size_t cap_boxes = (size_t)(n0 * 8 + 4096);
+    F2_TRY(recs.reserve(cap_boxes * sizeof(BoxRec<2>), 0, stream, 1.0));
+    F2_TRY(work.reserve(cap_boxes * sizeof(Work), 0, stream, 1.0));
+    F2_TRY(be::dev_copy(recs.p, d->recs_in, n0 * sizeof(BoxRec<2>), stream));
+    size_t cap_results = (size_t)(n0 * 4 + 1024), cap_nodes = cap_results;
+    F2_TRY(results.reserve(cap_results * sizeof(ResultRec<2>), 0, stream, 1.0));
+    F2_TRY(nodes.reserve(cap_nodes * sizeof(NodeRec<2>), 0, stream, 1.0));
+
+    Args a;
+    memset(&a, 0, sizeof(a));
+    a.ctl = static_cast<Ctl*>(ctlbuf.p);
+    a.tab.nt = nt;
+    for (int m = 0; m < 2; ++m) for (int h = 0; h < 2; ++h) { a.tab.mat[m][h] = mats + (size_t)(2 * m + h) * P; a.tab.rows_after[m][h] = rows + (size_t)(2 * m + h) * nt; }
+    memcpy(&a.prm, &d->prm, sizeof(a.prm));
+    a.result_base = d->result_base; a.node_base = d->node_base;
+
+    Ctl h;                               // host copy of the control block
+    memset(&h, 0, sizeof(h));
+    auto carve_lists = [&](DevBuf& buf, size_t per_list) -> int {
+        if (buf.reserve((size_t)kOps * kClasses * per_list * 4 + 64, 0, stream, 1.25)) return -1;
+        unsigned int* base = static_cast<unsigned int*>(buf.p);
+        for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) a.lists[o][c] = base + (size_t)(o * kClasses + c) * per_list;
+        return 0;
+    };
+    auto bind_tables = [&]() {
+        a.recs = static_cast<BoxRec<2>*>(recs.p); a.work = static_cast<Work*>(work.p); a.cap_boxes = cap_boxes;
+        a.results = static_cast<ResultRec<2>*>(results.p); a.cap_results = cap_results;
+        a.nodes = static_cast<NodeRec<2>*>(nodes.p); a.cap_nodes = cap_nodes;
+    };
+
+    // round -1: adopt the level-0 boxes (they arrive packed, from yr_init_boxes) and queue their first pass
+    int cur = 0;
+    F2_TRY(carve_lists(lists[cur], (size_t)n0));
+    bind_tables();
+    a.data_in = d->data_in;
+    F2_TRY(be::launch_import(a, n0, stream));
+    F2_TRY(be::to_host(&h, ctlbuf.p, sizeof(Ctl), stream));
+    unsigned long long n_boxes = n0, n_results = 0, n_nodes = 0;
+    const double* data_in = d->data_in;
+    unsigned int* cur_lists[kOps][kClasses];
+    unsigned long long rounds = 0, launches = 2;
+    int out_arena = 0;
+    for (;;) {
+        unsigned long long n_res = 0, n_sub = 0;
+        for (int c = 0; c < kClasses; ++c) { n_res += h.n_list[0][c]; n_sub += h.n_list[1][c]; }
+        if (n_res + n_sub == 0) break;
+        if (++rounds > 1000000ull) { cleanup(false); return fail("yr_frontier_solve: round loop did not terminate"); }
+        const unsigned long long produced = n_res + 4 * n_sub;            // boxes the scalar step of this round may see
+        for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) cur_lists[o][c] = a.lists[o][c];
+        // capacities for everything this round can append
+        if (n_boxes + 4 * n_sub > cap_boxes) {
+            const size_t want = (size_t)((n_boxes + 4 * n_sub) * 1.5) + 4096;
+            F2_TRY(recs.reserve(want * sizeof(BoxRec<2>), n_boxes * sizeof(BoxRec<2>), stream, 1.0));
+            F2_TRY(work.reserve(want * sizeof(Work), n_boxes * sizeof(Work), stream, 1.0));
+            cap_boxes = want;
+        }
+        if (n_results + produced > cap_results) {
+            const size_t want = (size_t)((n_results + produced) * 1.5) + 1024;
+            F2_TRY(results.reserve(want * sizeof(ResultRec<2>), n_results * sizeof(ResultRec<2>), stream, 1.0));
+            cap_results = want;
+        }
+        if (n_nodes + produced > cap_nodes) {
+            const size_t want = (size_t)((n_nodes + produced) * 1.5) + 1024;
+            F2_TRY(nodes.reserve(want * sizeof(NodeRec<2>), n_nodes * sizeof(NodeRec<2>), stream, 1.0));
+            cap_nodes = want;
+        }
+        F2_TRY(arena[out_arena].reserve((size_t)(h.out_bound + 16) * 8, 0, stream, 1.25));
+        F2_TRY(carve_lists(lists[cur ^ 1], (size_t)produced));
+        bind_tables();
+        a.results = static_cast<ResultRec<2>*>(results.p) + n_results; a.cap_results = cap_results - n_results;
+        a.nodes = static_cast<NodeRec<2>*>(nodes.p) + n_nodes; a.cap_nodes = cap_nodes - n_nodes;
+        a.result_base = d->result_base + n_results; a.node_base = d->node_base + n_nodes;
+        a.data_in = data_in; a.data_out = static_cast<double*>(arena[out_arena].p); a.cap_data_out = arena[out_arena].cap / 8;
+        // per-round part of the control block: queues, bounds, arena cursor; slot counters restart at their totals
+        F2_TRY(be::dev_zero(ctlbuf.p, offsetof(Ctl, n_boxes), stream));
+        F2_TRY(be::dev_zero(&a.ctl->n_results, 2 * sizeof(unsigned long long), stream));
+        be::timer_mark(0, 1, stream);
+        for (int o = 0; o < kOps; ++o)
+            for (int c = 0; c < kClasses; ++c) {
+                if (!h.n_list[o][c]) continue;
+                if (h.need_max[o][c] + (o ? 2ull * panel_doubles((int)(h.ext_max[c] < 4 ? 4 : h.ext_max[c])) : 0ull) > kMaxNeed) { cleanup(false); return fail("yr_frontier_solve: a box exceeds the shared-memory budget"); }
+                F2_TRY(be::launch_tensor(a, o == 0 ? (int)kTRestrict : (int)kTSubdivide, c, cur_lists[o][c], h.n_list[o][c],
+                                         h.need_max[o][c], (int)(o ? h.ext_max[c] : 0), stream));
+                ++launches;
+            }
+        be::timer_mark(0, 0, stream);
+        be::Segments sg;
+        for (int c = 0; c < kClasses; ++c) { sg.list[c] = cur_lists[0][c]; sg.n[c] = h.n_list[0][c]; }
+        sg.child_lo = n_boxes; sg.child_bound = 4 * n_sub;
+        be::timer_mark(1, 1, stream);
+        F2_TRY(be::launch_scalar(a, sg, stream));
+        be::timer_mark(1, 0, stream);
+        ++launches;
+        F2_TRY(be::to_host(&h, ctlbuf.p, sizeof(Ctl), stream));
+        if (h.overflow) { cleanup(false); return fail("yr_frontier_solve: internal buffer overflow"); }
+        if (h.bad_mid) { cleanup(false); return fail("yr_frontier_solve: unexpected split point (nextTransformPoints)"); }
+        n_boxes = h.n_boxes; n_results += h.n_results; n_nodes += h.n_nodes;
+        data_in = a.data_out;
+        out_arena ^= 1; cur ^= 1;
+    }
+    out->results = results.p; out->n_results = n_results;
+    out->nodes = nodes.p; out->n_nodes = n_nodes;
+    out->rounds = rounds; out->launches = launches; out->slots = n_boxes;
+    yr_counters& c = out->counters;
+    c.n_results = n_results; c.n_nodes = n_nodes; c.boxes = h.boxes; c.zooms = h.zooms; c.subdivisions = h.subdivisions;
+    c.discard_const = h.dconst; c.discard_quad = h.dquad; c.discard_zoom = h.dzoom; c.entry_coeffs = h.entry_coeffs;
+    c.restrict_macs = h.restrict_macs; c.max_level = h.max_level;
+    be::timer_collect(&out->tensor_ms, &out->scalar_ms);
+    cleanup(true);
+    return 0;
+#undef F2_TRY
+}
+
+inline int release(yr_frontier_out* out, void* stream) {
+    if (!out) return 0;
+    if (out->results) yr_f2_backend::dev_free(out->results, stream);
+    if (out->nodes) yr_f2_backend::dev_free(out->nodes, stream);
+    out->results = nullptr; out->nodes = nullptr;
+    return 0;
+}
+
+}  // namespace yr_f2_host

@@ -1,0 +1,381 @@
+// CUDA backend (sm_100a) of the 2-D frontier pipeline: yr_frontier_solve / yr_frontier_release / yr_fetch.
+//
+// Kernels (see yr_f2.h for what a round is):
+//   f2_tensor_warp<OP,FMA>   4 independent warp teams per CTA, each with its own slice of dynamic shared memory
+//   f2_tensor_cta<OP,FMA>    one team of 128 / 256 threads per CTA
+//   f2_scalar_kernel         thread per box
+//   f2_import_kernel, f2_tables_kernel
+// Grids are sized to the machine: teams = min(boxes, SMs x resident teams), every team strides the list.
+// Compiled with -fmad=false like the rest of the library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "yr_f2_host.h"
+
+using namespace yr;
+using namespace yr::f2;
+
+namespace {
+
+struct WarpTeam {
+    int tid, nthreads;
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+    __device__ __forceinline__ double sum(double v) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        return v;
+    }
+    __device__ __forceinline__ unsigned long long bcast(unsigned long long v) { return __shfl_sync(0xffffffffu, v, 0); }
+    __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+};
+
+struct CtaTeam {
+    int tid, nthreads;
+    double* red;                   // [32] + one 64-bit slot at red[32]
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ double sum(double v) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        double t = 0.0;
+        const int nw = nthreads >> 5;
+        for (int w = 0; w < nw; ++w) t += red[w];
+        __syncthreads();
+        return t;
+    }
+    __device__ __forceinline__ unsigned long long bcast(unsigned long long v) {
+        unsigned long long* slot = reinterpret_cast<unsigned long long*>(red + 32);
+        if (tid == 0) *slot = v;
+        __syncthreads();
+        const unsigned long long r = *slot;
+        __syncthreads();
+        return r;
+    }
+    __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+};
+
+// copy the m = 0 subdivision matrices into shared memory, re-laid out for extent `snt` (<= table extent)
+__device__ void stage_submats(const Args& a, double* smat, int snt) {
+    const int nt = a.tab.nt;
+    const int B = (snt + 3) >> 2;
+    const int P = panel_doubles(snt);
+    for (int h = 0; h < 2; ++h) {
+        const double* src = a.tab.mat[0][h];
+        double* dst = smat + h * P;
+        for (int b = 0; b < B; ++b) {
+            const int cnt = (snt - 4 * b) * 4;
+            const double* s = src + panel_off(b, nt);
+            double* d = dst + panel_off(b, snt);
+            for (int e = threadIdx.x; e < cnt; e += blockDim.x) d[e] = s[e];
+        }
+    }
+    __syncthreads();
+}
+
+template <int OP, bool FMA>
+__global__ void __launch_bounds__(128) f2_tensor_warp(const Args a, const unsigned int* __restrict__ list, unsigned long long n,
+                                                      unsigned slice_doubles, int snt) {
+    extern __shared__ __align__(16) double dyn[];
+    double* smat = dyn;
+    int smat_doubles = 0;
+    if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a, smat, snt); }
+    const int w = threadIdx.x >> 5;
+    double* slice = dyn + smat_doubles + (size_t)w * slice_doubles;
+    WarpTeam tm; tm.tid = threadIdx.x & 31; tm.nthreads = 32;
+    const unsigned long long team = (unsigned long long)blockIdx.x * 4 + w, nteams = (unsigned long long)gridDim.x * 4;
+    unsigned long long macs = 0;
+    for (unsigned long long i = team; i < n; i += nteams) {
+        const unsigned int b = list[i];
+        if (OP == kTRestrict) restrict_box<FMA>(tm, a, b, slice, macs);
+        else subdivide_box<FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
+        __syncwarp();
+    }
+    if (tm.tid == 0 && macs) atomicAdd(&a.ctl->restrict_macs, macs);
+}
+
+template <int OP, bool FMA>
+__global__ void __launch_bounds__(256) f2_tensor_cta(const Args a, const unsigned int* __restrict__ list, unsigned long long n, int snt) {
+    extern __shared__ __align__(16) double dyn[];
+    __shared__ double red[34];
+    double* smat = dyn;
+    int smat_doubles = 0;
+    if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a, smat, snt); }
+    double* slice = dyn + smat_doubles;
+    CtaTeam tm; tm.tid = threadIdx.x; tm.nthreads = blockDim.x; tm.red = red;
+    unsigned long long macs = 0;
+    for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x) {
+        const unsigned int b = list[i];
+        if (OP == kTRestrict) restrict_box<FMA>(tm, a, b, slice, macs);
+        else subdivide_box<FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
+        __syncthreads();
+    }
+    if (tm.tid == 0 && macs) atomicAdd(&a.ctl->restrict_macs, macs);
+}
+
+struct DevAt {
+    __device__ __forceinline__ unsigned long long add(unsigned long long* p, unsigned long long v) const { return atomicAdd(p, v); }
+    __device__ __forceinline__ void max(unsigned long long* p, unsigned long long v) const { atomicMax(p, v); }
+};
+
+__device__ __forceinline__ unsigned long long warp_add(unsigned long long v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max(unsigned long long v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off); v = o > v ? o : v; }
+    return v;
+}
+
+// queue a warp's boxes with one atomic per (op, class) present in the warp, and flush its statistics
+__device__ void commit_warp(const Args& a, unsigned int b, const Decision& dc) {
+    const int lane = threadIdx.x & 31;
+    const int key = dc.op == kTNone ? -1 : op_slot(dc.op) * kClasses + dc.cls;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key >= 0) {
+        const int leader = __ffs(peers) - 1;
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const unsigned need = __reduce_max_sync(peers, (unsigned)dc.need);
+        const unsigned ext = __reduce_max_sync(peers, (unsigned)dc.ext);
+        unsigned long long base = 0;
+        const int slot = op_slot(dc.op);
+        if (lane == leader) {
+            base = atomicAdd(&a.ctl->n_list[slot][dc.cls], (unsigned long long)__popc(peers));
+            atomicMax(&a.ctl->need_max[slot][dc.cls], (unsigned long long)need);
+            if (slot == 1) atomicMax(&a.ctl->ext_max[dc.cls], (unsigned long long)ext);
+        }
+        base = __shfl_sync(peers, base, leader);
+        a.lists[slot][dc.cls][base + rank] = b;
+    }
+    const unsigned long long bsum = warp_add(dc.op == kTNone ? 0ull : dc.bound);
+    unsigned long long v[7] = {dc.boxes, dc.zooms, dc.dconst, dc.dquad, dc.dzoom, dc.coeffs, dc.subdiv};
+#pragma unroll
+    for (int q = 0; q < 7; ++q) v[q] = warp_add(v[q]);
+    const unsigned long long mx = warp_max(dc.maxlevel);
+    if (lane == 0) {
+        Ctl* c = a.ctl;
+        if (bsum) atomicAdd(&c->out_bound, bsum);
+        if (v[0]) atomicAdd(&c->boxes, v[0]);
+        if (v[1]) atomicAdd(&c->zooms, v[1]);
+        if (v[2]) atomicAdd(&c->dconst, v[2]);
+        if (v[3]) atomicAdd(&c->dquad, v[3]);
+        if (v[4]) atomicAdd(&c->dzoom, v[4]);
+        if (v[5]) atomicAdd(&c->entry_coeffs, v[5]);
+        if (v[6]) atomicAdd(&c->subdivisions, v[6]);
+        if (mx) atomicMax(&c->max_level, mx);
+    }
+}
+
+__global__ void __launch_bounds__(128) f2_scalar_kernel(const Args a, const yr_f2_backend::Segments sg) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Decision dc;
+    memset(&dc, 0, sizeof(dc));
+    bool have = false;
+    unsigned int b = 0;
+#pragma unroll
+    for (int c = 0; c < kClasses; ++c) {
+        if (!have) { if (i < sg.n[c]) { b = sg.list[c][i]; have = true; } else i -= sg.n[c]; }
+    }
+    if (!have) {
+        const unsigned long long nchild = a.ctl->n_boxes - sg.child_lo;
+        if (i < nchild) { b = (unsigned int)(sg.child_lo + i); have = true; }
+    }
+    if (have) scalar_step(a, b, dc, DevAt());
+    commit_warp(a, b, dc);
+}
+
+__global__ void __launch_bounds__(128) f2_import_kernel(const Args a, unsigned long long n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Decision dc;
+    memset(&dc, 0, sizeof(dc));
+    if (i < n) import_box(a, (unsigned int)i, dc, DevAt());
+    commit_warp(a, (unsigned int)i, dc);
+}
+
+// the four level-independent matrices: CTA m builds (mid, half) = (m >> 1, m & 1)
+__global__ void __launch_bounds__(256) f2_tables_kernel(double* mats, int* rows, int nt) {
+    __shared__ double red[34];
+    CtaTeam tm; tm.tid = threadIdx.x; tm.nthreads = blockDim.x; tm.red = red;
+    const int m = blockIdx.x;
+    const double mid = (m >> 1) ? kFirstSplit : 0.0;
+    const double alpha = (mid + 1) / 2, beta = (mid - 1) / 2;           // :1089
+    const bool upper = m & 1;
+    build_panels(tm, mats + (size_t)m * panel_doubles(nt), rows + (size_t)m * nt, nt, upper ? -beta : alpha, upper ? alpha : beta);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    char buf[400];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    yr_set_error(buf);
+    return -1;
+}
+
+struct Dev { int sm = 0, smem_cta = 0, smem_sm = 0; };
+const Dev& dev() {
+    static Dev d;
+    if (!d.sm) {
+        int id = 0; cudaGetDevice(&id);
+        cudaDeviceGetAttribute(&d.sm, cudaDevAttrMultiProcessorCount, id);
+        cudaDeviceGetAttribute(&d.smem_cta, cudaDevAttrMaxSharedMemoryPerBlockOptin, id);
+        cudaDeviceGetAttribute(&d.smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, id);
+        // keep freed frontier buffers in the stream-ordered pool across the per-round synchronisations
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return d;
+}
+
+// opt in to large dynamic shared memory, once per kernel (static shared memory counts against the CTA limit)
+constexpr size_t kStaticReserve = 1024;
+template <class K>
+int ensure_smem(K kernel, size_t bytes) {
+    static std::vector<const void*> done;
+    if (bytes <= 48 * 1024) return 0;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (const void* k : done) if (k == key) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev().smem_cta - (int)kStaticReserve);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    done.push_back(key);
+    return 0;
+}
+
+template <int OP, bool FMA>
+int launch_tensor_t(const Args& a, int cls, const unsigned int* list, unsigned long long n, unsigned long long need, int ext, cudaStream_t st) {
+    const Dev& d = dev();
+    const int snt = (OP == kTSubdivide) ? (ext < 4 ? 4 : ext) : 0;
+    const size_t smat = (OP == kTSubdivide) ? (size_t)2 * panel_doubles(snt) * 8 : 0;
+    const size_t slice = ((size_t)need + 1) & ~(size_t)1;
+    if (cls <= 1) {
+        const size_t smem = smat + 4 * slice * 8;
+        if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: warp-team launch exceeds shared memory"); return -1; }
+        if (ensure_smem(f2_tensor_warp<OP, FMA>, smem)) return -1;
+        long per_sm = (long)((size_t)d.smem_sm / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
+        unsigned long long want = (n + 3) / 4, cap = (unsigned long long)d.sm * per_sm;
+        const unsigned grid = (unsigned)(want < cap ? want : cap);
+        f2_tensor_warp<OP, FMA><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
+    } else {
+        const int threads = class_threads(cls);
+        const size_t smem = smat + slice * 8;
+        if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: CTA-team launch exceeds shared memory"); return -1; }
+        if (ensure_smem(f2_tensor_cta<OP, FMA>, smem)) return -1;
+        long per_sm = (long)((size_t)d.smem_sm / (smem + 1024)); const long tcap = 2048 / threads; if (per_sm > tcap) per_sm = tcap; if (per_sm < 1) per_sm = 1;
+        unsigned long long cap = (unsigned long long)d.sm * per_sm;
+        const unsigned grid = (unsigned)(n < cap ? n : cap);
+        f2_tensor_cta<OP, FMA><<<grid, threads, smem, st>>>(a, list, n, snt);
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "f2 tensor launch");
+}
+
+struct Timer {
+    int enabled = 0;
+    std::vector<cudaEvent_t> ev[2];          // begin/end pairs per family
+    size_t used[2] = {0, 0};
+} g_timer;
+
+}  // namespace
+
+namespace yr_f2_backend {
+
+void* dev_alloc(size_t bytes, void* stream) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, (cudaStream_t)stream);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMallocAsync"); return nullptr; }
+    return p;
+}
+void dev_free(void* p, void* stream) { if (p) cudaFreeAsync(p, (cudaStream_t)stream); }
+int dev_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaMemcpyAsync (d2d)");
+}
+int dev_zero(void* p, size_t bytes, void* stream) {
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "cudaMemsetAsync");
+}
+int to_host(void* dst, const void* src, size_t bytes, void* stream) {
+    static void* pinned = nullptr; static size_t cap = 0;
+    if (bytes <= 4096) {
+        if (!pinned) { cudaError_t e0 = cudaHostAlloc(&pinned, 4096, cudaHostAllocDefault); if (e0 != cudaSuccess) return cuda_fail(e0, "cudaHostAlloc"); cap = 4096; }
+        cudaError_t e = cudaMemcpyAsync(pinned, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "control block read-back");
+        memcpy(dst, pinned, bytes);
+        return 0;
+    }
+    (void)cap;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "device -> host copy");
+}
+
+int launch_tables(double* mats, int* rows, int nt, void* stream) {
+    f2_tables_kernel<<<4, 256, 0, (cudaStream_t)stream>>>(mats, rows, nt);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "f2_tables_kernel launch");
+}
+
+int launch_import(const Args& a, unsigned long long n, void* stream) {
+    f2_import_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, n);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "f2_import_kernel launch");
+}
+
+int launch_tensor(const Args& a, int op, int cls, const unsigned int* list, unsigned long long n, unsigned long long need, int ext, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fma = a.prm.use_fma != 0;
+    if (op == kTRestrict) return fma ? launch_tensor_t<kTRestrict, true>(a, cls, list, n, need, ext, st) : launch_tensor_t<kTRestrict, false>(a, cls, list, n, need, ext, st);
+    return fma ? launch_tensor_t<kTSubdivide, true>(a, cls, list, n, need, ext, st) : launch_tensor_t<kTSubdivide, false>(a, cls, list, n, need, ext, st);
+}
+
+int launch_scalar(const Args& a, const Segments& s, void* stream) {
+    unsigned long long total = s.child_bound;
+    for (int c = 0; c < kClasses; ++c) total += s.n[c];
+    if (!total) return 0;
+    f2_scalar_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, s);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "f2_scalar_kernel launch");
+}
+
+void timer_reset(int enable) { g_timer.enabled = enable; g_timer.used[0] = g_timer.used[1] = 0; }
+void timer_mark(int which, int begin, void* stream) {
+    if (!g_timer.enabled) return;
+    (void)begin;
+    auto& v = g_timer.ev[which];
+    if (g_timer.used[which] == v.size()) { cudaEvent_t e; cudaEventCreate(&e); v.push_back(e); }
+    cudaEventRecord(v[g_timer.used[which]++], (cudaStream_t)stream);
+}
+void timer_collect(double* tensor_ms, double* scalar_ms) {
+    double out[2] = {0.0, 0.0};
+    if (g_timer.enabled)
+        for (int w = 0; w < 2; ++w)
+            for (size_t i = 0; i + 1 < g_timer.used[w]; i += 2) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, g_timer.ev[w][i], g_timer.ev[w][i + 1]) == cudaSuccess) out[w] += ms;
+            }
+    *tensor_ms = out[0]; *scalar_ms = out[1];
+}
+
+}  // namespace yr_f2_backend
+
+extern "C" {
+
+int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) {
+    if (!d || !out) { yr_set_error("null descriptor"); return -1; }
+    return yr_f2_host::solve(d, out, stream);
+}
+
+int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
+int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
+
+int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void* stream) {
+    if (!bytes) return 0;
+    return yr_f2_backend::to_host(host_dst, dev_src, (size_t)bytes, stream);
+}
+
+}  // extern "C"

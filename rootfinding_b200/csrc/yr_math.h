@@ -21,7 +21,7 @@
 
 #if defined(__CUDACC__)
 #define YR_HD __host__ __device__ __forceinline__
-#define YR_HDN __host__ __device__ __noinline__      /* one copy: instruction-cache footprint matters (profiles/) */
+#define YR_HDN static __host__ __device__ __noinline__   /* one copy per translation unit: instruction-cache footprint matters (profiles/) */
 #else
 #define YR_HD inline
 #define YR_HDN inline

@@ -138,7 +138,9 @@ class SubdivisionEngine:
         self.warp_min_items = int(os.environ.get("YR_WARP_MIN_ITEMS", "1024"))  # fewer boxes than this: CTA-per-box (latency)
         self.warp_teams = int(os.environ.get("YR_WARP_TEAMS", "16"))          # warp-teams per SM (register bound: 16 x 32 x 128)
         self.warp_mode = int(os.environ.get("YR_WARP_MODE", "1"))             # 1: independent warp-teams, 2: lock-step CTA
-        self.pipeline = int(os.environ.get("YR_PIPELINE", "1"))               # 0: fused kernel per level, 1: phase-split kernels
+        # 2: round-based 2-D frontier pipeline (yr_frontier_solve) where it applies, else phase-split;
+        # 1: phase-split kernels per level; 0: one fused kernel per level
+        self.pipeline = int(os.environ.get("YR_PIPELINE", "2"))
 
     def params(self, **kw):
         p = _lib.default_params(self.lib)
@@ -235,6 +237,9 @@ class SolveSession:
         self.retry_ms = 0.0              # time of launches that overflowed their optimistic buffers
         self._reserve("results", max(256, 4 * self.nsys))
         self._reserve("nodes", max(256, 4 * self.nsys))
+        # 2-D, plain arithmetic, tensors that fit shared memory: the round-based frontier pipeline serves the session
+        self.use_frontier = bool(engine.pipeline == 2 and D == 2 and not prm.exact and self.nsys > 0
+                                 and self.lib.yr_frontier_fits(int(self.sys_max_extent.max())))
 
     # -- growable append-only device arrays ------------------------------------------------
     def _reserve(self, which, want):
@@ -307,6 +312,8 @@ class SolveSession:
         D, m, eng = self.dim, self.mem, self.eng
         first_result = self.n_results
         recs, data, c = self._init_boxes(jobs)
+        if self.use_frontier:
+            return self._run_frontier(recs, data, c, first_result)
         n_in, data_used = c["n_children"], c["data_used"]
         big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
         fan = 1 << D
@@ -320,7 +327,7 @@ class SolveSession:
                 # the frontier's growth factor changes slowly from level to level: last factor + 30 %
                 cap_recs = min(worst_recs, max(4096, int(1.3 * growth[0] * n_in) + 1024))
                 cap_data = min(worst_data, max(1 << 16, int(1.3 * growth[1] * data_used) + (1 << 16)))
-            pipeline = eng.pipeline
+            pipeline = min(eng.pipeline, 1)
             if pipeline == 1 and warp == 2:
                 warp = 1                                                 # lock-step exists for the fused kernel only
             work = m.empty(int(self.lib.yr_level_work_bytes(D, n_in))) if pipeline == 1 else None
@@ -383,6 +390,45 @@ class SolveSession:
             n_in, data_used = c["n_children"], c["data_used"]
             big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
         return first_result, self.n_results - first_result
+
+    def _run_frontier(self, recs, data, c, first_result):
+        """2-D systems: the whole search in one call (include/yroots_b200.h: yr_frontier_solve)."""
+        m, lib = self.mem, self.lib
+        d = _lib.YrFrontierDesc()
+        d.dim, d.time_kernels = 2, int(bool(self.time_kernels))
+        d.recs_in, d.data_in, d.n_in = recs.ptr, data.ptr, int(c["n_children"])
+        d.max_extent = int(c["max_child_extent"])
+        d.result_base, d.node_base = self.n_results, self.n_nodes
+        d.prm = self.prm
+        out = _lib.YrFrontierOut()
+        stream = m.stream()
+        _lib.check(lib, lib.yr_frontier_solve(C.byref(d), C.byref(out), stream), "yr_frontier_solve")
+        try:
+            nres, nnod = int(out.n_results), int(out.n_nodes)
+            self.results(), self.nodes()                          # anything earlier level launches left on the device
+            if nres:
+                host = np.empty(nres, dtype=self.rdt)
+                _lib.check(lib, lib.yr_fetch(host.ctypes.data, out.results, host.nbytes, stream), "yr_fetch")
+                self._results_host = np.concatenate([self._results_host, host])
+                m.d2h_bytes += host.nbytes
+            if nnod:
+                host = np.empty(nnod, dtype=self.ndt)
+                _lib.check(lib, lib.yr_fetch(host.ctypes.data, out.nodes, host.nbytes, stream), "yr_fetch")
+                self._nodes_host = np.concatenate([self._nodes_host, host])
+                m.d2h_bytes += host.nbytes
+        finally:
+            lib.yr_frontier_release(C.byref(out), stream)
+        self.n_results += nres
+        self.n_nodes += nnod
+        cc = {k: int(getattr(out.counters, k)) for k in _lib.COUNTER_FIELDS}
+        self.stats.add(cc)
+        self.stats.levels += int(out.rounds)
+        self.stats.launches += int(out.launches)
+        self.stats.rounds = getattr(self.stats, "rounds", 0) + int(out.rounds)
+        if self.time_kernels:
+            self.kernel_ms.append((float(out.tensor_ms), 16 * cc["entry_coeffs"], cc["boxes"]))
+            self.scalar_ms = getattr(self, "scalar_ms", 0.0) + float(out.scalar_ms)
+        return first_result, nres
 
     def unit_jobs(self, systems=None):
         """One job per system: the whole unit cube (ChebyshevSubdivisionSolver.py:1423)."""

@@ -25,7 +25,9 @@ for rep in range(reps):
     st = sess.stats
     kms = sum(k[0] for k in sess.kernel_ms)
     print(f"rep {rep}: B={B} deg={deg} dim={dim} boxes {st.boxes} time {dt*1e3:.1f} ms kernels {kms:.1f} ms -> {st.boxes/dt:.3e} boxes/s "
-          f"({16*st.entry_coeffs/kms/1e6:.1f} GB/s algorithmic) retries {st.retries}")
+          f"({16*st.entry_coeffs/kms/1e6:.1f} GB/s algorithmic) retries {st.retries} "
+          f"rounds {getattr(st, 'rounds', 0)} launches {st.launches} scalar {getattr(sess, 'scalar_ms', 0.0):.1f} ms "
+          f"zooms {st.zooms} subdiv {st.subdivisions} discards c/q/z {st.discard_const}/{st.discard_quad}/{st.discard_zoom}")
 for (lvl, k) in zip(st.per_level, sess.kernel_ms):
     print("  level: in %7d out %7d res %6d smem %s ctas %5d thr %3d ws %6d warp %s | %8.3f ms %8.1f GB/s %9.0f boxes/ms" %
           (lvl + (k[0], k[1] / k[0] / 1e6, k[2] / k[0])))

@@ -14,6 +14,7 @@
 
 #include "../../rootfinding_b200/csrc/yr_api_impl.h"
 #include "../../rootfinding_b200/csrc/yr_approx.h"
+#include "../../rootfinding_b200/csrc/yr_f2_host.h"
 
 namespace {
 
@@ -306,3 +307,136 @@ int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t 
 }
 
 }  // namespace yr_backend
+
+// ---- 2-D frontier pipeline (yr_f2.h) on pthreads ---------------------------------------------------
+namespace {
+
+struct F2Team {
+    int tid, nthreads;
+    Team* team;
+    void sync() { team->bar.wait(); }
+    double sum(double v) {
+        team->scratch[tid] = v; sync();
+        double t = 0; for (int i = 0; i < nthreads; ++i) t += team->scratch[i];
+        sync(); return t;
+    }
+    unsigned long long bcast(unsigned long long v) {
+        if (tid == 0) memcpy(&team->scratch[0], &v, 8);
+        sync();
+        unsigned long long r; memcpy(&r, &team->scratch[0], 8);
+        sync(); return r;
+    }
+    unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+};
+
+struct F2At {
+    unsigned long long add(unsigned long long* p, unsigned long long v) const { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+    void max(unsigned long long* p, unsigned long long v) const { if (*p < v) *p = v; }
+};
+
+template <class Body>
+void f2_run_team(int T, Body body) {
+    Team team; team.T = T; team.lanes = T; team.bar.n = T; team.scratch.assign(T + 2, 0.0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t]() { F2Team tm; tm.tid = t; tm.nthreads = T; tm.team = &team; body(tm); });
+    for (auto& x : th) x.join();
+}
+
+void f2_flush(const yr::f2::Args& a, const yr::f2::Decision& dc) {
+    yr::f2::Ctl* c = a.ctl;
+    c->boxes += dc.boxes; c->zooms += dc.zooms; c->dconst += dc.dconst; c->dquad += dc.dquad; c->dzoom += dc.dzoom;
+    c->entry_coeffs += dc.coeffs; c->subdivisions += dc.subdiv;
+    if (dc.maxlevel > c->max_level) c->max_level = dc.maxlevel;
+}
+
+}  // namespace
+
+namespace yr_f2_backend {
+void* dev_alloc(size_t bytes, void*) { return malloc(bytes ? bytes : 16); }
+void dev_free(void* p, void*) { free(p); }
+int dev_copy(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
+int dev_zero(void* p, size_t bytes, void*) { memset(p, 0, bytes); return 0; }
+int to_host(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
+
+int launch_tables(double* mats, int* rows, int nt, void*) {
+    const int P = yr::f2::panel_doubles(nt);
+    for (int m = 0; m < 4; ++m) {
+        const double mid = (m >> 1) ? yr::kFirstSplit : 0.0;
+        const double alpha = (mid + 1) / 2, beta = (mid - 1) / 2;
+        const bool upper = m & 1;
+        f2_run_team(4, [&](F2Team& tm) { yr::f2::build_panels(tm, mats + (size_t)m * P, rows + (size_t)m * nt, nt, upper ? -beta : alpha, upper ? alpha : beta); });
+    }
+    return 0;
+}
+
+int launch_import(const yr::f2::Args& a, unsigned long long n, void*) {
+    for (unsigned long long i = 0; i < n; ++i) {
+        yr::f2::Decision dc; memset(&dc, 0, sizeof(dc));
+        yr::f2::import_box(a, (unsigned int)i, dc, F2At());
+        yr::f2::commit_decision(a, (unsigned int)i, dc, F2At());
+    }
+    return 0;
+}
+
+int launch_tensor(const yr::f2::Args& a, int op, int cls, const unsigned int* list, unsigned long long n,
+                  unsigned long long need, int ext, void*) {
+    const int T = cls <= 1 ? env_int("YR_EMUL_LANES", 4) : env_int("YR_EMUL_THREADS", 8);
+    // the m = 0 matrices re-laid out for `ext`, as the CUDA kernels stage them in shared memory
+    std::vector<double> smat;
+    int snt = 0;
+    if (op == yr::f2::kTSubdivide) {
+        snt = ext < 4 ? 4 : ext;
+        const int P = yr::f2::panel_doubles(snt), B = (snt + 3) >> 2;
+        smat.assign(2 * (size_t)P, 0.0);
+        for (int h = 0; h < 2; ++h)
+            for (int b = 0; b < B; ++b)
+                memcpy(&smat[(size_t)h * P + yr::f2::panel_off(b, snt)], a.tab.mat[0][h] + yr::f2::panel_off(b, a.tab.nt), (size_t)(snt - 4 * b) * 4 * 8);
+    }
+    std::vector<double> slice((size_t)need + 8, 0.0);
+    const bool fma = a.prm.use_fma != 0;
+    unsigned long long macs_total = 0;
+    f2_run_team(T, [&](F2Team& tm) {
+        unsigned long long macs = 0;
+        for (unsigned long long i = 0; i < n; ++i) {
+            const unsigned int b = list[i];
+            if (op == yr::f2::kTRestrict) { if (fma) yr::f2::restrict_box<true>(tm, a, b, slice.data(), macs); else yr::f2::restrict_box<false>(tm, a, b, slice.data(), macs); }
+            else {
+                const double* lo = smat.data(); const double* hi = smat.data() + yr::f2::panel_doubles(snt);
+                if (fma) yr::f2::subdivide_box<true>(tm, a, b, slice.data(), lo, hi, snt, macs); else yr::f2::subdivide_box<false>(tm, a, b, slice.data(), lo, hi, snt, macs);
+            }
+            tm.sync();
+        }
+        if (tm.tid == 0) macs_total = macs;
+    });
+    a.ctl->restrict_macs += macs_total;
+    return 0;
+}
+
+int launch_scalar(const yr::f2::Args& a, const Segments& s, void*) {
+    auto one = [&](unsigned int b) {
+        yr::f2::Decision dc; memset(&dc, 0, sizeof(dc));
+        yr::f2::scalar_step(a, b, dc, F2At());
+        yr::f2::commit_decision(a, b, dc, F2At());
+        f2_flush(a, dc);
+    };
+    for (int c = 0; c < yr::f2::kClasses; ++c) for (unsigned long long i = 0; i < s.n[c]; ++i) one(s.list[c][i]);
+    const unsigned long long hi = a.ctl->n_boxes;
+    for (unsigned long long b = s.child_lo; b < hi; ++b) one((unsigned int)b);
+    return 0;
+}
+
+void timer_reset(int) {}
+void timer_mark(int, int, void*) {}
+void timer_collect(double* t, double* s) { *t = 0; *s = 0; }
+}  // namespace yr_f2_backend
+
+extern "C" {
+int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) {
+    if (!d || !out) return yr_api::fail("null descriptor");
+    return yr_f2_host::solve(d, out, stream);
+}
+int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
+int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
+int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void*) { memcpy(host_dst, dev_src, bytes); return 0; }
+}

@@ -183,7 +183,9 @@ def test_engine_overflow_retry_and_global_workspace(emu):
     systems = H.seeded_systems(2, 10, 2)
     errs = [np.full(2, 2. ** -52)] * 2
     old = (emu.worst_case_budget, emu.max_smem_cta)
+    pipe = emu.pipeline
     try:
+        emu.pipeline = 1                        # the level-synchronous pipeline (serves dim != 2 and exact mode)
         emu.worst_case_budget = 0               # never allocate the worst case up front
         emu.max_smem_cta = 1024                 # nothing fits "shared memory"
         sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
@@ -191,6 +193,7 @@ def test_engine_overflow_retry_and_global_workspace(emu):
         assert not any(lvl[3] for lvl in sess.stats.per_level)       # every level ran from the global workspace
     finally:
         emu.worst_case_budget, emu.max_smem_cta = old
+        emu.pipeline = pipe
 
 
 def test_argument_errors():
@@ -207,7 +210,9 @@ def test_emulated_warp_per_box(emu, dim, deg, N, mode):
     systems = H.seeded_systems(dim, deg, N)
     errs = [np.full(dim, 2. ** -52)] * N
     old = emu.warp_min_items
+    pipe = emu.pipeline
     try:
+        emu.pipeline = 1
         emu.warp_min_items = 1                  # every level runs warp-per-box
         emu.warp_mode = mode
         sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
@@ -216,13 +221,16 @@ def test_emulated_warp_per_box(emu, dim, deg, N, mode):
     finally:
         emu.warp_min_items = old
         emu.warp_mode = 1
+        emu.pipeline = pipe
 
 
 def test_emulated_warp_shuffle_matrix_build(emu):
     """32-lane warp-teams exercise the shuffle-based restriction-matrix build (extents <= warp width);
     the search tree and roots must not change, and restrictions stay bit-exact."""
     old = (emu.warp_min_items, os.environ.get("YR_EMUL_LANES"), os.environ.get("YR_EMUL_THREADS"))
+    pipe = emu.pipeline
     try:
+        emu.pipeline = 1
         emu.warp_min_items = 1
         os.environ["YR_EMUL_LANES"] = "32"
         os.environ["YR_EMUL_THREADS"] = "32"
@@ -233,5 +241,50 @@ def test_emulated_warp_shuffle_matrix_build(emu):
         assert all(lvl[7] for lvl in sess.stats.per_level)
     finally:
         emu.warp_min_items = old[0]
+        emu.pipeline = pipe
         os.environ["YR_EMUL_LANES"] = old[1] or "4"
         os.environ["YR_EMUL_THREADS"] = old[2] or "8"
+
+
+@pytest.mark.parametrize("deg,N,kind", [(5, 4, "randn"), (10, 3, "randn"), (12, 2, "randint"), (20, 2, "randn")])
+def test_emulated_frontier_pipeline(emu, deg, N, kind):
+    """The round-based 2-D frontier pipeline (yr_frontier_solve): same search tree and roots as the oracle."""
+    systems = H.seeded_systems(2, deg, N, kind)
+    errs = [np.full(2, 2. ** -52)] * N
+    assert emu.pipeline == 2
+    sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
+    assert sess.use_frontier and sess.stats.rounds > 0
+    assert sess.stats.boxes == boxes and worst < 1e-14
+
+
+def test_emulated_frontier_matches_level_pipeline(emu):
+    """Both device pipelines visit the same boxes and report identical records (restrictions are bit-exact in both)."""
+    systems = H.seeded_systems(2, 9, 3)
+    errs = [np.full(2, 2. ** -52)] * 3
+    pipe = emu.pipeline
+    try:
+        out = []
+        for p in (2, 1):
+            emu.pipeline = p
+            roots, sess = S.solve_batch(systems, errs, engine=emu, return_session=True)
+            out.append((roots, sess.stats.boxes, sess.stats.zooms, sess.stats.subdivisions))
+        assert out[0][1:] == out[1][1:]
+        for a, b in zip(out[0][0], out[1][0]):
+            assert a.shape == b.shape and np.max(np.abs(a - b), initial=0.0) < 1e-15
+    finally:
+        emu.pipeline = pipe
+
+
+def test_emulated_frontier_fma_and_unit_extents(emu):
+    """use_fma and degenerate shapes (a polynomial that is constant along an axis) through the frontier pipeline."""
+    rng = np.random.RandomState(5)
+    f = rng.randn(6, 1)                          # depends on x only
+    g = rng.randn(1, 7)                          # depends on y only
+    errs = [np.full(2, 2. ** -52)]
+    sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, [[f, g]], errs, engine=emu)
+    assert sess.use_frontier and sess.stats.boxes == boxes
+    systems = H.seeded_systems(2, 8, 2)
+    got = S.solve_batch(systems, [np.full(2, 2. ** -52)] * 2, use_fma=True, engine=emu)
+    want = S.solve_batch(systems, [np.full(2, 2. ** -52)] * 2, engine=emu)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.max(np.abs(a - b), initial=0.0) < 1e-10

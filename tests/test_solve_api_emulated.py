@@ -27,8 +27,17 @@ def test_chebfun_suite_emulated(yr, tid, golden_dir):
         warnings.simplefilter("ignore")
         roots = np.asarray(yr.solve(funcs, a, b), dtype=float).reshape(-1, 2)
     ref = z[f"roots_{tid}"]
-    assert len(roots) == len(ref)
     truth = cc.polished_roots(tid, golden_dir)
+    if tid in cc.COUNT_EXEMPT:
+        # 6.1 has a double root at the origin: the reference reports it as one or as two roots 2e-8 apart depending
+        # on a 1-ulp perturbation of its input, and its own suite exempts the system from the count and
+        # norm checks (chebfun2_suite.py:168,:202).  Accept either count; every reported root must be a reference root.
+        assert len(roots) in (len(ref), len(truth))
+        assert cc.residual_check(funcs, roots, cc.resid_tol(tid))
+        for r in roots:
+            assert np.min(np.max(np.abs(ref - r), axis=1)) < 1e-7
+        return
+    assert len(roots) == len(ref)
     if tid not in cc.COUNT_EXEMPT:
         assert len(roots) == len(truth) == cc.EXPECTED_COUNT[tid]
         ok, n0, n1 = cc.norm_check(roots, truth, cc.norm_tol(tid))
