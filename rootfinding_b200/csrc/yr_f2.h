@@ -61,7 +61,7 @@ YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
 
 YR_HD int class_threads(int cls) { return cls <= 1 ? 32 : (cls == 2 ? 128 : 256); }
 YR_HD int class_of(unsigned long long need) {         // need = per-team shared-memory doubles
-    return need <= 768ull ? 0 : (need <= 2048ull ? 1 : (need <= 6144ull ? 2 : 3));
+    return need <= 1024ull ? 0 : (need <= 2560ull ? 1 : (need <= 7168ull ? 2 : 3));
 }
 constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
 
@@ -75,7 +75,7 @@ YR_HD int panel_doubles(int nt) { const int B = (nt + 3) >> 2; return panel_off(
 YR_HD int panel_index(int i, int k, int nt) { const int b = i >> 2; return panel_off(b, nt) + ((k - 4 * b) << 2) + (i & 3); }
 
 YR_HD unsigned long long need_restrict(int T, int n0max, int n1max) {
-    return 2ull * T + panel_doubles(n0max) + panel_doubles(n1max) + (unsigned)((n0max + n1max + 1) / 2) + 2;
+    return 3ull * T + panel_doubles(n0max) + panel_doubles(n1max) + (unsigned)((n0max + n1max + 1) / 2) + 2;
 }
 YR_HD unsigned long long need_subdivide(int T) { return 4ull * T; }
 
@@ -168,6 +168,79 @@ YR_DEV void build_panels(Team& tm, double* Cp, int* rows_after, int nt, double a
     }
 }
 
+// The same matrix built by ONE warp: lane i keeps row i of the two live columns in registers, neighbours come
+// from shuffles, the lane walks its own panel row with a running pointer.  `seg` lanes form a segment that builds
+// one matrix (seg = 32: one matrix per warp; seg = 16: lanes 0-15 build matrix A while lanes 16-31 build matrix B,
+// both loops fused).  Same expressions, same order, same truncation rule as build_panels -> bit-identical.
+// Requires nt <= seg for every matrix built.  `W` provides lane, wshfl_up/down/idx(v, delta|src, width), wsync().
+struct PanelJob { double* Cp; int* rows_after; int nt; double alpha, beta; };
+
+template <class W>
+YR_DEV void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb, int seg) {
+    const int lane = w.lane;
+    const bool second = (seg == 16) && (lane >= 16);
+    const PanelJob& j = second ? jb : ja;
+    const int i = (seg == 16) ? (lane & 15) : lane;
+    const int nt = j.nt;
+    const int kmax = (seg == 16) ? (ja.nt > jb.nt ? ja.nt : jb.nt) : ja.nt;
+    const int B4 = ((nt + 3) >> 2) << 2;                       // rows that exist in the panels (zero rows pad the last one)
+    const int b = i >> 2;
+    double* ptr = j.Cp + panel_off(b, nt) + (i & 3);           // entry (i, k) lives at ptr[(k - 4b) * 4]
+    const double alpha = j.alpha, beta = j.beta, beta2 = 2 * beta;
+    const bool live = i < B4 && nt > 0;
+    double prev2 = (i == 0) ? 1.0 : 0.0;                       // column 0
+    double prev = (i == 0) ? beta : (i == 1 ? alpha : 0.0);    // column 1
+    if (live && b == 0) { ptr[0] = prev2; if (nt >= 2) ptr[4] = prev; }
+    if (i == 0 && nt > 0) { j.rows_after[0] = 1; if (nt >= 2) j.rows_after[1] = 2; }
+    int rows = 2;
+    for (int k = 2; k < kmax; ++k) {
+        double cm1 = w.wshfl_up(prev, 1, seg), cp1 = w.wshfl_down(prev, 1, seg);
+        if (i == 0) cm1 = 0.0;
+        if (i + 1 > k - 1 || i + 1 >= seg) cp1 = 0.0;
+        double val = 0.0;
+        int grow = 0;
+        if (i <= rows) {
+            double t;
+            if (i == 0) t = alpha * cp1;
+            else if (i == 1) t = alpha * (2 * cm1 + cp1);
+            else t = alpha * (cm1 + cp1);
+            val = (-prev2 + t) + beta2 * prev;
+            if (i == rows) {                                   // the reference's finalVal
+                val = alpha * cm1;
+                if (fabs(val) > 1e-16) grow = 1; else val = 0.0;
+            }
+        }
+        grow = w.wshfl_idx(grow, rows < seg ? rows : 0, seg);
+        if (k < nt) {
+            if (live && k >= 4 * b) ptr[(k - 4 * b) << 2] = val;
+            prev2 = prev; prev = val;
+            rows += grow;
+            if (i == (k & (seg - 1))) j.rows_after[k] = rows;
+        }
+    }
+    w.wsync();
+}
+
+// Team-level dispatcher: builds up to two matrices (either may be skipped with nt = 0).
+template <class Team>
+YR_DEV void build_two(Team& tm, const PanelJob& j0, const PanelJob& j1) {
+    const int big = j0.nt > j1.nt ? j0.nt : j1.nt;
+    if (Team::kShuffle && tm.lanes == 32 && big <= 32) {
+        if (tm.warps >= 2) {                                      // one warp per matrix
+            if (tm.warp == 0 && j0.nt > 0) build_panels_warp(tm, j0, j0, 32);
+            if (tm.warp == 1 && j1.nt > 0) build_panels_warp(tm, j1, j1, 32);
+        } else if (big <= 16 && j0.nt > 0 && j1.nt > 0) build_panels_warp(tm, j0, j1, 16);
+        else {
+            if (j0.nt > 0) build_panels_warp(tm, j0, j0, 32);
+            if (j1.nt > 0) build_panels_warp(tm, j1, j1, 32);
+        }
+        tm.sync();
+        return;
+    }
+    if (j0.nt > 0) build_panels(tm, j0.Cp, j0.rows_after, j0.nt, j0.alpha, j0.beta);
+    if (j1.nt > 0) build_panels(tm, j1.Cp, j1.rows_after, j1.nt, j1.alpha, j1.beta);
+}
+
 // ---- one restriction pass ---------------------------------------------------------------------------
 // src element (k, f) at src[k*sk + f*sf], k < n;  dst element (i, f) at dst[i*dk + f*df], i < r;  f < F.
 // An item is (row block b, fiber f): four output rows from one sweep over source rows 4b .. n-1.
@@ -201,7 +274,7 @@ YR_DEV double restrict_pass(Team& tm, const double* src, int sk, int sf, double*
         f += tm.nthreads;
         while (f >= F) { f -= F; ++b; }
     }
-    return tm.sum(asum);
+    return tm.sum_sync(asum);            // also the barrier that publishes dst
 }
 
 template <class Team>
@@ -226,7 +299,9 @@ YR_DEV double view_abs_sum(Team& tm, const double* M, int n0, int n1, int ld) {
 }
 
 // What every produced tensor leaves behind: low-order coefficients and the outcome of trimMs (:1131-1171)
-// for error `err` -- collective; thread 0 holds the results.
+// for error `err`.  Runs on the team's LEAD WARP only (callers guard with tm.warp == 0); lane 0 == thread 0
+// holds the results.  A trailing plane can only be dropped when its abs-sum is below the budget, so a single
+// element at or above the budget settles the (common) no-trim case with one vote instead of a reduction.
 struct Epilogue { double low[6]; int t0, t1; double tsum, terr; };
 
 template <class Team>
@@ -240,25 +315,29 @@ YR_DEV void tensor_epilogue(Team& tm, const double* M, int n0, int n1, int ld, d
     ep.low[5] = n1 > 2 ? M[2] : 0.0;
     int t0 = n0, t1 = n1;
     double budget = prm.trim_abs_tol + err * prm.trim_rel_tol;
-    bool trimmed = false;
+    double removed = 0.0;
     if (prm.trim) {
         while (t0 > 3) {                                      // axis 0: trailing rows
             double s = 0.0;
             const double* row = M + (t0 - 1) * ld;
-            for (int j = tm.tid; j < t1; j += tm.nthreads) s += fabs(row[j]);
-            s = tm.sum(s);
-            if (s < budget) { t0 -= 1; budget -= s; err += s; trimmed = true; } else break;
+            bool big = false;
+            for (int j = tm.lane; j < t1; j += tm.lanes) { const double v = fabs(row[j]); s += v; big = big || !(v < budget); }
+            if (tm.wany(big)) break;
+            s = tm.wsum(s);
+            if (s < budget) { t0 -= 1; budget -= s; err += s; removed += s; } else break;
         }
         while (t1 > 3) {                                      // axis 1: trailing columns of the remaining rows
             double s = 0.0;
             const double* col = M + (t1 - 1);
-            for (int i = tm.tid; i < t0; i += tm.nthreads) s += fabs(col[i * ld]);
-            s = tm.sum(s);
-            if (s < budget) { t1 -= 1; budget -= s; err += s; trimmed = true; } else break;
+            bool big = false;
+            for (int i = tm.lane; i < t0; i += tm.lanes) { const double v = fabs(col[i * ld]); s += v; big = big || !(v < budget); }
+            if (tm.wany(big)) break;
+            s = tm.wsum(s);
+            if (s < budget) { t1 -= 1; budget -= s; err += s; removed += s; } else break;
         }
     }
     ep.t0 = t0; ep.t1 = t1; ep.terr = err;
-    ep.tsum = trimmed ? view_abs_sum(tm, M, t0, t1, ld) : sumabs;
+    ep.tsum = sumabs - removed;          // == sum over the trimmed view up to rounding (removed < 1e-3 * err)
 }
 
 YR_HD void store_epilogue(Work& w, int p, const Epilogue& ep, double sumabs) {
@@ -268,7 +347,9 @@ YR_HD void store_epilogue(Work& w, int p, const Epilogue& ep, double sumabs) {
 }
 
 // ---- RESTRICT ------------------------------------------------------------------------------------------
-// slice: [A: T][B: T][C0 panels][C1 panels][rows_after ints]
+// slice: [A: T][B: T][X: T][C0 panels][C1 panels][rows_after ints]
+// Tensor 0 is fetched into A and tensor 1 into B with asynchronous copies that run behind the matrix build; each
+// tensor then ping-pongs with X:  axis 0: own region -> X,  axis 1: X -> own region.
 template <bool FMA, class Team>
 YR_DEV void restrict_box(Team& tm, const Args& a, unsigned int b, double* slice, unsigned long long& macs) {
     BoxRec<2>& rec = a.recs[b];
@@ -282,31 +363,42 @@ YR_DEV void restrict_box(Team& tm, const Args& a, unsigned int b, double* slice,
     const int T = sz0 > sz1 ? sz0 : sz1;
     const int n0max = shp[0][0] > shp[1][0] ? shp[0][0] : shp[1][0];
     const int n1max = shp[0][1] > shp[1][1] ? shp[0][1] : shp[1][1];
-    double* A = slice; double* Bf = slice + T;
-    double* C0 = slice + 2 * T; double* C1 = C0 + panel_doubles(n0max);
+    double* A = slice; double* Bf = slice + T; double* X = slice + 2 * T;
+    double* C0 = slice + 3 * T; double* C1 = C0 + panel_doubles(n0max);
     int* rows0 = reinterpret_cast<int*>(C1 + panel_doubles(n1max)); int* rows1 = rows0 + n0max;
     const double al0 = wk.alpha[0], be0 = wk.beta[0], al1 = wk.alpha[1], be1 = wk.beta[1];
     const bool id0 = copy_only || (al0 == 1.0 && be0 == 0.0), id1 = copy_only || (al1 == 1.0 && be1 == 0.0);
+    const unsigned long long off_in[2] = {wk.off[0], wk.off[1]};
+    double sum_in[2] = {wk.sumabs[0], wk.sumabs[1]};
+    double err_in[2] = {rec.err[0], rec.err[1]};
     // output space: never larger than the input (rows only shrink)
     unsigned long long base = 0;
     if (tm.tid == 0) base = tm.atomic_add(&a.ctl->data_used, (unsigned long long)(sz0 + sz1));
     base = tm.bcast(base);
     if (base + (unsigned long long)(sz0 + sz1) > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
-    tm.sync();                                                   // previous box's reads of the slice are over
-    if (!id0 && n0max > 1) build_panels(tm, C0, rows0, n0max, al0, be0);
-    if (!id1 && n1max > 1) build_panels(tm, C1, rows1, n1max, al1, be1);
+    tm.sync();                                                   // the previous box is done with the slice
+    // fetch both tensors (A <- tensor 0, B <- tensor 1) behind the matrix build
+    for (int p = 0; p < 2; ++p) {
+        double* dst = p ? Bf : A;
+        const int lds = p ? lds1 : lds0, n0 = shp[p][0], n1 = shp[p][1];
+        const double* src = a.data_in + off_in[p];
+        if (ldg[p] == lds && (off_in[p] & 1ull) == 0) tm.copy_async(dst, src, tensor_doubles(n0, lds));
+        else for (int e = tm.tid; e < n0 * n1; e += tm.nthreads) { const int i = e / n1, j = e - i * n1; dst[i * lds + j] = src[(long long)i * ldg[p] + j]; }
+    }
+    {
+        PanelJob j0 = {C0, rows0, (!id0 && n0max > 1) ? n0max : 0, al0, be0};
+        PanelJob j1 = {C1, rows1, (!id1 && n1max > 1) ? n1max : 0, al1, be1};
+        if (j0.nt > 0 || j1.nt > 0) build_two(tm, j0, j1);
+    }
+    tm.copy_wait();
+    tm.sync();
     unsigned long long out_off = base;
     for (int p = 0; p < 2; ++p) {
         const int n0 = shp[p][0], n1 = shp[p][1];
         const int lds = p ? lds1 : lds0;
-        const double* src = a.data_in + wk.off[p];
-        tm.sync();
-        if (ldg[p] == lds && (wk.off[p] & 1ull) == 0) copy_flat(tm, A, src, tensor_doubles(n0, lds));
-        else for (int e = tm.tid; e < n0 * n1; e += tm.nthreads) { const int i = e / n1, j = e - i * n1; A[i * lds + j] = src[(long long)i * ldg[p] + j]; }
-        tm.sync();
-        double s = copy_only ? view_abs_sum(tm, A, n0, n1, lds) : wk.sumabs[p];
-        double err = rec.err[p];
-        double* cur = A; double* oth = Bf;
+        double* cur = p ? Bf : A; double* oth = X;
+        double s = copy_only ? view_abs_sum(tm, cur, n0, n1, lds) : sum_in[p];
+        double err = err_in[p];
         int r0 = n0, r1 = n1, ld = lds;
         if (!copy_only) err += n0 * kMachEps * s;                    // charged before the axis (:860)
         if (!id0 && n0 > 1) {
@@ -314,7 +406,6 @@ YR_DEV void restrict_box(Team& tm, const Args& a, unsigned int b, double* slice,
             s = restrict_pass<FMA>(tm, cur, ld, 1, oth, ld, 1, n0, r0, n1, C0, n0max);
             if (tm.tid == 0) macs += (unsigned long long)n1 * ((unsigned long long)r0 * n0 - (unsigned long long)r0 * (r0 - 1) / 2);
             double* t = cur; cur = oth; oth = t;
-            tm.sync();
         }
         if (!copy_only) err += n1 * kMachEps * s;
         if (!id1 && n1 > 1) {
@@ -324,18 +415,20 @@ YR_DEV void restrict_box(Team& tm, const Args& a, unsigned int b, double* slice,
             if (tm.tid == 0) macs += (unsigned long long)r0 * ((unsigned long long)r1 * n1 - (unsigned long long)r1 * (r1 - 1) / 2);
             double* t = cur; cur = oth; oth = t;
             ld = ld2;
-            tm.sync();
         }
-        Epilogue ep;
-        tensor_epilogue(tm, cur, r0, r1, ld, s, err, prm, ep);
         const int osz = tensor_doubles(r0, ld);
-        copy_flat(tm, a.data_out + out_off, cur, osz);
-        if (tm.tid == 0) {
-            store_epilogue(wk, p, ep, s);
-            rec.shape[p][0] = r0; rec.shape[p][1] = r1; rec.err[p] = err;
-            wk.off[p] = out_off; wk.ld[p] = ld;
+        if (tm.warp == 0) {
+            Epilogue ep;
+            tensor_epilogue(tm, cur, r0, r1, ld, s, err, prm, ep);
+            if (tm.tid == 0) {
+                store_epilogue(wk, p, ep, s);
+                rec.shape[p][0] = r0; rec.shape[p][1] = r1; rec.err[p] = err;
+                wk.off[p] = out_off; wk.ld[p] = ld;
+            }
         }
+        copy_flat(tm, a.data_out + out_off, cur, osz);
         out_off += (unsigned long long)osz;
+        tm.sync();                                               // tensor 0 has left X before tensor 1's passes overwrite it
     }
     if (tm.tid == 0) { wk.op = kTNone; wk.copy_only = 0; wk.trim_valid = 1; }
 }
@@ -451,26 +544,28 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
             // extent-1 axis: TransformChebInPlaceND returns the tensor unchanged (:363)
             copy_flat(tm, L, S, tensor_doubles(n0, ld)); copy_flat(tm, U, S, tensor_doubles(n0, ld));
             sumL = sumU = wk.sumabs[p];
+            tm.sync();
         }
-        tm.sync();
         const int rank0 = (split_axes[0] == a1) ? 0 : 1;      // position of a1 in the ascending set of split axes
         for (int h1 = 0; h1 < 2; ++h1) {
             const double* H = h1 ? U : L;
             const int* shH = h1 ? shU : shL; const int ldH = h1 ? ldU : ldL; const double sumH = h1 ? sumU : sumL;
             if (k == 1) {
                 const int c = h1;
-                Epilogue ep;
-                tensor_epilogue(tm, H, shH[0], shH[1], ldH, sumH, terr1, prm, ep);
                 const int osz = tensor_doubles(shH[0], ldH);
                 const unsigned long long off = dbase + per_child * c + (p ? (unsigned long long)sz0 : 0ull);
-                copy_flat(tm, a.data_out + off, H, osz);
-                if (tm.tid == 0) {
-                    const unsigned int child = (unsigned int)(cbase + c);
-                    Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
-                    store_epilogue(ow, p, ep, sumH);
-                    orec.shape[p][0] = shH[0]; orec.shape[p][1] = shH[1]; orec.err[p] = terr1;
-                    ow.off[p] = off; ow.ld[p] = ldH;
+                if (tm.warp == 0) {
+                    Epilogue ep;
+                    tensor_epilogue(tm, H, shH[0], shH[1], ldH, sumH, terr1, prm, ep);
+                    if (tm.tid == 0) {
+                        const unsigned int child = (unsigned int)(cbase + c);
+                        Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
+                        store_epilogue(ow, p, ep, sumH);
+                        orec.shape[p][0] = shH[0]; orec.shape[p][1] = shH[1]; orec.err[p] = terr1;
+                        ow.off[p] = off; ow.ld[p] = ldH;
+                    }
                 }
+                copy_flat(tm, a.data_out + off, H, osz);
                 continue;
             }
             // stage 2 along a2 = order[p][1]: H -> (lower -> S, upper -> X)
@@ -504,25 +599,27 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
             } else {
                 copy_flat(tm, S, H, tensor_doubles(shH[0], ldH)); copy_flat(tm, X, H, tensor_doubles(shH[0], ldH));
                 sumA = sumB = sumH;
+                tm.sync();
             }
-            tm.sync();
             for (int h2 = 0; h2 < 2; ++h2) {
                 const double* O = h2 ? X : S;
                 const int* shO = h2 ? shB : shA; const int ldO = h2 ? ldB : ldA; const double sumO = h2 ? sumB : sumA;
                 // canonical child: split axes ascending, smallest axis most significant
                 const int c = (rank0 == 0) ? ((h1 << 1) | h2) : ((h2 << 1) | h1);
-                Epilogue ep;
-                tensor_epilogue(tm, O, shO[0], shO[1], ldO, sumO, terr2, prm, ep);
                 const int osz = tensor_doubles(shO[0], ldO);
                 const unsigned long long off = dbase + per_child * c + (p ? (unsigned long long)sz0 : 0ull);
-                copy_flat(tm, a.data_out + off, O, osz);
-                if (tm.tid == 0) {
-                    const unsigned int child = (unsigned int)(cbase + c);
-                    Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
-                    store_epilogue(ow, p, ep, sumO);
-                    orec.shape[p][0] = shO[0]; orec.shape[p][1] = shO[1]; orec.err[p] = terr2;
-                    ow.off[p] = off; ow.ld[p] = ldO;
+                if (tm.warp == 0) {
+                    Epilogue ep;
+                    tensor_epilogue(tm, O, shO[0], shO[1], ldO, sumO, terr2, prm, ep);
+                    if (tm.tid == 0) {
+                        const unsigned int child = (unsigned int)(cbase + c);
+                        Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
+                        store_epilogue(ow, p, ep, sumO);
+                        orec.shape[p][0] = shO[0]; orec.shape[p][1] = shO[1]; orec.err[p] = terr2;
+                        ow.off[p] = off; ow.ld[p] = ldO;
+                    }
                 }
+                copy_flat(tm, a.data_out + off, O, osz);
             }
         }
     }

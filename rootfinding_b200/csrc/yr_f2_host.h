@@ -3,6 +3,7 @@
 // test infrastructure) provide.
 #pragma once
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "../../include/yroots_b200.h"
@@ -28,6 +29,7 @@ int launch_scalar(const yr::f2::Args& a, const Segments& s, void* stream);
 void timer_reset(int enable);
 void timer_mark(int which, int begin, void* stream);      // which: 0 tensor, 1 scalar
 void timer_collect(double* tensor_ms, double* scalar_ms);
+double trace_sync_ms(void* stream);      // YR_F2_TRACE: synchronise and return host milliseconds since the previous call
 }  // namespace yr_f2_backend
 
 namespace yr_f2_host {
@@ -70,6 +72,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
     const int nt = (int)(d->max_extent < 4 ? 4 : d->max_extent);
     if (!fits(d->max_extent)) return fail("yr_frontier_solve: tensors too large for the shared-memory pipeline");
     be::timer_reset(d->time_kernels);
+    const bool trace = getenv("YR_F2_TRACE") != nullptr;
 
     DevBuf recs, work, results, nodes, arena[2], lists[2], tabs, ctlbuf;
     auto cleanup = [&](bool keep_out) {
@@ -164,6 +167,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         // per-round part of the control block: queues, bounds, arena cursor; slot counters restart at their totals
         F2_TRY(be::dev_zero(ctlbuf.p, offsetof(Ctl, n_boxes), stream));
         F2_TRY(be::dev_zero(&a.ctl->n_results, 2 * sizeof(unsigned long long), stream));
+        if (trace) fprintf(stderr, "f2 round %3llu: host %.3f ms |", rounds, be::trace_sync_ms(stream));
         be::timer_mark(0, 1, stream);
         for (int o = 0; o < kOps; ++o)
             for (int c = 0; c < kClasses; ++c) {
@@ -172,6 +176,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
                 F2_TRY(be::launch_tensor(a, o == 0 ? (int)kTRestrict : (int)kTSubdivide, c, cur_lists[o][c], h.n_list[o][c],
                                          h.need_max[o][c], (int)(o ? h.ext_max[c] : 0), stream));
                 ++launches;
+                if (trace) fprintf(stderr, " %s%d n=%llu need=%llu ext=%llu %.3f ms |", o ? "S" : "R", c, h.n_list[o][c], h.need_max[o][c], o ? h.ext_max[c] : 0ull, be::trace_sync_ms(stream));
             }
         be::timer_mark(0, 0, stream);
         be::Segments sg;
@@ -181,6 +186,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         F2_TRY(be::launch_scalar(a, sg, stream));
         be::timer_mark(1, 0, stream);
         ++launches;
+        if (trace) fprintf(stderr, " scalar %.3f ms\n", be::trace_sync_ms(stream));
         F2_TRY(be::to_host(&h, ctlbuf.p, sizeof(Ctl), stream));
         if (h.overflow) { cleanup(false); return fail("yr_frontier_solve: internal buffer overflow"); }
         if (h.bad_mid) { cleanup(false); return fail("yr_frontier_solve: unexpected split point (nextTransformPoints)"); }

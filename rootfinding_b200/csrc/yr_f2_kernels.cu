@@ -8,8 +8,10 @@
 // Grids are sized to the machine: teams = min(boxes, SMs x resident teams), every team strides the list.
 // Compiled with -fmad=false like the rest of the library.
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include "yr_f2_host.h"
 
@@ -18,43 +20,81 @@ using namespace yr::f2;
 
 namespace {
 
-struct WarpTeam {
-    int tid, nthreads;
-    __device__ __forceinline__ void sync() { __syncwarp(); }
-    __device__ __forceinline__ double sum(double v) {
+__device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        return v;
-    }
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// asynchronous global -> shared copy of n_even doubles (both 16-byte aligned): LDGSTS, no registers in between
+__device__ __forceinline__ void copy_async16(double* dst, const double* src, int n_even, int tid, int nthreads) {
+    const int n2 = n_even >> 1;
+    for (int e = tid; e < n2; e += nthreads) __pipeline_memcpy_async(dst + 2 * e, src + 2 * e, 16);
+    __pipeline_commit();
+}
+
+struct WarpTeam {
+    static constexpr bool kShuffle = true;
+    int tid, nthreads, lane, lanes, warp, warps;
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+    __device__ __forceinline__ void wsync() { __syncwarp(); }
+    __device__ __forceinline__ double sum(double v) { return warp_sum_d(v); }
+    __device__ __forceinline__ double sum_sync(double v) { __syncwarp(); return warp_sum_d(v); }
+    __device__ __forceinline__ double wsum(double v) { return warp_sum_d(v); }
+    __device__ __forceinline__ bool wany(bool p) { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(0xffffffffu, v, d, w); }
+    __device__ __forceinline__ double wshfl_down(double v, int d, int w) { return __shfl_down_sync(0xffffffffu, v, d, w); }
+    __device__ __forceinline__ int wshfl_idx(int v, int src, int w) { return __shfl_sync(0xffffffffu, v, src, w); }
     __device__ __forceinline__ unsigned long long bcast(unsigned long long v) { return __shfl_sync(0xffffffffu, v, 0); }
     __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+    __device__ __forceinline__ void copy_async(double* dst, const double* src, int n_even) { copy_async16(dst, src, n_even, tid, 32); }
+    __device__ __forceinline__ void copy_wait() { __pipeline_wait_prior(0); }
 };
+__device__ __forceinline__ WarpTeam make_warp_team() {
+    WarpTeam tm; tm.tid = tm.lane = threadIdx.x & 31; tm.nthreads = tm.lanes = 32; tm.warp = 0; tm.warps = 1; return tm;
+}
+
+struct CtaShared { double red[2][8]; unsigned long long slot; };
 
 struct CtaTeam {
-    int tid, nthreads;
-    double* red;                   // [32] + one 64-bit slot at red[32]
+    static constexpr bool kShuffle = true;
+    int tid, nthreads, lane, lanes, warp, warps;
+    int flip;
+    CtaShared* sh;
     __device__ __forceinline__ void sync() { __syncthreads(); }
-    __device__ __forceinline__ double sum(double v) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if ((tid & 31) == 0) red[tid >> 5] = v;
+    __device__ __forceinline__ void wsync() { __syncwarp(); }
+    // one barrier per reduction: partials alternate between two buffers, so a buffer is rewritten only after
+    // every thread has passed the barrier of the reduction in between
+    __device__ __forceinline__ double sum_sync(double v) {
+        v = warp_sum_d(v);
+        const int buf = flip; flip ^= 1;
+        if (lane == 0) sh->red[buf][warp] = v;
         __syncthreads();
         double t = 0.0;
-        const int nw = nthreads >> 5;
-        for (int w = 0; w < nw; ++w) t += red[w];
-        __syncthreads();
+        for (int w = 0; w < warps; ++w) t += sh->red[buf][w];
         return t;
     }
+    __device__ __forceinline__ double sum(double v) { return sum_sync(v); }
+    __device__ __forceinline__ double wsum(double v) { return warp_sum_d(v); }
+    __device__ __forceinline__ bool wany(bool p) { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(0xffffffffu, v, d, w); }
+    __device__ __forceinline__ double wshfl_down(double v, int d, int w) { return __shfl_down_sync(0xffffffffu, v, d, w); }
+    __device__ __forceinline__ int wshfl_idx(int v, int src, int w) { return __shfl_sync(0xffffffffu, v, src, w); }
     __device__ __forceinline__ unsigned long long bcast(unsigned long long v) {
-        unsigned long long* slot = reinterpret_cast<unsigned long long*>(red + 32);
-        if (tid == 0) *slot = v;
+        if (tid == 0) sh->slot = v;
         __syncthreads();
-        const unsigned long long r = *slot;
+        const unsigned long long r = sh->slot;
         __syncthreads();
         return r;
     }
     __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+    __device__ __forceinline__ void copy_async(double* dst, const double* src, int n_even) { copy_async16(dst, src, n_even, tid, nthreads); }
+    __device__ __forceinline__ void copy_wait() { __pipeline_wait_prior(0); }
 };
+__device__ __forceinline__ CtaTeam make_cta_team(CtaShared* sh) {
+    CtaTeam tm; tm.tid = threadIdx.x; tm.nthreads = blockDim.x; tm.lane = threadIdx.x & 31; tm.lanes = 32;
+    tm.warp = threadIdx.x >> 5; tm.warps = blockDim.x >> 5; tm.flip = 0; tm.sh = sh; return tm;
+}
 
 // copy the m = 0 subdivision matrices into shared memory, re-laid out for extent `snt` (<= table extent)
 __device__ void stage_submats(const Args& a, double* smat, int snt) {
@@ -83,7 +123,7 @@ __global__ void __launch_bounds__(128) f2_tensor_warp(const Args a, const unsign
     if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a, smat, snt); }
     const int w = threadIdx.x >> 5;
     double* slice = dyn + smat_doubles + (size_t)w * slice_doubles;
-    WarpTeam tm; tm.tid = threadIdx.x & 31; tm.nthreads = 32;
+    WarpTeam tm = make_warp_team();
     const unsigned long long team = (unsigned long long)blockIdx.x * 4 + w, nteams = (unsigned long long)gridDim.x * 4;
     unsigned long long macs = 0;
     for (unsigned long long i = team; i < n; i += nteams) {
@@ -98,12 +138,12 @@ __global__ void __launch_bounds__(128) f2_tensor_warp(const Args a, const unsign
 template <int OP, bool FMA>
 __global__ void __launch_bounds__(256) f2_tensor_cta(const Args a, const unsigned int* __restrict__ list, unsigned long long n, int snt) {
     extern __shared__ __align__(16) double dyn[];
-    __shared__ double red[34];
+    __shared__ CtaShared cta_sh;
     double* smat = dyn;
     int smat_doubles = 0;
     if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a, smat, snt); }
     double* slice = dyn + smat_doubles;
-    CtaTeam tm; tm.tid = threadIdx.x; tm.nthreads = blockDim.x; tm.red = red;
+    CtaTeam tm = make_cta_team(&cta_sh);
     unsigned long long macs = 0;
     for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x) {
         const unsigned int b = list[i];
@@ -197,8 +237,8 @@ __global__ void __launch_bounds__(128) f2_import_kernel(const Args a, unsigned l
 
 // the four level-independent matrices: CTA m builds (mid, half) = (m >> 1, m & 1)
 __global__ void __launch_bounds__(256) f2_tables_kernel(double* mats, int* rows, int nt) {
-    __shared__ double red[34];
-    CtaTeam tm; tm.tid = threadIdx.x; tm.nthreads = blockDim.x; tm.red = red;
+    __shared__ CtaShared cta_sh;
+    CtaTeam tm = make_cta_team(&cta_sh);
     const int m = blockIdx.x;
     const double mid = (m >> 1) ? kFirstSplit : 0.0;
     const double alpha = (mid + 1) / 2, beta = (mid - 1) / 2;           // :1089
@@ -340,6 +380,15 @@ int launch_scalar(const Args& a, const Segments& s, void* stream) {
     f2_scalar_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, s);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "f2_scalar_kernel launch");
+}
+
+double trace_sync_ms(void* stream) {
+    static double last = 0.0;
+    cudaStreamSynchronize((cudaStream_t)stream);
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6, d = now - last;
+    last = now;
+    return d;
 }
 
 void timer_reset(int enable) { g_timer.enabled = enable; g_timer.used[0] = g_timer.used[1] = 0; }

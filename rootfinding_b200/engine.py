@@ -229,6 +229,7 @@ class SolveSession:
         self.cap_nodes = 0
         self.n_nodes = 0
         self.d_nodes = None
+        self._pending = []
         self._results_host = np.empty(0, dtype=self.rdt)
         self._nodes_host = np.empty(0, dtype=self.ndt)
         self.stats = SolveStats()
@@ -403,21 +404,8 @@ class SolveSession:
         out = _lib.YrFrontierOut()
         stream = m.stream()
         _lib.check(lib, lib.yr_frontier_solve(C.byref(d), C.byref(out), stream), "yr_frontier_solve")
-        try:
-            nres, nnod = int(out.n_results), int(out.n_nodes)
-            self.results(), self.nodes()                          # anything earlier level launches left on the device
-            if nres:
-                host = np.empty(nres, dtype=self.rdt)
-                _lib.check(lib, lib.yr_fetch(host.ctypes.data, out.results, host.nbytes, stream), "yr_fetch")
-                self._results_host = np.concatenate([self._results_host, host])
-                m.d2h_bytes += host.nbytes
-            if nnod:
-                host = np.empty(nnod, dtype=self.ndt)
-                _lib.check(lib, lib.yr_fetch(host.ctypes.data, out.nodes, host.nbytes, stream), "yr_fetch")
-                self._nodes_host = np.concatenate([self._nodes_host, host])
-                m.d2h_bytes += host.nbytes
-        finally:
-            lib.yr_frontier_release(C.byref(out), stream)
+        nres, nnod = int(out.n_results), int(out.n_nodes)
+        self._pending.append(out)                                 # records stay on the device until results() / nodes()
         self.n_results += nres
         self.n_nodes += nnod
         cc = {k: int(getattr(out.counters, k)) for k in _lib.COUNTER_FIELDS}
@@ -441,8 +429,33 @@ class SolveSession:
                     level=np.zeros(n, np.int32), next_mid=np.full((n, D), FIRST_SPLIT), parent=np.full(n, -1, np.int32))
 
     # -- results -----------------------------------------------------------------------------
+    def _fetch_pending(self):
+        """Device -> host copy of the records the frontier pipeline produced (library-owned buffers)."""
+        lib, stream = self.lib, self.mem.stream()
+        while self._pending:
+            out = self._pending.pop(0)
+            try:
+                for ptr, n, dt, name in ((out.results, int(out.n_results), self.rdt, "_results_host"),
+                                         (out.nodes, int(out.n_nodes), self.ndt, "_nodes_host")):
+                    if n:
+                        host = np.empty(n, dtype=dt)
+                        _lib.check(lib, lib.yr_fetch(host.ctypes.data, ptr, host.nbytes, stream), "yr_fetch")
+                        setattr(self, name, np.concatenate([getattr(self, name), host]))
+                        self.mem.d2h_bytes += host.nbytes
+            finally:
+                lib.yr_frontier_release(C.byref(out), stream)
+
+    def __del__(self):
+        try:
+            for out in self._pending:
+                self.lib.yr_frontier_release(C.byref(out), self.mem.stream())
+        except Exception:
+            pass
+
     def results(self):
         """All result records so far as a numpy structured array (downloads only what is new)."""
+        if self._pending:
+            self._fetch_pending()
         have = len(self._results_host)
         if self.n_results > have:
             item = self.rdt.itemsize
@@ -451,6 +464,8 @@ class SolveSession:
         return self._results_host
 
     def nodes(self):
+        if self._pending:
+            self._fetch_pending()
         have = len(self._nodes_host)
         if self.n_nodes > have:
             item = self.ndt.itemsize

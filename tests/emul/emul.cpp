@@ -312,13 +312,34 @@ int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t 
 namespace {
 
 struct F2Team {
-    int tid, nthreads;
+    // the whole emulated team acts as one "warp" of `lanes` lanes
+    static constexpr bool kShuffle = true;
+    int tid, nthreads, lane, lanes, warp, warps;
     Team* team;
     void sync() { team->bar.wait(); }
+    void wsync() { sync(); }
     double sum(double v) {
         team->scratch[tid] = v; sync();
         double t = 0; for (int i = 0; i < nthreads; ++i) t += team->scratch[i];
         sync(); return t;
+    }
+    double sum_sync(double v) { return sum(v); }
+    double wsum(double v) { return sum(v); }
+    bool wany(bool p) { return sum(p ? 1.0 : 0.0) > 0.0; }
+    double wshfl_up(double v, int d, int w) {
+        team->scratch[tid] = v; sync();
+        const double r = ((tid % w) >= d) ? team->scratch[tid - d] : v;
+        sync(); return r;
+    }
+    double wshfl_down(double v, int d, int w) {
+        team->scratch[tid] = v; sync();
+        const double r = ((tid % w) + d < w && tid + d < nthreads) ? team->scratch[tid + d] : v;
+        sync(); return r;
+    }
+    int wshfl_idx(int v, int src, int w) {
+        team->scratch[tid] = (double)v; sync();
+        const int r = (int)team->scratch[(tid / w) * w + src];
+        sync(); return r;
     }
     unsigned long long bcast(unsigned long long v) {
         if (tid == 0) memcpy(&team->scratch[0], &v, 8);
@@ -327,6 +348,8 @@ struct F2Team {
         sync(); return r;
     }
     unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+    void copy_async(double* dst, const double* src, int n_even) { for (int e = tid; e < n_even; e += nthreads) dst[e] = src[e]; }
+    void copy_wait() {}
 };
 
 struct F2At {
@@ -339,7 +362,7 @@ void f2_run_team(int T, Body body) {
     Team team; team.T = T; team.lanes = T; team.bar.n = T; team.scratch.assign(T + 2, 0.0);
     std::vector<std::thread> th;
     for (int t = 0; t < T; ++t)
-        th.emplace_back([&, t]() { F2Team tm; tm.tid = t; tm.nthreads = T; tm.team = &team; body(tm); });
+        th.emplace_back([&, t]() { F2Team tm; tm.tid = tm.lane = t; tm.nthreads = tm.lanes = T; tm.warp = 0; tm.warps = 1; tm.team = &team; body(tm); });
     for (auto& x : th) x.join();
 }
 
@@ -426,6 +449,7 @@ int launch_scalar(const yr::f2::Args& a, const Segments& s, void*) {
     return 0;
 }
 
+double trace_sync_ms(void*) { return 0.0; }
 void timer_reset(int) {}
 void timer_mark(int, int, void*) {}
 void timer_collect(double* t, double* s) { *t = 0; *s = 0; }
