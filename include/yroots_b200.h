@@ -170,6 +170,8 @@ int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* str
 /* 1 when 2-D boxes with extents up to max_extent fit the pipeline's shared-memory budget (else use yr_process_level) */
 int yr_frontier_fits(uint64_t max_extent);
 int yr_frontier_release(yr_frontier_out* out, void* stream);
+/* the pipeline keeps its box tables, arenas and queues between solves (grow-only); this frees them */
+int yr_frontier_trim(void* stream);
 /* device -> host copy of `bytes` bytes on `stream`, synchronous (host_dst is a HOST pointer) */
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void* stream);
 

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libyroots_b200.so")
+CUDA_LIB_PATH = os.environ.get("YR_LIB_OVERRIDE") or os.path.join(_HERE, "csrc", "libyroots_b200.so")   # override: kernel experiments only
 
 u64, i64, i32 = C.c_uint64, C.c_int64, C.c_int32
 vp, dp = C.c_void_p, C.c_void_p          # device pointers travel as integers
@@ -75,7 +75,7 @@ COUNTER_BYTES = 8 * len(COUNTER_FIELDS)
 EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_params", "yr_record_layout",
            "yr_workspace_doubles", "yr_level_work_bytes", "yr_static_smem_bytes", "yr_device_limits", "yr_init_boxes", "yr_process_level", "yr_bils_batched",
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
-           "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_fetch"]
+           "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -119,6 +119,8 @@ def bind(lib):
     lib.yr_frontier_solve.restype = C.c_int
     lib.yr_frontier_release.argtypes = [C.POINTER(YrFrontierOut), vp]
     lib.yr_frontier_release.restype = C.c_int
+    lib.yr_frontier_trim.argtypes = [vp]
+    lib.yr_frontier_trim.restype = C.c_int
     lib.yr_frontier_fits.argtypes = [u64]
     lib.yr_frontier_fits.restype = C.c_int
     lib.yr_fetch.argtypes = [vp, vp, u64, vp]

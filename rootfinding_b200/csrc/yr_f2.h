@@ -45,6 +45,17 @@
 #endif
 #endif
 
+// inlining policy of the big per-box helpers (code size vs call overhead; see profiles/)
+#ifndef YR_F2_PASS
+#define YR_F2_PASS YR_DEV
+#endif
+#ifndef YR_F2_BUILD
+#define YR_F2_BUILD YR_DEV
+#endif
+#ifndef YR_F2_EPI
+#define YR_F2_EPI YR_DEV
+#endif
+
 namespace yr {
 namespace f2 {
 
@@ -60,9 +71,11 @@ enum Op : int32_t { kTNone = 0, kTRestrict = 1, kTSubdivide = 2 };
 YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
 
 YR_HD int class_threads(int cls) { return cls <= 1 ? 32 : (cls == 2 ? 128 : 256); }
-YR_HD int class_of(unsigned long long need) {         // need = per-team shared-memory doubles
-    return need <= 1024ull ? 0 : (need <= 2560ull ? 1 : (need <= 7168ull ? 2 : 3));
-}
+// Shared-memory need (doubles per team) decides the team: warp teams run the in-place fiber-per-lane passes and
+// need little; CTA teams run the item-parallel out-of-place passes.
+constexpr unsigned long long kWarp16Max = 512ull;     // class 0: two 16-lane teams per warp
+constexpr unsigned long long kWarp32Max = 1536ull;    // class 1: one 32-lane team per warp
+constexpr unsigned long long kCta128Max = 7168ull;    // class 2: CTA of 128; larger: class 3, CTA of 256
 constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
 
 YR_HD int odd_ld(int n1) { return n1 | 1; }
@@ -74,10 +87,18 @@ YR_HD int panel_off(int b, int nt) { return 4 * b * nt - 8 * b * (b - 1); }
 YR_HD int panel_doubles(int nt) { const int B = (nt + 3) >> 2; return panel_off(B, nt); }
 YR_HD int panel_index(int i, int k, int nt) { const int b = i >> 2; return panel_off(b, nt) + ((k - 4 * b) << 2) + (i & 3); }
 
-YR_HD unsigned long long need_restrict(int T, int n0max, int n1max) {
+YR_HD unsigned long long need_restrict(int T, int n0max, int n1max) {          // CTA teams: [A][B][X][C0][C1][rows]
     return 3ull * T + panel_doubles(n0max) + panel_doubles(n1max) + (unsigned)((n0max + n1max + 1) / 2) + 2;
 }
-YR_HD unsigned long long need_subdivide(int T) { return 4ull * T; }
+YR_HD unsigned long long need_subdivide(int T) { return 4ull * T; }              // CTA teams: [S][L][U][X]
+YR_HD unsigned long long need_restrict_w(int T, int n0max, int n1max) {        // warp teams: [A][C0][C1][rows]
+    return (unsigned long long)T + panel_doubles(n0max) + panel_doubles(n1max) + (unsigned)((n0max + n1max + 1) / 2) + 2;
+}
+YR_HD unsigned long long need_subdivide_w(int T) { return 3ull * T; }            // warp teams: [S][L][X]
+YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, unsigned long long& need, int& cls) {
+    if (need_w <= kWarp32Max) { need = need_w; cls = need_w <= kWarp16Max ? 0 : 1; }
+    else { need = need_cta; cls = need_cta <= kCta128Max ? 2 : 3; }
+}
 
 // Per-box state next to BoxRec<2> (same slot index).
 struct Work {
@@ -133,7 +154,7 @@ struct Args {
 // Column by column (the three-term recurrence couples neighbouring rows: columns sequential, rows parallel),
 // with rows_after[k] = the reference's `maxRow` after column k (:106-112).  Collective over the team.
 template <class Team>
-YR_DEV void build_panels(Team& tm, double* Cp, int* rows_after, int nt, double alpha, double beta) {
+YR_F2_BUILD void build_panels(Team& tm, double* Cp, int* rows_after, int nt, double alpha, double beta) {
     const int P = panel_doubles(nt);
     for (int e = tm.tid; e < P; e += tm.nthreads) Cp[e] = 0.0;
     tm.sync();
@@ -176,7 +197,7 @@ YR_DEV void build_panels(Team& tm, double* Cp, int* rows_after, int nt, double a
 struct PanelJob { double* Cp; int* rows_after; int nt; double alpha, beta; };
 
 template <class W>
-YR_DEV void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb, int seg) {
+YR_F2_BUILD void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb, int seg) {
     const int lane = w.lane;
     const bool second = (seg == 16) && (lane >= 16);
     const PanelJob& j = second ? jb : ja;
@@ -223,16 +244,16 @@ YR_DEV void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb, int 
 
 // Team-level dispatcher: builds up to two matrices (either may be skipped with nt = 0).
 template <class Team>
-YR_DEV void build_two(Team& tm, const PanelJob& j0, const PanelJob& j1) {
+YR_F2_BUILD void build_two(Team& tm, const PanelJob& j0, const PanelJob& j1) {
     const int big = j0.nt > j1.nt ? j0.nt : j1.nt;
-    if (Team::kShuffle && tm.lanes == 32 && big <= 32) {
+    if (Team::kShuffle && (tm.lanes == 32 || tm.lanes == 16) && big <= tm.lanes) {
         if (tm.warps >= 2) {                                      // one warp per matrix
             if (tm.warp == 0 && j0.nt > 0) build_panels_warp(tm, j0, j0, 32);
             if (tm.warp == 1 && j1.nt > 0) build_panels_warp(tm, j1, j1, 32);
-        } else if (big <= 16 && j0.nt > 0 && j1.nt > 0) build_panels_warp(tm, j0, j1, 16);
+        } else if (tm.lanes == 32 && big <= 16 && j0.nt > 0 && j1.nt > 0) build_panels_warp(tm, j0, j1, 16);
         else {
-            if (j0.nt > 0) build_panels_warp(tm, j0, j0, 32);
-            if (j1.nt > 0) build_panels_warp(tm, j1, j1, 32);
+            if (j0.nt > 0) build_panels_warp(tm, j0, j0, tm.lanes);
+            if (j1.nt > 0) build_panels_warp(tm, j1, j1, tm.lanes);
         }
         tm.sync();
         return;
@@ -246,8 +267,8 @@ YR_DEV void build_two(Team& tm, const PanelJob& j0, const PanelJob& j1) {
 // An item is (row block b, fiber f): four output rows from one sweep over source rows 4b .. n-1.
 // Returns the team-wide sum|dst|.  src and dst must not overlap.
 template <bool FMA, class Team>
-YR_DEV double restrict_pass(Team& tm, const double* src, int sk, int sf, double* dst, int dk, int df,
-                            int n, int r, int F, const double* Cp, int nt) {
+YR_F2_PASS double restrict_pass(Team& tm, const double* src, int sk, int sf, double* dst, int dk, int df,
+                             int n, int r, int F, const double* Cp, int nt, unsigned long long& macs) {
     const int B = (r + 3) >> 2;
     double asum = 0.0;
     int b = 0, f = tm.tid;
@@ -305,7 +326,7 @@ YR_DEV double view_abs_sum(Team& tm, const double* M, int n0, int n1, int ld) {
 struct Epilogue { double low[6]; int t0, t1; double tsum, terr; };
 
 template <class Team>
-YR_DEV void tensor_epilogue(Team& tm, const double* M, int n0, int n1, int ld, double sumabs, double err,
+YR_F2_EPI void tensor_epilogue(Team& tm, const double* M, int n0, int n1, int ld, double sumabs, double err,
                             const SolverParams& prm, Epilogue& ep) {
     ep.low[0] = M[0];
     ep.low[1] = n0 > 1 ? M[ld] : 0.0;
@@ -358,7 +379,9 @@ YR_DEV void restrict_box(Team& tm, const Args& a, unsigned int b, double* slice,
     const int copy_only = wk.copy_only;
     int shp[2][2], ldg[2];
     for (int p = 0; p < 2; ++p) { shp[p][0] = rec.shape[p][0]; shp[p][1] = rec.shape[p][1]; ldg[p] = wk.ld[p]; }
-    const int lds0 = odd_ld(shp[0][1]), lds1 = odd_ld(shp[1][1]);
+    // shared-memory row stride = the arena's when that is odd (flat copy; a trimmed view keeps its parent's stride)
+    const int lds0 = ((ldg[0] & 1) && ldg[0] >= shp[0][1]) ? ldg[0] : odd_ld(shp[0][1]);
+    const int lds1 = ((ldg[1] & 1) && ldg[1] >= shp[1][1]) ? ldg[1] : odd_ld(shp[1][1]);
     const int sz0 = tensor_doubles(shp[0][0], lds0), sz1 = tensor_doubles(shp[1][0], lds1);
     const int T = sz0 > sz1 ? sz0 : sz1;
     const int n0max = shp[0][0] > shp[1][0] ? shp[0][0] : shp[1][0];
@@ -403,16 +426,14 @@ YR_DEV void restrict_box(Team& tm, const Args& a, unsigned int b, double* slice,
         if (!copy_only) err += n0 * kMachEps * s;                    // charged before the axis (:860)
         if (!id0 && n0 > 1) {
             r0 = rows0[n0 - 1];
-            s = restrict_pass<FMA>(tm, cur, ld, 1, oth, ld, 1, n0, r0, n1, C0, n0max);
-            if (tm.tid == 0) macs += (unsigned long long)n1 * ((unsigned long long)r0 * n0 - (unsigned long long)r0 * (r0 - 1) / 2);
+            s = restrict_pass<FMA>(tm, cur, ld, 1, oth, ld, 1, n0, r0, n1, C0, n0max, macs);
             double* t = cur; cur = oth; oth = t;
         }
         if (!copy_only) err += n1 * kMachEps * s;
         if (!id1 && n1 > 1) {
             r1 = rows1[n1 - 1];
             const int ld2 = odd_ld(r1);
-            s = restrict_pass<FMA>(tm, cur, 1, ld, oth, 1, ld2, n1, r1, r0, C1, n1max);
-            if (tm.tid == 0) macs += (unsigned long long)r0 * ((unsigned long long)r1 * n1 - (unsigned long long)r1 * (r1 - 1) / 2);
+            s = restrict_pass<FMA>(tm, cur, 1, ld, oth, 1, ld2, n1, r1, r0, C1, n1max, macs);
             double* t = cur; cur = oth; oth = t;
             ld = ld2;
         }
@@ -531,14 +552,12 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
             const int rl = m1.rlo[n_a1 - 1], ru = m1.rhi[n_a1 - 1];
             if (a1 == 0) {
                 shL[0] = rl; shU[0] = ru;
-                sumL = restrict_pass<FMA>(tm, S, ld, 1, L, ld, 1, n0, rl, n1, m1.lo, m1.nt);
-                sumU = restrict_pass<FMA>(tm, S, ld, 1, U, ld, 1, n0, ru, n1, m1.hi, m1.nt);
-                if (tm.tid == 0) macs += (unsigned long long)n1 * (((unsigned long long)rl * n0 - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * n0 - (unsigned long long)ru * (ru - 1) / 2));
+                sumL = restrict_pass<FMA>(tm, S, ld, 1, L, ld, 1, n0, rl, n1, m1.lo, m1.nt, macs);
+                sumU = restrict_pass<FMA>(tm, S, ld, 1, U, ld, 1, n0, ru, n1, m1.hi, m1.nt, macs);
             } else {
                 shL[1] = rl; shU[1] = ru; ldL = odd_ld(rl); ldU = odd_ld(ru);
-                sumL = restrict_pass<FMA>(tm, S, 1, ld, L, 1, ldL, n1, rl, n0, m1.lo, m1.nt);
-                sumU = restrict_pass<FMA>(tm, S, 1, ld, U, 1, ldU, n1, ru, n0, m1.hi, m1.nt);
-                if (tm.tid == 0) macs += (unsigned long long)n0 * (((unsigned long long)rl * n1 - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * n1 - (unsigned long long)ru * (ru - 1) / 2));
+                sumL = restrict_pass<FMA>(tm, S, 1, ld, L, 1, ldL, n1, rl, n0, m1.lo, m1.nt, macs);
+                sumU = restrict_pass<FMA>(tm, S, 1, ld, U, 1, ldU, n1, ru, n0, m1.hi, m1.nt, macs);
             }
         } else {
             // extent-1 axis: TransformChebInPlaceND returns the tensor unchanged (:363)
@@ -587,14 +606,12 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
                 const int rl = m2.rlo[n_a2 - 1], ru = m2.rhi[n_a2 - 1];
                 if (a2 == 0) {
                     shA[0] = rl; shB[0] = ru;
-                    sumA = restrict_pass<FMA>(tm, H, ldH, 1, S, ldH, 1, shH[0], rl, shH[1], m2.lo, m2.nt);
-                    sumB = restrict_pass<FMA>(tm, H, ldH, 1, X, ldH, 1, shH[0], ru, shH[1], m2.hi, m2.nt);
-                    if (tm.tid == 0) macs += (unsigned long long)shH[1] * (((unsigned long long)rl * shH[0] - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * shH[0] - (unsigned long long)ru * (ru - 1) / 2));
+                    sumA = restrict_pass<FMA>(tm, H, ldH, 1, S, ldH, 1, shH[0], rl, shH[1], m2.lo, m2.nt, macs);
+                    sumB = restrict_pass<FMA>(tm, H, ldH, 1, X, ldH, 1, shH[0], ru, shH[1], m2.hi, m2.nt, macs);
                 } else {
                     shA[1] = rl; shB[1] = ru; ldA = odd_ld(rl); ldB = odd_ld(ru);
-                    sumA = restrict_pass<FMA>(tm, H, 1, ldH, S, 1, ldA, shH[1], rl, shH[0], m2.lo, m2.nt);
-                    sumB = restrict_pass<FMA>(tm, H, 1, ldH, X, 1, ldB, shH[1], ru, shH[0], m2.hi, m2.nt);
-                    if (tm.tid == 0) macs += (unsigned long long)shH[0] * (((unsigned long long)rl * shH[1] - (unsigned long long)rl * (rl - 1) / 2) + ((unsigned long long)ru * shH[1] - (unsigned long long)ru * (ru - 1) / 2));
+                    sumA = restrict_pass<FMA>(tm, H, 1, ldH, S, 1, ldA, shH[1], rl, shH[0], m2.lo, m2.nt, macs);
+                    sumB = restrict_pass<FMA>(tm, H, 1, ldH, X, 1, ldB, shH[1], ru, shH[0], m2.hi, m2.nt, macs);
                 }
             } else {
                 copy_flat(tm, S, H, tensor_doubles(shH[0], ldH)); copy_flat(tm, X, H, tensor_doubles(shH[0], ldH));
@@ -621,6 +638,238 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
                 }
                 copy_flat(tm, a.data_out + off, O, osz);
             }
+        }
+    }
+}
+
+// ---- warp teams: in-place, fiber per lane -----------------------------------------------------------------
+// Lane f owns fiber f and walks its row blocks in ascending order: block b reads source rows >= 4b and then
+// overwrites rows 4b..4b+3, which no later block reads -- so a pass can run in place (dst == src), every lane
+// has the same trip count, and a box needs one tensor region instead of three.  dst may also be another region
+// (same strides).  Returns the team-wide sum|dst|; ends with the team barrier.
+template <bool FMA, class Team>
+YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int sf, int n, int r, int F,
+                         const double* Cp, int nt, unsigned long long& macs) {
+    const int B = (r + 3) >> 2;
+    double asum = 0.0;
+    for (int f = tm.tid; f < F; f += tm.nthreads) {
+        const double* sc = src + f * sf;
+        double* dc = dst + f * sf;
+        for (int b = 0; b < B; ++b) {
+            const int i0 = b << 2;
+            const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));
+            const double* s = sc + i0 * sk;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+            for (int k = i0; k < n; ++k) {
+                const double x = *s; s += sk;
+                const pair_t c01 = cp[0], c23 = cp[1]; cp += 2;
+                if (FMA) { a0 = fma(c01.x, x, a0); a1 = fma(c01.y, x, a1); a2 = fma(c23.x, x, a2); a3 = fma(c23.y, x, a3); }
+                else { a0 = a0 + c01.x * x; a1 = a1 + c01.y * x; a2 = a2 + c23.x * x; a3 = a3 + c23.y * x; }
+            }
+            double* d = dc + i0 * sk;
+            const int rem = r - i0;
+            d[0] = a0; asum += fabs(a0);
+            if (rem > 1) { d[sk] = a1; asum += fabs(a1); }
+            if (rem > 2) { d[2 * sk] = a2; asum += fabs(a2); }
+            if (rem > 3) { d[3 * sk] = a3; asum += fabs(a3); }
+        }
+    }
+    if (tm.tid == 0) macs += (unsigned long long)(unsigned)(F * (r * n - r * (r - 1) / 2));
+    return tm.sum_sync(asum);
+}
+
+// tensor view (r0 x r1, row stride ld) in shared memory -> arena, re-laid out with row stride ld_out
+template <class Team>
+YR_DEV void copy_out_rows(Team& tm, double* dst, int ld_out, const double* M, int ld, int r0, int r1) {
+    if (ld_out == ld) { copy_flat(tm, dst, M, tensor_doubles(r0, ld)); return; }
+    if (r1 <= tm.nthreads) {
+        const int j = tm.tid;
+        if (j < r1) for (int i = 0; i < r0; ++i) dst[i * ld_out + j] = M[i * ld + j];
+    } else {
+        for (int i = 0; i < r0; ++i) for (int j = tm.tid; j < r1; j += tm.nthreads) dst[i * ld_out + j] = M[i * ld + j];
+    }
+}
+
+template <class Team>
+YR_DEV void fetch_tensor(Team& tm, double* dst, int lds, const double* src, int ldg, int n0, int n1, bool flat) {
+    if (flat) tm.copy_async(dst, src, tensor_doubles(n0, lds));
+    else for (int i = 0; i < n0; ++i) for (int j = tm.tid; j < n1; j += tm.nthreads) dst[i * lds + j] = src[(long long)i * ldg + j];
+}
+
+// RESTRICT, warp team.  slice: [A: T][C0 panels][C1 panels][rows_after ints]
+template <bool FMA, class Team>
+YR_DEV void restrict_box_w(Team& tm, const Args& a, unsigned int b, double* slice, unsigned long long& macs) {
+    BoxRec<2>& rec = a.recs[b];
+    Work& wk = a.work[b];
+    const SolverParams& prm = a.prm;
+    const int copy_only = wk.copy_only;
+    int shp[2][2], ldg[2], lds[2], sz[2];
+    bool flat[2];
+    unsigned long long off_in[2];
+    for (int p = 0; p < 2; ++p) {
+        shp[p][0] = rec.shape[p][0]; shp[p][1] = rec.shape[p][1]; ldg[p] = wk.ld[p]; off_in[p] = wk.off[p];
+        flat[p] = (ldg[p] & 1) && ldg[p] >= shp[p][1] && (off_in[p] & 1ull) == 0;
+        lds[p] = flat[p] ? ldg[p] : odd_ld(shp[p][1]);
+        sz[p] = tensor_doubles(shp[p][0], lds[p]);
+    }
+    const int T = sz[0] > sz[1] ? sz[0] : sz[1];
+    const int n0max = shp[0][0] > shp[1][0] ? shp[0][0] : shp[1][0];
+    const int n1max = shp[0][1] > shp[1][1] ? shp[0][1] : shp[1][1];
+    double* A = slice;
+    double* C0 = slice + T; double* C1 = C0 + panel_doubles(n0max);
+    int* rows0 = reinterpret_cast<int*>(C1 + panel_doubles(n1max)); int* rows1 = rows0 + n0max;
+    const double al0 = wk.alpha[0], be0 = wk.beta[0], al1 = wk.alpha[1], be1 = wk.beta[1];
+    const bool id0 = copy_only || (al0 == 1.0 && be0 == 0.0), id1 = copy_only || (al1 == 1.0 && be1 == 0.0);
+    const double sum_in[2] = {wk.sumabs[0], wk.sumabs[1]};
+    const double err_in[2] = {rec.err[0], rec.err[1]};
+    unsigned long long base = 0;
+    if (tm.tid == 0) base = tm.atomic_add(&a.ctl->data_used, (unsigned long long)(sz[0] + sz[1]));
+    base = tm.bcast(base);
+    if (base + (unsigned long long)(sz[0] + sz[1]) > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
+    tm.sync();                                                   // the previous box is done with the slice
+    fetch_tensor(tm, A, lds[0], a.data_in + off_in[0], ldg[0], shp[0][0], shp[0][1], flat[0]);   // runs behind the build
+    {
+        PanelJob j0 = {C0, rows0, (!id0 && n0max > 1) ? n0max : 0, al0, be0};
+        PanelJob j1 = {C1, rows1, (!id1 && n1max > 1) ? n1max : 0, al1, be1};
+        if (j0.nt > 0 || j1.nt > 0) build_two(tm, j0, j1);
+    }
+    unsigned long long out_off = base;
+    for (int p = 0; p < 2; ++p) {
+        const int n0 = shp[p][0], n1 = shp[p][1], ld = lds[p];
+        if (p == 1) fetch_tensor(tm, A, ld, a.data_in + off_in[1], ldg[1], n0, n1, flat[1]);
+        tm.copy_wait();
+        tm.sync();
+        double s = copy_only ? view_abs_sum(tm, A, n0, n1, ld) : sum_in[p];
+        double err = err_in[p];
+        int r0 = n0, r1 = n1;
+        if (!copy_only) err += n0 * kMachEps * s;                    // charged before the axis (:860)
+        if (!id0 && n0 > 1) { r0 = rows0[n0 - 1]; s = pass_fiber<FMA>(tm, A, A, ld, 1, n0, r0, n1, C0, n0max, macs); }
+        if (!copy_only) err += n1 * kMachEps * s;
+        if (!id1 && n1 > 1) { r1 = rows1[n1 - 1]; s = pass_fiber<FMA>(tm, A, A, 1, ld, n1, r1, r0, C1, n1max, macs); }
+        const int ld_out = odd_ld(r1), osz = tensor_doubles(r0, ld_out);
+        Epilogue ep;
+        tensor_epilogue(tm, A, r0, r1, ld, s, err, prm, ep);
+        copy_out_rows(tm, a.data_out + out_off, ld_out, A, ld, r0, r1);
+        if (tm.tid == 0) {
+            store_epilogue(wk, p, ep, s);
+            rec.shape[p][0] = r0; rec.shape[p][1] = r1; rec.err[p] = err;
+            wk.off[p] = out_off; wk.ld[p] = ld_out;
+        }
+        out_off += (unsigned long long)osz;
+        tm.sync();                                               // tensor 0 has left A before tensor 1 arrives
+    }
+    if (tm.tid == 0) { wk.op = kTNone; wk.copy_only = 0; wk.trim_valid = 1; }
+}
+
+// SUBDIVIDE, warp team.  slice: [S][L][X], each T doubles; every region keeps the source's row stride.
+//   stage 1:  L = lower(S) out of place, then S = upper(S) in place
+//   stage 2 (from H = L, then S):  X = upper(H) out of place, then H = lower(H) in place; both leave for the arena
+template <bool FMA, class Team>
+YR_DEV void subdivide_box_w(Team& tm, const Args& a, unsigned int b, double* slice, const double* smat_lo, const double* smat_hi,
+                            int smat_nt, unsigned long long& macs) {
+    const BoxRec<2>& rec = a.recs[b];
+    const Work& wk = a.work[b];
+    const SolverParams& prm = a.prm;
+    const int k = wk.nsplit, nchild = 1 << k;
+    int shp[2][2];
+    for (int p = 0; p < 2; ++p) { shp[p][0] = rec.shape[p][0]; shp[p][1] = rec.shape[p][1]; }
+    const int sz0 = tensor_doubles(shp[0][0], wk.ld[0]), sz1 = tensor_doubles(shp[1][0], wk.ld[1]);
+    const int T = sz0 > sz1 ? sz0 : sz1;
+    int split_axes[2]; { bool used[2] = {false, false}; for (int j = 0; j < k; ++j) used[wk.order[0][j]] = true; int j = 0; for (int ax = 0; ax < 2; ++ax) if (used[ax]) split_axes[j++] = ax; if (j < 2) split_axes[1] = split_axes[0]; }
+    int midsel[2];
+    for (int ax = 0; ax < 2; ++ax) midsel[ax] = (rec.st.next_mid[ax] == 0.0) ? 0 : 1;
+    unsigned long long cbase = 0, dbase = 0;
+    const unsigned long long per_child = (unsigned long long)(sz0 + sz1);
+    if (tm.tid == 0) {
+        cbase = tm.atomic_add(&a.ctl->n_boxes, (unsigned long long)nchild);
+        dbase = tm.atomic_add(&a.ctl->data_used, per_child * nchild);
+        for (int j = 0; j < k; ++j) { const double m = rec.st.next_mid[split_axes[j]]; if (m != 0.0 && m != kFirstSplit) tm.atomic_add(&a.ctl->bad_mid, 1ull); }
+    }
+    cbase = tm.bcast(cbase); dbase = tm.bcast(dbase);
+    if (cbase + nchild > a.cap_boxes || dbase + per_child * nchild > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
+    tm.sync();
+    tm.copy_async(slice, a.data_in + wk.off[0], sz0);           // tensor 0 arrives while the child records are written
+    if (tm.tid < nchild) child_record(tm, a, rec, wk, (unsigned int)(cbase + tm.tid), tm.tid, k, split_axes);
+    double* S = slice; double* L = slice + T; double* X = slice + 2 * T;
+    for (int p = 0; p < 2; ++p) {
+        const int n0 = shp[p][0], n1 = shp[p][1], ld = wk.ld[p];
+        if (p == 1) tm.copy_async(S, a.data_in + wk.off[1], sz1);
+        tm.copy_wait();
+        tm.sync();
+        const int a1 = wk.order[p][0];
+        const int n_a1 = a1 == 0 ? n0 : n1;
+        SubMats m1;
+        {
+            const int ms = midsel[a1];
+            const bool sm = (ms == 0 && smat_lo != nullptr);
+            m1.lo = sm ? smat_lo : a.tab.mat[ms][0]; m1.hi = sm ? smat_hi : a.tab.mat[ms][1];
+            m1.rlo = a.tab.rows_after[ms][0]; m1.rhi = a.tab.rows_after[ms][1]; m1.nt = sm ? smat_nt : a.tab.nt;
+        }
+        const double e1 = n_a1 * kMachEps * wk.sumabs[p];
+        const double terr1 = e1 + rec.err[p];
+        int shL[2] = {n0, n1}, shU[2] = {n0, n1};
+        double sumL, sumU;
+        if (n_a1 > 1) {
+            const int rl = m1.rlo[n_a1 - 1], ru = m1.rhi[n_a1 - 1];
+            shL[a1] = rl; shU[a1] = ru;
+            const int sk = a1 == 0 ? ld : 1, sf = a1 == 0 ? 1 : ld, F = a1 == 0 ? n1 : n0;
+            sumL = pass_fiber<FMA>(tm, S, L, sk, sf, n_a1, rl, F, m1.lo, m1.nt, macs);
+            sumU = pass_fiber<FMA>(tm, S, S, sk, sf, n_a1, ru, F, m1.hi, m1.nt, macs);
+        } else {
+            copy_flat(tm, L, S, tensor_doubles(n0, ld));         // extent-1 axis: unchanged (:363)
+            sumL = sumU = wk.sumabs[p];
+            tm.sync();
+        }
+        const int rank0 = (split_axes[0] == a1) ? 0 : 1;
+        for (int h1 = 0; h1 < 2; ++h1) {
+            double* H = h1 ? S : L;
+            const int* shH = h1 ? shU : shL; const double sumH = h1 ? sumU : sumL;
+            double* outs[2] = {H, X}; int shO[2][2] = {{shH[0], shH[1]}, {shH[0], shH[1]}}; double sumO[2] = {sumH, sumH};
+            double terr = terr1;
+            int nout = 1;
+            if (k == 2) {
+                const int a2 = wk.order[p][1];
+                const int n_a2 = shH[a2];
+                SubMats m2;
+                {
+                    const int ms = midsel[a2];
+                    const bool sm = (ms == 0 && smat_lo != nullptr);
+                    m2.lo = sm ? smat_lo : a.tab.mat[ms][0]; m2.hi = sm ? smat_hi : a.tab.mat[ms][1];
+                    m2.rlo = a.tab.rows_after[ms][0]; m2.rhi = a.tab.rows_after[ms][1]; m2.nt = sm ? smat_nt : a.tab.nt;
+                }
+                const double e2 = n_a2 * kMachEps * sumH;
+                terr = e2 + terr1;
+                nout = 2;
+                if (n_a2 > 1) {
+                    const int rl = m2.rlo[n_a2 - 1], ru = m2.rhi[n_a2 - 1];
+                    shO[0][a2] = rl; shO[1][a2] = ru;
+                    const int sk = a2 == 0 ? ld : 1, sf = a2 == 0 ? 1 : ld, F = a2 == 0 ? shH[1] : shH[0];
+                    sumO[1] = pass_fiber<FMA>(tm, H, X, sk, sf, n_a2, ru, F, m2.hi, m2.nt, macs);
+                    sumO[0] = pass_fiber<FMA>(tm, H, H, sk, sf, n_a2, rl, F, m2.lo, m2.nt, macs);
+                } else {
+                    copy_flat(tm, X, H, tensor_doubles(shH[0], ld));
+                    tm.sync();
+                }
+            }
+            for (int h2 = 0; h2 < nout; ++h2) {
+                // canonical child: split axes ascending, smallest axis most significant
+                const int c = (k == 1) ? h1 : ((rank0 == 0) ? ((h1 << 1) | h2) : ((h2 << 1) | h1));
+                const int r0 = shO[h2][0], r1 = shO[h2][1];
+                const int ld_out = odd_ld(r1);
+                const unsigned long long off = dbase + per_child * c + (p ? (unsigned long long)sz0 : 0ull);
+                Epilogue ep;
+                tensor_epilogue(tm, outs[h2], r0, r1, ld, sumO[h2], terr, prm, ep);
+                copy_out_rows(tm, a.data_out + off, ld_out, outs[h2], ld, r0, r1);
+                if (tm.tid == 0) {
+                    const unsigned int child = (unsigned int)(cbase + c);
+                    Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
+                    store_epilogue(ow, p, ep, sumO[h2]);
+                    orec.shape[p][0] = r0; orec.shape[p][1] = r1; orec.err[p] = terr;
+                    ow.off[p] = off; ow.ld[p] = ld_out;
+                }
+            }
+            tm.sync();                                           // X (and H) have left for the arena
         }
     }
 }
@@ -683,7 +932,7 @@ YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
         int T, n0m, n1m; unsigned long long total;
         sizes(T, n0m, n1m, total);
         wk.op = kTRestrict;
-        dc.op = kTRestrict; dc.need = need_restrict(T, n0m, n1m); dc.cls = class_of(dc.need); dc.bound = total;
+        dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), dc.need, dc.cls); dc.bound = total;
         dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
     };
 
@@ -798,7 +1047,7 @@ YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
             int T, n0m, n1m; unsigned long long total;
             sizes(T, n0m, n1m, total);
             wk.op = kTSubdivide;
-            dc.op = kTSubdivide; dc.need = need_subdivide(T); dc.cls = class_of(dc.need); dc.bound = total << k;
+            dc.op = kTSubdivide; pick_team(need_subdivide_w(T), need_subdivide(T), dc.need, dc.cls); dc.bound = total << k;
             dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
             dc.subdiv += 1;
         }
@@ -829,7 +1078,7 @@ YR_HD void import_box(const Args& a, unsigned int b, Decision& dc, At at) {
     w.node_level = rec.level; w.result_index = -1; w.node_index = -1; w.nsplit = 0;
     int T, n0m, n1m; unsigned long long total;
     box_sizes(rec, w, T, n0m, n1m, total);
-    dc.op = kTRestrict; dc.need = need_restrict(T, n0m, n1m); dc.cls = class_of(dc.need); dc.bound = total;
+    dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), dc.need, dc.cls); dc.bound = total;
     dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
     at.add(&a.ctl->n_boxes, 1ull);
 }

@@ -54,6 +54,16 @@ struct DevBuf {
     void release(void* stream) { if (p) yr_f2_backend::dev_free(p, stream); p = nullptr; cap = 0; }
 };
 
+struct Workspace { DevBuf recs, work, arena[2], lists[2], tabs, ctlbuf; int tabs_nt = 0; size_t hint_results = 0, hint_nodes = 0; };
+inline Workspace& workspace() { static Workspace w; return w; }
+inline int trim_workspace(void* stream) {
+    Workspace& w = workspace();
+    w.recs.release(stream); w.work.release(stream); w.arena[0].release(stream); w.arena[1].release(stream);
+    w.lists[0].release(stream); w.lists[1].release(stream); w.tabs.release(stream); w.ctlbuf.release(stream);
+    w.tabs_nt = 0;
+    return 0;
+}
+
 inline int fits(unsigned long long max_extent) {
     const int n = (int)(max_extent < 4 ? 4 : max_extent);
     if (max_extent > 4096) return 0;
@@ -74,10 +84,13 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
     be::timer_reset(d->time_kernels);
     const bool trace = getenv("YR_F2_TRACE") != nullptr;
 
-    DevBuf recs, work, results, nodes, arena[2], lists[2], tabs, ctlbuf;
+    // Box tables, arenas, queues, matrix tables and the control block persist between solves (grow-only, released
+    // by yr_frontier_trim); result / node arrays belong to the caller of this solve.
+    Workspace& ws = workspace();
+    DevBuf &recs = ws.recs, &work = ws.work, &tabs = ws.tabs, &ctlbuf = ws.ctlbuf;
+    DevBuf (&arena)[2] = ws.arena; DevBuf (&lists)[2] = ws.lists;
+    DevBuf results, nodes;
     auto cleanup = [&](bool keep_out) {
-        recs.release(stream); work.release(stream); arena[0].release(stream); arena[1].release(stream);
-        lists[0].release(stream); lists[1].release(stream); tabs.release(stream); ctlbuf.release(stream);
         if (!keep_out) { results.release(stream); nodes.release(stream); }
     };
 #define F2_TRY(expr) do { if (expr) { cleanup(false); return -1; } } while (0)
@@ -87,15 +100,18 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
     F2_TRY(tabs.reserve(4 * P * 8 + 4 * (size_t)nt * 4 + 64, 0, stream, 1.0));
     double* mats = static_cast<double*>(tabs.p);
     int* rows = reinterpret_cast<int*>(mats + 4 * P);
-    F2_TRY(be::launch_tables(mats, rows, nt, stream));
+    if (ws.tabs_nt != nt) { F2_TRY(be::launch_tables(mats, rows, nt, stream)); ws.tabs_nt = nt; }
 
     F2_TRY(ctlbuf.reserve(sizeof(Ctl), 0, stream, 1.0));
     F2_TRY(be::dev_zero(ctlbuf.p, sizeof(Ctl), stream));
     size_t cap_boxes = (size_t)(n0 * 8 + 4096);
     F2_TRY(recs.reserve(cap_boxes * sizeof(BoxRec<2>), 0, stream, 1.0));
     F2_TRY(work.reserve(cap_boxes * sizeof(Work), 0, stream, 1.0));
+    { const size_t have = recs.cap / sizeof(BoxRec<2>) < work.cap / sizeof(Work) ? recs.cap / sizeof(BoxRec<2>) : work.cap / sizeof(Work); if (have > cap_boxes) cap_boxes = have; }
     F2_TRY(be::dev_copy(recs.p, d->recs_in, n0 * sizeof(BoxRec<2>), stream));
     size_t cap_results = (size_t)(n0 * 4 + 1024), cap_nodes = cap_results;
+    if (ws.hint_results > cap_results) cap_results = ws.hint_results;          // what the previous solve ended with
+    if (ws.hint_nodes > cap_nodes) cap_nodes = ws.hint_nodes;
     F2_TRY(results.reserve(cap_results * sizeof(ResultRec<2>), 0, stream, 1.0));
     F2_TRY(nodes.reserve(cap_nodes * sizeof(NodeRec<2>), 0, stream, 1.0));
 
@@ -142,18 +158,18 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) cur_lists[o][c] = a.lists[o][c];
         // capacities for everything this round can append
         if (n_boxes + 4 * n_sub > cap_boxes) {
-            const size_t want = (size_t)((n_boxes + 4 * n_sub) * 1.5) + 4096;
+            const size_t want = (size_t)((n_boxes + 4 * n_sub) * 2) + 4096;
             F2_TRY(recs.reserve(want * sizeof(BoxRec<2>), n_boxes * sizeof(BoxRec<2>), stream, 1.0));
             F2_TRY(work.reserve(want * sizeof(Work), n_boxes * sizeof(Work), stream, 1.0));
             cap_boxes = want;
         }
         if (n_results + produced > cap_results) {
-            const size_t want = (size_t)((n_results + produced) * 1.5) + 1024;
+            const size_t want = (size_t)((n_results + produced) * 2) + 1024;
             F2_TRY(results.reserve(want * sizeof(ResultRec<2>), n_results * sizeof(ResultRec<2>), stream, 1.0));
             cap_results = want;
         }
         if (n_nodes + produced > cap_nodes) {
-            const size_t want = (size_t)((n_nodes + produced) * 1.5) + 1024;
+            const size_t want = (size_t)((n_nodes + produced) * 2) + 1024;
             F2_TRY(nodes.reserve(want * sizeof(NodeRec<2>), n_nodes * sizeof(NodeRec<2>), stream, 1.0));
             cap_nodes = want;
         }
@@ -194,6 +210,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         data_in = a.data_out;
         out_arena ^= 1; cur ^= 1;
     }
+    ws.hint_results = (size_t)(n_results + n_results / 8 + 1024); ws.hint_nodes = (size_t)(n_nodes + n_nodes / 8 + 1024);
     out->results = results.p; out->n_results = n_results;
     out->nodes = nodes.p; out->n_nodes = n_nodes;
     out->rounds = rounds; out->launches = launches; out->slots = n_boxes;

@@ -33,25 +33,38 @@ __device__ __forceinline__ void copy_async16(double* dst, const double* src, int
     __pipeline_commit();
 }
 
+// A team of LANES (32 or 16) lanes of one warp.  Two 16-lane teams share a warp: they run the same instruction
+// stream on different boxes (every shuffle / vote / barrier names only the team's own lanes), which halves the
+// per-box instruction cost of everything that cannot fill 32 lanes anyway (small boxes).
+template <int LANES>
 struct WarpTeam {
     static constexpr bool kShuffle = true;
     int tid, nthreads, lane, lanes, warp, warps;
-    __device__ __forceinline__ void sync() { __syncwarp(); }
-    __device__ __forceinline__ void wsync() { __syncwarp(); }
-    __device__ __forceinline__ double sum(double v) { return warp_sum_d(v); }
-    __device__ __forceinline__ double sum_sync(double v) { __syncwarp(); return warp_sum_d(v); }
-    __device__ __forceinline__ double wsum(double v) { return warp_sum_d(v); }
-    __device__ __forceinline__ bool wany(bool p) { return __any_sync(0xffffffffu, p); }
-    __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(0xffffffffu, v, d, w); }
-    __device__ __forceinline__ double wshfl_down(double v, int d, int w) { return __shfl_down_sync(0xffffffffu, v, d, w); }
-    __device__ __forceinline__ int wshfl_idx(int v, int src, int w) { return __shfl_sync(0xffffffffu, v, src, w); }
-    __device__ __forceinline__ unsigned long long bcast(unsigned long long v) { return __shfl_sync(0xffffffffu, v, 0); }
+    unsigned mask;
+    __device__ __forceinline__ void sync() { __syncwarp(mask); }
+    __device__ __forceinline__ void wsync() { __syncwarp(mask); }
+    __device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+        return v;
+    }
+    __device__ __forceinline__ double sum(double v) { return wsum(v); }
+    __device__ __forceinline__ double sum_sync(double v) { __syncwarp(mask); return wsum(v); }
+    __device__ __forceinline__ bool wany(bool p) { return (__ballot_sync(mask, p) & mask) != 0u; }
+    __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(mask, v, d, w < LANES ? w : LANES); }
+    __device__ __forceinline__ double wshfl_down(double v, int d, int w) { return __shfl_down_sync(mask, v, d, w < LANES ? w : LANES); }
+    __device__ __forceinline__ int wshfl_idx(int v, int src, int w) { return __shfl_sync(mask, v, src, w < LANES ? w : LANES); }
+    __device__ __forceinline__ unsigned long long bcast(unsigned long long v) { return __shfl_sync(mask, v, 0, LANES); }
     __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
-    __device__ __forceinline__ void copy_async(double* dst, const double* src, int n_even) { copy_async16(dst, src, n_even, tid, 32); }
+    __device__ __forceinline__ void copy_async(double* dst, const double* src, int n_even) { copy_async16(dst, src, n_even, tid, LANES); }
     __device__ __forceinline__ void copy_wait() { __pipeline_wait_prior(0); }
 };
-__device__ __forceinline__ WarpTeam make_warp_team() {
-    WarpTeam tm; tm.tid = tm.lane = threadIdx.x & 31; tm.nthreads = tm.lanes = 32; tm.warp = 0; tm.warps = 1; return tm;
+template <int LANES>
+__device__ __forceinline__ WarpTeam<LANES> make_warp_team() {
+    WarpTeam<LANES> tm;
+    tm.tid = tm.lane = threadIdx.x & (LANES - 1); tm.nthreads = tm.lanes = LANES; tm.warp = 0; tm.warps = 1;
+    tm.mask = LANES == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+    return tm;
 }
 
 struct CtaShared { double red[2][8]; unsigned long long slot; };
@@ -114,23 +127,24 @@ __device__ void stage_submats(const Args& a, double* smat, int snt) {
     __syncthreads();
 }
 
-template <int OP, bool FMA>
+template <int OP, bool FMA, int LANES>
 __global__ void __launch_bounds__(128) f2_tensor_warp(const Args a, const unsigned int* __restrict__ list, unsigned long long n,
                                                       unsigned slice_doubles, int snt) {
     extern __shared__ __align__(16) double dyn[];
+    constexpr int kTeams = 128 / LANES;
     double* smat = dyn;
     int smat_doubles = 0;
     if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a, smat, snt); }
-    const int w = threadIdx.x >> 5;
+    const int w = threadIdx.x / LANES;
     double* slice = dyn + smat_doubles + (size_t)w * slice_doubles;
-    WarpTeam tm = make_warp_team();
-    const unsigned long long team = (unsigned long long)blockIdx.x * 4 + w, nteams = (unsigned long long)gridDim.x * 4;
+    WarpTeam<LANES> tm = make_warp_team<LANES>();
+    const unsigned long long team = (unsigned long long)blockIdx.x * kTeams + w, nteams = (unsigned long long)gridDim.x * kTeams;
     unsigned long long macs = 0;
     for (unsigned long long i = team; i < n; i += nteams) {
         const unsigned int b = list[i];
-        if (OP == kTRestrict) restrict_box<FMA>(tm, a, b, slice, macs);
-        else subdivide_box<FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
-        __syncwarp();
+        if (OP == kTRestrict) restrict_box_w<FMA>(tm, a, b, slice, macs);
+        else subdivide_box_w<FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
+        tm.sync();
     }
     if (tm.tid == 0 && macs) atomicAdd(&a.ctl->restrict_macs, macs);
 }
@@ -292,13 +306,19 @@ int launch_tensor_t(const Args& a, int cls, const unsigned int* list, unsigned l
     const size_t smat = (OP == kTSubdivide) ? (size_t)2 * panel_doubles(snt) * 8 : 0;
     const size_t slice = ((size_t)need + 1) & ~(size_t)1;
     if (cls <= 1) {
-        const size_t smem = smat + 4 * slice * 8;
+        const int teams = cls == 0 ? 8 : 4;                      // class 0: two 16-lane teams per warp
+        const size_t smem = smat + teams * slice * 8;
         if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: warp-team launch exceeds shared memory"); return -1; }
-        if (ensure_smem(f2_tensor_warp<OP, FMA>, smem)) return -1;
         long per_sm = (long)((size_t)d.smem_sm / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
-        unsigned long long want = (n + 3) / 4, cap = (unsigned long long)d.sm * per_sm;
+        unsigned long long want = (n + teams - 1) / teams, cap = (unsigned long long)d.sm * per_sm;
         const unsigned grid = (unsigned)(want < cap ? want : cap);
-        f2_tensor_warp<OP, FMA><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
+        if (cls == 0) {
+            if (ensure_smem(f2_tensor_warp<OP, FMA, 16>, smem)) return -1;
+            f2_tensor_warp<OP, FMA, 16><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
+        } else {
+            if (ensure_smem(f2_tensor_warp<OP, FMA, 32>, smem)) return -1;
+            f2_tensor_warp<OP, FMA, 32><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
+        }
     } else {
         const int threads = class_threads(cls);
         const size_t smem = smat + slice * 8;
@@ -421,6 +441,7 @@ int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* str
 
 int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
 int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
+int yr_frontier_trim(void* stream) { return yr_f2_host::trim_workspace(stream); }
 
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void* stream) {
     if (!bytes) return 0;

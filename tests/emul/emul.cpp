@@ -423,10 +423,13 @@ int launch_tensor(const yr::f2::Args& a, int op, int cls, const unsigned int* li
         unsigned long long macs = 0;
         for (unsigned long long i = 0; i < n; ++i) {
             const unsigned int b = list[i];
-            if (op == yr::f2::kTRestrict) { if (fma) yr::f2::restrict_box<true>(tm, a, b, slice.data(), macs); else yr::f2::restrict_box<false>(tm, a, b, slice.data(), macs); }
-            else {
-                const double* lo = smat.data(); const double* hi = smat.data() + yr::f2::panel_doubles(snt);
-                if (fma) yr::f2::subdivide_box<true>(tm, a, b, slice.data(), lo, hi, snt, macs); else yr::f2::subdivide_box<false>(tm, a, b, slice.data(), lo, hi, snt, macs);
+            const double* lo = smat.data(); const double* hi = smat.data() + yr::f2::panel_doubles(snt);
+            if (cls <= 1) {                                       // warp teams: in-place fiber-per-lane passes
+                if (op == yr::f2::kTRestrict) { if (fma) yr::f2::restrict_box_w<true>(tm, a, b, slice.data(), macs); else yr::f2::restrict_box_w<false>(tm, a, b, slice.data(), macs); }
+                else if (fma) yr::f2::subdivide_box_w<true>(tm, a, b, slice.data(), lo, hi, snt, macs); else yr::f2::subdivide_box_w<false>(tm, a, b, slice.data(), lo, hi, snt, macs);
+            } else {
+                if (op == yr::f2::kTRestrict) { if (fma) yr::f2::restrict_box<true>(tm, a, b, slice.data(), macs); else yr::f2::restrict_box<false>(tm, a, b, slice.data(), macs); }
+                else if (fma) yr::f2::subdivide_box<true>(tm, a, b, slice.data(), lo, hi, snt, macs); else yr::f2::subdivide_box<false>(tm, a, b, slice.data(), lo, hi, snt, macs);
             }
             tm.sync();
         }
@@ -462,5 +465,6 @@ int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* str
 }
 int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
 int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
+int yr_frontier_trim(void* stream) { return yr_f2_host::trim_workspace(stream); }
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void*) { memcpy(host_dst, dev_src, bytes); return 0; }
 }
