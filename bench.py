@@ -12,8 +12,10 @@ solveChebyshevSubdivision(Ms, errors=2^-52).  Weak scaling: every rank owns its 
              device), inputs resident in HBM, CUDA events around the level loop, max over ranks
   e2e        the same metric through the public API rootfinding_b200.solve_batch with HOST buffers:
              pack + pinned H2D + solve + D2H of the result records + host post-pass, per step
-  roofline   for the dominant kernel (level_kernel<2>): algorithmic bytes (16 B per coefficient of
-             every box at entry) / summed kernel time from CUDA events around every launch
+  roofline   for the dominant kernel family (the frontier pipeline's tensor ops f2_tensor_warp /
+             f2_tensor_cta: restriction + subdivision of every box): algorithmic bytes (16 B per
+             coefficient of every box at entry) / their summed device time, from CUDA
+             events recorded inside yr_frontier_solve around the tensor launches of every round
   cpu_baseline  the oracle port of the reference solver on the host cores (one process per core)
 `--impl reference` times that CPU arm alone on the same workload (rank 0 only).
 """
@@ -226,12 +228,15 @@ def main():
                         "solves_per_s": args.batch * world * args.steps / e2e_s_max, "roots_per_step_rank0": int(nroots)},
                 "gpu_launches": launches_all,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "level_kernel<2> (all level launches of the timed steps, rank 0)",
+                             "traffic": None,
+                             "kernel": "f2_tensor_warp / f2_tensor_cta (restrict + subdivide launches of every round of the timed steps, rank 0)",
+                             "fp64_frac_of_measured_dmul_dadd_peak": (2.0 * stats.restrict_macs / 1e12 / max(kernel_ms / args.steps * 1e-3, 1e-12)) / 18.56,
+                             "scalar_kernel_ms_per_step": getattr(sess, "scalar_ms", 0.0),
                              "peak_source": peak_src,
                              "bytes_per_box": 16.0 * stats.entry_coeffs / max(stats.boxes, 1),
                              "kernel_share_of_step": kernel_ms / max(total_ms, 1e-9)},
                 "clocks": sampler.summary(),
-                "detail": {"boxes_per_step_rank0": stats.boxes, "levels": stats.levels, "retries": stats.retries,
+                "detail": {"boxes_per_step_rank0": stats.boxes, "rounds": getattr(stats, "rounds", stats.levels), "retries": stats.retries,
                            "zooms": stats.zooms, "subdivisions": stats.subdivisions,
                            "restrict_gflops_per_s": 2.0 * stats.restrict_macs / 1e9 / (total_ms / args.steps * 1e-3),
                            "build": eng.lib.yr_build_info().decode()}}

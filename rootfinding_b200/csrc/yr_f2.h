@@ -65,17 +65,19 @@ typedef double2 pair_t;
 struct alignas(16) pair_t { double x, y; };
 #endif
 
-constexpr int kClasses = 4;                 // 0,1: warp per box   2: CTA of 128   3: CTA of 256
+constexpr int kClasses = 5;                 // 0,1: 16-lane teams   2: 32-lane team   3: CTA of 128   4: CTA of 256
+constexpr int kWarpClasses = 3;             // classes below this run the warp-team code
 constexpr int kOps = 2;
 enum Op : int32_t { kTNone = 0, kTRestrict = 1, kTSubdivide = 2 };
 YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
 
-YR_HD int class_threads(int cls) { return cls <= 1 ? 32 : (cls == 2 ? 128 : 256); }
+YR_HD int class_threads(int cls) { return cls <= 1 ? 16 : (cls == 2 ? 32 : (cls == 3 ? 128 : 256)); }
 // Shared-memory need (doubles per team) decides the team: warp teams run the in-place fiber-per-lane passes and
 // need little; CTA teams run the item-parallel out-of-place passes.
-constexpr unsigned long long kWarp16Max = 512ull;     // class 0: two 16-lane teams per warp
-constexpr unsigned long long kWarp32Max = 1536ull;    // class 1: one 32-lane team per warp
-constexpr unsigned long long kCta128Max = 7168ull;    // class 2: CTA of 128; larger: class 3, CTA of 256
+constexpr unsigned long long kWarp16Small = 512ull;   // class 0: two 16-lane teams per warp, small slices
+constexpr unsigned long long kWarp16Max = 1024ull;    // class 1: two 16-lane teams per warp
+constexpr unsigned long long kWarp32Max = 2048ull;    // class 2: one 32-lane team per warp
+constexpr unsigned long long kCta128Max = 7168ull;    // class 3: CTA of 128; larger: class 4, CTA of 256
 constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
 
 YR_HD int odd_ld(int n1) { return n1 | 1; }
@@ -96,8 +98,8 @@ YR_HD unsigned long long need_restrict_w(int T, int n0max, int n1max) {        /
 }
 YR_HD unsigned long long need_subdivide_w(int T) { return 3ull * T; }            // warp teams: [S][L][X]
 YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, unsigned long long& need, int& cls) {
-    if (need_w <= kWarp32Max) { need = need_w; cls = need_w <= kWarp16Max ? 0 : 1; }
-    else { need = need_cta; cls = need_cta <= kCta128Max ? 2 : 3; }
+    if (need_w <= kWarp32Max) { need = need_w; cls = need_w <= kWarp16Small ? 0 : (need_w <= kWarp16Max ? 1 : 2); }
+    else { need = need_cta; cls = need_cta <= kCta128Max ? 3 : 4; }
 }
 
 // Per-box state next to BoxRec<2> (same slot index).
@@ -321,13 +323,13 @@ YR_DEV double view_abs_sum(Team& tm, const double* M, int n0, int n1, int ld) {
 
 // What every produced tensor leaves behind: low-order coefficients and the outcome of trimMs (:1131-1171)
 // for error `err`.  Runs on the team's LEAD WARP only (callers guard with tm.warp == 0); lane 0 == thread 0
-// holds the results.  A trailing plane can only be dropped when its abs-sum is below the budget, so a single
-// element at or above the budget settles the (common) no-trim case with one vote instead of a reduction.
+// holds the results.  Children of a subdivision typically lose several trailing planes per axis, so groups of
+// four lanes sum up to lanes/4 candidate planes at once and the accept / stop scan then walks those sums.
 struct Epilogue { double low[6]; int t0, t1; double tsum, terr; };
 
 template <class Team>
 YR_F2_EPI void tensor_epilogue(Team& tm, const double* M, int n0, int n1, int ld, double sumabs, double err,
-                            const SolverParams& prm, Epilogue& ep) {
+                               const SolverParams& prm, Epilogue& ep) {
     ep.low[0] = M[0];
     ep.low[1] = n0 > 1 ? M[ld] : 0.0;
     ep.low[2] = n1 > 1 ? M[1] : 0.0;
@@ -338,23 +340,28 @@ YR_F2_EPI void tensor_epilogue(Team& tm, const double* M, int n0, int n1, int ld
     double budget = prm.trim_abs_tol + err * prm.trim_rel_tol;
     double removed = 0.0;
     if (prm.trim) {
-        while (t0 > 3) {                                      // axis 0: trailing rows
-            double s = 0.0;
-            const double* row = M + (t0 - 1) * ld;
-            bool big = false;
-            for (int j = tm.lane; j < t1; j += tm.lanes) { const double v = fabs(row[j]); s += v; big = big || !(v < budget); }
-            if (tm.wany(big)) break;
-            s = tm.wsum(s);
-            if (s < budget) { t0 -= 1; budget -= s; err += s; removed += s; } else break;
-        }
-        while (t1 > 3) {                                      // axis 1: trailing columns of the remaining rows
-            double s = 0.0;
-            const double* col = M + (t1 - 1);
-            bool big = false;
-            for (int i = tm.lane; i < t0; i += tm.lanes) { const double v = fabs(col[i * ld]); s += v; big = big || !(v < budget); }
-            if (tm.wany(big)) break;
-            s = tm.wsum(s);
-            if (s < budget) { t1 -= 1; budget -= s; err += s; removed += s; } else break;
+        const int gs = tm.lanes >= 4 ? 4 : tm.lanes;                 // lanes per plane
+        const int G = tm.lanes / gs;                                  // planes per sweep
+        const int g = tm.lane / gs, gl = tm.lane - g * gs;
+        for (int axis = 0; axis < 2; ++axis) {
+            for (;;) {
+                const int t = axis ? t1 : t0;
+                if (t <= 3) break;
+                const int np = (t - 3) < G ? (t - 3) : G;         // candidate planes t-1, t-2, ...
+                double s = 0.0;
+                if (g < np) {
+                    if (axis == 0) { const double* row = M + (t0 - 1 - g) * ld; for (int j = gl; j < t1; j += gs) s += fabs(row[j]); }
+                    else { const double* col = M + (t1 - 1 - g); for (int i = gl; i < t0; i += gs) s += fabs(col[i * ld]); }
+                }
+                s = tm.wsum_w(s, gs);
+                int taken = 0;
+                for (int q = 0; q < np; ++q) {
+                    const double sq = tm.wshfl_idx_d(s, q * gs);
+                    if (sq < budget) { budget -= sq; err += sq; removed += sq; ++taken; } else break;
+                }
+                if (axis) t1 -= taken; else t0 -= taken;
+                if (taken < np) break;
+            }
         }
     }
     ep.t0 = t0; ep.t1 = t1; ep.terr = err;
@@ -683,11 +690,13 @@ YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int s
 template <class Team>
 YR_DEV void copy_out_rows(Team& tm, double* dst, int ld_out, const double* M, int ld, int r0, int r1) {
     if (ld_out == ld) { copy_flat(tm, dst, M, tensor_doubles(r0, ld)); return; }
-    if (r1 <= tm.nthreads) {
-        const int j = tm.tid;
-        if (j < r1) for (int i = 0; i < r0; ++i) dst[i * ld_out + j] = M[i * ld + j];
-    } else {
-        for (int i = 0; i < r0; ++i) for (int j = tm.tid; j < r1; j += tm.nthreads) dst[i * ld_out + j] = M[i * ld + j];
+    // element (i, j) per lane, advanced without divisions
+    int i = 0, j = tm.tid;
+    while (j >= r1) { j -= r1; ++i; }
+    while (i < r0) {
+        dst[i * ld_out + j] = M[i * ld + j];
+        j += tm.nthreads;
+        while (j >= r1) { j -= r1; ++i; }
     }
 }
 

@@ -51,6 +51,8 @@ struct WarpTeam {
     __device__ __forceinline__ double sum(double v) { return wsum(v); }
     __device__ __forceinline__ double sum_sync(double v) { __syncwarp(mask); return wsum(v); }
     __device__ __forceinline__ bool wany(bool p) { return (__ballot_sync(mask, p) & mask) != 0u; }
+    __device__ __forceinline__ double wsum_w(double v, int w) { for (int off = w >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off); return v; }
+    __device__ __forceinline__ double wshfl_idx_d(double v, int src) { return __shfl_sync(mask, v, src, LANES); }
     __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(mask, v, d, w < LANES ? w : LANES); }
     __device__ __forceinline__ double wshfl_down(double v, int d, int w) { return __shfl_down_sync(mask, v, d, w < LANES ? w : LANES); }
     __device__ __forceinline__ int wshfl_idx(int v, int src, int w) { return __shfl_sync(mask, v, src, w < LANES ? w : LANES); }
@@ -90,6 +92,8 @@ struct CtaTeam {
     __device__ __forceinline__ double sum(double v) { return sum_sync(v); }
     __device__ __forceinline__ double wsum(double v) { return warp_sum_d(v); }
     __device__ __forceinline__ bool wany(bool p) { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ double wsum_w(double v, int w) { for (int off = w >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off); return v; }
+    __device__ __forceinline__ double wshfl_idx_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
     __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(0xffffffffu, v, d, w); }
     __device__ __forceinline__ double wshfl_down(double v, int d, int w) { return __shfl_down_sync(0xffffffffu, v, d, w); }
     __device__ __forceinline__ int wshfl_idx(int v, int src, int w) { return __shfl_sync(0xffffffffu, v, src, w); }
@@ -305,14 +309,14 @@ int launch_tensor_t(const Args& a, int cls, const unsigned int* list, unsigned l
     const int snt = (OP == kTSubdivide) ? (ext < 4 ? 4 : ext) : 0;
     const size_t smat = (OP == kTSubdivide) ? (size_t)2 * panel_doubles(snt) * 8 : 0;
     const size_t slice = ((size_t)need + 1) & ~(size_t)1;
-    if (cls <= 1) {
-        const int teams = cls == 0 ? 8 : 4;                      // class 0: two 16-lane teams per warp
+    if (cls < kWarpClasses) {
+        const int teams = cls <= 1 ? 8 : 4;                      // classes 0, 1: two 16-lane teams per warp
         const size_t smem = smat + teams * slice * 8;
         if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: warp-team launch exceeds shared memory"); return -1; }
         long per_sm = (long)((size_t)d.smem_sm / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
         unsigned long long want = (n + teams - 1) / teams, cap = (unsigned long long)d.sm * per_sm;
         const unsigned grid = (unsigned)(want < cap ? want : cap);
-        if (cls == 0) {
+        if (cls <= 1) {
             if (ensure_smem(f2_tensor_warp<OP, FMA, 16>, smem)) return -1;
             f2_tensor_warp<OP, FMA, 16><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
         } else {

@@ -32,9 +32,9 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, cap
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 # mangled-name match: strip template punctuation from the ncu name
-m0 = re.search(r"(\w+)<\(int\)(\d+), \(bool\)(\d)>", blk["name"])
+m0 = re.search(r"(\w+)<\(int\)(\d+), \(bool\)(\d)(?:, \(int\)(\d+))?>", blk["name"])
 if m0:
-    key = f"{m0.group(1)}ILi{m0.group(2)}ELb{m0.group(3)}E"
+    key = f"{m0.group(1)}ILi{m0.group(2)}ELb{m0.group(3)}E" + (f"Li{m0.group(4)}E" if m0.group(4) else "")
 else:
     key = re.search(r"(\w+)\(", blk["name"]).group(1)
 line_of, infn, curline = {}, False, ("?", 0)

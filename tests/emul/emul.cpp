@@ -326,6 +326,16 @@ struct F2Team {
     double sum_sync(double v) { return sum(v); }
     double wsum(double v) { return sum(v); }
     bool wany(bool p) { return sum(p ? 1.0 : 0.0) > 0.0; }
+    double wsum_w(double v, int w) {
+        team->scratch[tid] = v; sync();
+        double t = 0; const int lo = (tid / w) * w; for (int i = lo; i < lo + w && i < nthreads; ++i) t += team->scratch[i];
+        sync(); return t;
+    }
+    double wshfl_idx_d(double v, int src) {
+        team->scratch[tid] = v; sync();
+        const double r = team->scratch[src];
+        sync(); return r;
+    }
     double wshfl_up(double v, int d, int w) {
         team->scratch[tid] = v; sync();
         const double r = ((tid % w) >= d) ? team->scratch[tid - d] : v;
@@ -404,7 +414,7 @@ int launch_import(const yr::f2::Args& a, unsigned long long n, void*) {
 
 int launch_tensor(const yr::f2::Args& a, int op, int cls, const unsigned int* list, unsigned long long n,
                   unsigned long long need, int ext, void*) {
-    const int T = cls <= 1 ? env_int("YR_EMUL_LANES", 4) : env_int("YR_EMUL_THREADS", 8);
+    const int T = cls < yr::f2::kWarpClasses ? env_int("YR_EMUL_LANES", 4) : env_int("YR_EMUL_THREADS", 8);
     // the m = 0 matrices re-laid out for `ext`, as the CUDA kernels stage them in shared memory
     std::vector<double> smat;
     int snt = 0;
@@ -424,7 +434,7 @@ int launch_tensor(const yr::f2::Args& a, int op, int cls, const unsigned int* li
         for (unsigned long long i = 0; i < n; ++i) {
             const unsigned int b = list[i];
             const double* lo = smat.data(); const double* hi = smat.data() + yr::f2::panel_doubles(snt);
-            if (cls <= 1) {                                       // warp teams: in-place fiber-per-lane passes
+            if (cls < yr::f2::kWarpClasses) {                       // warp teams: in-place fiber-per-lane passes
                 if (op == yr::f2::kTRestrict) { if (fma) yr::f2::restrict_box_w<true>(tm, a, b, slice.data(), macs); else yr::f2::restrict_box_w<false>(tm, a, b, slice.data(), macs); }
                 else if (fma) yr::f2::subdivide_box_w<true>(tm, a, b, slice.data(), lo, hi, snt, macs); else yr::f2::subdivide_box_w<false>(tm, a, b, slice.data(), lo, hi, snt, macs);
             } else {
