@@ -161,6 +161,8 @@ typedef struct yr_frontier_desc {
 typedef struct yr_frontier_out {
     void*    results; uint64_t n_results;   /* device arrays owned by the library */
     void*    nodes;   uint64_t n_nodes;
+    void*    order;                         /* uint32[n_results]: results[order[0]], results[order[1]], ... is the
+                                               reference's reporting order (system, then depth-first path) */
     yr_counters counters;                   /* totals of the solve (boxes, zooms, subdivisions, discards, ...) */
     uint64_t rounds, launches, slots;
     double   tensor_ms, scalar_ms;          /* summed device time of the two kernel families (time_kernels = 1) */

@@ -61,7 +61,8 @@ class YrFrontierDesc(C.Structure):
 
 
 class YrFrontierOut(C.Structure):
-    _fields_ = [("results", vp), ("n_results", u64), ("nodes", vp), ("n_nodes", u64), ("counters", YrCounters),
+    _fields_ = [("results", vp), ("n_results", u64), ("nodes", vp), ("n_nodes", u64), ("order", vp),
+                ("counters", YrCounters),
                 ("rounds", u64), ("launches", u64), ("slots", u64), ("tensor_ms", C.c_double), ("scalar_ms", C.c_double)]
 
 

@@ -29,6 +29,8 @@ int launch_scalar(const yr::f2::Args& a, const Segments& s, void* stream);
 void timer_reset(int enable);
 void timer_mark(int which, int begin, void* stream);      // which: 0 tensor, 1 scalar
 void timer_collect(double* tensor_ms, double* scalar_ms);
+// order[0..n) = record indices sorted by (system, path_hi, path_lo); returns a device buffer (or null)
+void* sort_results(const void* results, unsigned long long n, void* stream);
 double trace_sync_ms(void* stream);      // YR_F2_TRACE: synchronise and return host milliseconds since the previous call
 }  // namespace yr_f2_backend
 
@@ -211,6 +213,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         out_arena ^= 1; cur ^= 1;
     }
     ws.hint_results = (size_t)(n_results + n_results / 8 + 1024); ws.hint_nodes = (size_t)(n_nodes + n_nodes / 8 + 1024);
+    out->order = n_results ? be::sort_results(results.p, n_results, stream) : nullptr;
     out->results = results.p; out->n_results = n_results;
     out->nodes = nodes.p; out->n_nodes = n_nodes;
     out->rounds = rounds; out->launches = launches; out->slots = n_boxes;
@@ -228,7 +231,8 @@ inline int release(yr_frontier_out* out, void* stream) {
     if (!out) return 0;
     if (out->results) yr_f2_backend::dev_free(out->results, stream);
     if (out->nodes) yr_f2_backend::dev_free(out->nodes, stream);
-    out->results = nullptr; out->nodes = nullptr;
+    if (out->order) yr_f2_backend::dev_free(out->order, stream);
+    out->results = nullptr; out->nodes = nullptr; out->order = nullptr;
     return 0;
 }
 

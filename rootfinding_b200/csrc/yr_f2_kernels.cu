@@ -9,6 +9,7 @@
 // Compiled with -fmad=false like the rest of the library.
 #include <cuda_runtime.h>
 #include <cuda_pipeline.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdlib.h>
 #include <time.h>
@@ -404,6 +405,47 @@ int launch_scalar(const Args& a, const Segments& s, void* stream) {
     f2_scalar_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, s);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "f2_scalar_kernel launch");
+}
+
+// ---- reporting order: stable LSD radix sort of the record indices by path_lo, path_hi, system (CUB) ----
+__global__ void f2_sort_keys(const ResultRec<2>* res, const unsigned int* idx, unsigned long long n, int which,
+                             unsigned long long* k64, unsigned int* k32, unsigned int* iota) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int r = idx ? idx[i] : (unsigned int)i;
+    if (iota) iota[i] = (unsigned int)i;
+    if (which == 0) k64[i] = res[r].path_lo;
+    else if (which == 1) k64[i] = res[r].path_hi;
+    else k32[i] = (unsigned int)res[r].system;
+}
+
+void* sort_results(const void* results, unsigned long long n, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const ResultRec<2>* res = static_cast<const ResultRec<2>*>(results);
+    const size_t n_ = (size_t)n;
+    unsigned long long* k64a = (unsigned long long*)dev_alloc(n_ * 8, stream); unsigned long long* k64b = (unsigned long long*)dev_alloc(n_ * 8, stream);
+    unsigned int* k32a = (unsigned int*)dev_alloc(n_ * 4, stream); unsigned int* k32b = (unsigned int*)dev_alloc(n_ * 4, stream);
+    unsigned int* ia = (unsigned int*)dev_alloc(n_ * 4, stream); unsigned int* ib = (unsigned int*)dev_alloc(n_ * 4, stream);
+    void* result = nullptr;
+    if (k64a && k64b && k32a && k32b && ia && ib) {
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        size_t tb64 = 0, tb32 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb64, k64a, k64b, ia, ib, (int)n, 0, 64, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb32, k32a, k32b, ia, ib, (int)n, 0, 32, st);
+        void* tmp = dev_alloc(tb64 > tb32 ? tb64 : tb32, stream);
+        if (tmp) {
+            f2_sort_keys<<<grid, 256, 0, st>>>(res, nullptr, n, 0, k64a, nullptr, ia);
+            cub::DeviceRadixSort::SortPairs(tmp, tb64, k64a, k64b, ia, ib, (int)n, 0, 64, st);          // by path_lo -> ib
+            f2_sort_keys<<<grid, 256, 0, st>>>(res, ib, n, 1, k64a, nullptr, nullptr);
+            cub::DeviceRadixSort::SortPairs(tmp, tb64, k64a, k64b, ib, ia, (int)n, 0, 64, st);          // by path_hi -> ia
+            f2_sort_keys<<<grid, 256, 0, st>>>(res, ia, n, 2, nullptr, k32a, nullptr);
+            cub::DeviceRadixSort::SortPairs(tmp, tb32, k32a, k32b, ia, ib, (int)n, 0, 32, st);          // by system  -> ib
+            dev_free(tmp, stream);
+            if (cudaGetLastError() == cudaSuccess) { result = ib; ib = nullptr; }
+        }
+    }
+    dev_free(k64a, stream); dev_free(k64b, stream); dev_free(k32a, stream); dev_free(k32b, stream); dev_free(ia, stream); dev_free(ib, stream);
+    return result;
 }
 
 double trace_sync_ms(void* stream) {

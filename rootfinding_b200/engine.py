@@ -31,6 +31,37 @@ class _Buf:
         self.ptr, self.nbytes, self.owner = ptr, nbytes, owner
 
 
+class _Growable:
+    """Append-only structured host array on top of a byte buffer obtained from `alloc(nbytes, who)`."""
+
+    def __init__(self, dtype, alloc, who):
+        self.dtype, self.alloc, self.who = dtype, alloc, who
+        self.buf = np.empty(0, dtype=np.uint8)
+        self.n = 0
+
+    def tail(self, k):
+        """Room for k more records: returns the uint8 view to fill."""
+        item = self.dtype.itemsize
+        need = (self.n + k) * item
+        if need > self.buf.nbytes:
+            new = self.alloc(max(need + need // 8, 2 * self.buf.nbytes), self.who)
+            new[:self.n * item] = self.buf[:self.n * item]
+            self.buf = new
+        v = self.buf[self.n * item:need]
+        self.n += k
+        return v
+
+    def view(self):
+        return self.buf[:self.n * self.dtype.itemsize].view(self.dtype)
+
+    def detach(self):
+        """Move to private memory (the lender wants its buffer back)."""
+        self.buf = self.buf[:self.n * self.dtype.itemsize].copy()
+
+    def __len__(self):
+        return self.n
+
+
 class CudaMemory:
     """Device memory, stream and host staging through torch (cuda only)."""
 
@@ -43,6 +74,8 @@ class CudaMemory:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._staging = []
+        self._pinned = None
+        self._pinned_owner = None
 
     def empty(self, nbytes):
         n8 = max(1, (int(nbytes) + 7) // 8)
@@ -68,6 +101,22 @@ class CudaMemory:
             self._staging.append(pinned)                       # keep alive until the next synchronize
             self.h2d_bytes += arr.nbytes
         return b
+
+    def host_bytes(self, nbytes, who=None):
+        """Host buffer for record downloads.  One page-locked buffer is kept per engine and lent to the session
+        that downloads (a 200 MB device -> pageable copy costs several times the solve); a previous borrower that
+        is still alive first moves its records to private memory."""
+        import weakref
+        if nbytes < (1 << 20):
+            return np.empty(nbytes, dtype=np.uint8)
+        prev = self._pinned_owner() if self._pinned_owner is not None else None
+        if prev is not None and prev is not who:
+            prev._detach_host()
+        if self._pinned is None or self._pinned.numel() < nbytes:
+            self._pinned = None
+            self._pinned = self.torch.empty(int(nbytes), dtype=self.torch.uint8, pin_memory=True)
+        self._pinned_owner = weakref.ref(who) if who is not None else None
+        return self._pinned.numpy()[:nbytes]
 
     def timer(self):
         """CUDA event pair helper: returns (record_start, record_stop, elapsed_ms) bound to the current stream."""
@@ -230,8 +279,10 @@ class SolveSession:
         self.n_nodes = 0
         self.d_nodes = None
         self._pending = []
-        self._results_host = np.empty(0, dtype=self.rdt)
-        self._nodes_host = np.empty(0, dtype=self.ndt)
+        alloc = getattr(m, "host_bytes", lambda nbytes, who=None: np.empty(nbytes, dtype=np.uint8))
+        self._results_host = _Growable(self.rdt, alloc, self)
+        self._nodes_host = _Growable(self.ndt, lambda nbytes, who=None: np.empty(nbytes, dtype=np.uint8), self)
+        self._order_host = None           # depth-first order of the first frontier solve's records (device sort)
         self.stats = SolveStats()
         self.time_kernels = False        # bench.py: CUDA events around every level launch
         self.kernel_ms = []              # (ms, algorithmic bytes, boxes) per level launch
@@ -429,19 +480,27 @@ class SolveSession:
                     level=np.zeros(n, np.int32), next_mid=np.full((n, D), FIRST_SPLIT), parent=np.full(n, -1, np.int32))
 
     # -- results -----------------------------------------------------------------------------
+    def _detach_host(self):
+        self._results_host.detach()
+
     def _fetch_pending(self):
         """Device -> host copy of the records the frontier pipeline produced (library-owned buffers)."""
         lib, stream = self.lib, self.mem.stream()
         while self._pending:
             out = self._pending.pop(0)
             try:
-                for ptr, n, dt, name in ((out.results, int(out.n_results), self.rdt, "_results_host"),
-                                         (out.nodes, int(out.n_nodes), self.ndt, "_nodes_host")):
+                first = len(self._results_host) == 0
+                for ptr, n, grow in ((out.results, int(out.n_results), self._results_host),
+                                     (out.nodes, int(out.n_nodes), self._nodes_host)):
                     if n:
-                        host = np.empty(n, dtype=dt)
-                        _lib.check(lib, lib.yr_fetch(host.ctypes.data, ptr, host.nbytes, stream), "yr_fetch")
-                        setattr(self, name, np.concatenate([getattr(self, name), host]))
-                        self.mem.d2h_bytes += host.nbytes
+                        dst = grow.tail(n)
+                        _lib.check(lib, lib.yr_fetch(dst.ctypes.data, ptr, dst.nbytes, stream), "yr_fetch")
+                        self.mem.d2h_bytes += dst.nbytes
+                if first and int(out.n_results) and out.order:
+                    order = np.empty(int(out.n_results), dtype=np.uint32)
+                    _lib.check(lib, lib.yr_fetch(order.ctypes.data, out.order, order.nbytes, stream), "yr_fetch")
+                    self.mem.d2h_bytes += order.nbytes
+                    self._order_host = order
             finally:
                 lib.yr_frontier_release(C.byref(out), stream)
 
@@ -460,8 +519,8 @@ class SolveSession:
         if self.n_results > have:
             item = self.rdt.itemsize
             raw = self.mem.download(self.d_results, (self.n_results - have) * item, have * item)
-            self._results_host = np.concatenate([self._results_host, raw.view(self.rdt)])
-        return self._results_host
+            self._results_host.tail(self.n_results - have)[:] = raw
+        return self._results_host.view()
 
     def nodes(self):
         if self._pending:
@@ -470,5 +529,13 @@ class SolveSession:
         if self.n_nodes > have:
             item = self.ndt.itemsize
             raw = self.mem.download(self.d_nodes, (self.n_nodes - have) * item, have * item)
-            self._nodes_host = np.concatenate([self._nodes_host, raw.view(self.ndt)])
-        return self._nodes_host
+            self._nodes_host.tail(self.n_nodes - have)[:] = raw
+        return self._nodes_host.view()
+
+    def dfs_order(self):
+        """(order, n): permutation that puts records [0, n) in (system, depth-first path) order, sorted on the
+        device by yr_frontier_solve, or (None, 0) when the session has none."""
+        self.results()
+        if self._order_host is None:
+            return None, 0
+        return self._order_host, len(self._order_host)

@@ -190,7 +190,32 @@ def assemble(session, merge=True):
     alive, dup, extra = resolve_collectors(res)
     if merge:
         res, alive, dup, extra = merge_exterior(session, res, alive, dup, extra)
-    keep = _path_order(res, np.nonzero(alive)[0])
+    order, n_sorted = session.dfs_order() if hasattr(session, "dfs_order") else (None, 0)
+    if order is not None and n_sorted:
+        # the first n_sorted records arrive with their reporting order from the device (radix sort); records added
+        # later (re-solved merged boxes, a handful) are sorted here and merged in
+        main = order[alive[:n_sorted][order]].astype(np.int64)
+        late = np.nonzero(alive[n_sorted:])[0] + n_sorted
+        if len(late):
+            late = _path_order(res, late)
+            key = lambda i: (int(res["system"][i]), int(res["path_hi"][i]), int(res["path_lo"][i]))
+            main_keys_sys = res["system"][main]
+            pos = []
+            for i in late:                                   # binary search by full key
+                lo_, hi_ = int(np.searchsorted(main_keys_sys, res["system"][i], "left")), int(np.searchsorted(main_keys_sys, res["system"][i], "right"))
+                k = key(i)
+                while lo_ < hi_:
+                    mid = (lo_ + hi_) // 2
+                    if key(main[mid]) < k:
+                        lo_ = mid + 1
+                    else:
+                        hi_ = mid
+                pos.append(lo_)
+            keep = np.insert(main, pos, late)
+        else:
+            keep = main
+    else:
+        keep = _path_order(res, np.nonzero(alive)[0])
     return res, keep, dup, extra
 
 

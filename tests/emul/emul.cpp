@@ -5,6 +5,7 @@
 // and block reductions performed in the same order as on the device.  It exports the
 // same C ABI as the product library so tests can drive the real host code against it
 // on a machine without a GPU.  The product package never loads this library.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -462,6 +463,19 @@ int launch_scalar(const yr::f2::Args& a, const Segments& s, void*) {
     return 0;
 }
 
+void* sort_results(const void* results, unsigned long long n, void*) {
+    const yr::ResultRec<2>* res = static_cast<const yr::ResultRec<2>*>(results);
+    unsigned int* order = static_cast<unsigned int*>(malloc((size_t)n * 4 + 16));
+    std::vector<unsigned int> v((size_t)n);
+    for (size_t i = 0; i < v.size(); ++i) v[i] = (unsigned int)i;
+    std::stable_sort(v.begin(), v.end(), [&](unsigned int a, unsigned int b) {
+        if (res[a].system != res[b].system) return res[a].system < res[b].system;
+        if (res[a].path_hi != res[b].path_hi) return res[a].path_hi < res[b].path_hi;
+        return res[a].path_lo < res[b].path_lo;
+    });
+    memcpy(order, v.data(), v.size() * 4);
+    return order;
+}
 double trace_sync_ms(void*) { return 0.0; }
 void timer_reset(int) {}
 void timer_mark(int, int, void*) {}
