@@ -65,19 +65,22 @@ typedef double2 pair_t;
 struct alignas(16) pair_t { double x, y; };
 #endif
 
-constexpr int kClasses = 5;                 // 0,1: 16-lane teams   2: 32-lane team   3: CTA of 128   4: CTA of 256
-constexpr int kWarpClasses = 3;             // classes below this run the warp-team code
+// Size classes.  A class fixes the team (16 lanes, 32 lanes, CTA of 128 / 256) and bounds the shared memory a
+// box may need; a launch sizes every team's slice by the largest need actually queued in that class, so finer
+// classes mean more resident teams per SM for the typical box.
 constexpr int kOps = 2;
 enum Op : int32_t { kTNone = 0, kTRestrict = 1, kTSubdivide = 2 };
 YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
 
-YR_HD int class_threads(int cls) { return cls <= 1 ? 16 : (cls == 2 ? 32 : (cls == 3 ? 128 : 256)); }
-// Shared-memory need (doubles per team) decides the team: warp teams run the in-place fiber-per-lane passes and
-// need little; CTA teams run the item-parallel out-of-place passes.
-constexpr unsigned long long kWarp16Small = 512ull;   // class 0: two 16-lane teams per warp, small slices
-constexpr unsigned long long kWarp16Max = 1024ull;    // class 1: two 16-lane teams per warp
-constexpr unsigned long long kWarp32Max = 2048ull;    // class 2: one 32-lane team per warp
-constexpr unsigned long long kCta128Max = 7168ull;    // class 3: CTA of 128; larger: class 4, CTA of 256
+constexpr int kClasses = 9;
+constexpr int kWarpClasses = 7;             // classes below this run the warp-team code
+constexpr int kLane16Classes = 5;           // classes below this use two 16-lane teams per warp
+YR_HD unsigned long long class_bound(int c) {
+    const unsigned long long b[kClasses] = {384ull, 512ull, 640ull, 768ull, 1024ull, 1536ull, 2048ull, 7168ull, ~0ull};
+    return b[c];
+}
+YR_HD int class_threads(int cls) { return cls < kLane16Classes ? 16 : (cls < kWarpClasses ? 32 : (cls == kWarpClasses ? 128 : 256)); }
+constexpr unsigned long long kWarp32Max = 2048ull;    // largest need a warp team takes
 constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
 
 YR_HD int odd_ld(int n1) { return n1 | 1; }
@@ -98,8 +101,8 @@ YR_HD unsigned long long need_restrict_w(int T, int n0max, int n1max) {        /
 }
 YR_HD unsigned long long need_subdivide_w(int T) { return 3ull * T; }            // warp teams: [S][L][X]
 YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, unsigned long long& need, int& cls) {
-    if (need_w <= kWarp32Max) { need = need_w; cls = need_w <= kWarp16Small ? 0 : (need_w <= kWarp16Max ? 1 : 2); }
-    else { need = need_cta; cls = need_cta <= kCta128Max ? 3 : 4; }
+    if (need_w <= kWarp32Max) { need = need_w; cls = 0; while (need_w > class_bound(cls)) ++cls; }
+    else { need = need_cta; cls = need_cta <= class_bound(kWarpClasses) ? kWarpClasses : kWarpClasses + 1; }
 }
 
 // Per-box state next to BoxRec<2> (same slot index).
@@ -216,24 +219,19 @@ YR_F2_BUILD void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb,
     if (live && b == 0) { ptr[0] = prev2; if (nt >= 2) ptr[4] = prev; }
     if (i == 0 && nt > 0) { j.rows_after[0] = 1; if (nt >= 2) j.rows_after[1] = 2; }
     int rows = 2;
+    const int segshift = (seg == 16 && w.lanes == 32) ? (lane & 16) : 0;
     for (int k = 2; k < kmax; ++k) {
         double cm1 = w.wshfl_up(prev, 1, seg), cp1 = w.wshfl_down(prev, 1, seg);
         if (i == 0) cm1 = 0.0;
         if (i + 1 > k - 1 || i + 1 >= seg) cp1 = 0.0;
-        double val = 0.0;
-        int grow = 0;
-        if (i <= rows) {
-            double t;
-            if (i == 0) t = alpha * cp1;
-            else if (i == 1) t = alpha * (2 * cm1 + cp1);
-            else t = alpha * (cm1 + cp1);
-            val = (-prev2 + t) + beta2 * prev;
-            if (i == rows) {                                   // the reference's finalVal
-                val = alpha * cm1;
-                if (fabs(val) > 1e-16) grow = 1; else val = 0.0;
-            }
-        }
-        grow = w.wshfl_idx(grow, rows < seg ? rows : 0, seg);
+        // every lane evaluates both candidates; selects instead of branches (same expressions as build_panels)
+        const double t = alpha * ((i == 1 ? 2 * cm1 : cm1) + cp1);
+        const double inner = (-prev2 + t) + beta2 * prev;
+        const double fin = alpha * cm1;                          // the reference's finalVal, lane `rows` only
+        const bool last = (i == rows);
+        const bool g = last && (fabs(fin) > 1e-16);
+        const double val = last ? (g ? fin : 0.0) : (i < rows ? inner : 0.0);
+        const int grow = ((w.wballot(g) >> segshift) & (seg == 16 ? 0xffffu : 0xffffffffu)) != 0u;
         if (k < nt) {
             if (live && k >= 4 * b) ptr[(k - 4 * b) << 2] = val;
             prev2 = prev; prev = val;

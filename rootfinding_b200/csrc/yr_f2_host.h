@@ -22,6 +22,9 @@ int launch_import(const yr::f2::Args& a, unsigned long long n, void* stream);
 // boxes list[0 .. n): tensor op `op` with `need` doubles of shared memory per team, extents <= ext
 int launch_tensor(const yr::f2::Args& a, int op, int cls, const unsigned int* list, unsigned long long n,
                   unsigned long long need, int ext, void* stream);
+// the tensor launches of a round are independent: the backend may spread them over several streams between these
+void round_fork(void* stream);
+void round_join(void* stream);
 struct Segments { const unsigned int* list[yr::f2::kClasses]; unsigned long long n[yr::f2::kClasses];
                   unsigned long long child_lo, child_bound; };
 int launch_scalar(const yr::f2::Args& a, const Segments& s, void* stream);
@@ -187,7 +190,8 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         F2_TRY(be::dev_zero(&a.ctl->n_results, 2 * sizeof(unsigned long long), stream));
         if (trace) fprintf(stderr, "f2 round %3llu: host %.3f ms |", rounds, be::trace_sync_ms(stream));
         be::timer_mark(0, 1, stream);
-        for (int o = 0; o < kOps; ++o)
+        be::round_fork(stream);
+        for (int o = kOps - 1; o >= 0; --o)
             for (int c = 0; c < kClasses; ++c) {
                 if (!h.n_list[o][c]) continue;
                 if (h.need_max[o][c] + (o ? 2ull * panel_doubles((int)(h.ext_max[c] < 4 ? 4 : h.ext_max[c])) : 0ull) > kMaxNeed) { cleanup(false); return fail("yr_frontier_solve: a box exceeds the shared-memory budget"); }
@@ -196,6 +200,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
                 ++launches;
                 if (trace) fprintf(stderr, " %s%d n=%llu need=%llu ext=%llu %.3f ms |", o ? "S" : "R", c, h.n_list[o][c], h.need_max[o][c], o ? h.ext_max[c] : 0ull, be::trace_sync_ms(stream));
             }
+        be::round_join(stream);
         be::timer_mark(0, 0, stream);
         be::Segments sg;
         for (int c = 0; c < kClasses; ++c) { sg.list[c] = cur_lists[0][c]; sg.n[c] = h.n_list[0][c]; }

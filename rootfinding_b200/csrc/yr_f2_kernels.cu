@@ -52,6 +52,7 @@ struct WarpTeam {
     __device__ __forceinline__ double sum(double v) { return wsum(v); }
     __device__ __forceinline__ double sum_sync(double v) { __syncwarp(mask); return wsum(v); }
     __device__ __forceinline__ bool wany(bool p) { return (__ballot_sync(mask, p) & mask) != 0u; }
+    __device__ __forceinline__ unsigned wballot(bool p) { return LANES == 32 ? __ballot_sync(mask, p) : ((__ballot_sync(mask, p) >> (threadIdx.x & 16)) & 0xffffu); }
     __device__ __forceinline__ double wsum_w(double v, int w) { for (int off = w >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off); return v; }
     __device__ __forceinline__ double wshfl_idx_d(double v, int src) { return __shfl_sync(mask, v, src, LANES); }
     __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(mask, v, d, w < LANES ? w : LANES); }
@@ -93,6 +94,7 @@ struct CtaTeam {
     __device__ __forceinline__ double sum(double v) { return sum_sync(v); }
     __device__ __forceinline__ double wsum(double v) { return warp_sum_d(v); }
     __device__ __forceinline__ bool wany(bool p) { return __any_sync(0xffffffffu, p); }
+    __device__ __forceinline__ unsigned wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
     __device__ __forceinline__ double wsum_w(double v, int w) { for (int off = w >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off); return v; }
     __device__ __forceinline__ double wshfl_idx_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
     __device__ __forceinline__ double wshfl_up(double v, int d, int w) { return __shfl_up_sync(0xffffffffu, v, d, w); }
@@ -311,13 +313,13 @@ int launch_tensor_t(const Args& a, int cls, const unsigned int* list, unsigned l
     const size_t smat = (OP == kTSubdivide) ? (size_t)2 * panel_doubles(snt) * 8 : 0;
     const size_t slice = ((size_t)need + 1) & ~(size_t)1;
     if (cls < kWarpClasses) {
-        const int teams = cls <= 1 ? 8 : 4;                      // classes 0, 1: two 16-lane teams per warp
+        const int teams = cls < kLane16Classes ? 8 : 4;          // two 16-lane teams per warp for the small classes
         const size_t smem = smat + teams * slice * 8;
         if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: warp-team launch exceeds shared memory"); return -1; }
         long per_sm = (long)((size_t)d.smem_sm / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
         unsigned long long want = (n + teams - 1) / teams, cap = (unsigned long long)d.sm * per_sm;
         const unsigned grid = (unsigned)(want < cap ? want : cap);
-        if (cls <= 1) {
+        if (cls < kLane16Classes) {
             if (ensure_smem(f2_tensor_warp<OP, FMA, 16>, smem)) return -1;
             f2_tensor_warp<OP, FMA, 16><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
         } else {
@@ -391,8 +393,38 @@ int launch_import(const Args& a, unsigned long long n, void* stream) {
     return e == cudaSuccess ? 0 : cuda_fail(e, "f2_import_kernel launch");
 }
 
+// ---- a round's tensor launches fan out over a few streams and join before the scalar step ----
+namespace {
+constexpr int kFanStreams = 6;
+struct Fan { cudaStream_t st[kFanStreams]; cudaEvent_t done[kFanStreams]; cudaEvent_t start; bool ready = false, used[kFanStreams]; int next = 0; bool active = false; } g_fan;
+}
+void round_fork(void* stream) {
+    static const bool enabled = getenv("YR_F2_ONE_STREAM") == nullptr && getenv("YR_F2_TRACE") == nullptr;
+    g_fan.active = false;
+    if (!enabled) return;
+    if (!g_fan.ready) {
+        for (int i = 0; i < kFanStreams; ++i) { cudaStreamCreateWithFlags(&g_fan.st[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&g_fan.done[i], cudaEventDisableTiming); }
+        cudaEventCreateWithFlags(&g_fan.start, cudaEventDisableTiming);
+        g_fan.ready = true;
+    }
+    cudaEventRecord(g_fan.start, (cudaStream_t)stream);
+    for (int i = 0; i < kFanStreams; ++i) g_fan.used[i] = false;
+    g_fan.next = 0; g_fan.active = true;
+}
+void round_join(void* stream) {
+    if (!g_fan.active) return;
+    for (int i = 0; i < kFanStreams; ++i)
+        if (g_fan.used[i]) { cudaEventRecord(g_fan.done[i], g_fan.st[i]); cudaStreamWaitEvent((cudaStream_t)stream, g_fan.done[i], 0); }
+    g_fan.active = false;
+}
+
 int launch_tensor(const Args& a, int op, int cls, const unsigned int* list, unsigned long long n, unsigned long long need, int ext, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (g_fan.active) {
+        const int i = g_fan.next; g_fan.next = (g_fan.next + 1) % kFanStreams;
+        if (!g_fan.used[i]) { cudaStreamWaitEvent(g_fan.st[i], g_fan.start, 0); g_fan.used[i] = true; }
+        st = g_fan.st[i];
+    }
     const bool fma = a.prm.use_fma != 0;
     if (op == kTRestrict) return fma ? launch_tensor_t<kTRestrict, true>(a, cls, list, n, need, ext, st) : launch_tensor_t<kTRestrict, false>(a, cls, list, n, need, ext, st);
     return fma ? launch_tensor_t<kTSubdivide, true>(a, cls, list, n, need, ext, st) : launch_tensor_t<kTSubdivide, false>(a, cls, list, n, need, ext, st);

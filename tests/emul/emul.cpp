@@ -327,6 +327,11 @@ struct F2Team {
     double sum_sync(double v) { return sum(v); }
     double wsum(double v) { return sum(v); }
     bool wany(bool p) { return sum(p ? 1.0 : 0.0) > 0.0; }
+    unsigned wballot(bool p) {
+        team->scratch[tid] = p ? 1.0 : 0.0; sync();
+        unsigned r = 0; for (int i = 0; i < nthreads && i < 32; ++i) if (team->scratch[i] != 0.0) r |= 1u << i;
+        sync(); return r;
+    }
     double wsum_w(double v, int w) {
         team->scratch[tid] = v; sync();
         double t = 0; const int lo = (tid / w) * w; for (int i = lo; i < lo + w && i < nthreads; ++i) t += team->scratch[i];
@@ -477,6 +482,8 @@ void* sort_results(const void* results, unsigned long long n, void*) {
     return order;
 }
 double trace_sync_ms(void*) { return 0.0; }
+void round_fork(void*) {}
+void round_join(void*) {}
 void timer_reset(int) {}
 void timer_mark(int, int, void*) {}
 void timer_collect(double* t, double* s) { *t = 0; *s = 0; }
