@@ -372,6 +372,79 @@ YR_HD void store_epilogue(Work& w, int p, const Epilogue& ep, double sumabs) {
     w.tshape[p][0] = ep.t0; w.tshape[p][1] = ep.t1; w.tsumabs[p] = ep.tsum; w.terr[p] = ep.terr;
 }
 
+// ---- both halves of a subdivision in one sweep ---------------------------------------------------------
+// For the split point m = 0 the two restriction matrices are mirror images, C_hi[i][k] = (-1)^(i+k) C_lo[i][k],
+// EXACTLY (every step of the recurrence is sign-symmetric in IEEE arithmetic).  One product c*x therefore serves
+// both halves -- lower += p, upper += +-p -- and because x +- p rounds like x + (+-p) the upper half is still
+// bit-identical to a separate pass with C_hi: 4 DMUL + 8 DADD per source element instead of 8 + 8, half the
+// matrix loads, one sweep over the source.  Sign for row block base i0 = 4b (even), row q, source k: (-1)^(q+k).
+#define YR_F2_DUAL_STEP(SGN)                                                                                   \
+    {                                                                                                          \
+        const double x = *s; s += sk;                                                                          \
+        const pair_t c01 = cp[0], c23 = cp[1]; cp += 2;                                                        \
+        if (FMA) {                                                                                             \
+            l0 = fma(c01.x, x, l0); l1 = fma(c01.y, x, l1); l2 = fma(c23.x, x, l2); l3 = fma(c23.y, x, l3);    \
+            u0 = fma((SGN) * c01.x, x, u0); u1 = fma(-(SGN) * c01.y, x, u1);                                   \
+            u2 = fma((SGN) * c23.x, x, u2); u3 = fma(-(SGN) * c23.y, x, u3);                                   \
+        } else {                                                                                               \
+            const double p0 = c01.x * x, p1 = c01.y * x, p2 = c23.x * x, p3 = c23.y * x;                       \
+            l0 = l0 + p0; l1 = l1 + p1; l2 = l2 + p2; l3 = l3 + p3;                                            \
+            if ((SGN) > 0) { u0 = u0 + p0; u1 = u1 - p1; u2 = u2 + p2; u3 = u3 - p3; }                         \
+            else { u0 = u0 - p0; u1 = u1 + p1; u2 = u2 - p2; u3 = u3 + p3; }                                   \
+        }                                                                                                      \
+    }
+
+#define YR_F2_DUAL_BLOCK(SRC, DL, DU, STRIDE_OUT_L, STRIDE_OUT_U)                                              \
+    {                                                                                                          \
+        const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));                             \
+        const double* s = (SRC);                                                                               \
+        double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0, u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;                 \
+        int k = i0;                                                                                            \
+        for (; k + 1 < n; k += 2) { YR_F2_DUAL_STEP(1.0) YR_F2_DUAL_STEP(-1.0) }                               \
+        if (k < n) YR_F2_DUAL_STEP(1.0)                                                                        \
+        const int rem = r - i0;                                                                                \
+        double* dl = (DL); double* du = (DU);                                                                  \
+        dl[0] = l0; du[0] = u0; asl += fabs(l0); asu += fabs(u0);                                              \
+        if (rem > 1) { dl[STRIDE_OUT_L] = l1; du[STRIDE_OUT_U] = u1; asl += fabs(l1); asu += fabs(u1); }       \
+        if (rem > 2) { dl[2 * (STRIDE_OUT_L)] = l2; du[2 * (STRIDE_OUT_U)] = u2; asl += fabs(l2); asu += fabs(u2); } \
+        if (rem > 3) { dl[3 * (STRIDE_OUT_L)] = l3; du[3 * (STRIDE_OUT_U)] = u3; asl += fabs(l3); asu += fabs(u3); } \
+    }
+
+// warp teams: fiber per lane; either output may be src (in place: a block's stores follow all of its loads);
+// dstL != dstU; same strides everywhere
+template <bool FMA, class Team>
+YR_DEV void pass_fiber_dual(Team& tm, const double* src, double* dstL, double* dstU, int sk, int sf, int n, int r, int F,
+                            const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
+    const int B = (r + 3) >> 2;
+    double asl = 0.0, asu = 0.0;
+    for (int f = tm.tid; f < F; f += tm.nthreads) {
+        for (int b = 0; b < B; ++b) {
+            const int i0 = b << 2;
+            YR_F2_DUAL_BLOCK(src + f * sf + i0 * sk, dstL + f * sf + i0 * sk, dstU + f * sf + i0 * sk, sk, sk)
+        }
+    }
+    if (tm.tid == 0) macs += 2ull * (unsigned)(F * (r * n - r * (r - 1) / 2));
+    tm.sum2_sync(asl, asu, sumL, sumU);
+}
+
+// CTA teams: items (row block, fiber), out of place
+template <bool FMA, class Team>
+YR_DEV void restrict_pass_dual(Team& tm, const double* src, int sk, int sf, double* dstL, double* dstU, int dk, int df,
+                               int n, int r, int F, const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
+    const int B = (r + 3) >> 2;
+    double asl = 0.0, asu = 0.0;
+    int b = 0, f = tm.tid;
+    while (f >= F) { f -= F; ++b; }
+    while (b < B) {
+        const int i0 = b << 2;
+        YR_F2_DUAL_BLOCK(src + i0 * sk + f * sf, dstL + i0 * dk + f * df, dstU + i0 * dk + f * df, dk, dk)
+        f += tm.nthreads;
+        while (f >= F) { f -= F; ++b; }
+    }
+    if (tm.tid == 0) macs += 2ull * (unsigned)(F * (r * n - r * (r - 1) / 2));
+    tm.sum2_sync(asl, asu, sumL, sumU);
+}
+
 // ---- RESTRICT ------------------------------------------------------------------------------------------
 // slice: [A: T][B: T][X: T][C0 panels][C1 panels][rows_after ints]
 // Tensor 0 is fetched into A and tensor 1 into B with asynchronous copies that run behind the matrix build; each
@@ -555,14 +628,21 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
         double sumL, sumU;
         if (n_a1 > 1) {
             const int rl = m1.rlo[n_a1 - 1], ru = m1.rhi[n_a1 - 1];
+            const bool mirror = (midsel[a1] == 0) && (rl == ru);      // m = 0: C_hi = +-C_lo, one sweep for both
             if (a1 == 0) {
                 shL[0] = rl; shU[0] = ru;
-                sumL = restrict_pass<FMA>(tm, S, ld, 1, L, ld, 1, n0, rl, n1, m1.lo, m1.nt, macs);
-                sumU = restrict_pass<FMA>(tm, S, ld, 1, U, ld, 1, n0, ru, n1, m1.hi, m1.nt, macs);
+                if (mirror) restrict_pass_dual<FMA>(tm, S, ld, 1, L, U, ld, 1, n0, rl, n1, m1.lo, m1.nt, macs, sumL, sumU);
+                else {
+                    sumL = restrict_pass<FMA>(tm, S, ld, 1, L, ld, 1, n0, rl, n1, m1.lo, m1.nt, macs);
+                    sumU = restrict_pass<FMA>(tm, S, ld, 1, U, ld, 1, n0, ru, n1, m1.hi, m1.nt, macs);
+                }
             } else {
                 shL[1] = rl; shU[1] = ru; ldL = odd_ld(rl); ldU = odd_ld(ru);
-                sumL = restrict_pass<FMA>(tm, S, 1, ld, L, 1, ldL, n1, rl, n0, m1.lo, m1.nt, macs);
-                sumU = restrict_pass<FMA>(tm, S, 1, ld, U, 1, ldU, n1, ru, n0, m1.hi, m1.nt, macs);
+                if (mirror) restrict_pass_dual<FMA>(tm, S, 1, ld, L, U, 1, ldL, n1, rl, n0, m1.lo, m1.nt, macs, sumL, sumU);
+                else {
+                    sumL = restrict_pass<FMA>(tm, S, 1, ld, L, 1, ldL, n1, rl, n0, m1.lo, m1.nt, macs);
+                    sumU = restrict_pass<FMA>(tm, S, 1, ld, U, 1, ldU, n1, ru, n0, m1.hi, m1.nt, macs);
+                }
             }
         } else {
             // extent-1 axis: TransformChebInPlaceND returns the tensor unchanged (:363)
@@ -609,14 +689,21 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
             tm.sync();                                         // S / X are free (previous epilogue copies are done)
             if (n_a2 > 1) {
                 const int rl = m2.rlo[n_a2 - 1], ru = m2.rhi[n_a2 - 1];
+                const bool mirror = (midsel[a2] == 0) && (rl == ru);
                 if (a2 == 0) {
                     shA[0] = rl; shB[0] = ru;
-                    sumA = restrict_pass<FMA>(tm, H, ldH, 1, S, ldH, 1, shH[0], rl, shH[1], m2.lo, m2.nt, macs);
-                    sumB = restrict_pass<FMA>(tm, H, ldH, 1, X, ldH, 1, shH[0], ru, shH[1], m2.hi, m2.nt, macs);
+                    if (mirror) restrict_pass_dual<FMA>(tm, H, ldH, 1, S, X, ldH, 1, shH[0], rl, shH[1], m2.lo, m2.nt, macs, sumA, sumB);
+                    else {
+                        sumA = restrict_pass<FMA>(tm, H, ldH, 1, S, ldH, 1, shH[0], rl, shH[1], m2.lo, m2.nt, macs);
+                        sumB = restrict_pass<FMA>(tm, H, ldH, 1, X, ldH, 1, shH[0], ru, shH[1], m2.hi, m2.nt, macs);
+                    }
                 } else {
                     shA[1] = rl; shB[1] = ru; ldA = odd_ld(rl); ldB = odd_ld(ru);
-                    sumA = restrict_pass<FMA>(tm, H, 1, ldH, S, 1, ldA, shH[1], rl, shH[0], m2.lo, m2.nt, macs);
-                    sumB = restrict_pass<FMA>(tm, H, 1, ldH, X, 1, ldB, shH[1], ru, shH[0], m2.hi, m2.nt, macs);
+                    if (mirror) restrict_pass_dual<FMA>(tm, H, 1, ldH, S, X, 1, ldA, shH[1], rl, shH[0], m2.lo, m2.nt, macs, sumA, sumB);
+                    else {
+                        sumA = restrict_pass<FMA>(tm, H, 1, ldH, S, 1, ldA, shH[1], rl, shH[0], m2.lo, m2.nt, macs);
+                        sumB = restrict_pass<FMA>(tm, H, 1, ldH, X, 1, ldB, shH[1], ru, shH[0], m2.hi, m2.nt, macs);
+                    }
                 }
             } else {
                 copy_flat(tm, S, H, tensor_doubles(shH[0], ldH)); copy_flat(tm, X, H, tensor_doubles(shH[0], ldH));
@@ -821,8 +908,11 @@ YR_DEV void subdivide_box_w(Team& tm, const Args& a, unsigned int b, double* sli
             const int rl = m1.rlo[n_a1 - 1], ru = m1.rhi[n_a1 - 1];
             shL[a1] = rl; shU[a1] = ru;
             const int sk = a1 == 0 ? ld : 1, sf = a1 == 0 ? 1 : ld, F = a1 == 0 ? n1 : n0;
-            sumL = pass_fiber<FMA>(tm, S, L, sk, sf, n_a1, rl, F, m1.lo, m1.nt, macs);
-            sumU = pass_fiber<FMA>(tm, S, S, sk, sf, n_a1, ru, F, m1.hi, m1.nt, macs);
+            if (midsel[a1] == 0 && rl == ru) pass_fiber_dual<FMA>(tm, S, L, S, sk, sf, n_a1, rl, F, m1.lo, m1.nt, macs, sumL, sumU);
+            else {
+                sumL = pass_fiber<FMA>(tm, S, L, sk, sf, n_a1, rl, F, m1.lo, m1.nt, macs);
+                sumU = pass_fiber<FMA>(tm, S, S, sk, sf, n_a1, ru, F, m1.hi, m1.nt, macs);
+            }
         } else {
             copy_flat(tm, L, S, tensor_doubles(n0, ld));         // extent-1 axis: unchanged (:363)
             sumL = sumU = wk.sumabs[p];
@@ -852,8 +942,12 @@ YR_DEV void subdivide_box_w(Team& tm, const Args& a, unsigned int b, double* sli
                     const int rl = m2.rlo[n_a2 - 1], ru = m2.rhi[n_a2 - 1];
                     shO[0][a2] = rl; shO[1][a2] = ru;
                     const int sk = a2 == 0 ? ld : 1, sf = a2 == 0 ? 1 : ld, F = a2 == 0 ? shH[1] : shH[0];
-                    sumO[1] = pass_fiber<FMA>(tm, H, X, sk, sf, n_a2, ru, F, m2.hi, m2.nt, macs);
-                    sumO[0] = pass_fiber<FMA>(tm, H, H, sk, sf, n_a2, rl, F, m2.lo, m2.nt, macs);
+                    // lower stays in H (in place), upper goes to X
+                    if (midsel[a2] == 0 && rl == ru) pass_fiber_dual<FMA>(tm, H, H, X, sk, sf, n_a2, rl, F, m2.lo, m2.nt, macs, sumO[0], sumO[1]);
+                    else {
+                        sumO[1] = pass_fiber<FMA>(tm, H, X, sk, sf, n_a2, ru, F, m2.hi, m2.nt, macs);
+                        sumO[0] = pass_fiber<FMA>(tm, H, H, sk, sf, n_a2, rl, F, m2.lo, m2.nt, macs);
+                    }
                 } else {
                     copy_flat(tm, X, H, tensor_doubles(shH[0], ld));
                     tm.sync();

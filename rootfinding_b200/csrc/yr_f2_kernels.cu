@@ -51,6 +51,7 @@ struct WarpTeam {
     }
     __device__ __forceinline__ double sum(double v) { return wsum(v); }
     __device__ __forceinline__ double sum_sync(double v) { __syncwarp(mask); return wsum(v); }
+    __device__ __forceinline__ void sum2_sync(double a, double b, double& ra, double& rb) { __syncwarp(mask); ra = wsum(a); rb = wsum(b); }
     __device__ __forceinline__ bool wany(bool p) { return (__ballot_sync(mask, p) & mask) != 0u; }
     __device__ __forceinline__ unsigned wballot(bool p) { return LANES == 32 ? __ballot_sync(mask, p) : ((__ballot_sync(mask, p) >> (threadIdx.x & 16)) & 0xffffu); }
     __device__ __forceinline__ double wsum_w(double v, int w) { for (int off = w >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off); return v; }
@@ -71,7 +72,7 @@ __device__ __forceinline__ WarpTeam<LANES> make_warp_team() {
     return tm;
 }
 
-struct CtaShared { double red[2][8]; unsigned long long slot; };
+struct CtaShared { double red[2][16]; unsigned long long slot; };
 
 struct CtaTeam {
     static constexpr bool kShuffle = true;
@@ -90,6 +91,15 @@ struct CtaTeam {
         double t = 0.0;
         for (int w = 0; w < warps; ++w) t += sh->red[buf][w];
         return t;
+    }
+    __device__ __forceinline__ void sum2_sync(double a, double b, double& ra, double& rb) {
+        a = warp_sum_d(a); b = warp_sum_d(b);
+        const int buf = flip; flip ^= 1;
+        if (lane == 0) { sh->red[buf][warp] = a; sh->red[buf][8 + warp] = b; }
+        __syncthreads();
+        double ta = 0.0, tb = 0.0;
+        for (int w = 0; w < warps; ++w) { ta += sh->red[buf][w]; tb += sh->red[buf][8 + w]; }
+        ra = ta; rb = tb;
     }
     __device__ __forceinline__ double sum(double v) { return sum_sync(v); }
     __device__ __forceinline__ double wsum(double v) { return warp_sum_d(v); }

@@ -325,6 +325,7 @@ struct F2Team {
         sync(); return t;
     }
     double sum_sync(double v) { return sum(v); }
+    void sum2_sync(double a, double b, double& ra, double& rb) { ra = sum(a); rb = sum(b); }
     double wsum(double v) { return sum(v); }
     bool wany(bool p) { return sum(p ? 1.0 : 0.0) > 0.0; }
     unsigned wballot(bool p) {

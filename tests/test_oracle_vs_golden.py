@@ -218,3 +218,21 @@ def test_readme_and_univariate(golden_dir):
     r1 = oracle.solve(f1, -1, 2)
     assert len(r1) == 128 and np.max(np.abs(f1(r1))) < 1e-12          # :32-36
     assert np.array_equal(np.asarray(r1).reshape(-1, 1), z["roots_univariate"])
+
+
+def test_split_matrices_are_exact_mirror_images():
+    """The two halves of a subdivision at m = 0 use C(1/2, -1/2) and C(1/2, +1/2); the frontier pipeline's
+    mirrored sweep (csrc/yr_f2.h: pass_fiber_dual) relies on C_hi[i][k] == (-1)^(i+k) C_lo[i][k] holding bit for bit,
+    rows included.  Checked here on the oracle's restatement of TransformChebInPlace1D (:45-120)."""
+    from oracle import kernels as K
+    n = 101
+    eye = np.eye(n)
+    lo = K.restrict_axis(eye, 0, 0.5, -0.5)
+    hi = K.restrict_axis(eye, 0, 0.5, 0.5)
+    assert lo.shape == hi.shape
+    sign = (-1.0) ** (np.add.outer(np.arange(lo.shape[0]), np.arange(n)))
+    assert np.array_equal(hi, lo * sign)
+    # and a product shared between the halves rounds identically: x + (-(c*v)) == x - c*v
+    rng = np.random.RandomState(1)
+    c, v, x = rng.randn(1000), rng.randn(1000), rng.randn(1000)
+    assert np.array_equal(x + (-c) * v, x - c * v)
