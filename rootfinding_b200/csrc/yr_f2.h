@@ -841,7 +841,8 @@ YR_DEV void restrict_box_w(Team& tm, const Args& a, unsigned int b, double* slic
         if (!id0 && n0 > 1) { r0 = rows0[n0 - 1]; s = pass_fiber<FMA>(tm, A, A, ld, 1, n0, r0, n1, C0, n0max, macs); }
         if (!copy_only) err += n1 * kMachEps * s;
         if (!id1 && n1 > 1) { r1 = rows1[n1 - 1]; s = pass_fiber<FMA>(tm, A, A, 1, ld, n1, r1, r0, C1, n1max, macs); }
-        const int ld_out = odd_ld(r1), osz = tensor_doubles(r0, ld_out);
+        // re-laying the tensor out row by row only pays when it saves real space: keep the stride for a small gap
+        const int ld_out = (ld - odd_ld(r1) <= 2) ? ld : odd_ld(r1), osz = tensor_doubles(r0, ld_out);
         Epilogue ep;
         tensor_epilogue(tm, A, r0, r1, ld, s, err, prm, ep);
         copy_out_rows(tm, a.data_out + out_off, ld_out, A, ld, r0, r1);

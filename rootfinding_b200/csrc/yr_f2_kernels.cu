@@ -145,7 +145,10 @@ __device__ void stage_submats(const Args& a, double* smat, int snt) {
 }
 
 template <int OP, bool FMA, int LANES>
-__global__ void __launch_bounds__(128) f2_tensor_warp(const Args a, const unsigned int* __restrict__ list, unsigned long long n,
+#ifndef YR_F2_WARP_MINB
+#define YR_F2_WARP_MINB 1
+#endif
+__global__ void __launch_bounds__(128, YR_F2_WARP_MINB) f2_tensor_warp(const Args a, const unsigned int* __restrict__ list, unsigned long long n,
                                                       unsigned slice_doubles, int snt) {
     extern __shared__ __align__(16) double dyn[];
     constexpr int kTeams = 128 / LANES;
@@ -159,6 +162,13 @@ __global__ void __launch_bounds__(128) f2_tensor_warp(const Args a, const unsign
     unsigned long long macs = 0;
     for (unsigned long long i = team; i < n; i += nteams) {
         const unsigned int b = list[i];
+        if (i + nteams < n && tm.tid < 7) {
+            // the next box's records (BoxRec 3 lines, Work 3-4 lines) start their trip from HBM now
+            const unsigned int nb = list[i + nteams];
+            const char* p = tm.tid < 3 ? reinterpret_cast<const char*>(a.recs + nb) + 128 * tm.tid
+                                       : reinterpret_cast<const char*>(a.work + nb) + 128 * (tm.tid - 3);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
         if (OP == kTRestrict) restrict_box_w<FMA>(tm, a, b, slice, macs);
         else subdivide_box_w<FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
         tm.sync();

@@ -118,11 +118,14 @@ def _ancestors(nodes, start):
 def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
     """Step B.  May run more device jobs through `session`; returns the updated (res, alive, dup, extra)."""
     rounds = 0
+    # candidates: live records whose reported interval touches the cell they were created as; the set is small
+    # and is maintained incrementally (one pass over the records, not one per merge)
+    cand_set = set(np.nonzero(alive & ((res["flags"] & RES_TOUCH) != 0))[0].tolist())
     while rounds < max_rounds:
         rounds += 1
-        cand = np.nonzero(alive & ((res["flags"] & RES_TOUCH) != 0))[0]
-        if len(cand) < 2:
+        if len(cand_set) < 2:
             break
+        cand = np.fromiter(sorted(cand_set), dtype=np.int64, count=len(cand_set))
         pairs = []
         order = cand[np.argsort(res["system"][cand], kind="stable")]
         sysv = res["system"][order]
@@ -157,6 +160,7 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
             anc_iv = np.array([[-1., 1.]] * dim)
             anc_mid, anc_level = np.full(dim, 0.0394555475981047), 0
         alive[i] = alive[j] = False
+        cand_set.discard(i); cand_set.discard(j)
         session.stats_merges = getattr(session, "stats_merges", 0) + 1
         if np.array_equal(lo, anc_iv[:, 0]) and np.array_equal(hi, anc_iv[:, 1]):
             # :1370-1371 the merged box is the ancestor's whole box: keep it, do not re-solve
@@ -181,6 +185,8 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
         alive[first:first + count] = sub_alive
         dup.update(sub_dup)
         extra |= sub_extra
+        new = np.arange(first, first + count)
+        cand_set.update(new[sub_alive & ((res["flags"][first:first + count] & RES_TOUCH) != 0)].tolist())
     return res, alive, dup, extra
 
 
@@ -221,9 +227,9 @@ def assemble(session, merge=True):
 
 def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False):
     """Vectorised gathering of roots per system; special records are patched in afterwards."""
-    sysv = res["system"][keep]
+    sysv = np.take(res["system"], keep)
     bounds = np.searchsorted(sysv, np.arange(nsys + 1))
-    roots_all = res["root"][keep]
+    roots_all = np.take(res["root"], keep, axis=0)
     out_roots, out_boxes, has_dup, has_extra = [], [], False, False
     special = {int(k) for k in dup} | {int(k) for k in extra}
     for s in range(nsys):

@@ -17,4 +17,4 @@ for rep in range(2):
 pr = cProfile.Profile(); pr.enable()
 roots = S.solve_batch(systems, errs); torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
