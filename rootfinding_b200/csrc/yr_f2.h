@@ -997,7 +997,7 @@ YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
     const SolverParams& prm = a.prm;
     BoxRec<2>& rec = a.recs[b];
     Work& wk = a.work[b];
-    IntervalState<2> st = rec.st;
+    IntervalState<2>& st = rec.st;      // updated in place: only the fields a step touches travel
 
     auto emit = [&](uint32_t extra_flags) {
         const unsigned long long idx = at.add(&a.ctl->n_results, 1ull);
@@ -1155,7 +1155,7 @@ YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
         }
         break;
     }
-    rec.st = st;
+
 }
 
 // Level-0 boxes arrive packed from yr_init_boxes: give them their Work state and queue a copy-only pass that

@@ -35,6 +35,7 @@ void timer_collect(double* tensor_ms, double* scalar_ms);
 // order[0..n) = record indices sorted by (system, path_hi, path_lo); returns a device buffer (or null)
 void* sort_results(const void* results, unsigned long long n, void* stream);
 double trace_sync_ms(void* stream);      // YR_F2_TRACE: synchronise and return host milliseconds since the previous call
+double host_ms();                        // host clock, milliseconds
 }  // namespace yr_f2_backend
 
 namespace yr_f2_host {
@@ -59,12 +60,13 @@ struct DevBuf {
     void release(void* stream) { if (p) yr_f2_backend::dev_free(p, stream); p = nullptr; cap = 0; }
 };
 
-struct Workspace { DevBuf recs, work, arena[2], lists[2], tabs, ctlbuf; int tabs_nt = 0; size_t hint_results = 0, hint_nodes = 0; };
+struct Workspace { DevBuf recs, work, arena[2], lists[2], tabs, ctlbuf, results, nodes; int tabs_nt = 0; };
 inline Workspace& workspace() { static Workspace w; return w; }
 inline int trim_workspace(void* stream) {
     Workspace& w = workspace();
     w.recs.release(stream); w.work.release(stream); w.arena[0].release(stream); w.arena[1].release(stream);
     w.lists[0].release(stream); w.lists[1].release(stream); w.tabs.release(stream); w.ctlbuf.release(stream);
+    w.results.release(stream); w.nodes.release(stream);
     w.tabs_nt = 0;
     return 0;
 }
@@ -74,6 +76,15 @@ inline int fits(unsigned long long max_extent) {
     if (max_extent > 4096) return 0;
     const int T = even_up(n * odd_ld(n));
     return need_subdivide(T) + 2ull * panel_doubles(n) <= kMaxNeed && need_restrict(T, n, n) <= kMaxNeed;
+}
+
+inline int release(yr_frontier_out* out, void* stream) {
+    if (!out) return 0;
+    if (out->results) yr_f2_backend::dev_free(out->results, stream);
+    if (out->nodes) yr_f2_backend::dev_free(out->nodes, stream);
+    if (out->order) yr_f2_backend::dev_free(out->order, stream);
+    out->results = nullptr; out->nodes = nullptr; out->order = nullptr;
+    return 0;
 }
 
 inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) {
@@ -88,16 +99,19 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
     if (!fits(d->max_extent)) return fail("yr_frontier_solve: tensors too large for the shared-memory pipeline");
     be::timer_reset(d->time_kernels);
     const bool trace = getenv("YR_F2_TRACE") != nullptr;
+    const bool phases = getenv("YR_F2_PHASES") != nullptr;       // coarse host-clock phase summary (synchronises 3 times)
+    double ph[4] = {0, 0, 0, 0};
+    if (phases) be::trace_sync_ms(stream);
 
     // Box tables, arenas, queues, matrix tables and the control block persist between solves (grow-only, released
     // by yr_frontier_trim); result / node arrays belong to the caller of this solve.
     Workspace& ws = workspace();
     DevBuf &recs = ws.recs, &work = ws.work, &tabs = ws.tabs, &ctlbuf = ws.ctlbuf;
     DevBuf (&arena)[2] = ws.arena; DevBuf (&lists)[2] = ws.lists;
-    DevBuf results, nodes;
-    auto cleanup = [&](bool keep_out) {
-        if (!keep_out) { results.release(stream); nodes.release(stream); }
-    };
+    // result / node records accumulate in persistent buffers sized by the (loose) per-round bounds; the caller gets
+    // exactly sized copies at the end
+    DevBuf &results = ws.results, &nodes = ws.nodes;
+    auto cleanup = [&](bool) {};
 #define F2_TRY(expr) do { if (expr) { cleanup(false); return -1; } } while (0)
 
     // level-independent subdivision matrices
@@ -115,10 +129,10 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
     { const size_t have = recs.cap / sizeof(BoxRec<2>) < work.cap / sizeof(Work) ? recs.cap / sizeof(BoxRec<2>) : work.cap / sizeof(Work); if (have > cap_boxes) cap_boxes = have; }
     F2_TRY(be::dev_copy(recs.p, d->recs_in, n0 * sizeof(BoxRec<2>), stream));
     size_t cap_results = (size_t)(n0 * 4 + 1024), cap_nodes = cap_results;
-    if (ws.hint_results > cap_results) cap_results = ws.hint_results;          // what the previous solve ended with
-    if (ws.hint_nodes > cap_nodes) cap_nodes = ws.hint_nodes;
     F2_TRY(results.reserve(cap_results * sizeof(ResultRec<2>), 0, stream, 1.0));
     F2_TRY(nodes.reserve(cap_nodes * sizeof(NodeRec<2>), 0, stream, 1.0));
+    if (results.cap / sizeof(ResultRec<2>) > cap_results) cap_results = results.cap / sizeof(ResultRec<2>);
+    if (nodes.cap / sizeof(NodeRec<2>) > cap_nodes) cap_nodes = nodes.cap / sizeof(NodeRec<2>);
 
     Args a;
     memset(&a, 0, sizeof(a));
@@ -142,6 +156,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         a.nodes = static_cast<NodeRec<2>*>(nodes.p); a.cap_nodes = cap_nodes;
     };
 
+    if (phases) ph[0] = be::trace_sync_ms(stream);
     // round -1: adopt the level-0 boxes (they arrive packed, from yr_init_boxes) and queue their first pass
     int cur = 0;
     F2_TRY(carve_lists(lists[cur], (size_t)n0));
@@ -158,6 +173,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         unsigned long long n_res = 0, n_sub = 0;
         for (int c = 0; c < kClasses; ++c) { n_res += h.n_list[0][c]; n_sub += h.n_list[1][c]; }
         if (n_res + n_sub == 0) break;
+        const double t_round0 = phases ? be::host_ms() : 0.0;
         if (++rounds > 1000000ull) { cleanup(false); return fail("yr_frontier_solve: round loop did not terminate"); }
         const unsigned long long produced = n_res + 4 * n_sub;            // boxes the scalar step of this round may see
         for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) cur_lists[o][c] = a.lists[o][c];
@@ -210,17 +226,26 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         be::timer_mark(1, 0, stream);
         ++launches;
         if (trace) fprintf(stderr, " scalar %.3f ms\n", be::trace_sync_ms(stream));
+        const double t_issue = phases ? be::host_ms() : 0.0;
         F2_TRY(be::to_host(&h, ctlbuf.p, sizeof(Ctl), stream));
+        if (phases) { const double t_done = be::host_ms(); fprintf(stderr, " r%llu:%.2f+%.2f", rounds, t_issue - t_round0, t_done - t_issue); }
         if (h.overflow) { cleanup(false); return fail("yr_frontier_solve: internal buffer overflow"); }
         if (h.bad_mid) { cleanup(false); return fail("yr_frontier_solve: unexpected split point (nextTransformPoints)"); }
         n_boxes = h.n_boxes; n_results += h.n_results; n_nodes += h.n_nodes;
         data_in = a.data_out;
         out_arena ^= 1; cur ^= 1;
     }
-    ws.hint_results = (size_t)(n_results + n_results / 8 + 1024); ws.hint_nodes = (size_t)(n_nodes + n_nodes / 8 + 1024);
     out->order = n_results ? be::sort_results(results.p, n_results, stream) : nullptr;
-    out->results = results.p; out->n_results = n_results;
-    out->nodes = nodes.p; out->n_nodes = n_nodes;
+    if (phases) { ph[2] = be::trace_sync_ms(stream); fprintf(stderr, "f2 phases: setup %.2f ms, sort %.2f ms (%llu rounds, %llu launches)\n", ph[0], ph[2], rounds, launches); }
+    if (n_results) {
+        out->results = be::dev_alloc((size_t)n_results * sizeof(ResultRec<2>), stream);
+        if (!out->results || be::dev_copy(out->results, results.p, (size_t)n_results * sizeof(ResultRec<2>), stream)) { release(out, stream); return fail("device allocation failed (results)"); }
+    }
+    if (n_nodes) {
+        out->nodes = be::dev_alloc((size_t)n_nodes * sizeof(NodeRec<2>), stream);
+        if (!out->nodes || be::dev_copy(out->nodes, nodes.p, (size_t)n_nodes * sizeof(NodeRec<2>), stream)) { release(out, stream); return fail("device allocation failed (nodes)"); }
+    }
+    out->n_results = n_results; out->n_nodes = n_nodes;
     out->rounds = rounds; out->launches = launches; out->slots = n_boxes;
     yr_counters& c = out->counters;
     c.n_results = n_results; c.n_nodes = n_nodes; c.boxes = h.boxes; c.zooms = h.zooms; c.subdivisions = h.subdivisions;
@@ -230,15 +255,6 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
     cleanup(true);
     return 0;
 #undef F2_TRY
-}
-
-inline int release(yr_frontier_out* out, void* stream) {
-    if (!out) return 0;
-    if (out->results) yr_f2_backend::dev_free(out->results, stream);
-    if (out->nodes) yr_f2_backend::dev_free(out->nodes, stream);
-    if (out->order) yr_f2_backend::dev_free(out->order, stream);
-    out->results = nullptr; out->nodes = nullptr; out->order = nullptr;
-    return 0;
 }
 
 }  // namespace yr_f2_host

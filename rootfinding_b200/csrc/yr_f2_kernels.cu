@@ -500,6 +500,8 @@ void* sort_results(const void* results, unsigned long long n, void* stream) {
     return result;
 }
 
+double host_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
 double trace_sync_ms(void* stream) {
     static double last = 0.0;
     cudaStreamSynchronize((cudaStream_t)stream);

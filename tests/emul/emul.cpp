@@ -483,6 +483,7 @@ void* sort_results(const void* results, unsigned long long n, void*) {
     return order;
 }
 double trace_sync_ms(void*) { return 0.0; }
+double host_ms() { return 0.0; }
 void round_fork(void*) {}
 void round_join(void*) {}
 void timer_reset(int) {}
