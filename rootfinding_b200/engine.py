@@ -283,6 +283,7 @@ class SolveSession:
         self._results_host = _Growable(self.rdt, alloc, self)
         self._nodes_host = _Growable(self.ndt, lambda nbytes, who=None: np.empty(nbytes, dtype=np.uint8), self)
         self._order_host = None           # depth-first order of the first frontier solve's records (device sort)
+        self._order_base = 0
         self.stats = SolveStats()
         self.time_kernels = False        # bench.py: CUDA events around every level launch
         self.kernel_ms = []              # (ms, algorithmic bytes, boxes) per level launch
@@ -290,8 +291,8 @@ class SolveSession:
         self._reserve("results", max(256, 4 * self.nsys))
         self._reserve("nodes", max(256, 4 * self.nsys))
         # 2-D, plain arithmetic, tensors that fit shared memory: the round-based frontier pipeline serves the session
-        self.use_frontier = bool(engine.pipeline == 2 and D == 2 and not prm.exact and self.nsys > 0
-                                 and self.lib.yr_frontier_fits(int(self.sys_max_extent.max())))
+        self.use_frontier = bool(engine.pipeline == 2 and D == 2 and not prm.exact and self.nsys > 0)
+        self._segments = []               # record ranges in production order: ("level", start, count) / ("frontier", start, count, out)
 
     # -- growable append-only device arrays ------------------------------------------------
     def _reserve(self, which, want):
@@ -304,7 +305,7 @@ class SolveSession:
         old = getattr(self, "d_" + which)
         used = getattr(self, "n_" + which)
         if old is not None and used:
-            self.mem.copy(buf, old, used * item)
+            self.mem.copy(buf, old, min(used, cap) * item)      # (indices are global: ranges the frontier pipeline produced are holes here)
         setattr(self, "d_" + which, buf)
         setattr(self, "cap_" + which, new_cap)
 
@@ -364,7 +365,7 @@ class SolveSession:
         D, m, eng = self.dim, self.mem, self.eng
         first_result = self.n_results
         recs, data, c = self._init_boxes(jobs)
-        if self.use_frontier:
+        if self.use_frontier and self.lib.yr_frontier_fits(int(c["max_child_extent"])):
             return self._run_frontier(recs, data, c, first_result)
         n_in, data_used = c["n_children"], c["data_used"]
         big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
@@ -435,12 +436,18 @@ class SolveSession:
             self.stats.add(c)
             self.stats.levels += 1
             self.stats.per_level.append((n_in, c["n_children"], c["n_results"], bool(in_smem), ctas, threads, ws, bool(warp)))
+            if c["n_results"] or c["n_nodes"]:
+                self._segments.append(("level", self.n_results, int(c["n_results"]), self.n_nodes, int(c["n_nodes"])))
             self.n_results += c["n_results"]
             self.n_nodes += c["n_nodes"]
             growth = [max(0.25, c["n_children"] / n_in), max(0.25, c["data_used"] / max(data_used, 1))]
             recs, data = out_recs, out_data
             n_in, data_used = c["n_children"], c["data_used"]
             big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
+            if self.use_frontier and n_in > 0 and self.lib.yr_frontier_fits(int(big_extent)):
+                # large 2-D systems: the first levels run here, the rest of the search on the frontier pipeline
+                self._run_frontier(recs, data, c, first_result)
+                break
         return first_result, self.n_results - first_result
 
     def _run_frontier(self, recs, data, c, first_result):
@@ -457,6 +464,7 @@ class SolveSession:
         _lib.check(lib, lib.yr_frontier_solve(C.byref(d), C.byref(out), stream), "yr_frontier_solve")
         nres, nnod = int(out.n_results), int(out.n_nodes)
         self._pending.append(out)                                 # records stay on the device until results() / nodes()
+        self._segments.append(("frontier", self.n_results, nres, self.n_nodes, nnod, out))
         self.n_results += nres
         self.n_nodes += nnod
         cc = {k: int(getattr(out.counters, k)) for k in _lib.COUNTER_FIELDS}
@@ -484,24 +492,34 @@ class SolveSession:
         self._results_host.detach()
 
     def _fetch_pending(self):
-        """Device -> host copy of the records the frontier pipeline produced (library-owned buffers)."""
+        """Bring every record produced so far to the host, in production (= index) order.  Level-pipeline records
+        come from the session's own device arrays, frontier records from the library-owned buffers."""
         lib, stream = self.lib, self.mem.stream()
-        while self._pending:
-            out = self._pending.pop(0)
+        while self._segments:
+            seg = self._segments.pop(0)
+            if seg[0] == "level":
+                _, r0, rn, n0, nn = seg
+                if rn:
+                    item = self.rdt.itemsize
+                    self._results_host.tail(rn)[:] = self.mem.download(self.d_results, rn * item, r0 * item)
+                if nn:
+                    item = self.ndt.itemsize
+                    self._nodes_host.tail(nn)[:] = self.mem.download(self.d_nodes, nn * item, n0 * item)
+                continue
+            _, r0, rn, n0, nn, out = seg
             try:
-                first = len(self._results_host) == 0
-                for ptr, n, grow in ((out.results, int(out.n_results), self._results_host),
-                                     (out.nodes, int(out.n_nodes), self._nodes_host)):
+                for ptr, n, grow in ((out.results, rn, self._results_host), (out.nodes, nn, self._nodes_host)):
                     if n:
                         dst = grow.tail(n)
                         _lib.check(lib, lib.yr_fetch(dst.ctypes.data, ptr, dst.nbytes, stream), "yr_fetch")
                         self.mem.d2h_bytes += dst.nbytes
-                if first and int(out.n_results) and out.order:
-                    order = np.empty(int(out.n_results), dtype=np.uint32)
+                if self._order_host is None and rn and out.order:
+                    order = np.empty(rn, dtype=np.uint32)
                     _lib.check(lib, lib.yr_fetch(order.ctypes.data, out.order, order.nbytes, stream), "yr_fetch")
                     self.mem.d2h_bytes += order.nbytes
-                    self._order_host = order
+                    self._order_host, self._order_base = order, r0
             finally:
+                self._pending.remove(out)
                 lib.yr_frontier_release(C.byref(out), stream)
 
     def __del__(self):
@@ -513,29 +531,19 @@ class SolveSession:
 
     def results(self):
         """All result records so far as a numpy structured array (downloads only what is new)."""
-        if self._pending:
+        if self._segments:
             self._fetch_pending()
-        have = len(self._results_host)
-        if self.n_results > have:
-            item = self.rdt.itemsize
-            raw = self.mem.download(self.d_results, (self.n_results - have) * item, have * item)
-            self._results_host.tail(self.n_results - have)[:] = raw
         return self._results_host.view()
 
     def nodes(self):
-        if self._pending:
+        if self._segments:
             self._fetch_pending()
-        have = len(self._nodes_host)
-        if self.n_nodes > have:
-            item = self.ndt.itemsize
-            raw = self.mem.download(self.d_nodes, (self.n_nodes - have) * item, have * item)
-            self._nodes_host.tail(self.n_nodes - have)[:] = raw
         return self._nodes_host.view()
 
     def dfs_order(self):
-        """(order, n): permutation that puts records [0, n) in (system, depth-first path) order, sorted on the
-        device by yr_frontier_solve, or (None, 0) when the session has none."""
+        """(order, base, n): base + order puts records [base, base + n) in (system, depth-first path) order, sorted
+        on the device by yr_frontier_solve; (None, 0, 0) when the session has none."""
         self.results()
         if self._order_host is None:
-            return None, 0
-        return self._order_host, len(self._order_host)
+            return None, 0, 0
+        return self._order_host, self._order_base, len(self._order_host)

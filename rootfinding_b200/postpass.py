@@ -196,12 +196,12 @@ def assemble(session, merge=True):
     alive, dup, extra = resolve_collectors(res)
     if merge:
         res, alive, dup, extra = merge_exterior(session, res, alive, dup, extra)
-    order, n_sorted = session.dfs_order() if hasattr(session, "dfs_order") else (None, 0)
+    order, base, n_sorted = session.dfs_order() if hasattr(session, "dfs_order") else (None, 0, 0)
     if order is not None and n_sorted:
-        # the first n_sorted records arrive with their reporting order from the device (radix sort); records added
-        # later (re-solved merged boxes, a handful) are sorted here and merged in
-        main = order[alive[:n_sorted][order]].astype(np.int64)
-        late = np.nonzero(alive[n_sorted:])[0] + n_sorted
+        # records [base, base + n_sorted) arrive with their reporting order from the device (radix sort); the others
+        # (first levels of a large system, re-solved merged boxes: a handful) are sorted here and merged in
+        main = order[alive[base:base + n_sorted][order]].astype(np.int64) + base
+        late = np.r_[np.nonzero(alive[:base])[0], np.nonzero(alive[base + n_sorted:])[0] + base + n_sorted]
         if len(late):
             late = _path_order(res, late)
             key = lambda i: (int(res["system"][i]), int(res["path_hi"][i]), int(res["path_lo"][i]))

@@ -288,3 +288,40 @@ def test_emulated_frontier_fma_and_unit_extents(emu):
     want = S.solve_batch(systems, [np.full(2, 2. ** -52)] * 2, engine=emu)
     for a, b in zip(got, want):
         assert a.shape == b.shape and np.max(np.abs(a - b), initial=0.0) < 1e-10
+
+
+def test_emulated_hybrid_level_then_frontier(emu):
+    """Large 2-D systems start on the level pipeline and move to the frontier pipeline once their boxes fit its
+    shared-memory budget; here the budget is shrunk so a small problem takes that route.  Records of both
+    pipelines must come back in production order and the reporting order must match the oracle's."""
+    class Shim:
+        def __init__(self, lib):
+            self.lib, self.asked = lib, 0
+
+        def __getattr__(self, k):
+            if k == "yr_frontier_fits":
+                def fits(extent):                      # "too large" for the first three levels of every run
+                    self.asked += 1
+                    return int(self.asked % 4 == 0)
+                return fits
+            return getattr(self.lib, k)
+    systems = H.seeded_systems(2, 12, 3)
+    errs = [np.full(2, 2. ** -52)] * 3
+    real = emu.lib
+    try:
+        emu.lib = Shim(real)
+        sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
+    finally:
+        emu.lib = real
+    assert sess.stats.boxes == boxes and worst < 1e-14
+    assert sess.stats.rounds > 0 and sess.stats.levels > sess.stats.rounds      # both pipelines took part
+    ref = S.solve_batch(systems, errs, engine=emu)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        emu.lib = Shim(real)
+        try:
+            got = S.solve_batch(systems, errs, engine=emu)
+        finally:
+            emu.lib = real
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and np.max(np.abs(a - b), initial=0.0) < 1e-14    # same roots in the same (depth-first) order
