@@ -72,15 +72,15 @@ constexpr int kOps = 2;
 enum Op : int32_t { kTNone = 0, kTRestrict = 1, kTSubdivide = 2 };
 YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
 
-constexpr int kClasses = 9;
-constexpr int kWarpClasses = 7;             // classes below this run the warp-team code
+constexpr int kClasses = 11;
+constexpr int kWarpClasses = 9;             // classes below this run the warp-team code
 constexpr int kLane16Classes = 5;           // classes below this use two 16-lane teams per warp
 YR_HD unsigned long long class_bound(int c) {
-    const unsigned long long b[kClasses] = {384ull, 512ull, 640ull, 768ull, 1024ull, 1536ull, 2048ull, 7168ull, ~0ull};
+    const unsigned long long b[kClasses] = {384ull, 512ull, 640ull, 768ull, 1024ull, 1536ull, 2048ull, 3072ull, 4096ull, 7168ull, ~0ull};
     return b[c];
 }
 YR_HD int class_threads(int cls) { return cls < kLane16Classes ? 16 : (cls < kWarpClasses ? 32 : (cls == kWarpClasses ? 128 : 256)); }
-constexpr unsigned long long kWarp32Max = 2048ull;    // largest need a warp team takes
+constexpr unsigned long long kWarp32Max = 4096ull;    // largest need a warp team takes
 constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
 
 YR_HD int odd_ld(int n1) { return n1 | 1; }
