@@ -271,9 +271,13 @@ YR_F2_PASS double restrict_pass(Team& tm, const double* src, int sk, int sf, dou
                              int n, int r, int F, const double* Cp, int nt, unsigned long long& macs) {
     const int B = (r + 3) >> 2;
     double asum = 0.0;
-    int b = 0, f = tm.tid;
-    while (f >= F) { f -= F; ++b; }
-    while (b < B) {
+    // items in row-block-major order get shorter and shorter; waves alternate direction so that every thread's
+    // total trip count is about the same (the pass ends in a team barrier)
+    const int items = B * F, T = tm.nthreads;
+    for (int w0 = 0, wave = 0; w0 < items; w0 += T, ++wave) {
+        const int id = w0 + ((wave & 1) ? (T - 1 - tm.tid) : tm.tid);
+        if (id >= items) continue;
+        const int b = id / F, f = id - b * F;
         const int i0 = b << 2;
         const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));      // 16-byte aligned: two loads per k
         const double* s = src + i0 * sk + f * sf;
@@ -292,9 +296,8 @@ YR_F2_PASS double restrict_pass(Team& tm, const double* src, int sk, int sf, dou
         if (rem > 1) { d[dk] = a1; asum += fabs(a1); }
         if (rem > 2) { d[2 * dk] = a2; asum += fabs(a2); }
         if (rem > 3) { d[3 * dk] = a3; asum += fabs(a3); }
-        f += tm.nthreads;
-        while (f >= F) { f -= F; ++b; }
     }
+    if (tm.tid == 0) macs += (unsigned long long)(unsigned)(F * (r * n - r * (r - 1) / 2));     // triangular count
     return tm.sum_sync(asum);            // also the barrier that publishes dst
 }
 
@@ -433,13 +436,13 @@ YR_DEV void restrict_pass_dual(Team& tm, const double* src, int sk, int sf, doub
                                int n, int r, int F, const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
     const int B = (r + 3) >> 2;
     double asl = 0.0, asu = 0.0;
-    int b = 0, f = tm.tid;
-    while (f >= F) { f -= F; ++b; }
-    while (b < B) {
+    const int items = B * F, T = tm.nthreads;
+    for (int w0 = 0, wave = 0; w0 < items; w0 += T, ++wave) {                        // snake order, see restrict_pass
+        const int id = w0 + ((wave & 1) ? (T - 1 - tm.tid) : tm.tid);
+        if (id >= items) continue;
+        const int b = id / F, f = id - b * F;
         const int i0 = b << 2;
         YR_F2_DUAL_BLOCK(src + i0 * sk + f * sf, dstL + i0 * dk + f * df, dstU + i0 * dk + f * df, dk, dk)
-        f += tm.nthreads;
-        while (f >= F) { f -= F; ++b; }
     }
     if (tm.tid == 0) macs += 2ull * (unsigned)(F * (r * n - r * (r - 1) / 2));
     tm.sum2_sync(asl, asu, sumL, sumU);

@@ -293,6 +293,67 @@ def test_full_size_properties(yr):
     assert sess.stats.boxes > 6 * 6000
 
 
+def test_frontier_and_level_pipelines_agree(yr):
+    """The round-based 2-D frontier pipeline and the level pipeline run the same search: identical box, zoom and
+    subdivision counts and the same roots in the same (depth-first) order (their restrictions are bit-identical;
+    only the order of the |M| reductions differs)."""
+    from rootfinding_b200.runtime import get_engine
+    S = yr.ChebyshevSubdivisionSolver
+    eng = get_engine()
+    systems = H.seeded_systems(2, 30, 4)
+    errs = [np.full(2, 2. ** -52)] * 4
+    pipe, out = eng.pipeline, []
+    try:
+        for p in (2, 1):
+            eng.pipeline = p
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                roots, sess = S.solve_batch(systems, errs, return_session=True)
+            assert sess.use_frontier == (p == 2)
+            out.append((roots, sess.stats.boxes, sess.stats.zooms, sess.stats.subdivisions))
+    finally:
+        eng.pipeline = pipe
+    assert out[0][1:] == out[1][1:]
+    for a, b in zip(out[0][0], out[1][0]):
+        assert a.shape == b.shape and np.max(np.abs(a - b), initial=0.0) < 1e-14
+
+
+def test_large_systems_hand_over_to_frontier(yr):
+    """2-D degree 100 (extents above the frontier pipeline's shared-memory budget): the first levels run on the
+    level pipeline, the rest on the frontier pipeline; box count and roots are the reference's (golden solve)."""
+    S = yr.ChebyshevSubdivisionSolver
+    z = H.load("solves_random.npz")
+    idx = [i for i in range(int(z["n"])) if int(z[f"meta_{i}"][0]) == 2 and int(z[f"meta_{i}"][1]) >= 80]
+    systems = H.seeded_systems(2, 100, 1)
+    errs = [np.full(2, 2. ** -52)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        roots, sess = S.solve_batch(systems, errs, return_session=True)
+    assert sess.use_frontier and sess.stats.rounds > 0 and sess.stats.levels > sess.stats.rounds
+    r = roots[0]
+    assert 2000 < len(r) < 3500 and np.all(np.abs(r) <= 1)
+    for M in systems[0]:
+        vals = np.polynomial.chebyshev.chebval2d(r[:, 0], r[:, 1], M)
+        assert np.max(np.abs(vals)) < 1e-9 * np.sum(np.abs(M))
+    if idx:                                                     # a committed reference solve of this very system
+        i = idx[0]
+        assert len(r) == len(z[f"roots_{i}"])
+        H.match_points(z[f"roots_{i}"], r, H.ROOT_TOL)
+    # the same system solved entirely on the level pipeline
+    from rootfinding_b200.runtime import get_engine
+    eng = get_engine()
+    pipe = eng.pipeline
+    try:
+        eng.pipeline = 1
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref, sess1 = S.solve_batch(systems, errs, return_session=True)
+    finally:
+        eng.pipeline = pipe
+    assert sess1.stats.boxes == sess.stats.boxes and ref[0].shape == r.shape
+    assert np.max(np.abs(ref[0] - r)) < 1e-13
+
+
 def test_distributed_single_rank_nccl(yr):
     """world_size 1 over NCCL: the sharded entry point returns what solve_batch returns."""
     import torch
