@@ -100,9 +100,12 @@ YR_HD unsigned long long need_restrict_w(int T, int n0max, int n1max) {        /
     return (unsigned long long)T + panel_doubles(n0max) + panel_doubles(n1max) + (unsigned)((n0max + n1max + 1) / 2) + 2;
 }
 YR_HD unsigned long long need_subdivide_w(int T) { return 3ull * T; }            // warp teams: [S][L][X]
-YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, unsigned long long& need, int& cls) {
-    if (need_w <= kWarp32Max) { need = need_w; cls = 0; while (need_w > class_bound(cls)) ++cls; }
-    else { need = need_cta; cls = need_cta <= class_bound(kWarpClasses) ? kWarpClasses : kWarpClasses + 1; }
+YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, int coarse, unsigned long long& need, int& cls) {
+    if (need_w <= kWarp32Max) {
+        need = need_w; cls = 0; while (need_w > class_bound(cls)) ++cls;
+        // a small round is launch-latency bound: one class per team type, fewer launches
+        if (coarse) cls = cls < kLane16Classes ? kLane16Classes - 1 : kWarpClasses - 1;
+    } else { need = need_cta; cls = need_cta <= class_bound(kWarpClasses) ? kWarpClasses : kWarpClasses + 1; }
 }
 
 // Per-box state next to BoxRec<2> (same slot index).
@@ -150,6 +153,7 @@ struct Args {
     NodeRec<2>* nodes; unsigned long long cap_nodes, node_base;
     unsigned int* lists[kOps][kClasses];            // queues being filled for the next round
     unsigned long long cap_boxes;
+    int coarse;                                     // 1: the next round is small, queue into one class per team type
     Ctl* ctl;
     Tables tab;
     SolverParams prm;
@@ -1037,7 +1041,7 @@ YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
         int T, n0m, n1m; unsigned long long total;
         sizes(T, n0m, n1m, total);
         wk.op = kTRestrict;
-        dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), dc.need, dc.cls); dc.bound = total;
+        dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), a.coarse, dc.need, dc.cls); dc.bound = total;
         dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
     };
 
@@ -1152,7 +1156,7 @@ YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
             int T, n0m, n1m; unsigned long long total;
             sizes(T, n0m, n1m, total);
             wk.op = kTSubdivide;
-            dc.op = kTSubdivide; pick_team(need_subdivide_w(T), need_subdivide(T), dc.need, dc.cls); dc.bound = total << k;
+            dc.op = kTSubdivide; pick_team(need_subdivide_w(T), need_subdivide(T), a.coarse, dc.need, dc.cls); dc.bound = total << k;
             dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
             dc.subdiv += 1;
         }
@@ -1183,7 +1187,7 @@ YR_HD void import_box(const Args& a, unsigned int b, Decision& dc, At at) {
     w.node_level = rec.level; w.result_index = -1; w.node_index = -1; w.nsplit = 0;
     int T, n0m, n1m; unsigned long long total;
     box_sizes(rec, w, T, n0m, n1m, total);
-    dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), dc.need, dc.cls); dc.bound = total;
+    dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), a.coarse, dc.need, dc.cls); dc.bound = total;
     dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
     at.add(&a.ctl->n_boxes, 1ull);
 }

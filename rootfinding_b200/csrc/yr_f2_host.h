@@ -200,6 +200,7 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         a.results = static_cast<ResultRec<2>*>(results.p) + n_results; a.cap_results = cap_results - n_results;
         a.nodes = static_cast<NodeRec<2>*>(nodes.p) + n_nodes; a.cap_nodes = cap_nodes - n_nodes;
         a.result_base = d->result_base + n_results; a.node_base = d->node_base + n_nodes;
+        a.coarse = (produced < 8192ull) ? 1 : 0;
         a.data_in = data_in; a.data_out = static_cast<double*>(arena[out_arena].p); a.cap_data_out = arena[out_arena].cap / 8;
         // per-round part of the control block: queues, bounds, arena cursor; slot counters restart at their totals
         F2_TRY(be::dev_zero(ctlbuf.p, offsetof(Ctl, n_boxes), stream));
