@@ -264,7 +264,18 @@ __global__ void __launch_bounds__(128) f2_scalar_kernel(const Args a, const yr_f
         const unsigned long long nchild = a.ctl->n_boxes - sg.child_lo;
         if (i < nchild) { b = (unsigned int)(sg.child_lo + i); have = true; }
     }
-    if (have) scalar_step(a, b, dc, DevAt());
+    if (have) {
+        // the step touches most of both records, one dependent access after another: pull all six lines towards
+        // the SM first so the chain pays one memory round trip instead of many
+        const char* pr = reinterpret_cast<const char*>(a.recs + b);
+        const char* pw = reinterpret_cast<const char*>(a.work + b);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 128 * q));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pw + 128 * q));
+        }
+        scalar_step(a, b, dc, DevAt());
+    }
     commit_warp(a, b, dc);
 }
 
