@@ -158,11 +158,15 @@ typedef struct yr_frontier_desc {
     yr_params     prm;
 } yr_frontier_desc;
 
+/* one entry of yr_frontier_out.order */
+typedef struct yr_sorted_rec { uint32_t index; int32_t system; double root[2]; } yr_sorted_rec;
+
 typedef struct yr_frontier_out {
     void*    results; uint64_t n_results;   /* device arrays owned by the library */
     void*    nodes;   uint64_t n_nodes;
-    void*    order;                         /* uint32[n_results]: results[order[0]], results[order[1]], ... is the
-                                               reference's reporting order (system, then depth-first path) */
+    void*    order;                         /* yr_sorted_rec[n_results]: the records in the reference's reporting order
+                                               (system, then depth-first path) with the fields a host needs for the
+                                               common case, so that it can skip gathering from the full records */
     yr_counters counters;                   /* totals of the solve (boxes, zooms, subdivisions, discards, ...) */
     uint64_t rounds, launches, slots;
     double   tensor_ms, scalar_ms;          /* summed device time of the two kernel families (time_kernels = 1) */

@@ -118,7 +118,9 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
     elif sess.stats.max_level >= 15:
         warnings.warn("High subdivision depth!\nSubdivision on the search interval has now reached"
                       " at least depth 15. Runtime may be prolonged.")
-    roots, boxes = postpass.per_system_roots(res, keep, dup, extra, sess.nsys, sess.dim, want_boxes=returnBoundingBoxes)
+    roots, boxes = postpass.per_system_roots(res, keep, dup, extra, sess.nsys, sess.dim, want_boxes=returnBoundingBoxes,
+                                             sorted_fields=getattr(sess, "sorted_fields", None),
+                                             late_by_system=getattr(sess, "late_by_system", None))
     out = (roots, boxes) if returnBoundingBoxes else roots
     return (out, sess) if return_session else out
 

@@ -66,6 +66,9 @@ class YrFrontierOut(C.Structure):
                 ("rounds", u64), ("launches", u64), ("slots", u64), ("tensor_ms", C.c_double), ("scalar_ms", C.c_double)]
 
 
+# yr_sorted_rec (include/yroots_b200.h)
+SORTED_DTYPE = np.dtype([("index", np.uint32), ("system", np.int32), ("root", np.float64, (2,))])
+
 COUNTER_FIELDS = ["next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms", "subdivisions",
                   "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "restrict_macs",
                   "max_child_doubles", "max_child_extent", "max_level", "overflow", "max_child_tensor",

@@ -482,6 +482,15 @@ __global__ void f2_sort_keys(const ResultRec<2>* res, const unsigned int* idx, u
     else k32[i] = (unsigned int)res[r].system;
 }
 
+__global__ void f2_pack_sorted(const ResultRec<2>* res, const unsigned int* order, unsigned long long n, yr_sorted_rec* out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int r = order[i];
+    yr_sorted_rec o;
+    o.index = r; o.system = res[r].system; o.root[0] = res[r].root[0]; o.root[1] = res[r].root[1];
+    out[i] = o;
+}
+
 void* sort_results(const void* results, unsigned long long n, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const ResultRec<2>* res = static_cast<const ResultRec<2>*>(results);
@@ -504,7 +513,12 @@ void* sort_results(const void* results, unsigned long long n, void* stream) {
             f2_sort_keys<<<grid, 256, 0, st>>>(res, ia, n, 2, nullptr, k32a, nullptr);
             cub::DeviceRadixSort::SortPairs(tmp, tb32, k32a, k32b, ia, ib, (int)n, 0, 32, st);          // by system  -> ib
             dev_free(tmp, stream);
-            if (cudaGetLastError() == cudaSuccess) { result = ib; ib = nullptr; }
+            // pack (index, system, root) in reporting order
+            yr_sorted_rec* packed = (yr_sorted_rec*)dev_alloc(n_ * sizeof(yr_sorted_rec), stream);
+            if (packed) {
+                f2_pack_sorted<<<grid, 256, 0, st>>>(res, ib, n, packed);
+                if (cudaGetLastError() == cudaSuccess) result = packed; else dev_free(packed, stream);
+            }
         }
     }
     dev_free(k64a, stream); dev_free(k64b, stream); dev_free(k32a, stream); dev_free(k32b, stream); dev_free(ia, stream); dev_free(ib, stream);

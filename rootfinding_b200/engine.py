@@ -74,8 +74,8 @@ class CudaMemory:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._staging = []
-        self._pinned = None
-        self._pinned_owner = None
+        self._pinned = {}
+        self._pinned_owner = {}
 
     def empty(self, nbytes):
         n8 = max(1, (int(nbytes) + 7) // 8)
@@ -102,21 +102,23 @@ class CudaMemory:
             self.h2d_bytes += arr.nbytes
         return b
 
-    def host_bytes(self, nbytes, who=None):
-        """Host buffer for record downloads.  One page-locked buffer is kept per engine and lent to the session
-        that downloads (a 200 MB device -> pageable copy costs several times the solve); a previous borrower that
-        is still alive first moves its records to private memory."""
+    def host_bytes(self, nbytes, who=None, slot=0):
+        """Host buffer for record downloads.  One page-locked buffer per slot (0 results, 1 nodes) is kept per engine
+        and lent to the session that downloads (a 200 MB device -> pageable copy costs several times the solve); a
+        previous borrower that is still alive first moves its records to private memory."""
         import weakref
         if nbytes < (1 << 20):
             return np.empty(nbytes, dtype=np.uint8)
-        prev = self._pinned_owner() if self._pinned_owner is not None else None
+        owner = self._pinned_owner.get(slot)
+        prev = owner() if owner is not None else None
         if prev is not None and prev is not who:
-            prev._detach_host()
-        if self._pinned is None or self._pinned.numel() < nbytes:
-            self._pinned = None
-            self._pinned = self.torch.empty(int(nbytes), dtype=self.torch.uint8, pin_memory=True)
-        self._pinned_owner = weakref.ref(who) if who is not None else None
-        return self._pinned.numpy()[:nbytes]
+            prev._detach_host(slot)
+        buf = self._pinned.get(slot)
+        if buf is None or buf.numel() < nbytes:
+            self._pinned[slot] = None
+            buf = self._pinned[slot] = self.torch.empty(int(nbytes), dtype=self.torch.uint8, pin_memory=True)
+        self._pinned_owner[slot] = weakref.ref(who) if who is not None else None
+        return buf.numpy()[:nbytes]
 
     def timer(self):
         """CUDA event pair helper: returns (record_start, record_stop, elapsed_ms) bound to the current stream."""
@@ -281,7 +283,7 @@ class SolveSession:
         self._pending = []
         alloc = getattr(m, "host_bytes", lambda nbytes, who=None: np.empty(nbytes, dtype=np.uint8))
         self._results_host = _Growable(self.rdt, alloc, self)
-        self._nodes_host = _Growable(self.ndt, lambda nbytes, who=None: np.empty(nbytes, dtype=np.uint8), self)
+        self._nodes_host = _Growable(self.ndt, (lambda nbytes, who=None: alloc(nbytes, who, 1)) if hasattr(m, "host_bytes") else alloc, self)
         self._order_host = None           # depth-first order of the first frontier solve's records (device sort)
         self._order_base = 0
         self.stats = SolveStats()
@@ -488,8 +490,8 @@ class SolveSession:
                     level=np.zeros(n, np.int32), next_mid=np.full((n, D), FIRST_SPLIT), parent=np.full(n, -1, np.int32))
 
     # -- results -----------------------------------------------------------------------------
-    def _detach_host(self):
-        self._results_host.detach()
+    def _detach_host(self, slot=0):
+        (self._nodes_host if slot else self._results_host).detach()
 
     def _fetch_pending(self):
         """Bring every record produced so far to the host, in production (= index) order.  Level-pipeline records
@@ -514,7 +516,7 @@ class SolveSession:
                         _lib.check(lib, lib.yr_fetch(dst.ctypes.data, ptr, dst.nbytes, stream), "yr_fetch")
                         self.mem.d2h_bytes += dst.nbytes
                 if self._order_host is None and rn and out.order:
-                    order = np.empty(rn, dtype=np.uint32)
+                    order = np.empty(rn, dtype=_lib.SORTED_DTYPE)
                     _lib.check(lib, lib.yr_fetch(order.ctypes.data, out.order, order.nbytes, stream), "yr_fetch")
                     self.mem.d2h_bytes += order.nbytes
                     self._order_host, self._order_base = order, r0
@@ -541,8 +543,9 @@ class SolveSession:
         return self._nodes_host.view()
 
     def dfs_order(self):
-        """(order, base, n): base + order puts records [base, base + n) in (system, depth-first path) order, sorted
-        on the device by yr_frontier_solve; (None, 0, 0) when the session has none."""
+        """(order, base, n): base + order["index"] puts records [base, base + n) in (system, depth-first path) order,
+        sorted on the device by yr_frontier_solve (order also carries system and root of every record, gathered on
+        the device); (None, 0, 0) when the session has none."""
         self.results()
         if self._order_host is None:
             return None, 0, 0

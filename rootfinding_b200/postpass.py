@@ -169,6 +169,7 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
             res["box"][keep][:, 0] = np.minimum(res["box"][i][:, 0], res["box"][j][:, 0])
             res["box"][keep][:, 1] = np.maximum(res["box"][i][:, 1], res["box"][j][:, 1])
             res["root"][keep] = (res["box"][keep][:, 0] + res["box"][keep][:, 1]) / 2
+            session.patched_roots = getattr(session, "patched_roots", set()) | {int(keep)}
             res["flags"][keep] &= ~np.uint32(RES_TOUCH)
             alive[keep] = True
             continue
@@ -200,41 +201,50 @@ def assemble(session, merge=True):
     if order is not None and n_sorted:
         # records [base, base + n_sorted) arrive with their reporting order from the device (radix sort); the others
         # (first levels of a large system, re-solved merged boxes: a handful) are sorted here and merged in
-        main = order[alive[base:base + n_sorted][order]].astype(np.int64) + base
+        mask = alive[base:base + n_sorted][order["index"]]
+        packed = order[mask]                                    # (index, system, root) of the survivors, in reporting order
+        main = packed["index"].astype(np.int64) + base
         late = np.r_[np.nonzero(alive[:base])[0], np.nonzero(alive[base + n_sorted:])[0] + base + n_sorted]
-        if len(late):
-            late = _path_order(res, late)
-            key = lambda i: (int(res["system"][i]), int(res["path_hi"][i]), int(res["path_lo"][i]))
-            main_keys_sys = res["system"][main]
-            pos = []
-            for i in late:                                   # binary search by full key
-                lo_, hi_ = int(np.searchsorted(main_keys_sys, res["system"][i], "left")), int(np.searchsorted(main_keys_sys, res["system"][i], "right"))
-                k = key(i)
-                while lo_ < hi_:
-                    mid = (lo_ + hi_) // 2
-                    if key(main[mid]) < k:
-                        lo_ = mid + 1
-                    else:
-                        hi_ = mid
-                pos.append(lo_)
-            keep = np.insert(main, pos, late)
-        else:
-            keep = main
+        # late records stay out of `keep`; their systems are assembled individually in per_system_roots
+        by_sys = {}
+        for i in late.tolist():
+            by_sys.setdefault(int(res["system"][i]), []).append(i)
+        session.late_by_system = by_sys
+        keep = main
+        session.sorted_fields = (packed["system"], packed["root"])
+        touched = getattr(session, "patched_roots", None)
+        if touched:                                             # roots rewritten by a merge after the device gathered them
+            sysv, roots = session.sorted_fields
+            roots = np.array(roots)
+            for i in touched:
+                roots[keep == i] = res["root"][i]
+            session.sorted_fields = (sysv, roots)
     else:
         keep = _path_order(res, np.nonzero(alive)[0])
+        session.sorted_fields = None
+        session.late_by_system = {}
     return res, keep, dup, extra
 
 
-def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False):
-    """Vectorised gathering of roots per system; special records are patched in afterwards."""
-    sysv = np.take(res["system"], keep)
+def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_fields=None, late_by_system=None):
+    """Vectorised gathering of roots per system; special records are patched in afterwards.  `sorted_fields` =
+    (system, root) of the kept records in order, when the device already gathered them; `late_by_system` = live
+    records that are not in `keep` (produced after the device sorted), merged into their systems by path."""
+    if sorted_fields is not None:
+        sysv, roots_all = sorted_fields
+    else:
+        sysv = np.take(res["system"], keep)
+        roots_all = np.take(res["root"], keep, axis=0)
     bounds = np.searchsorted(sysv, np.arange(nsys + 1))
-    roots_all = np.take(res["root"], keep, axis=0)
+    late_by_system = late_by_system or {}
     out_roots, out_boxes, has_dup, has_extra = [], [], False, False
     special = {int(k) for k in dup} | {int(k) for k in extra}
     for s in range(nsys):
         idx = keep[bounds[s]:bounds[s + 1]]
-        if special and not special.isdisjoint(idx.tolist()):
+        late = late_by_system.get(s)
+        if late:
+            idx = _path_order(res, np.r_[idx, np.asarray(late, dtype=idx.dtype)])
+        if late or (special and not special.isdisjoint(idx.tolist())):
             rows = []
             for i in idx:
                 if int(i) in dup:

@@ -471,7 +471,6 @@ int launch_scalar(const yr::f2::Args& a, const Segments& s, void*) {
 
 void* sort_results(const void* results, unsigned long long n, void*) {
     const yr::ResultRec<2>* res = static_cast<const yr::ResultRec<2>*>(results);
-    unsigned int* order = static_cast<unsigned int*>(malloc((size_t)n * 4 + 16));
     std::vector<unsigned int> v((size_t)n);
     for (size_t i = 0; i < v.size(); ++i) v[i] = (unsigned int)i;
     std::stable_sort(v.begin(), v.end(), [&](unsigned int a, unsigned int b) {
@@ -479,7 +478,11 @@ void* sort_results(const void* results, unsigned long long n, void*) {
         if (res[a].path_hi != res[b].path_hi) return res[a].path_hi < res[b].path_hi;
         return res[a].path_lo < res[b].path_lo;
     });
-    memcpy(order, v.data(), v.size() * 4);
+    yr_sorted_rec* order = static_cast<yr_sorted_rec*>(malloc((size_t)n * sizeof(yr_sorted_rec) + 16));
+    for (size_t i = 0; i < v.size(); ++i) {
+        order[i].index = v[i]; order[i].system = res[v[i]].system;
+        order[i].root[0] = res[v[i]].root[0]; order[i].root[1] = res[v[i]].root[1];
+    }
     return order;
 }
 double trace_sync_ms(void*) { return 0.0; }
