@@ -163,7 +163,7 @@ struct Args {
 // Column by column (the three-term recurrence couples neighbouring rows: columns sequential, rows parallel),
 // with rows_after[k] = the reference's `maxRow` after column k (:106-112).  Collective over the team.
 template <class Team>
-YR_F2_BUILD void build_panels(Team& tm, double* Cp, int* rows_after, int nt, double alpha, double beta) {
+YR_DEVN void build_panels(Team& tm, double* Cp, int* rows_after, int nt, double alpha, double beta) {
     const int P = panel_doubles(nt);
     for (int e = tm.tid; e < P; e += tm.nthreads) Cp[e] = 0.0;
     tm.sync();
@@ -256,8 +256,9 @@ YR_F2_BUILD void build_two(Team& tm, const PanelJob& j0, const PanelJob& j1) {
             if (tm.warp == 1 && j1.nt > 0) build_panels_warp(tm, j1, j1, 32);
         } else if (tm.lanes == 32 && big <= 16 && j0.nt > 0 && j1.nt > 0) build_panels_warp(tm, j0, j1, 16);
         else {
-            if (j0.nt > 0) build_panels_warp(tm, j0, j0, tm.lanes);
-            if (j1.nt > 0) build_panels_warp(tm, j1, j1, tm.lanes);
+            const PanelJob* jobs[2] = {&j0, &j1};
+#pragma unroll 1
+            for (int m = 0; m < 2; ++m) if (jobs[m]->nt > 0) build_panels_warp(tm, *jobs[m], *jobs[m], tm.lanes);   // one copy of the loop body
         }
         tm.sync();
         return;
@@ -314,7 +315,7 @@ YR_DEV void copy_flat(Team& tm, double* dst, const double* src, int n_even) {
 }
 
 template <class Team>
-YR_DEV double view_abs_sum(Team& tm, const double* M, int n0, int n1, int ld) {
+YR_DEVN double view_abs_sum(Team& tm, const double* M, int n0, int n1, int ld) {
     double s = 0.0;
     if (n1 >= 12) {
         // lanes along rows
@@ -793,9 +794,13 @@ YR_DEV void copy_out_rows(Team& tm, double* dst, int ld_out, const double* M, in
 }
 
 template <class Team>
+YR_DEVN void fetch_strided(Team& tm, double* dst, int lds, const double* src, int ldg, int n0, int n1) {   // level-0 boxes only
+    for (int i = 0; i < n0; ++i) for (int j = tm.tid; j < n1; j += tm.nthreads) dst[i * lds + j] = src[(long long)i * ldg + j];
+}
+template <class Team>
 YR_DEV void fetch_tensor(Team& tm, double* dst, int lds, const double* src, int ldg, int n0, int n1, bool flat) {
     if (flat) tm.copy_async(dst, src, tensor_doubles(n0, lds));
-    else for (int i = 0; i < n0; ++i) for (int j = tm.tid; j < n1; j += tm.nthreads) dst[i * lds + j] = src[(long long)i * ldg + j];
+    else fetch_strided(tm, dst, lds, src, ldg, n0, n1);
 }
 
 // RESTRICT, warp team.  slice: [A: T][C0 panels][C1 panels][rows_after ints]
@@ -844,10 +849,15 @@ YR_DEV void restrict_box_w(Team& tm, const Args& a, unsigned int b, double* slic
         double s = copy_only ? view_abs_sum(tm, A, n0, n1, ld) : sum_in[p];
         double err = err_in[p];
         int r0 = n0, r1 = n1;
-        if (!copy_only) err += n0 * kMachEps * s;                    // charged before the axis (:860)
-        if (!id0 && n0 > 1) { r0 = rows0[n0 - 1]; s = pass_fiber<FMA>(tm, A, A, ld, 1, n0, r0, n1, C0, n0max, macs); }
-        if (!copy_only) err += n1 * kMachEps * s;
-        if (!id1 && n1 > 1) { r1 = rows1[n1 - 1]; s = pass_fiber<FMA>(tm, A, A, 1, ld, n1, r1, r0, C1, n1max, macs); }
+#pragma unroll 1
+        for (int axis = 0; axis < 2; ++axis) {                       // one copy of the pass in the instruction stream
+            const int n = axis ? n1 : n0;
+            if (!copy_only) err += n * kMachEps * s;                 // charged before the axis (:860)
+            if ((axis ? id1 : id0) || n <= 1) continue;
+            const int r = (axis ? rows1 : rows0)[n - 1];
+            s = pass_fiber<FMA>(tm, A, A, axis ? 1 : ld, axis ? ld : 1, n, r, axis ? r0 : n1, axis ? C1 : C0, axis ? n1max : n0max, macs);
+            if (axis) r1 = r; else r0 = r;
+        }
         // re-laying the tensor out row by row only pays when it saves real space: keep the stride for a small gap
         const int ld_out = (ld - odd_ld(r1) <= 2) ? ld : odd_ld(r1), osz = tensor_doubles(r0, ld_out);
         Epilogue ep;
