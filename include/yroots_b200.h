@@ -159,7 +159,7 @@ typedef struct yr_frontier_desc {
 } yr_frontier_desc;
 
 /* one entry of yr_frontier_out.order */
-typedef struct yr_sorted_rec { uint32_t index; int32_t system; double root[2]; } yr_sorted_rec;
+typedef struct yr_sorted_rec { uint32_t index; int32_t system; uint32_t flags; int32_t collector; double root[2]; } yr_sorted_rec;
 
 typedef struct yr_frontier_out {
     void*    results; uint64_t n_results;   /* device arrays owned by the library */

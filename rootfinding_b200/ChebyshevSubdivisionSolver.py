@@ -109,7 +109,7 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
                        low_dim_quad_check=int(bool(low_dim_quadratic_check)),
                        all_dim_quad_check=int(bool(all_dim_quadratic_check)), use_fma=int(bool(use_fma)))
     sess.run_jobs(sess.unit_jobs())
-    res, keep, dup, extra = postpass.assemble(sess)
+    res, keep, dup, extra = postpass.assemble(sess, need_records=returnBoundingBoxes)
     if sess.stats.max_level >= 25:
         warnings.warn("Extreme subdivision depth!\nSubdivision on the search interval has now reached"
                       " at least depth 25, which is unusual. The solver may not finish running."

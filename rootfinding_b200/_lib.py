@@ -67,7 +67,8 @@ class YrFrontierOut(C.Structure):
 
 
 # yr_sorted_rec (include/yroots_b200.h)
-SORTED_DTYPE = np.dtype([("index", np.uint32), ("system", np.int32), ("root", np.float64, (2,))])
+SORTED_DTYPE = np.dtype([("index", np.uint32), ("system", np.int32), ("flags", np.uint32), ("collector", np.int32),
+                         ("root", np.float64, (2,))])
 
 COUNTER_FIELDS = ["next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms", "subdivisions",
                   "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "restrict_macs",

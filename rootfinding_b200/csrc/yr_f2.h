@@ -133,6 +133,7 @@ struct Ctl {
     unsigned long long ext_max[kClasses];           // largest extent among queued subdivisions
     unsigned long long out_bound;                   // doubles the next round's tensor ops may write
     unsigned long long data_used;                   // doubles written to the current output arena
+    unsigned long long cursor[kOps][kClasses];      // this round's tensor launches: next queue position to hand out
     unsigned long long n_boxes, n_results, n_nodes; // slots in use
     unsigned long long overflow, bad_mid;
     unsigned long long boxes, zooms, subdivisions, dconst, dquad, dzoom, entry_coeffs, restrict_macs, max_level;

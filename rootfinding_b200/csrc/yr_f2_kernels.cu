@@ -146,10 +146,10 @@ __device__ void stage_submats(const Args& a, double* smat, int snt) {
 
 template <int OP, bool FMA, int LANES>
 #ifndef YR_F2_WARP_MINB
-#define YR_F2_WARP_MINB 1
+#define YR_F2_WARP_MINB 5
 #endif
 __global__ void __launch_bounds__(128, YR_F2_WARP_MINB) f2_tensor_warp(const Args a, const unsigned int* __restrict__ list, unsigned long long n,
-                                                      unsigned slice_doubles, int snt) {
+                                                      unsigned slice_doubles, int snt, unsigned long long* cursor) {
     extern __shared__ __align__(16) double dyn[];
     constexpr int kTeams = 128 / LANES;
     double* smat = dyn;
@@ -158,13 +158,17 @@ __global__ void __launch_bounds__(128, YR_F2_WARP_MINB) f2_tensor_warp(const Arg
     const int w = threadIdx.x / LANES;
     double* slice = dyn + smat_doubles + (size_t)w * slice_doubles;
     WarpTeam<LANES> tm = make_warp_team<LANES>();
-    const unsigned long long team = (unsigned long long)blockIdx.x * kTeams + w, nteams = (unsigned long long)gridDim.x * kTeams;
+    // The grid is one resident wave; teams take boxes from the queue one at a time (boxes of a class still differ in
+    // cost), always holding the NEXT position already so that its records can be prefetched.
     unsigned long long macs = 0;
-    for (unsigned long long i = team; i < n; i += nteams) {
+    auto grab = [&]() { unsigned long long v = 0; if (tm.tid == 0) v = atomicAdd(cursor, 1ull); return tm.bcast(v); };
+    unsigned long long i = grab();
+    while (i < n) {
+        const unsigned long long nxt = grab();
         const unsigned int b = list[i];
-        if (i + nteams < n && tm.tid < 7) {
+        if (nxt < n && tm.tid < 7) {
             // the next box's records (BoxRec 3 lines, Work 3-4 lines) start their trip from HBM now
-            const unsigned int nb = list[i + nteams];
+            const unsigned int nb = list[nxt];
             const char* p = tm.tid < 3 ? reinterpret_cast<const char*>(a.recs + nb) + 128 * tm.tid
                                        : reinterpret_cast<const char*>(a.work + nb) + 128 * (tm.tid - 3);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -172,12 +176,14 @@ __global__ void __launch_bounds__(128, YR_F2_WARP_MINB) f2_tensor_warp(const Arg
         if (OP == kTRestrict) restrict_box_w<FMA>(tm, a, b, slice, macs);
         else subdivide_box_w<FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
         tm.sync();
+        i = nxt;
     }
     if (tm.tid == 0 && macs) atomicAdd(&a.ctl->restrict_macs, macs);
 }
 
 template <int OP, bool FMA>
-__global__ void __launch_bounds__(256) f2_tensor_cta(const Args a, const unsigned int* __restrict__ list, unsigned long long n, int snt) {
+__global__ void __launch_bounds__(256) f2_tensor_cta(const Args a, const unsigned int* __restrict__ list, unsigned long long n, int snt,
+                                                     unsigned long long* cursor) {
     extern __shared__ __align__(16) double dyn[];
     __shared__ CtaShared cta_sh;
     double* smat = dyn;
@@ -186,7 +192,11 @@ __global__ void __launch_bounds__(256) f2_tensor_cta(const Args a, const unsigne
     double* slice = dyn + smat_doubles;
     CtaTeam tm = make_cta_team(&cta_sh);
     unsigned long long macs = 0;
-    for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x) {
+    for (;;) {
+        unsigned long long i = 0;
+        if (tm.tid == 0) i = atomicAdd(cursor, 1ull);
+        i = tm.bcast(i);
+        if (i >= n) break;
         const unsigned int b = list[i];
         if (OP == kTRestrict) restrict_box<FMA>(tm, a, b, slice, macs);
         else subdivide_box<FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
@@ -337,9 +347,19 @@ int ensure_smem(K kernel, size_t bytes) {
     return 0;
 }
 
+// CTAs of `kernel` one SM really holds at this shared-memory size (registers, shared memory, warps): the grid is
+// exactly one resident wave
+template <class K>
+int resident_ctas(K kernel, int threads, size_t smem) {
+    int r = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, kernel, threads, smem) != cudaSuccess || r < 1) { cudaGetLastError(); r = 1; }
+    return r;
+}
+
 template <int OP, bool FMA>
 int launch_tensor_t(const Args& a, int cls, const unsigned int* list, unsigned long long n, unsigned long long need, int ext, cudaStream_t st) {
     const Dev& d = dev();
+    unsigned long long* cursor = &a.ctl->cursor[op_slot(OP)][cls];
     const int snt = (OP == kTSubdivide) ? (ext < 4 ? 4 : ext) : 0;
     const size_t smat = (OP == kTSubdivide) ? (size_t)2 * panel_doubles(snt) * 8 : 0;
     const size_t slice = ((size_t)need + 1) & ~(size_t)1;
@@ -347,25 +367,24 @@ int launch_tensor_t(const Args& a, int cls, const unsigned int* list, unsigned l
         const int teams = cls < kLane16Classes ? 8 : 4;          // two 16-lane teams per warp for the small classes
         const size_t smem = smat + teams * slice * 8;
         if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: warp-team launch exceeds shared memory"); return -1; }
-        long per_sm = (long)((size_t)d.smem_sm / (smem + 1024)); if (per_sm > 12) per_sm = 12; if (per_sm < 1) per_sm = 1;
-        unsigned long long want = (n + teams - 1) / teams, cap = (unsigned long long)d.sm * per_sm;
-        const unsigned grid = (unsigned)(want < cap ? want : cap);
+        const unsigned long long want = (n + teams - 1) / teams;
         if (cls < kLane16Classes) {
             if (ensure_smem(f2_tensor_warp<OP, FMA, 16>, smem)) return -1;
-            f2_tensor_warp<OP, FMA, 16><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
+            const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(f2_tensor_warp<OP, FMA, 16>, 128, smem);
+            f2_tensor_warp<OP, FMA, 16><<<(unsigned)(want < cap ? want : cap), 128, smem, st>>>(a, list, n, (unsigned)slice, snt, cursor);
         } else {
             if (ensure_smem(f2_tensor_warp<OP, FMA, 32>, smem)) return -1;
-            f2_tensor_warp<OP, FMA, 32><<<grid, 128, smem, st>>>(a, list, n, (unsigned)slice, snt);
+            const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(f2_tensor_warp<OP, FMA, 32>, 128, smem);
+            f2_tensor_warp<OP, FMA, 32><<<(unsigned)(want < cap ? want : cap), 128, smem, st>>>(a, list, n, (unsigned)slice, snt, cursor);
         }
     } else {
         const int threads = class_threads(cls);
         const size_t smem = smat + slice * 8;
         if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: CTA-team launch exceeds shared memory"); return -1; }
         if (ensure_smem(f2_tensor_cta<OP, FMA>, smem)) return -1;
-        long per_sm = (long)((size_t)d.smem_sm / (smem + 1024)); const long tcap = 2048 / threads; if (per_sm > tcap) per_sm = tcap; if (per_sm < 1) per_sm = 1;
-        unsigned long long cap = (unsigned long long)d.sm * per_sm;
+        const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(f2_tensor_cta<OP, FMA>, threads, smem);
         const unsigned grid = (unsigned)(n < cap ? n : cap);
-        f2_tensor_cta<OP, FMA><<<grid, threads, smem, st>>>(a, list, n, snt);
+        f2_tensor_cta<OP, FMA><<<grid, threads, smem, st>>>(a, list, n, snt, cursor);
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "f2 tensor launch");
@@ -487,7 +506,8 @@ __global__ void f2_pack_sorted(const ResultRec<2>* res, const unsigned int* orde
     if (i >= n) return;
     const unsigned int r = order[i];
     yr_sorted_rec o;
-    o.index = r; o.system = res[r].system; o.root[0] = res[r].root[0]; o.root[1] = res[r].root[1];
+    o.index = r; o.system = res[r].system; o.flags = res[r].flags; o.collector = res[r].collector;
+    o.root[0] = res[r].root[0]; o.root[1] = res[r].root[1];
     out[i] = o;
 }
 

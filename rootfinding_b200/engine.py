@@ -491,6 +491,10 @@ class SolveSession:
 
     # -- results -----------------------------------------------------------------------------
     def _detach_host(self, slot=0):
+        if slot == 2:
+            if self._order_host is not None:
+                self._order_host = self._order_host.copy()
+            return
         (self._nodes_host if slot else self._results_host).detach()
 
     def _fetch_pending(self):
@@ -541,6 +545,27 @@ class SolveSession:
         if self._segments:
             self._fetch_pending()
         return self._nodes_host.view()
+
+    def slim_order(self):
+        """The device-sorted (index, system, flags, collector, root) entries of the session's records WITHOUT bringing
+        the full result / node records to the host -- possible when one frontier solve produced every record so far
+        (the common case: a batch of 2-D systems).  Returns None otherwise.  The full records stay on the device and
+        results() / nodes() still fetch them on demand."""
+        if self._order_host is not None and self._order_base == 0 and len(self._order_host) == self.n_results:
+            return self._order_host
+        if len(self._segments) != 1 or self._segments[0][0] != "frontier":
+            return None
+        _, r0, rn, n0, nn, out = self._segments[0]
+        if r0 != 0 or rn != self.n_results or not rn or not out.order:
+            return None
+        alloc = getattr(self.mem, "host_bytes", None)
+        nbytes = rn * _lib.SORTED_DTYPE.itemsize
+        raw = alloc(nbytes, self, 2) if alloc is not None else np.empty(nbytes, dtype=np.uint8)
+        _lib.check(self.lib, self.lib.yr_fetch(raw.ctypes.data, out.order, nbytes, self.mem.stream()), "yr_fetch")
+        self.mem.d2h_bytes += nbytes
+        self._order_raw = raw
+        self._order_host, self._order_base = raw.view(_lib.SORTED_DTYPE), 0
+        return self._order_host
 
     def dfs_order(self):
         """(order, base, n): base + order["index"] puts records [base, base + n) in (system, depth-first path) order,

@@ -191,8 +191,23 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
     return res, alive, dup, extra
 
 
-def assemble(session, merge=True):
-    """Turn the session's result records into per-system (roots, boxes) in depth-first order."""
+def assemble(session, merge=True, need_records=False):
+    """Turn the session's result records into per-system (roots, boxes) in depth-first order.  `need_records`: the
+    caller wants the full records (bounding boxes), not only the roots."""
+    slim = session.slim_order() if (not need_records and hasattr(session, "slim_order")) else None
+    if slim is not None:
+        # common case (a batch of ordinary systems): no final-step collectors, no touching exterior boxes that could
+        # merge -- the device-gathered (system, root) entries in reporting order are the whole answer and the full
+        # result / node records never leave the device
+        fl = slim["flags"]
+        ordinary = not np.any((fl & RES_COLLECTOR) != 0) and not np.any(slim["collector"] >= 0)
+        if ordinary and merge:
+            touch_sys = slim["system"][(fl & RES_TOUCH) != 0]
+            ordinary = len(touch_sys) < 2 or len(np.unique(touch_sys)) == len(touch_sys)   # merging needs two boxes of one system
+        if ordinary:
+            session.sorted_fields = (slim["system"], np.ascontiguousarray(slim["root"]))
+            session.late_by_system = {}
+            return None, slim["index"].astype(np.int64), {}, set()
     res = session.results()
     alive, dup, extra = resolve_collectors(res)
     if merge:

@@ -480,7 +480,7 @@ void* sort_results(const void* results, unsigned long long n, void*) {
     });
     yr_sorted_rec* order = static_cast<yr_sorted_rec*>(malloc((size_t)n * sizeof(yr_sorted_rec) + 16));
     for (size_t i = 0; i < v.size(); ++i) {
-        order[i].index = v[i]; order[i].system = res[v[i]].system;
+        order[i].index = v[i]; order[i].system = res[v[i]].system; order[i].flags = res[v[i]].flags; order[i].collector = res[v[i]].collector;
         order[i].root[0] = res[v[i]].root[0]; order[i].root[1] = res[v[i]].root[1];
     }
     return order;

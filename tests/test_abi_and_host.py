@@ -325,3 +325,25 @@ def test_emulated_hybrid_level_then_frontier(emu):
             emu.lib = real
     for a, b in zip(got, ref):
         assert a.shape == b.shape and np.max(np.abs(a - b), initial=0.0) < 1e-14    # same roots in the same (depth-first) order
+
+
+def test_slim_result_path_matches_full_records():
+    """solve_batch answers ordinary batches from the device-gathered (system, root) entries alone; the full result
+    records (requested with returnBoundingBoxes) must give the same roots in the same order."""
+    from emul.backend import emulated_engine
+    from rootfinding_b200 import ChebyshevSubdivisionSolver as S
+    from oracle.gen_golden import rand_coeffs
+    eng = emulated_engine()
+    np.random.seed(5)
+    arr = rand_coeffs(2, 9, 6)
+    systems = [[np.ascontiguousarray(m) for m in arr[s]] for s in range(6)]
+    errs = [np.full(2, 2.0 ** -52)] * 6
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        slim, s1 = S.solve_batch(systems, errs, engine=eng, return_session=True)
+        (full, boxes), s2 = S.solve_batch(systems, errs, returnBoundingBoxes=True, engine=eng, return_session=True)
+    assert s1._results_host.n == 0, "the slim path must not download the full records"
+    assert s2._results_host.n == s2.n_results > 0
+    for a, b, bx in zip(slim, full, boxes):
+        assert np.array_equal(np.asarray(a), np.asarray(b)) and len(bx) == len(b)
+    assert sum(len(r) for r in slim) > 10
