@@ -87,7 +87,8 @@ class TrackedInterval:
 
 
 def _check_system(Ms, errors):
-    if np.any([np.ndim(M) != len(Ms) for M in Ms]):
+    n = len(Ms)
+    if any(np.ndim(M) != n for M in Ms):
         raise ValueError("Solver Takes in N polynomials of dimension N!")
     if len(Ms) != len(errors):
         raise ValueError("Ms and errors must be same length!")
@@ -104,7 +105,7 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
     for Ms, e in zip(systems, errors):
         _check_system(Ms, e)
     eng = get_engine() if engine is None else engine
-    sess = eng.session([[np.asarray(M, dtype=np.float64) for M in Ms] for Ms in systems], errors,
+    sess = eng.session(systems, errors,
                        exact=int(bool(exact)), constant_check=int(bool(constant_check)),
                        low_dim_quad_check=int(bool(low_dim_quadratic_check)),
                        all_dim_quad_check=int(bool(all_dim_quadratic_check)), use_fma=int(bool(use_fma)))
@@ -120,7 +121,8 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
                       " at least depth 15. Runtime may be prolonged.")
     roots, boxes = postpass.per_system_roots(res, keep, dup, extra, sess.nsys, sess.dim, want_boxes=returnBoundingBoxes,
                                              sorted_fields=getattr(sess, "sorted_fields", None),
-                                             late_by_system=getattr(sess, "late_by_system", None))
+                                             late_by_system=getattr(sess, "late_by_system", None),
+                                             redo_systems=getattr(sess, "redo_systems", None), alive=getattr(sess, "alive", None))
     out = (roots, boxes) if returnBoundingBoxes else roots
     return (out, sess) if return_session else out
 

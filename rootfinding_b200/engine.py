@@ -248,18 +248,22 @@ class SolveSession:
         if not 1 <= D <= 6:
             raise ValueError("yroots_b200 supports systems of dimension 1..6")
         self.nsys = len(systems)
-        shapes = np.ones((self.nsys, D, D), dtype=np.int32)
-        offs = np.zeros((self.nsys, D), dtype=np.int64)
-        chunks, pos = [], 0
-        for s, Ms in enumerate(systems):
-            for p, M in enumerate(Ms):
-                M = np.asarray(M, dtype=np.float64)
+        chunks, shape_list = [], []
+        f64 = np.dtype(np.float64)
+        for Ms in systems:                                        # one pass: this loop is on the end-to-end path
+            if len(Ms) != D:
+                raise ValueError("Solver Takes in N polynomials of dimension N!")
+            for M in Ms:
+                if type(M) is not np.ndarray or M.dtype != f64:
+                    M = np.asarray(M, dtype=np.float64)
                 if M.ndim != D:
                     raise ValueError("Solver Takes in N polynomials of dimension N!")
-                shapes[s, p] = M.shape
-                offs[s, p] = pos
-                chunks.append(np.ascontiguousarray(M).reshape(-1))
-                pos += M.size
+                shape_list.append(M.shape)
+                chunks.append(M.reshape(-1))                      # copies only a non-contiguous tensor
+        shapes = np.array(shape_list, dtype=np.int32).reshape(self.nsys, D, D) if shape_list else np.ones((0, D, D), np.int32)
+        sizes = shapes.prod(axis=2, dtype=np.int64).reshape(-1)
+        offs = (np.cumsum(sizes) - sizes).reshape(self.nsys, D)
+        pos = int(sizes.sum())
         self.shapes_h, self.total_coeffs = shapes, pos
         self.sys_total = shapes.prod(axis=2).sum(axis=1)          # coefficients per system
         self.sys_max_tensor = shapes.prod(axis=2).max(axis=1)

@@ -115,12 +115,15 @@ def _ancestors(nodes, start):
     return chain
 
 
-def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
-    """Step B.  May run more device jobs through `session`; returns the updated (res, alive, dup, extra)."""
+def merge_exterior(session, res, alive, dup, extra, max_rounds=64, cand=None):
+    """Step B.  May run more device jobs through `session`; returns the updated (res, alive, dup, extra).
+    `cand`: the live records flagged RES_TOUCH, when the caller already knows them."""
     rounds = 0
     # candidates: live records whose reported interval touches the cell they were created as; the set is small
     # and is maintained incrementally (one pass over the records, not one per merge)
-    cand_set = set(np.nonzero(alive & ((res["flags"] & RES_TOUCH) != 0))[0].tolist())
+    if cand is None:
+        cand = np.nonzero(alive & ((res["flags"] & RES_TOUCH) != 0))[0]
+    cand_set = set(np.asarray(cand).tolist())
     while rounds < max_rounds:
         rounds += 1
         if len(cand_set) < 2:
@@ -142,42 +145,50 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
         if not pairs:
             break
         nodes = session.nodes()
-        best = None
-        for i, j in pairs:                      # deepest common ancestor first, like the unwinding recursion
+        # Per system: the pair with the deepest common ancestor first, like the unwinding recursion.  Systems never
+        # interact, so one round merges one pair in EVERY system that has one and re-solves them in one device call.
+        best = {}
+        for i, j in pairs:
             ai = _ancestors(nodes, res["parent_node"][i])
             aj = set(_ancestors(nodes, res["parent_node"][j]))
             lca = next((k for k in ai if k in aj), -1)
             lvl = int(nodes["level"][lca]) if lca >= 0 else 0
-            if best is None or lvl > best[0]:
-                best = (lvl, i, j, lca)
-        lvl, i, j, lca = best
+            sysid = int(res["system"][i])
+            if sysid not in best or lvl > best[sysid][0]:
+                best[sysid] = (lvl, i, j, lca)
         dim = res["comb_iv"].shape[1]
-        lo = np.minimum(res["comb_iv"][i][:, 0], res["comb_iv"][j][:, 0])
-        hi = np.maximum(res["comb_iv"][i][:, 1], res["comb_iv"][j][:, 1])
-        if lca >= 0:
-            anc_iv, anc_mid, anc_level = nodes["iv"][lca], nodes["next_mid"][lca], int(nodes["level"][lca])
-        else:                                   # the two boxes come from different level-0 jobs of one system
-            anc_iv = np.array([[-1., 1.]] * dim)
-            anc_mid, anc_level = np.full(dim, 0.0394555475981047), 0
-        alive[i] = alive[j] = False
-        cand_set.discard(i); cand_set.discard(j)
-        session.stats_merges = getattr(session, "stats_merges", 0) + 1
-        if np.array_equal(lo, anc_iv[:, 0]) and np.array_equal(hi, anc_iv[:, 1]):
-            # :1370-1371 the merged box is the ancestor's whole box: keep it, do not re-solve
-            keep = i
-            res["comb_iv"][keep][:, 0], res["comb_iv"][keep][:, 1] = lo, hi
-            res["box"][keep][:, 0] = np.minimum(res["box"][i][:, 0], res["box"][j][:, 0])
-            res["box"][keep][:, 1] = np.maximum(res["box"][i][:, 1], res["box"][j][:, 1])
-            res["root"][keep] = (res["box"][keep][:, 0] + res["box"][keep][:, 1]) / 2
-            session.patched_roots = getattr(session, "patched_roots", set()) | {int(keep)}
-            res["flags"][keep] &= ~np.uint32(RES_TOUCH)
-            alive[keep] = True
+        jobs = []
+        for sysid in sorted(best):
+            lvl, i, j, lca = best[sysid]
+            lo = np.minimum(res["comb_iv"][i][:, 0], res["comb_iv"][j][:, 0])
+            hi = np.maximum(res["comb_iv"][i][:, 1], res["comb_iv"][j][:, 1])
+            if lca >= 0:
+                anc_iv, anc_mid, anc_level = nodes["iv"][lca], nodes["next_mid"][lca], int(nodes["level"][lca])
+            else:                                   # the two boxes come from different level-0 jobs of one system
+                anc_iv = np.array([[-1., 1.]] * dim)
+                anc_mid, anc_level = np.full(dim, 0.0394555475981047), 0
+            alive[i] = alive[j] = False
+            cand_set.discard(i); cand_set.discard(j)
+            session.stats_merges = getattr(session, "stats_merges", 0) + 1
+            if np.array_equal(lo, anc_iv[:, 0]) and np.array_equal(hi, anc_iv[:, 1]):
+                # :1370-1371 the merged box is the ancestor's whole box: keep it, do not re-solve
+                keep = i
+                res["comb_iv"][keep][:, 0], res["comb_iv"][keep][:, 1] = lo, hi
+                res["box"][keep][:, 0] = np.minimum(res["box"][i][:, 0], res["box"][j][:, 0])
+                res["box"][keep][:, 1] = np.maximum(res["box"][i][:, 1], res["box"][j][:, 1])
+                res["root"][keep] = (res["box"][keep][:, 0] + res["box"][keep][:, 1]) / 2
+                session.patched_roots = getattr(session, "patched_roots", set()) | {int(keep)}
+                res["flags"][keep] &= ~np.uint32(RES_TOUCH)
+                alive[keep] = True
+                continue
+            jobs.append((sysid, lo, hi, anc_level, np.array(anc_mid), lca))
+        if not jobs:
             continue
-        iv = np.stack([lo, hi], axis=1)[None]
-        job = dict(system=np.array([res["system"][i]], np.int32), restrict=np.ones(1, np.int32),
-                   alpha=((hi - lo) / 2)[None], beta=((hi + lo) / 2)[None], iv=iv,
-                   level=np.array([anc_level], np.int32), next_mid=np.array(anc_mid)[None],
-                   parent=np.array([lca], np.int32))
+        los, his = np.array([q[1] for q in jobs]), np.array([q[2] for q in jobs])
+        job = dict(system=np.array([q[0] for q in jobs], np.int32), restrict=np.ones(len(jobs), np.int32),
+                   alpha=(his - los) / 2, beta=(his + los) / 2, iv=np.stack([los, his], axis=2),
+                   level=np.array([q[3] for q in jobs], np.int32), next_mid=np.array([q[4] for q in jobs]),
+                   parent=np.array([q[5] for q in jobs], np.int32))
         first, count = session.run_jobs(job)
         res = session.results()
         grow = len(res) - len(alive)
@@ -193,21 +204,49 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64):
 
 def assemble(session, merge=True, need_records=False):
     """Turn the session's result records into per-system (roots, boxes) in depth-first order.  `need_records`: the
-    caller wants the full records (bounding boxes), not only the roots."""
-    slim = session.slim_order() if (not need_records and hasattr(session, "slim_order")) else None
+    caller wants the full records (bounding boxes), not only the roots.
+
+    Returns (res, keep, dup, extra) for per_system_roots and leaves on the session
+      sorted_fields   (system, root) of `keep` in reporting order when the device gathered them,
+      late_by_system  live records outside `keep` (first levels of a large system, re-solved merged boxes),
+      redo_systems    systems that lost records of `keep` to a merge or a collector (assembled one by one).
+    """
+    slim = session.slim_order() if hasattr(session, "slim_order") else None
+    session.redo_systems = set()
     if slim is not None:
-        # common case (a batch of ordinary systems): no final-step collectors, no touching exterior boxes that could
-        # merge -- the device-gathered (system, root) entries in reporting order are the whole answer and the full
-        # result / node records never leave the device
+        # one frontier solve produced every record: the device-gathered entries (reporting order) carry what the
+        # common case needs; the full records come to the host only for bounding boxes, collectors or merges
         fl = slim["flags"]
-        ordinary = not np.any((fl & RES_COLLECTOR) != 0) and not np.any(slim["collector"] >= 0)
-        if ordinary and merge:
-            touch_sys = slim["system"][(fl & RES_TOUCH) != 0]
-            ordinary = len(touch_sys) < 2 or len(np.unique(touch_sys)) == len(touch_sys)   # merging needs two boxes of one system
-        if ordinary:
-            session.sorted_fields = (slim["system"], np.ascontiguousarray(slim["root"]))
-            session.late_by_system = {}
-            return None, slim["index"].astype(np.int64), {}, set()
+        special = bool(np.any((fl & RES_COLLECTOR) != 0) or np.any(slim["collector"] >= 0))
+        touch_pos = np.nonzero((fl & RES_TOUCH) != 0)[0]
+        touch_sys = slim["system"][touch_pos]
+        may_merge = merge and len(touch_pos) >= 2 and len(np.unique(touch_sys)) < len(touch_sys)
+        keep = slim["index"]
+        session.sorted_fields = (slim["system"], np.ascontiguousarray(slim["root"]))
+        session.late_by_system = {}
+        if not special and not may_merge:
+            return (session.results() if need_records else None), keep, {}, set()
+        res = session.results()
+        if special:
+            alive, dup, extra = resolve_collectors(res)
+        else:
+            alive, dup, extra = np.ones(len(res), dtype=bool), {}, set()
+        n0 = len(res)
+        if merge:
+            cand = slim["index"][touch_pos].astype(np.int64)
+            res, alive, dup, extra = merge_exterior(session, res, alive, dup, extra, cand=cand[alive[cand]])
+        dead = np.nonzero(~alive[:n0])[0]
+        late = np.nonzero(alive[n0:])[0] + n0
+        by_sys = {}
+        for i in late.tolist():
+            by_sys.setdefault(int(res["system"][i]), []).append(i)
+        session.late_by_system = by_sys
+        session.redo_systems = set(np.unique(res["system"][dead]).tolist()) | set(by_sys)
+        session.alive = alive
+        touched = getattr(session, "patched_roots", None)
+        if touched:                                             # roots rewritten by a merge after the device gathered them
+            session.redo_systems |= {int(res["system"][i]) for i in touched}
+        return res, keep, dup, extra
     res = session.results()
     alive, dup, extra = resolve_collectors(res)
     if merge:
@@ -241,10 +280,12 @@ def assemble(session, merge=True, need_records=False):
     return res, keep, dup, extra
 
 
-def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_fields=None, late_by_system=None):
+def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_fields=None, late_by_system=None,
+                     redo_systems=None, alive=None):
     """Vectorised gathering of roots per system; special records are patched in afterwards.  `sorted_fields` =
     (system, root) of the kept records in order, when the device already gathered them; `late_by_system` = live
-    records that are not in `keep` (produced after the device sorted), merged into their systems by path."""
+    records that are not in `keep` (produced after the device sorted), merged into their systems by path;
+    `redo_systems` = systems whose slice of `keep` contains dead records (`alive` says which)."""
     if sorted_fields is not None:
         sysv, roots_all = sorted_fields
     else:
@@ -252,14 +293,19 @@ def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_
         roots_all = np.take(res["root"], keep, axis=0)
     bounds = np.searchsorted(sysv, np.arange(nsys + 1))
     late_by_system = late_by_system or {}
+    redo_systems = redo_systems or set()
     out_roots, out_boxes, has_dup, has_extra = [], [], False, False
     special = {int(k) for k in dup} | {int(k) for k in extra}
+    special_systems = {int(res["system"][k]) for k in special} if special else set()
     for s in range(nsys):
         idx = keep[bounds[s]:bounds[s + 1]]
+        redo = s in redo_systems
+        if redo:
+            idx = idx[alive[idx]]
         late = late_by_system.get(s)
         if late:
-            idx = _path_order(res, np.r_[idx, np.asarray(late, dtype=idx.dtype)])
-        if late or (special and not special.isdisjoint(idx.tolist())):
+            idx = _path_order(res, np.r_[idx.astype(np.int64), np.asarray(late, dtype=np.int64)])
+        if late or redo or s in special_systems:
             rows = []
             for i in idx:
                 if int(i) in dup:

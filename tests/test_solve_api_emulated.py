@@ -86,3 +86,27 @@ def test_value_errors(yr):
     with pytest.raises(ValueError) as e:
         yr.solve([f, 3.0], [-1, -1], [1, 1])
     assert e.value.args[0] == "Invalid input: input function 1 is not callable"
+
+
+def test_batch_with_merging_system_matches_individual_solves(yr):
+    """A batch mixing ordinary systems with one whose exterior boxes merge (Chebfun 7.2: two merges): the batch is
+    answered from the device-sorted entries, the affected system alone is re-assembled from the full records, and
+    every system's roots equal those of its individual solve."""
+    from rootfinding_b200 import ChebyshevApproximator as A, ChebyshevSubdivisionSolver as S
+    from oracle.gen_golden import rand_coeffs
+    funcs, a, b = cc.system("7.2")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Ms, errs = zip(*[A.chebApproximate(f, a, b) for f in funcs])
+        np.random.seed(11)
+        arr = rand_coeffs(2, 8, 3)
+        systems = [[arr[0][0], arr[0][1]], [np.asarray(M) for M in Ms], [arr[1][0], arr[1][1]], [arr[2][0], arr[2][1]],
+                   [np.asarray(M) for M in Ms]]                    # two merging systems: their re-solves share a device call
+        errors = [np.full(2, 2.0 ** -52), np.asarray(errs, dtype=float), np.full(2, 2.0 ** -52), np.full(2, 2.0 ** -52),
+                  np.asarray(errs, dtype=float)]
+        batch, sess = S.solve_batch(systems, errors, return_session=True)
+        assert getattr(sess, "stats_merges", 0) >= 2 and {1, 4} <= sess.redo_systems
+        for s, (M, e) in enumerate(zip(systems, errors)):
+            one = S.solve_batch([M], [e])[0]
+            assert np.array_equal(np.asarray(batch[s]).reshape(-1, 2), np.asarray(one).reshape(-1, 2)), s
+    assert len(batch[1]) == cc.EXPECTED_COUNT["7.2"]
