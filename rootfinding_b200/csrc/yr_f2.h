@@ -1010,12 +1010,13 @@ struct Decision {
     unsigned long long boxes, zooms, dconst, dquad, dzoom, coeffs, maxlevel, subdiv;
 };
 
+// `rec` / `wk` are the box's records -- in place (emulator) or a thread-private copy that the caller loads in one
+// burst and writes back only when the box lives on (CUDA: the step is a long chain of small dependent accesses,
+// which on scattered global records is one memory round trip after another).
 template <class At>
-YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
+YR_HDN void scalar_step_on(const Args& a, BoxRec<2>& rec, Work& wk, Decision& dc, At at) {
     const SolverParams& prm = a.prm;
-    BoxRec<2>& rec = a.recs[b];
-    Work& wk = a.work[b];
-    IntervalState<2>& st = rec.st;      // updated in place: only the fields a step touches travel
+    IntervalState<2>& st = rec.st;
 
     auto emit = [&](uint32_t extra_flags) {
         const unsigned long long idx = at.add(&a.ctl->n_results, 1ull);
@@ -1175,6 +1176,9 @@ YR_HDN void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) {
     }
 
 }
+
+template <class At>
+YR_HD void scalar_step(const Args& a, unsigned int b, Decision& dc, At at) { scalar_step_on(a, a.recs[b], a.work[b], dc, at); }
 
 // Level-0 boxes arrive packed from yr_init_boxes: give them their Work state and queue a copy-only pass that
 // re-lays the tensors out (odd row stride) and computes sums / low-order coefficients / trim outcome.

@@ -35,7 +35,10 @@ class _Growable:
     """Append-only structured host array on top of a byte buffer obtained from `alloc(nbytes, who)`."""
 
     def __init__(self, dtype, alloc, who):
-        self.dtype, self.alloc, self.who = dtype, alloc, who
+        import weakref
+        # weak: the owner holds this object; a cycle would keep a finished session (and the page-locked buffers it
+        # borrowed) alive until the cyclic collector runs
+        self.dtype, self.alloc, self.who = dtype, alloc, weakref.ref(who)
         self.buf = np.empty(0, dtype=np.uint8)
         self.n = 0
 
@@ -44,7 +47,7 @@ class _Growable:
         item = self.dtype.itemsize
         need = (self.n + k) * item
         if need > self.buf.nbytes:
-            new = self.alloc(max(need + need // 8, 2 * self.buf.nbytes), self.who)
+            new = self.alloc(max(need + need // 8, 2 * self.buf.nbytes), self.who())
             new[:self.n * item] = self.buf[:self.n * item]
             self.buf = new
         v = self.buf[self.n * item:need]

@@ -1,5 +1,4 @@
-out=gpurun_out; tag=t52
-python -m pytest tests -m gpu -x -q > $out/${tag}_tests.log 2>&1
-python scripts/profile_e2e.py > $out/${tag}_e2e.log 2>&1
-python bench.py --no-cpu-baseline > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+out=gpurun_out; tag=t55
+for m in 0 1 2; do YR_F2_SCALAR=$m python scripts/profile_solve.py 1024 50 2 3 2>&1 | grep "^rep [12]" > $out/${tag}_s$m.log; done
+YR_F2_SCALAR=1 python -m pytest tests -m gpu -x -q > $out/${tag}_tests.log 2>&1
 echo done

@@ -347,3 +347,27 @@ def test_slim_result_path_matches_full_records():
     for a, b, bx in zip(slim, full, boxes):
         assert np.array_equal(np.asarray(a), np.asarray(b)) and len(bx) == len(b)
     assert sum(len(r) for r in slim) > 10
+
+
+def test_session_is_freed_without_the_cyclic_collector():
+    """A finished session must die by reference counting: it borrows the engine's page-locked download buffers, and
+    a live previous borrower costs the next solve a copy of everything it downloaded."""
+    import gc
+    import weakref
+    from emul.backend import emulated_engine
+    from rootfinding_b200 import ChebyshevSubdivisionSolver as S
+    from oracle.gen_golden import rand_coeffs
+    eng = emulated_engine()
+    np.random.seed(2)
+    arr = rand_coeffs(2, 8, 2)
+    systems = [[arr[s][0], arr[s][1]] for s in range(2)]
+    gc.disable()
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            roots, sess = S.solve_batch(systems, [np.full(2, 2.0 ** -52)] * 2, engine=eng, return_session=True)
+        ref = weakref.ref(sess)
+        del sess
+        assert ref() is None
+    finally:
+        gc.enable()
