@@ -36,6 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 DIM, DEG = 2, 50
+print_line = lambda obj: print(json.dumps(obj))
 METRIC = "subdivision boxes/sec"
 UNIT = "boxes/s"
 
@@ -110,7 +111,7 @@ def run_reference(args, rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, base["cores"]), "cpu_baseline": base, "gpu_launches": 0,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print_line(line)
 
 
 def workload_config(args, systems_per_step):
@@ -135,6 +136,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warnings.simplefilter("ignore")
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_line
+    print_line = lambda obj: (real_stdout.write(json.dumps(obj) + "\n"), real_stdout.flush())
     if args.impl == "reference":
         return run_reference(args, rank)
 
@@ -247,7 +254,7 @@ def main():
                            "build": eng.lib.yr_build_info().decode()}}
         if base is not None:
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        print_line(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -13,5 +13,6 @@ from .Combined_Solver import solve                     # noqa: F401
 from . import ChebyshevApproximator, ChebyshevSubdivisionSolver, QuadraticCheck, Combined_Solver  # noqa: F401
 from .ChebyshevSubdivisionSolver import solve_batch    # noqa: F401
 from .ChebyshevApproximator import chebApproximate as approximate   # noqa: F401  (docs of the reference name it so)
+from .ChebyshevApproximator import device_function     # noqa: F401  torch-vectorised callables are sampled on the device
 
-__all__ = ["solve", "solve_batch", "approximate", "MultiCheb", "MultiPower"]
+__all__ = ["solve", "solve_batch", "approximate", "device_function", "MultiCheb", "MultiPower"]

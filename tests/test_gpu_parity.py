@@ -293,6 +293,42 @@ def test_full_size_properties(yr):
     assert sess.stats.boxes > 6 * 6000
 
 
+def test_device_function_sampling(yr):
+    """torch-vectorised callables are sampled on the device (north-star item 1): same degrees, coefficients within
+    1e-12 * sup norm of the host-sampled ones (GPU vs host libm differ by an ulp or two per sample), same roots to
+    1e-10; and the host never evaluates the grid."""
+    import torch
+    A = yr.ChebyshevApproximator
+    pair = lambda xp: (lambda x, y: xp.sin(x * y) + x * xp.log(y + 3) - x ** 2 + 1 / (y - 4),
+                       lambda x, y: xp.cos(3 * x * y) + xp.exp(3 * y / (x - 2)) - x - 6)
+    fn, gn = pair(np)
+    calls = {"n": 0}
+
+    def counted(h):
+        def w(x, y):
+            calls["n"] += 1
+            assert x.is_cuda or x.ndim == 0                    # grids arrive as device tensors, probes as scalars
+            return h(x, y)
+        return yr.device_function(w)
+
+    ft, gt = (counted(h) for h in pair(torch))
+    a, b = np.array([-1., -2.]), np.array([0., 1.])
+    for hn, ht in ((fn, ft), (gn, gt)):
+        cn, en = A.chebApproximate(hn, a, b)
+        ct, et = A.chebApproximate(ht, a, b)
+        assert cn.shape == ct.shape
+        assert np.max(np.abs(cn - ct)) < 1e-12 * max(1.0, np.max(np.abs(cn)))
+    assert calls["n"] < 200                                     # a few dozen grids + probes, not one call per point
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rn = np.asarray(yr.solve([fn, gn], a, b))
+        rt = np.asarray(yr.solve([ft, gt], a, b))
+    assert rn.shape == rt.shape == (2, 2)
+    H.match_points(rn, rt, 1e-10)
+    want = np.array([[-0.410034, -1.40471685], [-0.73720226, -1.65461673]])     # README / notebook values
+    H.match_points(want, rt, 1e-7)
+
+
 def test_frontier_and_level_pipelines_agree(yr):
     """The round-based 2-D frontier pipeline and the level pipeline run the same search: identical box, zoom and
     subdivision counts and the same roots in the same (depth-first) order (their restrictions are bit-identical;

@@ -110,3 +110,34 @@ def test_batch_with_merging_system_matches_individual_solves(yr):
             one = S.solve_batch([M], [e])[0]
             assert np.array_equal(np.asarray(batch[s]).reshape(-1, 2), np.asarray(one).reshape(-1, 2)), s
     assert len(batch[1]) == cc.EXPECTED_COUNT["7.2"]
+
+
+def _readme_pair(xp):
+    f = lambda x, y: xp.sin(x * y) + x * xp.log(y + 3) - x ** 2 + 1 / (y - 4)
+    g = lambda x, y: xp.cos(3 * x * y) + xp.exp(3 * y / (x - 2)) - x - 6
+    return f, g
+
+
+def test_device_function_sampling_matches_host_sampling(yr):
+    """torch-vectorised callables (yr.device_function) are sampled on the whole grid in one call; coefficients agree
+    with the point-by-point host sampling of the same function to rounding, degrees and roots are the same."""
+    import torch
+    from rootfinding_b200 import ChebyshevApproximator as A
+    fn, gn = _readme_pair(np)
+    ft, gt = (yr.device_function(h) for h in _readme_pair(torch))
+    a, b = np.array([-1., -2.]), np.array([0., 1.])
+    assert abs(ft(-0.3, 0.2) - fn(-0.3, 0.2)) < 1e-15                  # still an ordinary callable of scalars
+    for hn, ht in ((fn, ft), (gn, gt)):
+        cn, en = A.chebApproximate(hn, a, b)
+        ct, et = A.chebApproximate(ht, a, b)
+        assert cn.shape == ct.shape
+        assert np.max(np.abs(cn - ct)) < 1e-13 * max(1.0, np.max(np.abs(cn)))
+        assert abs(en - et) <= 1e-3 * en + 1e-18
+    rn = np.asarray(yr.solve([fn, gn], a, b))
+    rt = np.asarray(yr.solve([ft, gt], a, b))
+    assert rn.shape == rt.shape == (2, 2)
+    H.match_points(rn, rt, 1e-10)
+    # a function that ignores a variable still fills the grid (broadcast), and a MultiCheb may sit next to it
+    h = yr.device_function(lambda x, y: x - 0.25)
+    r = np.asarray(yr.solve([h, yr.device_function(lambda x, y: torch.cos(y) - x - 0.5)], [-1, -1], [1, 1]))
+    assert r.shape == (2, 2) and np.max(np.abs(r[:, 0] - 0.25)) < 1e-12 and np.max(np.abs(np.cos(r[:, 1]) - 0.75)) < 1e-12
