@@ -49,6 +49,18 @@ def workload(batch, seed):
     return systems, [np.full(DIM, 2.0 ** -52)] * batch
 
 
+def measured_traffic():
+    """DRAM bytes per tensor-kernel launch from the committed ncu launch list (profiles/r01_traffic.json: dram__bytes_read
+    + dram__bytes_write summed over every tensor launch of two solves of this workload / number of launches)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        return float(t["dram_bytes_per_launch"]), float(t["traffic_over_algorithmic"])
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -197,7 +209,7 @@ def main():
         device_step(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    total_ms, boxes, launches, kernel_ms, kernel_bytes, scalar_ms = 0.0, 0, 0, 0.0, 0, 0.0
+    total_ms, boxes, launches, kernel_ms, kernel_bytes, scalar_ms, tensor_launches = 0.0, 0, 0, 0.0, 0, 0.0, 0
     for _ in range(args.steps):
         sess, ms = device_step(True)
         total_ms += ms
@@ -207,6 +219,7 @@ def main():
         kernel_bytes += sum(k[1] for k in sess.kernel_ms)
         scalar_ms += getattr(sess, "scalar_ms", 0.0)
         stats = sess.stats
+        tensor_launches += sess.stats.launches - getattr(sess.stats, "rounds", 0) - 2      # minus scalar steps, import, tables
     e2e_s, e2e_boxes, h2d, d2h, nroots = 0.0, 0, 0, 0, 0
     api_step()                                                 # warm the API path once
     for _ in range(args.steps):
@@ -232,6 +245,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        traffic, traffic_ratio = measured_traffic()
         line = {"metric": METRIC, "value": boxes_all / (total_ms_max * 1e-3), "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -240,7 +254,9 @@ def main():
                         "solves_per_s": args.batch * world * args.steps / e2e_s_max, "roots_per_step_rank0": int(nroots)},
                 "gpu_launches": launches_all,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None,
+                             "traffic": traffic, "traffic_over_algorithmic": traffic_ratio,
+                             "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per tensor launch, same workload)",
+                             "algorithmic_bytes_per_launch": kernel_bytes / max(tensor_launches, 1),
                              "kernel": "f2_tensor_warp / f2_tensor_cta (restrict + subdivide launches of every round of the timed steps, rank 0)",
                              "fp64_frac_of_measured_dmul_dadd_peak": (2.0 * stats.restrict_macs / 1e12 / max(kernel_ms / args.steps * 1e-3, 1e-12)) / 18.56,
                              "scalar_kernel_ms_per_step": scalar_ms / args.steps,
