@@ -104,6 +104,9 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
     """
     for Ms, e in zip(systems, errors):
         _check_system(Ms, e)
+    if len(systems) == 0:                                  # an empty batch has an empty answer and needs no device
+        out = ([], []) if returnBoundingBoxes else []
+        return (out, None) if return_session else out
     eng = get_engine() if engine is None else engine
     sess = eng.session(systems, errors,
                        exact=int(bool(exact)), constant_check=int(bool(constant_check)),

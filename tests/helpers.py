@@ -65,3 +65,36 @@ def check_batch_against_oracle(solve_batch, systems, errs, engine=None, **kw):
         if len(want):
             worst = max(worst, match_points(want, g, ROOT_TOL))
     return sess, boxes, worst
+
+
+def edge_case_systems():
+    """(name, Ms, errors) inputs at the edges of the domain: constant / ragged / extent-1 tensors, one variable, no
+    roots, huge error bounds, a NaN coefficient, an extent beyond the shared-memory pipeline (80 > 79)."""
+    e1, e2 = np.full(1, 2.0 ** -52), np.full(2, 2.0 ** -52)
+    rs = np.random.RandomState(5)
+    return [
+        ("constant 1x1", [np.array([[1.0]]), np.array([[2.0]])], e2),
+        ("ragged 2x7 / 9x1", [np.random.RandomState(0).randn(2, 7), np.random.RandomState(1).randn(9, 1)], e2),
+        ("linear", [np.array([[0.1, 0.0], [1.0, 0.0]]), np.array([[-0.2, 1.0], [0.0, 0.0]])], e2),
+        ("no roots", [np.array([[5.0, 1.0], [1.0, 0.0]]), np.array([[0.0, 1.0], [1.0, 0.0]])], e2),
+        ("1-D degree 30", [np.random.RandomState(3).randn(31)], e1),
+        ("1-D constant", [np.array([3.0])], e1),
+        ("extent 80", [rs.randn(80, 3), rs.randn(3, 80)], e2),
+        ("huge error", [rs.randn(5, 5), rs.randn(5, 5)], np.full(2, 1e3)),
+        ("nan coefficient", [np.array([[np.nan, 1.0], [1.0, 0.0]]), np.array([[0.0, 1.0], [1.0, 0.0]])], e2),
+    ]
+
+
+def check_edge_cases(S, osub):
+    """Every edge case through solveChebyshevSubdivision `S` against the oracle: same root count, roots within ROOT_TOL."""
+    import warnings
+    for name, Ms, errs in edge_case_systems():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = np.asarray(S.solveChebyshevSubdivision([m.copy() for m in Ms], errs.copy())).reshape(-1, len(Ms))
+            want = np.asarray(osub.solve_chebyshev_subdivision([m.copy() for m in Ms], errs.copy())).reshape(-1, len(Ms))
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        if len(want):
+            match_points(want, got, ROOT_TOL)
+    assert S.solve_batch([], []) == []
+    assert S.solve_batch([], [], returnBoundingBoxes=True) == ([], [])

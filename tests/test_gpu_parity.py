@@ -329,6 +329,12 @@ def test_device_function_sampling(yr):
     H.match_points(want, rt, 1e-7)
 
 
+def test_edge_cases_match_oracle(yr):
+    """Constant / ragged / extent-1 tensors, one variable, no roots, huge error bounds, NaN, extent 80, empty batch."""
+    from oracle import subdivision as osub
+    H.check_edge_cases(yr.ChebyshevSubdivisionSolver, osub)
+
+
 def test_frontier_and_level_pipelines_agree(yr):
     """The round-based 2-D frontier pipeline and the level pipeline run the same search: identical box, zoom and
     subdivision counts and the same roots in the same (depth-first) order (their restrictions are bit-identical;

@@ -141,3 +141,8 @@ def test_device_function_sampling_matches_host_sampling(yr):
     h = yr.device_function(lambda x, y: x - 0.25)
     r = np.asarray(yr.solve([h, yr.device_function(lambda x, y: torch.cos(y) - x - 0.5)], [-1, -1], [1, 1]))
     assert r.shape == (2, 2) and np.max(np.abs(r[:, 0] - 0.25)) < 1e-12 and np.max(np.abs(np.cos(r[:, 1]) - 0.75)) < 1e-12
+
+
+def test_edge_cases_match_oracle(yr):
+    from oracle import subdivision as osub
+    H.check_edge_cases(yr.ChebyshevSubdivisionSolver, osub)
