@@ -105,6 +105,18 @@ class CudaMemory:
             self.h2d_bytes += arr.nbytes
         return b
 
+    def upload_concat(self, chunks, total):
+        """Host -> device of the concatenation of 1-D float64 `chunks` (`total` elements): gathered straight into the
+        pinned staging buffer, so the packed tensor data is written once on the host."""
+        b = self.empty(total * 8)
+        if total:
+            pinned = self.torch.empty(total * 8, dtype=self.torch.uint8, pin_memory=True)
+            np.concatenate(chunks, out=pinned.numpy().view(np.float64))
+            b.owner.view(self.torch.uint8)[:total * 8].copy_(pinned, non_blocking=True)
+            self._staging.append(pinned)
+            self.h2d_bytes += total * 8
+        return b
+
     def host_bytes(self, nbytes, who=None, slot=0):
         """Host buffer for record downloads.  One page-locked buffer per slot (0 results, 1 nodes) is kept per engine
         and lent to the session that downloads (a 200 MB device -> pageable copy costs several times the solve); a
@@ -273,7 +285,10 @@ class SolveSession:
         self.sys_max_extent = shapes.reshape(self.nsys, -1).max(axis=1)
         errs = np.ascontiguousarray(np.asarray(errors, dtype=np.float64).reshape(self.nsys, D))
         m = self.mem
-        self.d_coeffs = m.upload(np.concatenate(chunks) if chunks else np.zeros(0))
+        if hasattr(m, "upload_concat"):
+            self.d_coeffs = m.upload_concat(chunks, pos)
+        else:
+            self.d_coeffs = m.upload(np.concatenate(chunks) if chunks else np.zeros(0))
         self.d_off = m.upload(offs)
         self.d_shapes = m.upload(shapes)
         self.d_errs = m.upload(errs)
