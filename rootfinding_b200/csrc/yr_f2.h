@@ -52,6 +52,9 @@
 #ifndef YR_F2_BUILD
 #define YR_F2_BUILD YR_DEV
 #endif
+#ifndef YR_F2_PAIR_BUILD
+#define YR_F2_PAIR_BUILD 0
+#endif
 #ifndef YR_F2_EPI
 #define YR_F2_EPI YR_DEV
 #endif
@@ -247,6 +250,58 @@ YR_F2_BUILD void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb,
     w.wsync();
 }
 
+// Two matrices at once, every lane holding row i of BOTH (16-lane teams: their two builds are two independent
+// dependency chains of shuffles and separately rounded multiply-adds; interleaved they hide each other's latency).
+// Same expressions, order and truncation rule per matrix as build_panels_warp -> bit-identical.  nt <= lanes, both > 0.
+template <class W>
+YR_F2_BUILD void build_panels_pair(W& w, const PanelJob& ja, const PanelJob& jb) {
+    const int seg = w.lanes;
+    const int i = w.lane;
+    const int nta = ja.nt, ntb = jb.nt;
+    const int kmax = nta > ntb ? nta : ntb;
+    const int b = i >> 2;
+    double* pa = ja.Cp + panel_off(b, nta) + (i & 3);
+    double* pb = jb.Cp + panel_off(b, ntb) + (i & 3);
+    const bool livea = i < (((nta + 3) >> 2) << 2), liveb = i < (((ntb + 3) >> 2) << 2);
+    const double ala = ja.alpha, be2a = 2 * ja.beta, alb = jb.alpha, be2b = 2 * jb.beta;
+    double p2a = (i == 0) ? 1.0 : 0.0, p2b = p2a;
+    double p1a = (i == 0) ? ja.beta : (i == 1 ? ala : 0.0), p1b = (i == 0) ? jb.beta : (i == 1 ? alb : 0.0);
+    if (b == 0) {
+        if (livea) { pa[0] = p2a; if (nta >= 2) pa[4] = p1a; }
+        if (liveb) { pb[0] = p2b; if (ntb >= 2) pb[4] = p1b; }
+    }
+    if (i == 0) {
+        ja.rows_after[0] = 1; if (nta >= 2) ja.rows_after[1] = 2;
+        jb.rows_after[0] = 1; if (ntb >= 2) jb.rows_after[1] = 2;
+    }
+    int rowsa = 2, rowsb = 2;
+    for (int k = 2; k < kmax; ++k) {
+        double cm1a = w.wshfl_up(p1a, 1, seg), cp1a = w.wshfl_down(p1a, 1, seg);
+        double cm1b = w.wshfl_up(p1b, 1, seg), cp1b = w.wshfl_down(p1b, 1, seg);
+        if (i == 0) { cm1a = 0.0; cm1b = 0.0; }
+        if (i + 1 > k - 1 || i + 1 >= seg) { cp1a = 0.0; cp1b = 0.0; }
+        const double ta = ala * ((i == 1 ? 2 * cm1a : cm1a) + cp1a), tb = alb * ((i == 1 ? 2 * cm1b : cm1b) + cp1b);
+        const double ina = (-p2a + ta) + be2a * p1a, inb = (-p2b + tb) + be2b * p1b;
+        const double fa = ala * cm1a, fb = alb * cm1b;
+        const bool lasta = (i == rowsa), lastb = (i == rowsb);
+        const bool ga = lasta && (fabs(fa) > 1e-16), gb = lastb && (fabs(fb) > 1e-16);
+        const double va = lasta ? (ga ? fa : 0.0) : (i < rowsa ? ina : 0.0);
+        const double vb = lastb ? (gb ? fb : 0.0) : (i < rowsb ? inb : 0.0);
+        const int growa = w.wballot(ga) != 0u, growb = w.wballot(gb) != 0u;
+        if (k < nta) {
+            if (livea && k >= 4 * b) pa[(k - 4 * b) << 2] = va;
+            p2a = p1a; p1a = va; rowsa += growa;
+            if (i == (k & (seg - 1))) ja.rows_after[k] = rowsa;
+        }
+        if (k < ntb) {
+            if (liveb && k >= 4 * b) pb[(k - 4 * b) << 2] = vb;
+            p2b = p1b; p1b = vb; rowsb += growb;
+            if (i == (k & (seg - 1))) jb.rows_after[k] = rowsb;
+        }
+    }
+    w.wsync();
+}
+
 // Team-level dispatcher: builds up to two matrices (either may be skipped with nt = 0).
 template <class Team>
 YR_F2_BUILD void build_two(Team& tm, const PanelJob& j0, const PanelJob& j1) {
@@ -256,6 +311,7 @@ YR_F2_BUILD void build_two(Team& tm, const PanelJob& j0, const PanelJob& j1) {
             if (tm.warp == 0 && j0.nt > 0) build_panels_warp(tm, j0, j0, 32);
             if (tm.warp == 1 && j1.nt > 0) build_panels_warp(tm, j1, j1, 32);
         } else if (tm.lanes == 32 && big <= 16 && j0.nt > 0 && j1.nt > 0) build_panels_warp(tm, j0, j1, 16);
+        else if (YR_F2_PAIR_BUILD && tm.lanes == 16 && j0.nt > 0 && j1.nt > 0) build_panels_pair(tm, j0, j1);
         else {
             const PanelJob* jobs[2] = {&j0, &j1};
 #pragma unroll 1

@@ -1,10 +1,6 @@
-out=gpurun_out; tag=t59
-python -m pytest tests -m gpu -x -q > $out/${tag}_tests.log 2>&1
-python scripts/sanitize_case.py > $out/${tag}_plain.log 2>&1 &&
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python scripts/sanitize_case.py > $out/${tag}_memcheck.log 2>&1
-echo "memcheck rc $?" >> $out/${tag}_memcheck.log
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python scripts/sanitize_case.py > $out/${tag}_racecheck.log 2>&1
-echo "racecheck rc $?" >> $out/${tag}_racecheck.log
-python scripts/profile_e2e.py > $out/${tag}_e2e.log 2>&1
-python bench.py --no-cpu-baseline > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+out=gpurun_out; tag=t61
+python scripts/profile_solve.py 1024 50 2 3 2>&1 | grep "^rep [12]" > $out/${tag}_base.log
+export YR_LIB_OVERRIDE=$PWD/rootfinding_b200/csrc/_var/lib_pair.so
+python scripts/profile_solve.py 1024 50 2 3 2>&1 | grep "^rep [12]" > $out/${tag}_pair.log
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "oracle or golden or full_size or chebfun" > $out/${tag}_tests_pair.log 2>&1
 echo done
