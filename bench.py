@@ -121,7 +121,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, base["cores"]), "cpu_baseline": base, "gpu_launches": 0,
+            "config": workload_config(args, args.batch), "cpu_baseline": base, "gpu_launches": 0,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_line(line)
 
