@@ -42,7 +42,7 @@ UNIT = "boxes/s"
 
 
 def workload(batch, seed):
-    from oracle.gen_golden import rand_coeffs           # generator only (restates tests/random_tests.py:5-19)
+    from rootfinding_b200.workloads import rand_coeffs  # restates the reference generator tests/random_tests.py:5-19
     np.random.seed(seed)
     arr = rand_coeffs(DIM, DEG, batch, "randn")
     systems = [[np.ascontiguousarray(m) for m in arr[s]] for s in range(batch)]

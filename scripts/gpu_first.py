@@ -8,7 +8,7 @@ warnings.simplefilter("ignore")
 from rootfinding_b200 import ChebyshevSubdivisionSolver as S
 from rootfinding_b200.runtime import get_engine
 from oracle import subdivision as osub
-from oracle.gen_golden import rand_coeffs
+from rootfinding_b200.workloads import rand_coeffs
 
 print(torch.cuda.get_device_name(0))
 eng = get_engine()

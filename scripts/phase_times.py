@@ -3,7 +3,7 @@ sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 import numpy as np, torch
 warnings.simplefilter("ignore")
 from rootfinding_b200.runtime import get_engine
-from oracle.gen_golden import rand_coeffs
+from rootfinding_b200.workloads import rand_coeffs
 B=1024
 np.random.seed(2); arr = rand_coeffs(2, 50, B)
 systems = [[np.ascontiguousarray(m) for m in arr[s]] for s in range(B)]

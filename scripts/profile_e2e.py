@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 warnings.simplefilter("ignore")
 from rootfinding_b200 import ChebyshevSubdivisionSolver as S
-from oracle.gen_golden import rand_coeffs
+from rootfinding_b200.workloads import rand_coeffs
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 deg = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 np.random.seed(2)

@@ -371,3 +371,17 @@ def test_session_is_freed_without_the_cyclic_collector():
         assert ref() is None
     finally:
         gc.enable()
+
+
+def test_workload_generator_matches_reference_stream():
+    """rootfinding_b200.workloads.rand_coeffs (what bench.py feeds the GPU) draws the same numbers as the generator
+    the golden vectors were made with (oracle/gen_golden.py, restating tests/random_tests.py:5-19)."""
+    from rootfinding_b200.workloads import rand_coeffs, random_systems
+    from oracle.gen_golden import rand_coeffs as ref
+    for dim, deg, N, kind in [(2, 50, 2, "randn"), (2, 7, 3, "randint"), (3, 4, 2, "randn"), (1, 9, 2, "randn")]:
+        np.random.seed(2); a = rand_coeffs(dim, deg, N, kind)
+        np.random.seed(2); b = ref(dim, deg, N, kind)
+        assert a.shape == (N, dim) + (deg + 1,) * dim and np.array_equal(a, b)
+    systems, errs = random_systems(2, 6, 3)
+    assert len(systems) == 3 and systems[0][1].shape == (7, 7) and errs[0][0] == 2.0 ** -52
+    assert systems[0][0][6, 1] == 0.0 and systems[0][0][5, 1] != 0.0          # zero beyond total degree
