@@ -208,7 +208,8 @@ def main():
     for _ in range(args.warmup):
         device_step(False)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:                                              # one sampler per job: rank 0 prints the line
+        sampler.start()
     total_ms, boxes, launches, kernel_ms, kernel_bytes, scalar_ms, tensor_launches = 0.0, 0, 0, 0.0, 0, 0.0, 0
     for _ in range(args.steps):
         sess, ms = device_step(True)
@@ -228,7 +229,8 @@ def main():
         e2e_boxes += nb
         h2d, d2h = hb, db
     sampler.stop_flag.set()
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         # bounded sample of the same workload on the host cores; after the GPU arms so that 16 busy worker
