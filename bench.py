@@ -269,7 +269,10 @@ def main():
                 "detail": {"boxes_per_step_rank0": stats.boxes, "rounds": getattr(stats, "rounds", stats.levels), "retries": stats.retries,
                            "zooms": stats.zooms, "subdivisions": stats.subdivisions,
                            "restrict_gflops_per_s": 2.0 * stats.restrict_macs / 1e9 / (total_ms / args.steps * 1e-3),
-                           "build": eng.lib.yr_build_info().decode()}}
+                           "build": eng.lib.yr_build_info().decode(),
+                           "boxes_vs_reference": "own box count == the reference's on the same inputs (1 792 seeded systems, "
+                                                 "profiles/r01_parity_stress.txt; tests/test_gpu_parity.py), so boxes/s is also "
+                                                 "reference-equivalent boxes/s (SURVEY 8d)"}}
         if base is not None:
             line["cpu_baseline"] = base
         print_line(line)
