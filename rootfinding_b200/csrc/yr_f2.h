@@ -840,13 +840,14 @@ YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int s
 template <class Team>
 YR_DEV void copy_out_rows(Team& tm, double* dst, int ld_out, const double* M, int ld, int r0, int r1) {
     if (ld_out == ld) { copy_flat(tm, dst, M, tensor_doubles(r0, ld)); return; }
-    // element (i, j) per lane, advanced without divisions
-    int i = 0, j = tm.tid;
-    while (j >= r1) { j -= r1; ++i; }
-    while (i < r0) {
-        dst[i * ld_out + j] = M[i * ld + j];
-        j += tm.nthreads;
-        while (j >= r1) { j -= r1; ++i; }
+    // four lanes per row (one 32-byte sector per store), nthreads / 4 rows per sweep: two counted loops, no index
+    // arithmetic per element
+    const int cg = tm.nthreads >= 4 ? 4 : tm.nthreads;             // lanes per row (teams are powers of two)
+    const int rows_per_sweep = tm.nthreads / cg, a = tm.tid / cg, b = tm.tid - a * cg;
+    for (int i = a; i < r0; i += rows_per_sweep) {
+        const double* s = M + i * ld;
+        double* d = dst + i * ld_out;
+        for (int j = b; j < r1; j += cg) d[j] = s[j];
     }
 }
 
