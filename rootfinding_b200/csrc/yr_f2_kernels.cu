@@ -260,7 +260,10 @@ __device__ void commit_warp(const Args& a, unsigned int b, const Decision& dc) {
     }
 }
 
-__global__ void __launch_bounds__(128) f2_scalar_kernel(const Args a, const yr_f2_backend::Segments sg) {
+#ifndef YR_F2_SCALAR_MINB
+#define YR_F2_SCALAR_MINB 1
+#endif
+__global__ void __launch_bounds__(128, YR_F2_SCALAR_MINB) f2_scalar_kernel(const Args a, const yr_f2_backend::Segments sg) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     Decision dc;
     memset(&dc, 0, sizeof(dc));
