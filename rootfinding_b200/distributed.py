@@ -32,16 +32,25 @@ def all_gather_roots(local_roots, local_ids, n_systems, dim, group=None, device=
     if len(local_roots) and sum(len(r) for r in local_roots):
         flat = np.concatenate([np.asarray(r, dtype=np.float64).reshape(-1, dim) for r in local_roots])
         mine[:len(flat)] = torch.as_tensor(flat, device=dev)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
+    # one receive buffer, one device -> host copy (page-locked on GPUs), per-system views instead of copies: the cost
+    # of handing every rank the whole answer stays a small part of the solve as the number of ranks grows
+    big = torch.empty((world, max(cap, 1), dim), dtype=torch.float64, device=dev)
+    dist.all_gather([big[r] for r in range(world)], mine, group=group)
+    if big.is_cuda:
+        host = torch.empty(big.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(big, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        blocks = host.numpy()
+    else:
+        blocks = big.numpy()
     out = [None] * n_systems
     for r in range(world):
-        block = gathered[r].cpu().numpy()
-        pos = 0
-        for s in shard(n_systems, r, world):
-            k = int(counts_h[s])
-            out[s] = block[pos:pos + k].copy()
-            pos += k
+        ids = shard(n_systems, r, world)
+        if not len(ids):
+            continue
+        ends = np.cumsum(counts_h[ids])
+        for s_id, piece in zip(ids.tolist(), np.split(blocks[r][:int(ends[-1])], ends[:-1])):
+            out[s_id] = piece
     return out
 
 
