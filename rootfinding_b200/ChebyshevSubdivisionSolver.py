@@ -94,6 +94,11 @@ def _check_system(Ms, errors):
         raise ValueError("Ms and errors must be same length!")
 
 
+def _is_out_of_memory(exc):
+    msg = str(exc).lower()
+    return "out of memory" in msg or "allocation failed" in msg
+
+
 def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constant_check=True,
                 low_dim_quadratic_check=True, all_dim_quadratic_check=False, use_fma=False, engine=None,
                 return_session=False):
@@ -108,11 +113,33 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
         out = ([], []) if returnBoundingBoxes else []
         return (out, None) if return_session else out
     eng = get_engine() if engine is None else engine
-    sess = eng.session(systems, errors,
-                       exact=int(bool(exact)), constant_check=int(bool(constant_check)),
-                       low_dim_quad_check=int(bool(low_dim_quadratic_check)),
-                       all_dim_quad_check=int(bool(all_dim_quadratic_check)), use_fma=int(bool(use_fma)))
-    sess.run_jobs(sess.unit_jobs())
+    sess = None
+    try:
+        sess = eng.session(systems, errors,
+                           exact=int(bool(exact)), constant_check=int(bool(constant_check)),
+                           low_dim_quad_check=int(bool(low_dim_quadratic_check)),
+                           all_dim_quad_check=int(bool(all_dim_quadratic_check)), use_fma=int(bool(use_fma)))
+        sess.run_jobs(sess.unit_jobs())
+    except RuntimeError as exc:
+        if not _is_out_of_memory(exc) or len(systems) < 2:
+            raise
+        sess = None                                        # (the retry runs outside this block: the traceback pins
+                                                           #  the failed attempt's device buffers until it is gone)
+    if sess is None:
+        # the frontier of the whole batch does not fit the device: solve it in two halves, one after the other
+        # (systems never interact, so the answer is the same; a single system that does not fit still raises)
+        eng.release_cached()
+        half = len(systems) // 2
+        parts = [solve_batch(systems[lo:hi], errors[lo:hi], returnBoundingBoxes, exact, constant_check,
+                             low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, True)
+                 for lo, hi in ((0, half), (half, len(systems)))]
+        last = parts[-1][1]
+        last.chunk_sessions = [q for p in parts for q in getattr(p[1], "chunk_sessions", [p[1]])]
+        if returnBoundingBoxes:
+            out = (parts[0][0][0] + parts[1][0][0], parts[0][0][1] + parts[1][0][1])
+        else:
+            out = parts[0][0] + parts[1][0]
+        return (out, last) if return_session else out
     res, keep, dup, extra = postpass.assemble(sess, need_records=returnBoundingBoxes)
     if sess.stats.max_level >= 25:
         warnings.warn("Extreme subdivision depth!\nSubdivision on the search interval has now reached"

@@ -250,6 +250,17 @@ class SubdivisionEngine:
         ctas = int(max(1, min(n_items, self.sm_count * per_sm)))
         return threads, ctas, in_smem, ws, False
 
+    def release_cached(self):
+        """Give cached device memory back (after an out-of-memory failure, before retrying with a smaller batch)."""
+        try:
+            self.lib.yr_frontier_trim(self.mem.stream())
+        except Exception:
+            pass
+        t = getattr(self.mem, "torch", None)
+        if t is not None:
+            t.cuda.synchronize()
+            t.cuda.empty_cache()
+
     def session(self, systems, errors, **params):
         return SolveSession(self, systems, errors, self.params(**params))
 
@@ -455,7 +466,10 @@ class SolveSession:
                 if pipeline == 1 and first_c is None:
                     first_c = dict(c)
                     first_c["restrict_macs"] = 0                             # (counted again by the re-run's subdivision only partly; keep it simple)
-                cap_recs, cap_data = worst_recs, worst_data
+                # grow geometrically towards the worst case (a jump to fan x the level's data can exceed the device:
+                # 512 3-D degree-10 systems hold ~30 GB per level)
+                cap_recs, cap_data = min(worst_recs, 2 * cap_recs + 4096), min(worst_data, 2 * cap_data + (1 << 16))
+                del out_recs, out_data
             del work
             self.stats.add(c)
             self.stats.levels += 1

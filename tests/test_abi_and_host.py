@@ -385,3 +385,34 @@ def test_workload_generator_matches_reference_stream():
     systems, errs = random_systems(2, 6, 3)
     assert len(systems) == 3 and systems[0][1].shape == (7, 7) and errs[0][0] == 2.0 ** -52
     assert systems[0][0][6, 1] == 0.0 and systems[0][0][5, 1] != 0.0          # zero beyond total degree
+
+
+def test_batch_that_does_not_fit_is_solved_in_halves(monkeypatch):
+    """A device out-of-memory failure of a batch falls back to solving its halves one after the other (systems never
+    interact); a single system that does not fit still raises."""
+    from emul.backend import emulated_engine
+    from rootfinding_b200 import ChebyshevSubdivisionSolver as S
+    from rootfinding_b200.workloads import random_systems
+    eng = emulated_engine()
+    systems, errs = random_systems(2, 6, 5, seed=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = S.solve_batch(systems, errs, engine=eng)
+    real, calls = eng.session, []
+
+    def limited(sy, er, **kw):
+        calls.append(len(sy))
+        if len(sy) > 2:
+            raise RuntimeError("CUDA out of memory. Tried to allocate 259.09 GiB")
+        return real(sy, er, **kw)
+    monkeypatch.setattr(eng, "session", limited)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, sess = S.solve_batch(systems, errs, engine=eng, return_session=True)
+        (got_b, boxes), _ = S.solve_batch(systems, errs, returnBoundingBoxes=True, engine=eng, return_session=True)
+    assert calls[:4] == [5, 2, 3, 1] and len(sess.chunk_sessions) == 3
+    for a, b, c, bx in zip(want, got, got_b, boxes):
+        assert np.array_equal(a, b) and np.array_equal(a, c) and len(bx) == len(a)
+    monkeypatch.setattr(eng, "session", lambda sy, er, **kw: (_ for _ in ()).throw(RuntimeError("CUDA out of memory")))
+    with pytest.raises(RuntimeError):
+        S.solve_batch(systems[:1], errs[:1], engine=eng)
