@@ -99,6 +99,28 @@ def _is_out_of_memory(exc):
     return "out of memory" in msg or "allocation failed" in msg
 
 
+def _solve_chunks(systems, errors, ranges, returnBoundingBoxes, exact, constant_check, low_dim_quadratic_check,
+                  all_dim_quadratic_check, use_fma, eng, return_session):
+    """solve_batch over consecutive sub-batches, one after the other; the last session carries all of them in
+    `chunk_sessions` (statistics)."""
+    roots, boxes, sessions = [], [], []
+    for lo, hi in ranges:
+        out, sess = solve_batch(systems[lo:hi], errors[lo:hi], returnBoundingBoxes, exact, constant_check,
+                                low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, True)
+        if returnBoundingBoxes:
+            roots += out[0]; boxes += out[1]
+        else:
+            roots += out
+        if sess is not None:
+            sessions += getattr(sess, "chunk_sessions", [sess])
+        del sess
+    last = sessions[-1] if sessions else None
+    if last is not None:
+        last.chunk_sessions = sessions
+    out = (roots, boxes) if returnBoundingBoxes else roots
+    return (out, last) if return_session else out
+
+
 def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constant_check=True,
                 low_dim_quadratic_check=True, all_dim_quadratic_check=False, use_fma=False, engine=None,
                 return_session=False):
@@ -113,6 +135,20 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
         out = ([], []) if returnBoundingBoxes else []
         return (out, None) if return_session else out
     eng = get_engine() if engine is None else engine
+    # Very large batches are solved as a sequence of sub-batches sized for the device: box records of a 2-D solve take
+    # ~1 KB per box and a random system produces ~1.3 boxes per coefficient, so 24 M coefficients (4096 degree-50
+    # systems) keep the frontier's tables well inside 180 GB, and a sub-batch that size already fills the machine.
+    limit = getattr(eng, "max_batch_coeffs", 24_000_000)
+    if len(systems) > 1:
+        sizes = np.fromiter((sum(np.size(M) for M in Ms) for Ms in systems), dtype=np.int64, count=len(systems))
+        total = int(sizes.sum())
+        if total > limit:
+            nchunk = min(len(systems), -(-total // limit))
+            edges = np.searchsorted(np.cumsum(sizes), np.arange(1, nchunk) * (total / nchunk), side="left") + 1
+            bounds = np.unique(np.clip(np.r_[0, edges, len(systems)], 0, len(systems)))
+            if len(bounds) > 2:
+                return _solve_chunks(systems, errors, list(zip(bounds[:-1], bounds[1:])), returnBoundingBoxes, exact,
+                                     constant_check, low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, return_session)
     sess = None
     try:
         sess = eng.session(systems, errors,
@@ -130,16 +166,8 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
         # (systems never interact, so the answer is the same; a single system that does not fit still raises)
         eng.release_cached()
         half = len(systems) // 2
-        parts = [solve_batch(systems[lo:hi], errors[lo:hi], returnBoundingBoxes, exact, constant_check,
-                             low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, True)
-                 for lo, hi in ((0, half), (half, len(systems)))]
-        last = parts[-1][1]
-        last.chunk_sessions = [q for p in parts for q in getattr(p[1], "chunk_sessions", [p[1]])]
-        if returnBoundingBoxes:
-            out = (parts[0][0][0] + parts[1][0][0], parts[0][0][1] + parts[1][0][1])
-        else:
-            out = parts[0][0] + parts[1][0]
-        return (out, last) if return_session else out
+        return _solve_chunks(systems, errors, [(0, half), (half, len(systems))], returnBoundingBoxes, exact, constant_check,
+                             low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, return_session)
     res, keep, dup, extra = postpass.assemble(sess, need_records=returnBoundingBoxes)
     if sess.stats.max_level >= 25:
         warnings.warn("Extreme subdivision depth!\nSubdivision on the search interval has now reached"

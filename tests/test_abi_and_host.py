@@ -416,3 +416,21 @@ def test_batch_that_does_not_fit_is_solved_in_halves(monkeypatch):
     monkeypatch.setattr(eng, "session", lambda sy, er, **kw: (_ for _ in ()).throw(RuntimeError("CUDA out of memory")))
     with pytest.raises(RuntimeError):
         S.solve_batch(systems[:1], errs[:1], engine=eng)
+
+
+def test_very_large_batches_are_pre_split(monkeypatch):
+    """Batches above the engine's coefficient budget are solved as consecutive sub-batches; same answer."""
+    from emul.backend import emulated_engine
+    from rootfinding_b200 import ChebyshevSubdivisionSolver as S
+    from rootfinding_b200.workloads import random_systems
+    eng = emulated_engine()
+    systems, errs = random_systems(2, 6, 7, seed=4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = S.solve_batch(systems, errs, engine=eng)
+        monkeypatch.setattr(eng, "max_batch_coeffs", 3 * 98, raising=False)        # 98 coefficients per system
+        got, sess = S.solve_batch(systems, errs, engine=eng, return_session=True)
+    assert len(sess.chunk_sessions) == 3 and sum(c.nsys for c in sess.chunk_sessions) == 7
+    assert sum(c.stats.boxes for c in sess.chunk_sessions) > 0
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
