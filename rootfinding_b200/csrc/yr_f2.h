@@ -52,6 +52,9 @@
 #ifndef YR_F2_BUILD
 #define YR_F2_BUILD YR_DEV
 #endif
+#ifndef YR_F2_TRIM_QUICK
+#define YR_F2_TRIM_QUICK 0
+#endif
 #ifndef YR_F2_PAIR_BUILD
 #define YR_F2_PAIR_BUILD 0
 #endif
@@ -410,6 +413,15 @@ YR_F2_EPI void tensor_epilogue(Team& tm, const double* M, int n0, int n1, int ld
             for (;;) {
                 const int t = axis ? t1 : t0;
                 if (t <= 3) break;
+                if (YR_F2_TRIM_QUICK) {
+                    // One element of the last plane at or above the budget already rules the plane out (a rounded
+                    // sum of non-negative terms is never below one of them): the common outcome "nothing to trim
+                    // along this axis" costs one load and one vote instead of a sweep.  Same decision, exactly.
+                    bool big = false;
+                    if (axis == 0) { const double* row = M + (t0 - 1) * ld; for (int j = tm.lane; j < t1; j += tm.lanes) big = big || (fabs(row[j]) >= budget); }
+                    else { const double* col = M + (t1 - 1); for (int i = tm.lane; i < t0; i += tm.lanes) big = big || (fabs(col[i * ld]) >= budget); }
+                    if (tm.wany(big)) break;
+                }
                 const int np = (t - 3) < G ? (t - 3) : G;         // candidate planes t-1, t-2, ...
                 double s = 0.0;
                 if (g < np) {
