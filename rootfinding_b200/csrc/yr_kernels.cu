@@ -355,7 +355,12 @@ int set_smem(K kernel, size_t bytes) {
 
 namespace yr_backend {
 
-const char* build_info() { return "cuda sm_100a (nvcc " __VERSION__ ", -fmad=false)"; }
+#define YR_STR2(x) #x
+#define YR_STR(x) YR_STR2(x)
+const char* build_info() {
+    return "cuda sm_100a (nvcc " YR_STR(__CUDACC_VER_MAJOR__) "." YR_STR(__CUDACC_VER_MINOR__) "." YR_STR(__CUDACC_VER_BUILD__)
+           ", host compiler " __VERSION__ ", -fmad=false)";
+}
 
 int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm) {
     int dev = 0, v = 0;

@@ -297,7 +297,14 @@ def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_
     out_roots, out_boxes, has_dup, has_extra = [], [], False, False
     special = {int(k) for k in dup} | {int(k) for k in extra}
     special_systems = {int(res["system"][k]) for k in special} if special else set()
-    for s in range(nsys):
+    if not want_boxes:
+        # ordinary systems are slices of the sorted roots: one split for all of them, then only the special ones
+        # (lost records to a merge / collector, late records, duplicate or extra roots) are rebuilt record by record
+        out_roots = np.split(roots_all, bounds[1:-1]) if nsys else []
+        todo = sorted((set(redo_systems) | set(late_by_system) | special_systems) & set(range(nsys)))
+    else:
+        todo = range(nsys)
+    for s in todo:
         idx = keep[bounds[s]:bounds[s + 1]]
         redo = s in redo_systems
         if redo:
@@ -318,9 +325,11 @@ def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_
             r = np.array(rows).reshape(-1, dim)
         else:
             r = roots_all[bounds[s]:bounds[s + 1]]
-        out_roots.append(r)
         if want_boxes:
+            out_roots.append(r)
             out_boxes.append([ResultBox(res[i], dup.get(int(i)), int(i) in extra) for i in idx])
+        else:
+            out_roots[s] = r
     if has_extra:
         warnings.warn("Might Have Extra Roots! See Bounding Boxes for details!")
     if has_dup:
