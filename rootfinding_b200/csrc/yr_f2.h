@@ -81,9 +81,16 @@ YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
 constexpr int kClasses = 11;
 constexpr int kWarpClasses = 9;             // classes below this run the warp-team code
 constexpr int kLane16Classes = 5;           // classes below this use two 16-lane teams per warp
-YR_HD unsigned long long class_bound(int c) {
-    const unsigned long long b[kClasses] = {384ull, 512ull, 640ull, 768ull, 1024ull, 1536ull, 2048ull, 3072ull, 4096ull, 7168ull, ~0ull};
-    return b[c];
+YR_HD unsigned long long class_bound(int c) {               // no table: an indexed local array would live on the stack
+    switch (c) {
+        case 0: return 384ull; case 1: return 512ull; case 2: return 640ull; case 3: return 768ull; case 4: return 1024ull;
+        case 5: return 1536ull; case 6: return 2048ull; case 7: return 3072ull; case 8: return 4096ull; case 9: return 7168ull;
+        default: return ~0ull;
+    }
+}
+YR_HD int warp_class(unsigned long long need) {             // smallest warp class whose bound holds `need` (<= kWarp32Max)
+    return (need > 384ull) + (need > 512ull) + (need > 640ull) + (need > 768ull) + (need > 1024ull) + (need > 1536ull) +
+           (need > 2048ull) + (need > 3072ull);
 }
 YR_HD int class_threads(int cls) { return cls < kLane16Classes ? 16 : (cls < kWarpClasses ? 32 : (cls == kWarpClasses ? 128 : 256)); }
 constexpr unsigned long long kWarp32Max = 4096ull;    // largest need a warp team takes
@@ -108,7 +115,7 @@ YR_HD unsigned long long need_restrict_w(int T, int n0max, int n1max) {        /
 YR_HD unsigned long long need_subdivide_w(int T) { return 3ull * T; }            // warp teams: [S][L][X]
 YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, int coarse, unsigned long long& need, int& cls) {
     if (need_w <= kWarp32Max) {
-        need = need_w; cls = 0; while (need_w > class_bound(cls)) ++cls;
+        need = need_w; cls = warp_class(need_w);
         // a small round is launch-latency bound: one class per team type, fewer launches
         if (coarse) cls = cls < kLane16Classes ? kLane16Classes - 1 : kWarpClasses - 1;
     } else { need = need_cta; cls = need_cta <= class_bound(kWarpClasses) ? kWarpClasses : kWarpClasses + 1; }
@@ -1083,7 +1090,7 @@ struct Decision {
 // burst and writes back only when the box lives on (CUDA: the step is a long chain of small dependent accesses,
 // which on scattered global records is one memory round trip after another).
 template <class At>
-YR_HDN void scalar_step_on(const Args& a, BoxRec<2>& rec, Work& wk, Decision& dc, At at) {
+YR_HDM void scalar_step_on(const Args& a, BoxRec<2>& rec, Work& wk, Decision& dc, At at) {
     const SolverParams& prm = a.prm;
     IntervalState<2>& st = rec.st;
 

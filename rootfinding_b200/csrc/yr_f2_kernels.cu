@@ -14,6 +14,12 @@
 #include <stdlib.h>
 #include <time.h>
 
+#ifndef YR_F2_INLINE_MATH
+#define YR_F2_INLINE_MATH 1
+#endif
+#if YR_F2_INLINE_MATH
+#define YR_HDM static __host__ __device__ __forceinline__     // see yr_math.h
+#endif
 #include "yr_f2_host.h"
 
 using namespace yr;

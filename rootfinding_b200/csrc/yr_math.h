@@ -26,6 +26,12 @@
 #define YR_HD inline
 #define YR_HDN inline
 #endif
+// Per-box mathematics with small array parameters (SVD, BILS, subdivision axes, 2-D quadratic check).  Out of line by
+// default; a translation unit may define YR_HDM as force-inline so that the arrays live in registers instead of the
+// stack (the 2-D frontier pipeline's thread-per-box scalar kernel does: its stack traffic was its bottleneck).
+#ifndef YR_HDM
+#define YR_HDM YR_HDN
+#endif
 
 namespace yr {
 
@@ -164,7 +170,7 @@ YR_HD bool add_transform(IntervalState<D>& s, double sub[D][2], double alpha[D],
 // return sig[] holds the singular values (unsorted), W = U*diag(sig), V the
 // right vectors.
 template <int D>
-YR_HDN void jacobi_svd(const double A[D][D], double W[D][D], double V[D][D], double sig[D]) {
+YR_HDM void jacobi_svd(const double A[D][D], double W[D][D], double V[D][D], double sig[D]) {
     for (int i = 0; i < D; ++i)
         for (int j = 0; j < D; ++j) { W[i][j] = A[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
     for (int sweep = 0; sweep < 30; ++sweep) {
@@ -236,7 +242,7 @@ struct BilsOut { bool changed, should_stop, throw_out; };
 //   lin[p][d]  linear coefficient of polynomial p along axis d (getLinearTerms)
 //   c0[p]      constant coefficient, sumabs[p] = sum|M_p|, errors[p] approximation error
 template <int D>
-YR_HDN BilsOut bounding_interval(const double lin[D][D], const double c0[D], const double sumabs[D],
+YR_HDM BilsOut bounding_interval(const double lin[D][D], const double c0[D], const double sumabs[D],
                                  const double errors_in[D], bool final_step, double out[D][2]) {
     double A[D][D], consts[D], total[D], lsum[D], err[D], errors[D];
     const double shrink_floor = 0.99;
@@ -362,7 +368,7 @@ YR_HDN BilsOut bounding_interval(const double lin[D][D], const double c0[D], con
 // getSubdivisionDims :1013-1049.  order[p][0..k-1] = axes to halve tensor p along, in
 // order; returns k (identical for every polynomial).  shape[p][d] are the extents.
 template <int D>
-YR_HDN int subdivision_axes(const int shape[D][D], const double iv[D][2], int level, int order[D][D]) {
+YR_HDM int subdivision_axes(const int shape[D][D], const double iv[D][2], int level, int order[D][D]) {
     int cand[D]; int nc = 0;
     for (int i = 0; i < D; ++i) cand[nc++] = i;
     for (int i = 0; i < D; ++i) {
@@ -421,7 +427,7 @@ struct RangeWitness {
 };
 
 // c = {c00, c10, c01, c20, c11, c02};  sumabs = sum|M|;  returns true when no root is possible.
-YR_HDN bool quad_check_2d(const double c[6], double sumabs, double tol) {
+YR_HDM bool quad_check_2d(const double c[6], double sumabs, double tol) {
     double s = 0; for (int i = 0; i < 6; ++i) s = s + fabs(c[i]);
     RangeWitness r{sumabs - s + tol, false, false};
     const double k0 = c[0] - c[3] - c[5], k3 = 2 * c[3], k5 = 2 * c[5];
