@@ -627,17 +627,24 @@ YR_DEV void child_record(Team& tm, const Args& a, const BoxRec<2>& rec, const Wo
     // :1111-1128 -- thread-serial
     BoxRec<2>& out = a.recs[child];
     Work& ow = a.work[child];
+    // every array index below is a compile-time constant (selects instead of indexing by the axis), so the interval
+    // state stays in registers: indexed by a run-time axis it lives on the stack, one local-memory trip per access
     IntervalState<2> st = rec.st;
-    for (int j = 0; j < k; ++j) {
-        const int ax = split_axes[j];
-        const int half = (c >> (k - 1 - j)) & 1;
-        const double mid = st.next_mid[ax];
-        double sub[2][2], al[2], be[2];
-        for (int d = 0; d < 2; ++d) { sub[d][0] = -1.0; sub[d][1] = 1.0; }
-        if (half) sub[ax][0] = mid; else sub[ax][1] = mid;
-        add_transform<2>(st, sub, al, be);
+    const int ax0 = split_axes[0], ax1 = split_axes[1];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (j < k) {
+            const int ax = j ? ax1 : ax0;
+            const int half = (c >> (k - 1 - j)) & 1;
+            const double mid = ax ? st.next_mid[1] : st.next_mid[0];
+            double sub[2][2], al[2], be[2];
+            sub[0][0] = (ax == 0 && half) ? mid : -1.0; sub[0][1] = (ax == 0 && !half) ? mid : 1.0;
+            sub[1][0] = (ax == 1 && half) ? mid : -1.0; sub[1][1] = (ax == 1 && !half) ? mid : 1.0;
+            add_transform<2>(st, sub, al, be);
+        }
     }
-    for (int j = 0; j < k; ++j) st.next_mid[split_axes[j]] = 0.0;
+    if (k > 0) { if (ax0 == 0) st.next_mid[0] = 0.0; else st.next_mid[1] = 0.0; }
+    if (k > 1) { if (ax1 == 0) st.next_mid[0] = 0.0; else st.next_mid[1] = 0.0; }
     out.st = st;
     out.data_off = 0;
     out.system = rec.system;
