@@ -78,23 +78,34 @@ constexpr int kOps = 2;
 enum Op : int32_t { kTNone = 0, kTRestrict = 1, kTSubdivide = 2 };
 YR_HD int op_slot(int op) { return op == kTSubdivide ? 1 : 0; }
 
-constexpr int kClasses = 11;
+constexpr int kClasses = 15;
 constexpr int kWarpClasses = 9;             // classes below this run the warp-team code
 constexpr int kLane16Classes = 5;           // classes below this use two 16-lane teams per warp
+constexpr int kCta128Classes = 13;          // CTA classes below this run 128 threads per box, the rest 256
 YR_HD unsigned long long class_bound(int c) {               // no table: an indexed local array would live on the stack
     switch (c) {
         case 0: return 384ull; case 1: return 512ull; case 2: return 640ull; case 3: return 768ull; case 4: return 1024ull;
-        case 5: return 1536ull; case 6: return 2048ull; case 7: return 3072ull; case 8: return 4096ull; case 9: return 7168ull;
+        case 5: return 1536ull; case 6: return 2048ull; case 7: return 3072ull; case 8: return 4096ull;
+        case 9: return 2048ull; case 10: return 3072ull; case 11: return 4608ull; case 12: return 7168ull;
+        case 13: return 12288ull;
         default: return ~0ull;
     }
 }
-YR_HD int warp_class(unsigned long long need) {             // smallest warp class whose bound holds `need` (<= kWarp32Max)
+YR_HD int warp_class(unsigned long long need) {             // smallest warp class whose bound holds `need` (<= 4096)
     return (need > 384ull) + (need > 512ull) + (need > 640ull) + (need > 768ull) + (need > 1024ull) + (need > 1536ull) +
            (need > 2048ull) + (need > 3072ull);
 }
-YR_HD int class_threads(int cls) { return cls < kLane16Classes ? 16 : (cls < kWarpClasses ? 32 : (cls == kWarpClasses ? 128 : 256)); }
-constexpr unsigned long long kWarp32Max = 4096ull;    // largest need a warp team takes
+YR_HD int cta_class(unsigned long long need, unsigned long long split) {   // `split`: largest need a 128-thread CTA takes
+    if (need <= split) return kWarpClasses + (need > 2048ull) + (need > 3072ull) + (need > 4608ull);
+    return kCta128Classes + (need > 12288ull);
+}
+YR_HD int class_threads(int cls) { return cls < kLane16Classes ? 16 : (cls < kWarpClasses ? 32 : (cls < kCta128Classes ? 128 : 256)); }
+constexpr unsigned long long kWarp32Max = 4096ull;    // largest need a warp team can take
 constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
+
+// Launch-shape policy (host-tunable; defaults from profiles/r02_team_sweep.txt): the largest warp-team need per op
+// (boxes above it run one CTA per box) and the largest 128-thread CTA need.
+struct TeamPolicy { unsigned long long warp_max[2]; unsigned long long cta128_max; };
 
 YR_HD int odd_ld(int n1) { return n1 | 1; }
 YR_HD int even_up(int x) { return (x + 1) & ~1; }
@@ -113,12 +124,16 @@ YR_HD unsigned long long need_restrict_w(int T, int n0max, int n1max) {        /
     return (unsigned long long)T + panel_doubles(n0max) + panel_doubles(n1max) + (unsigned)((n0max + n1max + 1) / 2) + 2;
 }
 YR_HD unsigned long long need_subdivide_w(int T) { return 3ull * T; }            // warp teams: [S][L][X]
-YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, int coarse, unsigned long long& need, int& cls) {
-    if (need_w <= kWarp32Max) {
+YR_HD void pick_team(unsigned long long need_w, unsigned long long need_cta, int coarse, const TeamPolicy& pol, int slot,
+                     unsigned long long& need, int& cls) {
+    if (need_w <= pol.warp_max[slot]) {
         need = need_w; cls = warp_class(need_w);
         // a small round is launch-latency bound: one class per team type, fewer launches
         if (coarse) cls = cls < kLane16Classes ? kLane16Classes - 1 : kWarpClasses - 1;
-    } else { need = need_cta; cls = need_cta <= class_bound(kWarpClasses) ? kWarpClasses : kWarpClasses + 1; }
+    } else {
+        need = need_cta; cls = cta_class(need_cta, pol.cta128_max);
+        if (coarse) cls = cls < kCta128Classes ? kCta128Classes - 1 : kClasses - 1;
+    }
 }
 
 // Per-box state next to BoxRec<2> (same slot index).
@@ -168,6 +183,7 @@ struct Args {
     unsigned int* lists[kOps][kClasses];            // queues being filled for the next round
     unsigned long long cap_boxes;
     int coarse;                                     // 1: the next round is small, queue into one class per team type
+    TeamPolicy pol;
     Ctl* ctl;
     Tables tab;
     SolverParams prm;
@@ -1136,7 +1152,7 @@ YR_HDM void scalar_step_on(const Args& a, BoxRec<2>& rec, Work& wk, Decision& dc
         int T, n0m, n1m; unsigned long long total;
         sizes(T, n0m, n1m, total);
         wk.op = kTRestrict;
-        dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), a.coarse, dc.need, dc.cls); dc.bound = total;
+        dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), a.coarse, a.pol, 0, dc.need, dc.cls); dc.bound = total;
         dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
     };
 
@@ -1251,7 +1267,7 @@ YR_HDM void scalar_step_on(const Args& a, BoxRec<2>& rec, Work& wk, Decision& dc
             int T, n0m, n1m; unsigned long long total;
             sizes(T, n0m, n1m, total);
             wk.op = kTSubdivide;
-            dc.op = kTSubdivide; pick_team(need_subdivide_w(T), need_subdivide(T), a.coarse, dc.need, dc.cls); dc.bound = total << k;
+            dc.op = kTSubdivide; pick_team(need_subdivide_w(T), need_subdivide(T), a.coarse, a.pol, 1, dc.need, dc.cls); dc.bound = total << k;
             dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
             dc.subdiv += 1;
         }
@@ -1285,7 +1301,7 @@ YR_HD void import_box(const Args& a, unsigned int b, Decision& dc, At at) {
     w.node_level = rec.level; w.result_index = -1; w.node_index = -1; w.nsplit = 0;
     int T, n0m, n1m; unsigned long long total;
     box_sizes(rec, w, T, n0m, n1m, total);
-    dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), a.coarse, dc.need, dc.cls); dc.bound = total;
+    dc.op = kTRestrict; pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), a.coarse, a.pol, 0, dc.need, dc.cls); dc.bound = total;
     dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
     at.add(&a.ctl->n_boxes, 1ull);
 }

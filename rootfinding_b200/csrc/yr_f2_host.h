@@ -141,6 +141,15 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
     for (int m = 0; m < 2; ++m) for (int h = 0; h < 2; ++h) { a.tab.mat[m][h] = mats + (size_t)(2 * m + h) * P; a.tab.rows_after[m][h] = rows + (size_t)(2 * m + h) * nt; }
     memcpy(&a.prm, &d->prm, sizeof(a.prm));
     a.result_base = d->result_base; a.node_base = d->node_base;
+    {
+        // team policy: warp teams up to these needs (doubles), one CTA per box above; overridable for experiments
+        auto env_ull = [](const char* name, unsigned long long dflt) { const char* v = getenv(name); return v ? strtoull(v, nullptr, 10) : dflt; };
+        a.pol.warp_max[0] = env_ull("YR_F2_WARP_MAX_R", kWarp32Max);
+        a.pol.warp_max[1] = env_ull("YR_F2_WARP_MAX_S", kWarp32Max);
+        a.pol.cta128_max = env_ull("YR_F2_CTA128_MAX", 7168ull);
+        for (int o = 0; o < 2; ++o) if (a.pol.warp_max[o] > kWarp32Max) a.pol.warp_max[o] = kWarp32Max;
+        if (a.pol.cta128_max > 7168ull) a.pol.cta128_max = 7168ull;
+    }
 
     Ctl h;                               // host copy of the control block
     memset(&h, 0, sizeof(h));

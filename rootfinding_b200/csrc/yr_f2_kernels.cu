@@ -187,8 +187,11 @@ __global__ void __launch_bounds__(128, YR_F2_WARP_MINB) f2_tensor_warp(const Arg
     if (tm.tid == 0 && macs) atomicAdd(&a.ctl->restrict_macs, macs);
 }
 
-template <int OP, bool FMA>
-__global__ void __launch_bounds__(256) f2_tensor_cta(const Args a, const unsigned int* __restrict__ list, unsigned long long n, int snt,
+#ifndef YR_F2_CTA128_MINB
+#define YR_F2_CTA128_MINB 5
+#endif
+template <int OP, bool FMA, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? YR_F2_CTA128_MINB : 2) f2_tensor_cta(const Args a, const unsigned int* __restrict__ list, unsigned long long n, int snt,
                                                      unsigned long long* cursor) {
     extern __shared__ __align__(16) double dyn[];
     __shared__ CtaShared cta_sh;
@@ -390,10 +393,15 @@ int launch_tensor_t(const Args& a, int cls, const unsigned int* list, unsigned l
         const int threads = class_threads(cls);
         const size_t smem = smat + slice * 8;
         if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("f2: CTA-team launch exceeds shared memory"); return -1; }
-        if (ensure_smem(f2_tensor_cta<OP, FMA>, smem)) return -1;
-        const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(f2_tensor_cta<OP, FMA>, threads, smem);
-        const unsigned grid = (unsigned)(n < cap ? n : cap);
-        f2_tensor_cta<OP, FMA><<<grid, threads, smem, st>>>(a, list, n, snt, cursor);
+        if (threads == 128) {
+            if (ensure_smem(f2_tensor_cta<OP, FMA, 128>, smem)) return -1;
+            const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(f2_tensor_cta<OP, FMA, 128>, 128, smem);
+            f2_tensor_cta<OP, FMA, 128><<<(unsigned)(n < cap ? n : cap), 128, smem, st>>>(a, list, n, snt, cursor);
+        } else {
+            if (ensure_smem(f2_tensor_cta<OP, FMA, 256>, smem)) return -1;
+            const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(f2_tensor_cta<OP, FMA, 256>, 256, smem);
+            f2_tensor_cta<OP, FMA, 256><<<(unsigned)(n < cap ? n : cap), 256, smem, st>>>(a, list, n, snt, cursor);
+        }
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "f2 tensor launch");

@@ -115,75 +115,128 @@ def _ancestors(nodes, start):
     return chain
 
 
+def _exterior_at(res, nodes, i, node, chain, resolved_under):
+    """Is live record i in `resultExterior` when the reference's recursion unwinds to subdividing node `node`?
+    (`chain` = ancestors of i, innermost first.)  A box travels upwards as long as it shares an endpoint with the
+    cell of every call it leaves (:1381, isExteriorInterval); boxes a merge re-solved are passed on unchecked by
+    the node that re-solved them (:1376-1380)."""
+    if node < 0:
+        pos = len(chain)
+    else:
+        pos = chain.index(node)
+    if not (res["flags"][i] & RES_TOUCH):
+        return False
+    iv = res["comb_iv"][i]
+    for k in chain[:pos]:                           # cells left on the way up: the subdividing calls below `node`
+        if resolved_under.get(int(i)) == k:         # re-solved by the merge at k: passed on unchecked
+            continue
+        c = nodes["iv"][k]
+        if not (np.any(iv[:, 0] == c[:, 0]) or np.any(iv[:, 1] == c[:, 1])):
+            return False
+    return True
+
+
 def merge_exterior(session, res, alive, dup, extra, max_rounds=64, cand=None):
     """Step B.  May run more device jobs through `session`; returns the updated (res, alive, dup, extra).
-    `cand`: the live records flagged RES_TOUCH, when the caller already knows them."""
+    `cand`: the live records flagged RES_TOUCH, when the caller already knows them.
+
+    Per system and round: the deepest subdividing node two overlapping exterior boxes have in common is where the
+    unwinding recursion meets them first.  There the reference merges EVERY transitively overlapping exterior box
+    of that node's subtree into growing bounding boxes (:1323-1367) and re-solves each merged box once (:1369-1380);
+    three or more boxes that meet in one point (a root on a corner of the subdivision grid) therefore become one
+    re-solve, not several pairs."""
     rounds = 0
     # candidates: live records whose reported interval touches the cell they were created as; the set is small
     # and is maintained incrementally (one pass over the records, not one per merge)
     if cand is None:
         cand = np.nonzero(alive & ((res["flags"] & RES_TOUCH) != 0))[0]
     cand_set = set(np.asarray(cand).tolist())
+    resolved_under = getattr(session, "_resolved_under", None)
+    if resolved_under is None:
+        resolved_under = session._resolved_under = {}
+    dim = res["comb_iv"].shape[1]
     while rounds < max_rounds:
         rounds += 1
         if len(cand_set) < 2:
             break
         cand = np.fromiter(sorted(cand_set), dtype=np.int64, count=len(cand_set))
-        pairs = []
         order = cand[np.argsort(res["system"][cand], kind="stable")]
         sysv = res["system"][order]
         starts = np.nonzero(np.r_[True, sysv[1:] != sysv[:-1], True])[0]
+        nodes = None
+        jobs, progress = [], False
         for s, e in zip(starts[:-1], starts[1:]):
             grp = order[s:e]
             if len(grp) < 2:
                 continue
             iv = res["comb_iv"][grp]
-            for x in range(len(grp)):
-                for y in range(x + 1, len(grp)):
-                    if _overlap(iv[x], iv[y]):
-                        pairs.append((int(grp[x]), int(grp[y])))
-        if not pairs:
-            break
-        nodes = session.nodes()
-        # Per system: the pair with the deepest common ancestor first, like the unwinding recursion.  Systems never
-        # interact, so one round merges one pair in EVERY system that has one and re-solves them in one device call.
-        best = {}
-        for i, j in pairs:
-            ai = _ancestors(nodes, res["parent_node"][i])
-            aj = set(_ancestors(nodes, res["parent_node"][j]))
-            lca = next((k for k in ai if k in aj), -1)
-            lvl = int(nodes["level"][lca]) if lca >= 0 else 0
-            sysid = int(res["system"][i])
-            if sysid not in best or lvl > best[sysid][0]:
-                best[sysid] = (lvl, i, j, lca)
-        dim = res["comb_iv"].shape[1]
-        jobs = []
-        for sysid in sorted(best):
-            lvl, i, j, lca = best[sysid]
-            lo = np.minimum(res["comb_iv"][i][:, 0], res["comb_iv"][j][:, 0])
-            hi = np.maximum(res["comb_iv"][i][:, 1], res["comb_iv"][j][:, 1])
+            pairs = [(x, y) for x in range(len(grp)) for y in range(x + 1, len(grp)) if _overlap(iv[x], iv[y])]
+            if not pairs:
+                continue
+            if nodes is None:
+                nodes = session.nodes()
+            chains = [_ancestors(nodes, res["parent_node"][g]) for g in grp]
+            # the node the unwinding recursion merges at first: the deepest common ancestor over all overlapping pairs
+            best = None
+            for x, y in pairs:
+                sy = set(chains[y])
+                lca = next((k for k in chains[x] if k in sy), -1)
+                lvl = int(nodes["level"][lca]) if lca >= 0 else 0
+                if best is None or lvl > best[0]:
+                    best = (lvl, lca)
+            lvl, lca = best
             if lca >= 0:
                 anc_iv, anc_mid, anc_level = nodes["iv"][lca], nodes["next_mid"][lca], int(nodes["level"][lca])
-            else:                                   # the two boxes come from different level-0 jobs of one system
+            else:                                   # the boxes come from different level-0 jobs of one system
                 anc_iv = np.array([[-1., 1.]] * dim)
                 anc_mid, anc_level = np.full(dim, 0.0394555475981047), 0
-            alive[i] = alive[j] = False
-            cand_set.discard(i); cand_set.discard(j)
-            session.stats_merges = getattr(session, "stats_merges", 0) + 1
-            if np.array_equal(lo, anc_iv[:, 0]) and np.array_equal(hi, anc_iv[:, 1]):
-                # :1370-1371 the merged box is the ancestor's whole box: keep it, do not re-solve
-                keep = i
-                res["comb_iv"][keep][:, 0], res["comb_iv"][keep][:, 1] = lo, hi
-                res["box"][keep][:, 0] = np.minimum(res["box"][i][:, 0], res["box"][j][:, 0])
-                res["box"][keep][:, 1] = np.maximum(res["box"][i][:, 1], res["box"][j][:, 1])
-                res["root"][keep] = (res["box"][keep][:, 0] + res["box"][keep][:, 1]) / 2
-                session.patched_roots = getattr(session, "patched_roots", set()) | {int(keep)}
-                res["flags"][keep] &= ~np.uint32(RES_TOUCH)
-                alive[keep] = True
-                continue
-            jobs.append((sysid, lo, hi, anc_level, np.array(anc_mid), lca))
+            # resultExterior of that call, in the reference's (depth-first) order
+            members = [x for x in range(len(grp)) if (lca < 0 or lca in chains[x])
+                       and _exterior_at(res, nodes, int(grp[x]), lca, chains[x], resolved_under)]
+            members = [int(g) for g in _path_order(res, grp[members])]
+            # the reference's double loop :1326-1367 on (interval, member records)
+            work = [(res["comb_iv"][g].copy(), [g]) for g in members]
+            i1 = 0
+            while i1 < len(work):
+                i2 = i1 + 1
+                while i2 < len(work):
+                    if _overlap(work[i1][0], work[i2][0]):
+                        a, b = work[i1], work[i2]
+                        box = np.stack([np.minimum(a[0][:, 0], b[0][:, 0]), np.maximum(a[0][:, 1], b[0][:, 1])], axis=1)
+                        del work[i2]
+                        del work[i1]
+                        work.append((box, a[1] + b[1]))
+                        i2 = i1 + 1
+                    else:
+                        i2 += 1
+                i1 += 1
+            sysid = int(res["system"][grp[0]])
+            for box, recs in work:
+                if len(recs) < 2:
+                    continue
+                lo, hi = box[:, 0], box[:, 1]
+                progress = True
+                for g in recs:
+                    alive[g] = False
+                    cand_set.discard(g)
+                session.stats_merges = getattr(session, "stats_merges", 0) + 1
+                if np.array_equal(lo, anc_iv[:, 0]) and np.array_equal(hi, anc_iv[:, 1]):
+                    # :1370-1371 the merged box is the ancestor's whole box: keep it, do not re-solve
+                    keep = recs[0]
+                    res["comb_iv"][keep][:, 0], res["comb_iv"][keep][:, 1] = lo, hi
+                    res["box"][keep][:, 0] = np.min(res["box"][recs][:, :, 0], axis=0)
+                    res["box"][keep][:, 1] = np.max(res["box"][recs][:, :, 1], axis=0)
+                    res["root"][keep] = (res["box"][keep][:, 0] + res["box"][keep][:, 1]) / 2
+                    session.patched_roots = getattr(session, "patched_roots", set()) | {int(keep)}
+                    res["flags"][keep] &= ~np.uint32(RES_TOUCH)
+                    alive[keep] = True
+                    continue
+                jobs.append((sysid, lo.copy(), hi.copy(), anc_level, np.array(anc_mid), lca))
         if not jobs:
+            if not progress:
+                break                                # no overlapping pair anywhere (or none the reference would merge)
             continue
+        n_old_nodes = len(nodes)
         los, his = np.array([q[1] for q in jobs]), np.array([q[2] for q in jobs])
         job = dict(system=np.array([q[0] for q in jobs], np.int32), restrict=np.ones(len(jobs), np.int32),
                    alpha=(his - los) / 2, beta=(his + los) / 2, iv=np.stack([los, his], axis=2),
@@ -198,7 +251,15 @@ def merge_exterior(session, res, alive, dup, extra, max_rounds=64, cand=None):
         dup.update(sub_dup)
         extra |= sub_extra
         new = np.arange(first, first + count)
-        cand_set.update(new[sub_alive & ((res["flags"][first:first + count] & RES_TOUCH) != 0)].tolist())
+        fresh = new[sub_alive & ((res["flags"][first:first + count] & RES_TOUCH) != 0)].tolist()
+        cand_set.update(fresh)
+        if fresh:
+            nodes = session.nodes()
+            for g in fresh:                          # the node whose merge re-solved this box passes it on unchecked
+                k = int(res["parent_node"][g])
+                while k >= n_old_nodes:
+                    k = int(nodes["parent_node"][k])
+                resolved_under[int(g)] = k
     return res, alive, dup, extra
 
 

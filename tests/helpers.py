@@ -98,3 +98,40 @@ def check_edge_cases(S, osub):
             match_points(want, got, ROOT_TOL)
     assert S.solve_batch([], []) == []
     assert S.solve_batch([], [], returnBoundingBoxes=True) == ([], [])
+
+
+FIRST_SPLIT = 0.0394555475981047
+
+
+def corner_system(seed, dim=2, deg=3):
+    """A system with a root ON a corner of the subdivision grid: polynomial `ax` is (x_ax - m) * random, with m the
+    reference's first split point (ChebyshevSubdivisionSolver.py:414).  All 2^dim level-1 cells report an exterior box at
+    (m, ..., m); the reference merges them into ONE re-solve (:1323-1380)."""
+    import numpy.polynomial.chebyshev as Ch
+    rs = np.random.RandomState(seed)
+    Ms = []
+    for ax in range(dim):
+        p = rs.randn(*([deg + 1] * dim))
+        q = np.apply_along_axis(lambda c: Ch.chebmulx(c) - FIRST_SPLIT * np.r_[c, 0.0], ax, p)
+        Ms.append(np.ascontiguousarray(q))
+    return Ms
+
+
+def match_boxes(want_roots, want_boxes, got_roots, got_boxes, tol):
+    """Pairs roots like match_points and compares the bounding box reported with each (max-norm on the endpoints)."""
+    want_roots = np.asarray(want_roots, float).reshape(len(want_boxes), -1)
+    got_roots = np.asarray(got_roots, float).reshape(len(got_boxes), -1)
+    assert len(want_boxes) == len(got_boxes), (len(want_boxes), len(got_boxes))
+    worst = 0.0
+    used = np.zeros(len(got_roots), dtype=bool)
+    for r, bx in zip(want_roots, np.asarray(want_boxes, float)):
+        d = np.max(np.abs(got_roots - r), axis=1)
+        d[used] = np.inf
+        j = int(np.argmin(d))
+        used[j] = True
+        diff = float(np.max(np.abs(np.asarray(got_boxes[j], float) - bx)))
+        # a reported box is itself an error bound: endpoints agree to `tol` plus a few per cent of the reference box's width
+        lim = tol + 0.05 * float(np.max(bx[:, 1] - bx[:, 0]))
+        assert diff < lim, f"bounding box of root {r} differs by {diff} (limit {lim})"
+        worst = max(worst, diff)
+    return worst

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def yr():
     import torch
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     import rootfinding_b200
     from rootfinding_b200 import _lib
     from rootfinding_b200.runtime import get_engine, set_engine

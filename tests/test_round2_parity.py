@@ -1,0 +1,230 @@
+"""Round-2 parity cases (VERDICT r01 "next round" item 1 + ADVICE): corner roots that need a transitive merge,
+degree 75 / 100 reference solves, bounding boxes, BASELINE configs 4 and 5 (devastating example, notebook demos,
+tests/high_dim/4d_examples.py), all_dim_quadratic_check at dimension >= 4.
+
+CPU tier: through the real host code on the kernel-source emulator.  GPU tier (`-m gpu`): through the CUDA library.
+Golden vectors come from the unmodified reference (oracle/gen_golden_r2.py -> tests/golden/solves_r2.npz)."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cases_r2 as cz
+import chebfun_cases as cc
+import helpers as H
+
+
+@pytest.fixture(scope="module")
+def emu_yr():
+    from emul.backend import emulated_engine
+    import rootfinding_b200
+    from rootfinding_b200.runtime import set_engine
+    set_engine(emulated_engine())
+    yield rootfinding_b200
+    set_engine(None)
+
+
+@pytest.fixture(scope="module")
+def gpu_yr():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import rootfinding_b200
+    from rootfinding_b200 import _lib
+    from rootfinding_b200.runtime import get_engine, set_engine
+    set_engine(None)
+    eng = get_engine()
+    assert b"cuda sm_100a" in eng.lib.yr_build_info() and eng.lib._name == _lib.CUDA_LIB_PATH
+    return rootfinding_b200
+
+
+def _solve(yr, Ms, errs, **kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got, sess = yr.ChebyshevSubdivisionSolver.solve_batch([Ms], [errs], return_session=True, **kw)
+    return np.asarray(got[0], float).reshape(-1, len(Ms)), sess
+
+
+# ---- three or more exterior boxes meeting in one point -------------------------------------
+def _corner_roots(yr, seeds, dim, deg):
+    for seed in seeds:
+        Ms = H.corner_system(seed, dim, deg)
+        errs = np.full(dim, 2.0 ** -52)
+        want, trace = H.oracle_solve(Ms, errs)
+        got, _ = _solve(yr, Ms, errs)
+        assert len(got) == len(want), (seed, len(got), len(want))
+        H.match_points(want, got, 1e-9)           # the corner root itself is ill conditioned by construction
+
+
+def test_corner_roots_emulated(emu_yr):
+    _corner_roots(emu_yr, range(12), 2, 3)
+
+
+def test_corner_roots_level_pipeline_emulated(emu_yr):
+    from rootfinding_b200.runtime import get_engine
+    eng = get_engine()
+    old = eng.pipeline
+    eng.pipeline = 1
+    try:
+        _corner_roots(emu_yr, range(6), 2, 3)
+        _corner_roots(emu_yr, range(2), 3, 2)
+    finally:
+        eng.pipeline = old
+
+
+@pytest.mark.gpu
+def test_corner_roots_gpu(gpu_yr):
+    _corner_roots(gpu_yr, range(30), 2, 3)
+    _corner_roots(gpu_yr, range(4), 3, 2)
+
+
+# ---- reference solves the round-1 fixture lacked -----------------------------------------------------------------
+def _golden_random(yr, pick):
+    z = H.load("solves_r2.npz")
+    sizes = {(d, g, k == "randint"): n for d, g, n, k in cz.RANDOM_PLAN}
+    done = 0
+    for i in range(int(z["rnd_n"])):
+        dim, deg, s, randint, nbox = (int(v) for v in z[f"rnd_meta_{i}"])
+        if not pick(dim, deg):
+            continue
+        Ms = H.seeded_systems(dim, deg, sizes[(dim, deg, bool(randint))], "randint" if randint else "randn")[s]
+        got, sess = _solve(yr, Ms, np.full(dim, 2.0 ** -52))
+        want = z[f"rnd_roots_{i}"]
+        assert len(got) == len(want), (dim, deg, s, len(got), len(want))
+        if len(want):
+            H.match_points(want, got, H.ROOT_TOL)
+        assert sess.stats.boxes == nbox, (dim, deg, s, sess.stats.boxes, nbox)       # the reference's own box count
+        done += 1
+    assert done
+
+
+def test_golden_random_r2_emulated(emu_yr):
+    _golden_random(emu_yr, lambda dim, deg: (dim, deg) in ((3, 8), (5, 2)))
+
+
+@pytest.mark.gpu
+def test_golden_random_r2_gpu(gpu_yr):
+    """2-D degree 75 and 100 (level pipeline hands over to the frontier pipeline), 3-D degree 8 / 10, 4-D degree 4 / 5,
+    5-D degree 2 against the unmodified reference: same roots (1e-10), same number of solvePolyRecursive calls."""
+    _golden_random(gpu_yr, lambda dim, deg: True)
+
+
+# ---- all_dim_quadratic_check at dimension >= 4 --------------------------------------------------
+def _alldim(yr, pick):
+    z = H.load("solves_r2.npz")
+    sizes = {(d, g): n for d, g, n, k in cz.ALLDIM_PLAN}
+    done = 0
+    for i in range(int(z["alld_n"])):
+        dim, deg, s, nb_on, nb_off = (int(v) for v in z[f"alld_meta_{i}"])
+        if not pick(dim, deg):
+            continue
+        Ms = H.seeded_systems(dim, deg, sizes[(dim, deg)])[s]
+        got, sess = _solve(yr, Ms, np.full(dim, 2.0 ** -52), all_dim_quadratic_check=True)
+        want = z[f"alld_roots_{i}"]
+        assert len(got) == len(want)
+        if len(want):
+            H.match_points(want, got, H.ROOT_TOL)
+        assert sess.stats.boxes == nb_on                    # the check prunes: fewer calls than without it
+        assert nb_on <= nb_off
+        done += 1
+    assert done
+
+
+def test_all_dim_quadratic_check_emulated(emu_yr):
+    _alldim(emu_yr, lambda dim, deg: (dim, deg) == (4, 3))
+
+
+@pytest.mark.gpu
+def test_all_dim_quadratic_check_gpu(gpu_yr):
+    _alldim(gpu_yr, lambda dim, deg: True)
+
+
+# ---- BASELINE config 5: the devastating example -------------------------------------------------------------------
+def _devastating(yr):
+    z = H.load("solves_r2.npz")
+    for kind, dim, eps in cz.DEVASTATING:
+        Ms = cz.devastating_coeffs(kind, dim, eps)
+        key = cz.dev_key(kind, dim, eps)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            roots, boxes = yr.solve([yr.MultiCheb(m) for m in Ms], -np.ones(dim), np.ones(dim), returnBoundingBoxes=True)
+        want = z[key + "_roots"]
+        roots = np.asarray(roots, float).reshape(-1, dim)
+        assert len(roots) == len(want), (key, len(roots), len(want))
+        if len(want):
+            # eps = 1e-6: the Jacobian at the root is O(eps), the reference's own bounding boxes are ~1e-8 wide and a 1-ulp
+            # change of a coefficient moves the root by ~1e-10: there the roots must agree to within the reference's box
+            wb = z[key + "_boxes"]
+            tol = H.ROOT_TOL if eps > 1e-5 else max(H.ROOT_TOL, float(np.max(wb[:, :, 1] - wb[:, :, 0])))
+            H.match_points(want, roots, tol)
+            H.match_boxes(want, wb, roots, boxes, H.ROOT_TOL)
+
+
+def test_devastating_example_emulated(emu_yr):
+    _devastating(emu_yr)
+
+
+@pytest.mark.gpu
+def test_devastating_example_gpu(gpu_yr):
+    _devastating(gpu_yr)
+
+
+# ---- notebook demos (many-root systems of BASELINE config 5) and the 4-D examples (config 4) --------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(cz.NOTEBOOK))
+def test_notebook_demo_gpu(gpu_yr, name):
+    z = H.load("solves_r2.npz")
+    if f"nb_{name}_roots" not in z.files:
+        pytest.skip("no reference output committed for this demo")
+    funcs, a, b = cz.NOTEBOOK[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        roots, boxes = gpu_yr.solve(funcs, a, b, returnBoundingBoxes=True)
+    want = z[f"nb_{name}_roots"]
+    dim = len(a)
+    roots = np.asarray(roots, float).reshape(-1, dim)
+    assert len(roots) == len(want), (name, len(roots), len(want))
+    scale = max(np.max(np.abs(a)), np.max(np.abs(b)))
+    H.match_points(want / scale, roots / scale, H.ROOT_TOL)
+    H.match_boxes(want / scale, z[f"nb_{name}_boxes"] / scale, roots / scale, np.asarray(boxes, float) / scale, H.ROOT_TOL)
+    resid = max(float(np.max(np.abs(f(*roots.T)))) for f in funcs)
+    assert resid < 1e-9, resid
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(cz.FOUR_D))
+def test_4d_examples_gpu(gpu_yr, name):
+    """tests/high_dim/4d_examples.py: roots by residual (threshold line 2.22e-13 of the script) and, where the reference's
+    own output is committed, the same roots."""
+    funcs = cz.FOUR_D[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        roots = np.asarray(gpu_yr.solve(funcs, -np.ones(4), np.ones(4)), float).reshape(-1, 4)
+    if len(roots):
+        resid = max(float(np.max(np.abs(f(*roots.T)))) for f in funcs)
+        assert resid < cz.FOUR_D_RESIDUAL, (name, resid)
+    z = H.load("solves_r2.npz")
+    if f"{name}_roots" in z.files:
+        want = z[f"{name}_roots"]
+        assert len(roots) == len(want), (name, len(roots), len(want))
+        if len(want):
+            H.match_points(want, roots, H.ROOT_TOL)
+
+
+# ---- bounding boxes of the Chebfun2 suite (returnBoundingBoxes is part of the drop-in contract) -----------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("tid", [t for t in cc.IDS if t not in cc.COUNT_EXEMPT])
+def test_chebfun_bounding_boxes_gpu(gpu_yr, tid):
+    z = H.load("solves_chebfun.npz")
+    funcs, a, b = cc.system(tid)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        roots, boxes = gpu_yr.solve(funcs, a, b, returnBoundingBoxes=True)
+    want_r, want_b = z[f"roots_{tid}"], z[f"boxes_{tid}"]
+    scale = max(np.max(np.abs(a)), np.max(np.abs(b)))
+    tol = {"1.2": 1e-7, "7.2": 1e-8}.get(tid, H.ROOT_TOL)
+    roots = np.asarray(roots, float).reshape(-1, 2)
+    assert len(roots) == len(want_r)
+    H.match_boxes(want_r / scale, want_b / scale, roots / scale, np.asarray(boxes, float) / scale, tol)
+    for r, bx in zip(roots, np.asarray(boxes, float)):
+        assert np.all(bx[:, 0] <= r) and np.all(r <= bx[:, 1])
