@@ -61,6 +61,9 @@
 #ifndef YR_F2_EPI
 #define YR_F2_EPI YR_DEV
 #endif
+#ifndef YR_F2_SKIP_DEAD
+#define YR_F2_SKIP_DEAD 1
+#endif
 
 namespace yr {
 namespace f2 {
@@ -510,18 +513,39 @@ YR_HD void store_epilogue(Work& w, int p, const Epilogue& ep, double sumabs) {
         if (rem > 3) { dl[3 * (STRIDE_OUT_L)] = l3; du[3 * (STRIDE_OUT_U)] = u3; asl += fabs(l3); asu += fabs(u3); } \
     }
 
-// warp teams: fiber per lane; either output may be src (in place: a block's stores follow all of its loads);
-// dstL != dstU; same strides everywhere
+// warp teams: items (row block, fiber) handed to the lanes in waves, block-major.  Either output may be src (in place):
+// within a wave every lane finishes its loads before any lane stores (team barrier), and a later wave only reads rows
+// >= 4b' of its own fiber, which earlier waves (blocks b <= b') have not written.  dstL != dstU; same strides everywhere.
 template <bool FMA, class Team>
 YR_DEV void pass_fiber_dual(Team& tm, const double* src, double* dstL, double* dstU, int sk, int sf, int n, int r, int F,
                             const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
     const int B = (r + 3) >> 2;
+    const int items = B * F, W = tm.nthreads;
     double asl = 0.0, asu = 0.0;
-    for (int f = tm.tid; f < F; f += tm.nthreads) {
-        for (int b = 0; b < B; ++b) {
-            const int i0 = b << 2;
-            YR_F2_DUAL_BLOCK(src + f * sf + i0 * sk, dstL + f * sf + i0 * sk, dstU + f * sf + i0 * sk, sk, sk)
+    int b = 0, f = tm.tid;
+    while (f >= F && b < B) { f -= F; ++b; }
+    for (int w0 = 0; w0 < items; w0 += W) {
+        const bool have = b < B;
+        const int i0 = b << 2;
+        double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0, u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+        if (have) {
+            const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));
+            const double* s = src + f * sf + i0 * sk;
+            int k = i0;
+            for (; k + 1 < n; k += 2) { YR_F2_DUAL_STEP(1.0) YR_F2_DUAL_STEP(-1.0) }
+            if (k < n) YR_F2_DUAL_STEP(1.0)
         }
+        tm.wsync();
+        if (have) {
+            const int rem = r - i0;
+            double* dl = dstL + f * sf + i0 * sk; double* du = dstU + f * sf + i0 * sk;
+            dl[0] = l0; du[0] = u0; asl += fabs(l0); asu += fabs(u0);
+            if (rem > 1) { dl[sk] = l1; du[sk] = u1; asl += fabs(l1); asu += fabs(u1); }
+            if (rem > 2) { dl[2 * sk] = l2; du[2 * sk] = u2; asl += fabs(l2); asu += fabs(u2); }
+            if (rem > 3) { dl[3 * sk] = l3; du[3 * sk] = u3; asl += fabs(l3); asu += fabs(u3); }
+        }
+        f += W;
+        while (f >= F && b < B) { f -= F; ++b; }
     }
     if (tm.tid == 0) macs += 2ull * (unsigned)(F * (r * n - r * (r - 1) / 2));
     tm.sum2_sync(asl, asu, sumL, sumU);
@@ -841,24 +865,28 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
     }
 }
 
-// ---- warp teams: in-place, fiber per lane -----------------------------------------------------------------
-// Lane f owns fiber f and walks its row blocks in ascending order: block b reads source rows >= 4b and then
-// overwrites rows 4b..4b+3, which no later block reads -- so a pass can run in place (dst == src), every lane
-// has the same trip count, and a box needs one tensor region instead of three.  dst may also be another region
-// (same strides).  Returns the team-wide sum|dst|; ends with the team barrier.
+// ---- warp teams: in-place, items (row block, fiber) in waves ------------------------------------------------------
+// Block b of a fiber reads source rows >= 4b and then overwrites rows 4b..4b+3, which no later block reads -- so a
+// pass can run in place (dst == src) and a box needs one tensor region instead of three.  Items are handed to the lanes
+// block-major, one wave of `lanes` items at a time: every lane of a wave finishes its loads before any lane stores
+// (team barrier), later waves never read what earlier waves wrote.  A tensor with fewer fibers than lanes (the
+// typical restricted box) still fills the team.  dst may also be another region (same strides).  Returns the team-wide
+// sum|dst|; ends with the team barrier.
 template <bool FMA, class Team>
 YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int sf, int n, int r, int F,
                          const double* Cp, int nt, unsigned long long& macs) {
     const int B = (r + 3) >> 2;
+    const int items = B * F, W = tm.nthreads;
     double asum = 0.0;
-    for (int f = tm.tid; f < F; f += tm.nthreads) {
-        const double* sc = src + f * sf;
-        double* dc = dst + f * sf;
-        for (int b = 0; b < B; ++b) {
-            const int i0 = b << 2;
+    int b = 0, f = tm.tid;
+    while (f >= F && b < B) { f -= F; ++b; }
+    for (int w0 = 0; w0 < items; w0 += W) {
+        const bool have = b < B;
+        const int i0 = b << 2;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (have) {
             const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));
-            const double* s = sc + i0 * sk;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double* s = src + f * sf + i0 * sk;
 #pragma unroll 2
             for (int k = i0; k < n; ++k) {
                 const double x = *s; s += sk;
@@ -866,13 +894,18 @@ YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int s
                 if (FMA) { a0 = fma(c01.x, x, a0); a1 = fma(c01.y, x, a1); a2 = fma(c23.x, x, a2); a3 = fma(c23.y, x, a3); }
                 else { a0 = a0 + c01.x * x; a1 = a1 + c01.y * x; a2 = a2 + c23.x * x; a3 = a3 + c23.y * x; }
             }
-            double* d = dc + i0 * sk;
+        }
+        tm.wsync();
+        if (have) {
+            double* d = dst + f * sf + i0 * sk;
             const int rem = r - i0;
             d[0] = a0; asum += fabs(a0);
             if (rem > 1) { d[sk] = a1; asum += fabs(a1); }
             if (rem > 2) { d[2 * sk] = a2; asum += fabs(a2); }
             if (rem > 3) { d[3 * sk] = a3; asum += fabs(a3); }
         }
+        f += W;
+        while (f >= F && b < B) { f -= F; ++b; }
     }
     if (tm.tid == 0) macs += (unsigned long long)(unsigned)(F * (r * n - r * (r - 1) / 2));
     return tm.sum_sync(asum);
@@ -881,7 +914,7 @@ YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int s
 // tensor view (r0 x r1, row stride ld) in shared memory -> arena, re-laid out with row stride ld_out
 template <class Team>
 YR_DEV void copy_out_rows(Team& tm, double* dst, int ld_out, const double* M, int ld, int r0, int r1) {
-    if (ld_out == ld) { copy_flat(tm, dst, M, tensor_doubles(r0, ld)); return; }
+    if (ld_out == ld) { tm.store_async(dst, M, tensor_doubles(r0, ld)); return; }      // asynchronous: tm.store_wait() before M is reused
     // four lanes per row (one 32-byte sector per store), nthreads / 4 rows per sweep: two counted loops, no index
     // arithmetic per element
     const int cg = tm.nthreads >= 4 ? 4 : tm.nthreads;             // lanes per row (teams are powers of two)
@@ -969,6 +1002,7 @@ YR_DEV void restrict_box_w(Team& tm, const Args& a, unsigned int b, double* slic
             wk.off[p] = out_off; wk.ld[p] = ld_out;
         }
         out_off += (unsigned long long)osz;
+        tm.store_wait();
         tm.sync();                                               // tensor 0 has left A before tensor 1 arrives
     }
     if (tm.tid == 0) { wk.op = kTNone; wk.copy_only = 0; wk.trim_valid = 1; }
@@ -1004,6 +1038,7 @@ YR_DEV void subdivide_box_w(Team& tm, const Args& a, unsigned int b, double* sli
     tm.copy_async(slice, a.data_in + wk.off[0], sz0);           // tensor 0 arrives while the child records are written
     if (tm.tid < nchild) child_record(tm, a, rec, wk, (unsigned int)(cbase + tm.tid), tm.tid, k, split_axes);
     double* S = slice; double* L = slice + T; double* X = slice + 2 * T;
+    unsigned dead_children = 0;                                  // children already known to fail the constant check
     for (int p = 0; p < 2; ++p) {
         const int n0 = shp[p][0], n1 = shp[p][1], ld = wk.ld[p];
         if (p == 1) tm.copy_async(S, a.data_in + wk.off[1], sz1);
@@ -1075,11 +1110,23 @@ YR_DEV void subdivide_box_w(Team& tm, const Args& a, unsigned int b, double* sli
                 // canonical child: split axes ascending, smallest axis most significant
                 const int c = (k == 1) ? h1 : ((rank0 == 0) ? ((h1 << 1) | h2) : ((h2 << 1) | h1));
                 const int r0 = shO[h2][0], r1 = shO[h2][1];
-                const int ld_out = odd_ld(r1);
+                const int ld_out = odd_ld(r1);        // children are re-laid out tightly (keeping the parent's stride: +3 % step time, profiles/r02_experiments.txt)
                 const unsigned long long off = dbase + per_child * c + (p ? (unsigned long long)sz0 : 0ull);
                 Epilogue ep;
-                tensor_epilogue(tm, outs[h2], r0, r1, ld, sumO[h2], terr, prm, ep);
-                copy_out_rows(tm, a.data_out + off, ld_out, outs[h2], ld, r0, r1);
+                // A child the constant check (:1213) is going to discard needs neither its trim outcome nor its tensors
+                // in the arena: the scalar step repeats the same comparison on the same numbers (sum|M|, c0, error)
+                // and drops the box before anything else is read.  About a quarter of all children end here.
+                const double c0 = outs[h2][0];
+                const bool dead_now = YR_F2_SKIP_DEAD && prm.constant_check && (fabs(c0) > sumO[h2] - fabs(c0) + terr);
+                if (dead_now) dead_children |= 1u << c;
+                const bool dead = (dead_children >> c) & 1u;
+                if (!dead) {
+                    tensor_epilogue(tm, outs[h2], r0, r1, ld, sumO[h2], terr, prm, ep);
+                    copy_out_rows(tm, a.data_out + off, ld_out, outs[h2], ld, r0, r1);
+                } else {
+                    for (int q = 0; q < 6; ++q) ep.low[q] = 0.0;
+                    ep.low[0] = c0; ep.t0 = r0; ep.t1 = r1; ep.tsum = sumO[h2]; ep.terr = terr;
+                }
                 if (tm.tid == 0) {
                     const unsigned int child = (unsigned int)(cbase + c);
                     Work& ow = a.work[child]; BoxRec<2>& orec = a.recs[child];
@@ -1088,6 +1135,7 @@ YR_DEV void subdivide_box_w(Team& tm, const Args& a, unsigned int b, double* sli
                     ow.off[p] = off; ow.ld[p] = ld_out;
                 }
             }
+            tm.store_wait();
             tm.sync();                                           // X (and H) have left for the arena
         }
     }

@@ -40,6 +40,42 @@ __device__ __forceinline__ void copy_async16(double* dst, const double* src, int
     __pipeline_commit();
 }
 
+// ---- TMA bulk copies (cp.async.bulk, sm_90+): one lane moves a whole tensor between an arena and shared memory ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Measured on the bench workload (profiles/r02_experiments.txt): bulk STORES of finished tensors are a small gain
+// (one issuing lane instead of a copy loop), bulk LOADS of these 1-3 KB tensors are a loss against LDGSTS (the team
+// waits on the mbarrier for longer than the per-lane copies take).
+#ifndef YR_F2_TMA_LOAD
+#define YR_F2_TMA_LOAD 0
+#endif
+#ifndef YR_F2_TMA_STORE
+#define YR_F2_TMA_STORE 1
+#endif
+
 // A team of LANES (32 or 16) lanes of one warp.  Two 16-lane teams share a warp: they run the same instruction
 // stream on different boxes (every shuffle / vote / barrier names only the team's own lanes), which halves the
 // per-box instruction cost of everything that cannot fill 32 lanes anyway (small boxes).
@@ -48,6 +84,9 @@ struct WarpTeam {
     static constexpr bool kShuffle = true;
     int tid, nthreads, lane, lanes, warp, warps;
     unsigned mask;
+    uint64_t* bar;            // the team's mbarrier (TMA loads)
+    uint32_t phase;           // its parity
+    bool tma_pending, store_pending;
     __device__ __forceinline__ void sync() { __syncwarp(mask); }
     __device__ __forceinline__ void wsync() { __syncwarp(mask); }
     __device__ __forceinline__ double wsum(double v) {
@@ -67,14 +106,48 @@ struct WarpTeam {
     __device__ __forceinline__ int wshfl_idx(int v, int src, int w) { return __shfl_sync(mask, v, src, w < LANES ? w : LANES); }
     __device__ __forceinline__ unsigned long long bcast(unsigned long long v) { return __shfl_sync(mask, v, 0, LANES); }
     __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
-    __device__ __forceinline__ void copy_async(double* dst, const double* src, int n_even) { copy_async16(dst, src, n_even, tid, LANES); }
-    __device__ __forceinline__ void copy_wait() { __pipeline_wait_prior(0); }
+    // global -> shared, both 16-byte aligned, n_even even.  The team must have synchronised after its last use of dst.
+    __device__ __forceinline__ void copy_async(double* dst, const double* src, int n_even) {
+        if (YR_F2_TMA_LOAD && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && n_even > 0) {
+            if (tid == 0) {
+                fence_proxy_async();                      // earlier generic-proxy accesses to dst are ordered before the bulk write
+                mbar_arrive_expect_tx(bar, (uint32_t)n_even * 8u);
+                tma_bulk_g2s(dst, src, (uint32_t)n_even * 8u, bar);
+            }
+            tma_pending = true;
+        } else copy_async16(dst, src, n_even, tid, LANES);
+    }
+    __device__ __forceinline__ void copy_wait() {
+        if (tma_pending) { while (!mbar_try_wait(bar, phase)) {} phase ^= 1u; tma_pending = false; }
+        __pipeline_wait_prior(0);
+    }
+    // shared -> global of a flat block; the caller's data must be complete in shared memory (this synchronises the team)
+    __device__ __forceinline__ void store_async(double* dst, const double* src, int n_even) {
+        if (YR_F2_TMA_STORE && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && n_even > 0) {
+            __syncwarp(mask);
+            if (tid == 0) { fence_proxy_async(); tma_bulk_s2g(dst, src, (uint32_t)n_even * 8u); }
+            store_pending = true;
+        } else {
+            const double2* s2 = reinterpret_cast<const double2*>(src); double2* d2 = reinterpret_cast<double2*>(dst);
+            if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) for (int e = tid; e < (n_even >> 1); e += LANES) d2[e] = s2[e];
+            else for (int e = tid; e < n_even; e += LANES) dst[e] = src[e];
+        }
+    }
+    // the shared-memory sources of every store_async so far may be overwritten after this
+    __device__ __forceinline__ void store_wait() {
+        if (store_pending) { if (tid == 0) tma_store_wait_read(); store_pending = false; }
+    }
+    __device__ __forceinline__ void store_drain() { if (tid == 0) tma_store_wait_all(); }
 };
 template <int LANES>
-__device__ __forceinline__ WarpTeam<LANES> make_warp_team() {
+__device__ __forceinline__ WarpTeam<LANES> make_warp_team(uint64_t* bars) {
     WarpTeam<LANES> tm;
     tm.tid = tm.lane = threadIdx.x & (LANES - 1); tm.nthreads = tm.lanes = LANES; tm.warp = 0; tm.warps = 1;
     tm.mask = LANES == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+    tm.bar = bars + threadIdx.x / LANES; tm.phase = 0; tm.tma_pending = false; tm.store_pending = false;
+    if (tm.tid == 0) mbar_init(tm.bar, 1);
+    fence_mbar_init();
+    __syncthreads();
     return tm;
 }
 
@@ -126,6 +199,8 @@ struct CtaTeam {
     __device__ __forceinline__ unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
     __device__ __forceinline__ void copy_async(double* dst, const double* src, int n_even) { copy_async16(dst, src, n_even, tid, nthreads); }
     __device__ __forceinline__ void copy_wait() { __pipeline_wait_prior(0); }
+    __device__ __forceinline__ void store_async(double* dst, const double* src, int n_even) { for (int e = tid; e < n_even; e += nthreads) dst[e] = src[e]; }
+    __device__ __forceinline__ void store_wait() {}
 };
 __device__ __forceinline__ CtaTeam make_cta_team(CtaShared* sh) {
     CtaTeam tm; tm.tid = threadIdx.x; tm.nthreads = blockDim.x; tm.lane = threadIdx.x & 31; tm.lanes = 32;
@@ -161,9 +236,10 @@ __global__ void __launch_bounds__(128, YR_F2_WARP_MINB) f2_tensor_warp(const Arg
     double* smat = dyn;
     int smat_doubles = 0;
     if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a, smat, snt); }
+    __shared__ uint64_t team_bars[8];
     const int w = threadIdx.x / LANES;
     double* slice = dyn + smat_doubles + (size_t)w * slice_doubles;
-    WarpTeam<LANES> tm = make_warp_team<LANES>();
+    WarpTeam<LANES> tm = make_warp_team<LANES>(team_bars);
     // The grid is one resident wave; teams take boxes from the queue one at a time (boxes of a class still differ in
     // cost), always holding the NEXT position already so that its records can be prefetched.
     unsigned long long macs = 0;

@@ -367,6 +367,8 @@ struct F2Team {
     unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
     void copy_async(double* dst, const double* src, int n_even) { for (int e = tid; e < n_even; e += nthreads) dst[e] = src[e]; }
     void copy_wait() {}
+    void store_async(double* dst, const double* src, int n_even) { sync(); for (int e = tid; e < n_even; e += nthreads) dst[e] = src[e]; }
+    void store_wait() {}
 };
 
 struct F2At {

@@ -117,21 +117,22 @@ def corner_system(seed, dim=2, deg=3):
     return Ms
 
 
-def match_boxes(want_roots, want_boxes, got_roots, got_boxes, tol):
-    """Pairs roots like match_points and compares the bounding box reported with each (max-norm on the endpoints)."""
-    want_roots = np.asarray(want_roots, float).reshape(len(want_boxes), -1)
-    got_roots = np.asarray(got_roots, float).reshape(len(got_boxes), -1)
+def match_boxes(want_roots, want_boxes, got_roots, got_boxes, tol, rel=0.05):
+    """Pairs the reported bounding boxes by their centres and compares the endpoints (max-norm).  (Roots are not used for
+    the pairing: a box with possibleDuplicateRoots reports several roots.)"""
+    want_boxes, got_boxes = np.asarray(want_boxes, float), np.asarray(got_boxes, float)
     assert len(want_boxes) == len(got_boxes), (len(want_boxes), len(got_boxes))
     worst = 0.0
-    used = np.zeros(len(got_roots), dtype=bool)
-    for r, bx in zip(want_roots, np.asarray(want_boxes, float)):
-        d = np.max(np.abs(got_roots - r), axis=1)
+    used = np.zeros(len(got_boxes), dtype=bool)
+    gc = got_boxes.mean(axis=2)
+    for bx in want_boxes:
+        d = np.max(np.abs(gc - bx.mean(axis=1)), axis=1)
         d[used] = np.inf
         j = int(np.argmin(d))
         used[j] = True
-        diff = float(np.max(np.abs(np.asarray(got_boxes[j], float) - bx)))
+        diff = float(np.max(np.abs(got_boxes[j] - bx)))
         # a reported box is itself an error bound: endpoints agree to `tol` plus a few per cent of the reference box's width
-        lim = tol + 0.05 * float(np.max(bx[:, 1] - bx[:, 0]))
-        assert diff < lim, f"bounding box of root {r} differs by {diff} (limit {lim})"
+        lim = tol + rel * float(np.max(bx[:, 1] - bx[:, 0]))
+        assert diff < lim, f"bounding box {bx.tolist()} differs by {diff} (limit {lim})"
         worst = max(worst, diff)
     return worst
