@@ -134,6 +134,50 @@ def workload_config(args, systems_per_step):
             "arithmetic": "fma" if args.fma else "separately rounded mul/add (restrictions bit-identical to the reference)"}
 
 
+def run_strong(args, rank, world, eng):
+    """Box-level multi-GPU mode: one fixed batch, its frontier sharded over the ranks (rootfinding_b200.distributed.
+    solve_sharded: queue lengths all-gathered every `--every` rounds, surplus boxes shipped with NCCL send/recv).  Timed with
+    CUDA events on each rank's stream from the first level-0 launch to the arrival of the broadcast roots, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from rootfinding_b200.distributed import solve_sharded
+    from rootfinding_b200.workloads import rand_coeffs
+    np.random.seed(2)
+    arr = rand_coeffs(DIM, args.strong_degree, args.strong_systems, "randn")
+    systems = [[np.ascontiguousarray(m) for m in arr[s]] for s in range(args.strong_systems)]
+    errs = [np.full(DIM, 2.0 ** -52)] * len(systems)
+    total_ms, boxes, info, solve_ms, asm_ms = 0.0, 0, None, 0.0, 0.0
+    for it in range(args.warmup + args.steps):
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        roots, info = solve_sharded(systems, errs, every=args.every, use_fma=bool(args.fma), return_stats=True, start=args.strong_start)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        if it >= args.warmup:
+            total_ms += e0.elapsed_time(e1)
+            boxes += info["boxes"]
+            solve_ms += info["solve_ms"]; asm_ms += info["assemble_ms"]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0])
+        # value: the sharded search itself (H2D of the coefficients, level-0 boxes, every frontier round and rebalance; slowest
+        # rank, host clock bracketed by stream synchronisations); e2e: the whole call, CUDA events, incl. the record gather
+        # to rank 0, the serial tree bookkeeping there and the broadcast of the roots
+        print_line({"metric": METRIC, "value": boxes / (solve_ms * 1e-3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": solve_ms / args.steps,
+                    "e2e": {"value": boxes / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps, "assemble_ms_per_step": asm_ms / args.steps}, "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f64", "data": "synthetic", "mode": "strong",
+                    "config": {"workload": f"ONE batch of {args.strong_systems} random dense 2-D degree-{args.strong_degree} systems "
+                                           f"(rand_coeffs, seed 2), frontier sharded over the GPUs, rebalanced every {args.every} rounds, start={args.strong_start}",
+                               "dim": DIM, "degree": args.strong_degree, "systems_total": args.strong_systems},
+                    "detail": {"roots": int(sum(len(r) for r in roots)), "boxes_per_step": info["boxes"], "boxes_per_rank": info["boxes_per_rank"],
+                               "boxes_moved_per_step": info["boxes_moved"], "bytes_moved_per_step": info["bytes_moved"],
+                               "rebalances_per_step": info["rebalances"]}})
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +187,14 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("YR_BENCH_BATCH", "1024")))
     ap.add_argument("--fma", type=int, default=int(os.environ.get("YR_BENCH_FMA", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
+                    help="strong: a FIXED batch of few large systems, its frontier sharded over the GPUs with NCCL "
+                         "load rebalancing (documented side measurement, not the headline)")
+    ap.add_argument("--strong-systems", type=int, default=8)
+    ap.add_argument("--strong-degree", type=int, default=100)
+    ap.add_argument("--every", type=int, default=2, help="strong mode: rounds between two rebalancing points")
+    ap.add_argument("--strong-start", default="round_robin", choices=["round_robin", "rank0"],
+                    help="strong mode: who starts the systems (rank0: the rebalancer has to spread the whole frontier)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -168,7 +220,12 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.mode == "strong":
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{29400 + os.getpid() % 500}", rank=0, world_size=1,
+                                device_id=torch.device("cuda", local_rank))
     eng = get_engine()
+    if args.mode == "strong":
+        return run_strong(args, rank, world, eng)
     systems, errs = workload(args.batch, seed=2 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 

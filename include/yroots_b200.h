@@ -173,6 +173,30 @@ typedef struct yr_frontier_out {
 } yr_frontier_out;
 
 int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream);
+
+/* The same solve in resumable pieces: yr_frontier_solve == begin + advance(0) + finish.  Between two advance calls the
+ * host may move queued boxes to another process' frontier -- the box-level multi-GPU mode (one system's frontier
+ * sharded over the GPUs of a node, SURVEY 8e: sibling boxes are independent, ChebyshevSubdivisionSolver.py:1314-1317).
+ * One solve per process at a time.  n_in may be 0 (a rank that only receives boxes).
+ *   advance   runs rounds until the queues are empty or max_rounds rounds have run (0: no limit)
+ *   export    removes up to n_take queued boxes (tails of the pending queues, every (op, class) in proportion), packs
+ *             BoxRec + Work + both tensors of each into xbuf (device memory, >= yr_frontier_export_bound(n_take) bytes);
+ *             needs at least one completed round
+ *   import    adopts the boxes of such a buffer: records into fresh slots, tensors into the input arena, queue entries
+ *             for their pending tensor op.  parent_node / collector links keep the exporter's global indices
+ *             (yr_frontier_desc.result_base / node_base must give every process its own index range). */
+typedef struct yr_frontier_progress {
+    uint64_t pending, pending_restrict, pending_subdivide;   /* boxes queued for the next round */
+    uint64_t rounds;                                         /* rounds run so far */
+    uint64_t boxes;                                          /* solvePolyRecursive invocations so far */
+    uint64_t arena_doubles;                                  /* coefficient data (doubles) the live boxes occupy, upper bound */
+} yr_frontier_progress;
+int yr_frontier_begin(const yr_frontier_desc* d, void* stream);
+int yr_frontier_advance(uint64_t max_rounds, yr_frontier_progress* p, void* stream);
+uint64_t yr_frontier_export_bound(uint64_t n_take);
+int yr_frontier_export(uint64_t n_take, void* xbuf, uint64_t cap_bytes, uint64_t* n_taken, uint64_t* bytes, void* stream);
+int yr_frontier_import(const void* xbuf, uint64_t bytes, void* stream);
+int yr_frontier_finish(yr_frontier_out* out, void* stream);
 /* 1 when 2-D boxes with extents up to max_extent fit the pipeline's shared-memory budget (else use yr_process_level) */
 int yr_frontier_fits(uint64_t max_extent);
 int yr_frontier_release(yr_frontier_out* out, void* stream);

@@ -66,6 +66,11 @@ class YrFrontierOut(C.Structure):
                 ("rounds", u64), ("launches", u64), ("slots", u64), ("tensor_ms", C.c_double), ("scalar_ms", C.c_double)]
 
 
+class YrFrontierProgress(C.Structure):
+    _fields_ = [("pending", u64), ("pending_restrict", u64), ("pending_subdivide", u64), ("rounds", u64), ("boxes", u64),
+                ("arena_doubles", u64)]
+
+
 # yr_sorted_rec (include/yroots_b200.h)
 SORTED_DTYPE = np.dtype([("index", np.uint32), ("system", np.int32), ("flags", np.uint32), ("collector", np.int32),
                          ("root", np.float64, (2,))])
@@ -80,7 +85,9 @@ COUNTER_BYTES = 8 * len(COUNTER_FIELDS)
 EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_params", "yr_record_layout",
            "yr_workspace_doubles", "yr_level_work_bytes", "yr_static_smem_bytes", "yr_device_limits", "yr_init_boxes", "yr_process_level", "yr_bils_batched",
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
-           "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch"]
+           "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch",
+           "yr_frontier_begin", "yr_frontier_advance", "yr_frontier_export_bound", "yr_frontier_export",
+           "yr_frontier_import", "yr_frontier_finish"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -130,6 +137,18 @@ def bind(lib):
     lib.yr_frontier_fits.restype = C.c_int
     lib.yr_fetch.argtypes = [vp, vp, u64, vp]
     lib.yr_fetch.restype = C.c_int
+    lib.yr_frontier_begin.argtypes = [C.POINTER(YrFrontierDesc), vp]
+    lib.yr_frontier_begin.restype = C.c_int
+    lib.yr_frontier_advance.argtypes = [u64, C.POINTER(YrFrontierProgress), vp]
+    lib.yr_frontier_advance.restype = C.c_int
+    lib.yr_frontier_export_bound.argtypes = [u64]
+    lib.yr_frontier_export_bound.restype = u64
+    lib.yr_frontier_export.argtypes = [u64, vp, u64, C.POINTER(u64), C.POINTER(u64), vp]
+    lib.yr_frontier_export.restype = C.c_int
+    lib.yr_frontier_import.argtypes = [vp, u64, vp]
+    lib.yr_frontier_import.restype = C.c_int
+    lib.yr_frontier_finish.argtypes = [C.POINTER(YrFrontierOut), vp]
+    lib.yr_frontier_finish.restype = C.c_int
     if lib.yr_abi_version() != 1:
         raise RuntimeError("yroots_b200: ABI version mismatch")
     return lib

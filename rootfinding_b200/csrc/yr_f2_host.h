@@ -87,60 +87,171 @@ inline int release(yr_frontier_out* out, void* stream) {
     return 0;
 }
 
-inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) {
+// ---- a solve as a resumable object ----------------------------------------------------------------------------
+// yr_frontier_solve = begin + advance(until empty) + finish.  The pieces are exported on their own
+// (yr_frontier_begin / _advance / _export / _import / _finish) so that a host can stop between rounds, move queued
+// boxes to another process' frontier (multi-GPU load rebalancing: rootfinding_b200/distributed.py) and go on.
+struct Frontier {
+    bool active = false;
+    Args a; Ctl h;
+    unsigned long long n0 = 0, n_boxes = 0, n_results = 0, n_nodes = 0, rounds = 0, launches = 0;
+    unsigned long long result_base0 = 0, node_base0 = 0;
+    unsigned long long in_used = 0;             // doubles of the current input arena in use (valid once own_input)
+    const double* data_in = nullptr;
+    bool own_input = false;                     // data_in is one of our arenas (false: the caller's level-0 pool)
+    int cur = 0, out_arena = 0, in_arena = -1;
+    size_t cap_boxes = 0, cap_results = 0, cap_nodes = 0, per_list[2] = {0, 0};
+    int time_kernels = 0, nt = 0;
+    bool trace = false, phases = false;
+};
+inline Frontier& frontier() { static Frontier f; return f; }
+
+// Exchange buffer of yr_frontier_export / _import (device memory): XHeader, BoxRec<2>[n], Work[n], double data[].
+// Work::off of an exported box is relative to the data section.
+struct XHeader { unsigned long long magic, n_boxes, data_doubles, reserved; };
+constexpr unsigned long long kXMagic = 0x5952463258ull;       // "YRF2X"
+YR_HD size_t xbuf_rec_off() { return sizeof(XHeader); }
+YR_HD size_t xbuf_work_off(unsigned long long n) { return sizeof(XHeader) + (size_t)n * sizeof(BoxRec<2>); }
+YR_HD size_t xbuf_data_off(unsigned long long n) { return xbuf_work_off(n) + (size_t)n * sizeof(Work); }
+struct XTake { unsigned long long first[kOps][kClasses], count[kOps][kClasses]; };
+
+}  // namespace yr_f2_host
+
+namespace yr_f2_backend {
+int to_device(void* dst, const void* src, size_t bytes, void* stream);          // host -> device, synchronises
+// pack the queued boxes named by `take` (positions first .. first + count of the pending lists) into `xbuf`
+int launch_export(const yr::f2::Args& a, const yr_f2_host::XTake& take, unsigned long long n, unsigned char* xbuf, const double* data_in, void* stream);
+// adopt n boxes of `xbuf` as slots slot_base ..: records (offsets shifted by data_base) and queue entries
+int launch_import_x(const yr::f2::Args& a, unsigned long long n, const unsigned char* xbuf, unsigned long long slot_base,
+                    unsigned long long data_base, void* stream);
+}  // namespace yr_f2_backend
+
+namespace yr_f2_host {
+
+// device code shared by both backends --------------------------------------------------------------------------
+// one exported box: records + both tensors into the exchange buffer at data offset `at` (lanes copy in parallel; the
+// caller synchronises them and then lets one lane call export_fix_offsets)
+YR_HD void export_one(const Args& a, unsigned int b, unsigned long long j, unsigned long long n, unsigned char* xbuf,
+                      const double* data_in, int lane, int lanes, unsigned long long at) {
+    const BoxRec<2>& rec = a.recs[b];
+    const Work& wk = a.work[b];
+    const int sz0 = tensor_doubles(rec.shape[0][0], wk.ld[0]), sz1 = tensor_doubles(rec.shape[1][0], wk.ld[1]);
+    double* data = reinterpret_cast<double*>(xbuf + xbuf_data_off(n));
+    for (int e = lane; e < sz0; e += lanes) data[at + e] = data_in[wk.off[0] + e];
+    for (int e = lane; e < sz1; e += lanes) data[at + sz0 + e] = data_in[wk.off[1] + e];
+    unsigned long long* rdst = reinterpret_cast<unsigned long long*>(xbuf + xbuf_rec_off() + (size_t)j * sizeof(BoxRec<2>));
+    const unsigned long long* rsrc = reinterpret_cast<const unsigned long long*>(&rec);
+    for (int e = lane; e < (int)(sizeof(BoxRec<2>) / 8); e += lanes) rdst[e] = rsrc[e];
+    unsigned long long* wd = reinterpret_cast<unsigned long long*>(reinterpret_cast<Work*>(xbuf + xbuf_work_off(n)) + j);
+    const unsigned long long* wsrc = reinterpret_cast<const unsigned long long*>(&wk);
+    for (int e = lane; e < (int)(sizeof(Work) / 8); e += lanes) wd[e] = wsrc[e];
+}
+YR_HD int export_doubles(const Args& a, unsigned int b, int& sz0) {
+    const BoxRec<2>& rec = a.recs[b];
+    const Work& wk = a.work[b];
+    sz0 = tensor_doubles(rec.shape[0][0], wk.ld[0]);
+    return sz0 + tensor_doubles(rec.shape[1][0], wk.ld[1]);
+}
+YR_HD void export_fix_offsets(unsigned long long j, unsigned long long n, unsigned char* xbuf, unsigned long long at, int sz0) {
+    Work* w = reinterpret_cast<Work*>(xbuf + xbuf_work_off(n)) + j;
+    w->off[0] = at; w->off[1] = at + (unsigned long long)sz0;
+}
+// queue position j of an export -> the box it names
+YR_HD unsigned int export_box_of(const Args& a, const XTake& take, unsigned long long j) {
+    for (int o = 0; o < kOps; ++o)
+        for (int c = 0; c < kClasses; ++c) {
+            if (j < take.count[o][c]) return a.lists[o][c][take.first[o][c] + j];
+            j -= take.count[o][c];
+        }
+    return 0u;
+}
+// one imported box: records into slot `slot`, decision for its pending tensor op (thread-serial)
+template <class At>
+YR_HD void import_one(const Args& a, unsigned long long j, unsigned long long n, const unsigned char* xbuf, unsigned int slot,
+                      unsigned long long data_base, Decision& dc, At at) {
+    const BoxRec<2>* rsrc = reinterpret_cast<const BoxRec<2>*>(xbuf + xbuf_rec_off()) + j;
+    const Work* wsrc = reinterpret_cast<const Work*>(xbuf + xbuf_work_off(n)) + j;
+    a.recs[slot] = *rsrc;
+    Work w = *wsrc;
+    w.off[0] += data_base; w.off[1] += data_base;
+    a.work[slot] = w;
+    const BoxRec<2>& rec = a.recs[slot];
+    int T, n0m, n1m; unsigned long long total;
+    box_sizes(rec, w, T, n0m, n1m, total);
+    dc.op = w.op;
+    dc.ext = (unsigned long long)(n0m > n1m ? n0m : n1m);
+    if (w.op == kTRestrict) { pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), a.coarse, a.pol, 0, dc.need, dc.cls); dc.bound = total; }
+    else if (w.op == kTSubdivide) { pick_team(need_subdivide_w(T), need_subdivide(T), a.coarse, a.pol, 1, dc.need, dc.cls); dc.bound = total << w.nsplit; }
+    (void)at;
+}
+
+inline void carve(Frontier& f, DevBuf& buf, size_t per_list) {
+    unsigned int* base = static_cast<unsigned int*>(buf.p);
+    for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) f.a.lists[o][c] = base + (size_t)(o * kClasses + c) * per_list;
+}
+inline void bind_tables(Frontier& f) {
+    Workspace& ws = workspace();
+    f.a.recs = static_cast<BoxRec<2>*>(ws.recs.p); f.a.work = static_cast<Work*>(ws.work.p); f.a.cap_boxes = f.cap_boxes;
+    f.a.results = static_cast<ResultRec<2>*>(ws.results.p); f.a.cap_results = f.cap_results;
+    f.a.nodes = static_cast<NodeRec<2>*>(ws.nodes.p); f.a.cap_nodes = f.cap_nodes;
+}
+inline unsigned long long pending(const Ctl& h) {
+    unsigned long long t = 0;
+    for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) t += h.n_list[o][c];
+    return t;
+}
+
+#define F2_TRY(expr) do { if (expr) { f.active = false; return -1; } } while (0)
+
+inline int begin(const yr_frontier_desc* d, void* stream) {
     namespace be = yr_f2_backend;
-    memset(out, 0, sizeof(*out));
+    Frontier& f = frontier();
+    if (f.active) return fail("yr_frontier_begin: a frontier solve is already in progress (one per process)");
     if (d->dim != 2) return fail("yr_frontier_solve: dim must be 2");
     if (d->prm.exact) return fail("yr_frontier_solve: exact mode is served by yr_process_level");
     const unsigned long long n0 = d->n_in;
-    if (n0 == 0) return 0;
     if (n0 > 0x3FFFFFFFull) return fail("yr_frontier_solve: too many level-0 boxes");
     const int nt = (int)(d->max_extent < 4 ? 4 : d->max_extent);
     if (!fits(d->max_extent)) return fail("yr_frontier_solve: tensors too large for the shared-memory pipeline");
+    f = Frontier();
+    f.active = true; f.n0 = n0; f.nt = nt; f.time_kernels = d->time_kernels;
     be::timer_reset(d->time_kernels);
-    const bool trace = getenv("YR_F2_TRACE") != nullptr;
-    const bool phases = getenv("YR_F2_PHASES") != nullptr;       // coarse host-clock phase summary (synchronises 3 times)
-    double ph[4] = {0, 0, 0, 0};
-    if (phases) be::trace_sync_ms(stream);
+    f.trace = getenv("YR_F2_TRACE") != nullptr;
+    f.phases = getenv("YR_F2_PHASES") != nullptr;       // coarse host-clock phase summary (synchronises)
+    if (f.phases) be::trace_sync_ms(stream);
 
     // Box tables, arenas, queues, matrix tables and the control block persist between solves (grow-only, released
-    // by yr_frontier_trim); result / node arrays belong to the caller of this solve.
+    // by yr_frontier_trim); result / node records accumulate in persistent buffers sized by the (loose) per-round
+    // bounds, the caller gets exactly sized copies at the end.
     Workspace& ws = workspace();
-    DevBuf &recs = ws.recs, &work = ws.work, &tabs = ws.tabs, &ctlbuf = ws.ctlbuf;
-    DevBuf (&arena)[2] = ws.arena; DevBuf (&lists)[2] = ws.lists;
-    // result / node records accumulate in persistent buffers sized by the (loose) per-round bounds; the caller gets
-    // exactly sized copies at the end
-    DevBuf &results = ws.results, &nodes = ws.nodes;
-    auto cleanup = [&](bool) {};
-#define F2_TRY(expr) do { if (expr) { cleanup(false); return -1; } } while (0)
-
     // level-independent subdivision matrices
     const size_t P = (size_t)panel_doubles(nt);
-    F2_TRY(tabs.reserve(4 * P * 8 + 4 * (size_t)nt * 4 + 64, 0, stream, 1.0));
-    double* mats = static_cast<double*>(tabs.p);
+    F2_TRY(ws.tabs.reserve(4 * P * 8 + 4 * (size_t)nt * 4 + 64, 0, stream, 1.0));
+    double* mats = static_cast<double*>(ws.tabs.p);
     int* rows = reinterpret_cast<int*>(mats + 4 * P);
     if (ws.tabs_nt != nt) { F2_TRY(be::launch_tables(mats, rows, nt, stream)); ws.tabs_nt = nt; }
 
-    F2_TRY(ctlbuf.reserve(sizeof(Ctl), 0, stream, 1.0));
-    F2_TRY(be::dev_zero(ctlbuf.p, sizeof(Ctl), stream));
-    size_t cap_boxes = (size_t)(n0 * 8 + 4096);
-    F2_TRY(recs.reserve(cap_boxes * sizeof(BoxRec<2>), 0, stream, 1.0));
-    F2_TRY(work.reserve(cap_boxes * sizeof(Work), 0, stream, 1.0));
-    { const size_t have = recs.cap / sizeof(BoxRec<2>) < work.cap / sizeof(Work) ? recs.cap / sizeof(BoxRec<2>) : work.cap / sizeof(Work); if (have > cap_boxes) cap_boxes = have; }
-    F2_TRY(be::dev_copy(recs.p, d->recs_in, n0 * sizeof(BoxRec<2>), stream));
-    size_t cap_results = (size_t)(n0 * 4 + 1024), cap_nodes = cap_results;
-    F2_TRY(results.reserve(cap_results * sizeof(ResultRec<2>), 0, stream, 1.0));
-    F2_TRY(nodes.reserve(cap_nodes * sizeof(NodeRec<2>), 0, stream, 1.0));
-    if (results.cap / sizeof(ResultRec<2>) > cap_results) cap_results = results.cap / sizeof(ResultRec<2>);
-    if (nodes.cap / sizeof(NodeRec<2>) > cap_nodes) cap_nodes = nodes.cap / sizeof(NodeRec<2>);
+    F2_TRY(ws.ctlbuf.reserve(sizeof(Ctl), 0, stream, 1.0));
+    F2_TRY(be::dev_zero(ws.ctlbuf.p, sizeof(Ctl), stream));
+    f.cap_boxes = (size_t)(n0 * 8 + 4096);
+    F2_TRY(ws.recs.reserve(f.cap_boxes * sizeof(BoxRec<2>), 0, stream, 1.0));
+    F2_TRY(ws.work.reserve(f.cap_boxes * sizeof(Work), 0, stream, 1.0));
+    { const size_t have = ws.recs.cap / sizeof(BoxRec<2>) < ws.work.cap / sizeof(Work) ? ws.recs.cap / sizeof(BoxRec<2>) : ws.work.cap / sizeof(Work); if (have > f.cap_boxes) f.cap_boxes = have; }
+    if (n0) F2_TRY(be::dev_copy(ws.recs.p, d->recs_in, n0 * sizeof(BoxRec<2>), stream));
+    f.cap_results = (size_t)(n0 * 4 + 1024); f.cap_nodes = f.cap_results;
+    F2_TRY(ws.results.reserve(f.cap_results * sizeof(ResultRec<2>), 0, stream, 1.0));
+    F2_TRY(ws.nodes.reserve(f.cap_nodes * sizeof(NodeRec<2>), 0, stream, 1.0));
+    if (ws.results.cap / sizeof(ResultRec<2>) > f.cap_results) f.cap_results = ws.results.cap / sizeof(ResultRec<2>);
+    if (ws.nodes.cap / sizeof(NodeRec<2>) > f.cap_nodes) f.cap_nodes = ws.nodes.cap / sizeof(NodeRec<2>);
 
-    Args a;
+    Args& a = f.a;
     memset(&a, 0, sizeof(a));
-    a.ctl = static_cast<Ctl*>(ctlbuf.p);
+    a.ctl = static_cast<Ctl*>(ws.ctlbuf.p);
     a.tab.nt = nt;
     for (int m = 0; m < 2; ++m) for (int h = 0; h < 2; ++h) { a.tab.mat[m][h] = mats + (size_t)(2 * m + h) * P; a.tab.rows_after[m][h] = rows + (size_t)(2 * m + h) * nt; }
     memcpy(&a.prm, &d->prm, sizeof(a.prm));
     a.result_base = d->result_base; a.node_base = d->node_base;
+    f.result_base0 = d->result_base; f.node_base0 = d->node_base;
     {
         // team policy: warp teams up to these needs (doubles), one CTA per box above; overridable for experiments
         auto env_ull = [](const char* name, unsigned long long dflt) { const char* v = getenv(name); return v ? strtoull(v, nullptr, 10) : dflt; };
@@ -150,121 +261,249 @@ inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) 
         for (int o = 0; o < 2; ++o) if (a.pol.warp_max[o] > kWarp32Max) a.pol.warp_max[o] = kWarp32Max;
         if (a.pol.cta128_max > 7168ull) a.pol.cta128_max = 7168ull;
     }
-
-    Ctl h;                               // host copy of the control block
-    memset(&h, 0, sizeof(h));
-    auto carve_lists = [&](DevBuf& buf, size_t per_list) -> int {
-        if (buf.reserve((size_t)kOps * kClasses * per_list * 4 + 64, 0, stream, 1.25)) return -1;
-        unsigned int* base = static_cast<unsigned int*>(buf.p);
-        for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) a.lists[o][c] = base + (size_t)(o * kClasses + c) * per_list;
-        return 0;
-    };
-    auto bind_tables = [&]() {
-        a.recs = static_cast<BoxRec<2>*>(recs.p); a.work = static_cast<Work*>(work.p); a.cap_boxes = cap_boxes;
-        a.results = static_cast<ResultRec<2>*>(results.p); a.cap_results = cap_results;
-        a.nodes = static_cast<NodeRec<2>*>(nodes.p); a.cap_nodes = cap_nodes;
-    };
-
-    if (phases) ph[0] = be::trace_sync_ms(stream);
+    memset(&f.h, 0, sizeof(f.h));
     // round -1: adopt the level-0 boxes (they arrive packed, from yr_init_boxes) and queue their first pass
-    int cur = 0;
-    F2_TRY(carve_lists(lists[cur], (size_t)n0));
-    bind_tables();
+    f.cur = 0;
+    f.per_list[0] = (size_t)(n0 ? n0 : 1);
+    F2_TRY(ws.lists[0].reserve((size_t)kOps * kClasses * f.per_list[0] * 4 + 64, 0, stream, 1.25));
+    carve(f, ws.lists[0], f.per_list[0]);
+    bind_tables(f);
     a.data_in = d->data_in;
-    F2_TRY(be::launch_import(a, n0, stream));
-    F2_TRY(be::to_host(&h, ctlbuf.p, sizeof(Ctl), stream));
-    unsigned long long n_boxes = n0, n_results = 0, n_nodes = 0;
-    const double* data_in = d->data_in;
+    f.data_in = d->data_in; f.own_input = false; f.in_arena = -1; f.in_used = 0;
+    f.n_boxes = n0; f.launches = 2;
+    if (n0) {
+        F2_TRY(be::launch_import(a, n0, stream));
+        F2_TRY(be::to_host(&f.h, ws.ctlbuf.p, sizeof(Ctl), stream));
+    }
+    f.out_arena = 0;
+    return 0;
+}
+
+// runs rounds until the queues are empty or `max_rounds` rounds have run (0: no limit)
+inline int advance(unsigned long long max_rounds, void* stream) {
+    namespace be = yr_f2_backend;
+    Frontier& f = frontier();
+    if (!f.active) return fail("yr_frontier_advance: no frontier solve in progress");
+    Workspace& ws = workspace();
+    Args& a = f.a; Ctl& h = f.h;
     unsigned int* cur_lists[kOps][kClasses];
-    unsigned long long rounds = 0, launches = 2;
-    int out_arena = 0;
+    unsigned long long done_rounds = 0;
     for (;;) {
         unsigned long long n_res = 0, n_sub = 0;
         for (int c = 0; c < kClasses; ++c) { n_res += h.n_list[0][c]; n_sub += h.n_list[1][c]; }
         if (n_res + n_sub == 0) break;
-        const double t_round0 = phases ? be::host_ms() : 0.0;
-        if (++rounds > 1000000ull) { cleanup(false); return fail("yr_frontier_solve: round loop did not terminate"); }
+        if (max_rounds && done_rounds >= max_rounds) break;
+        ++done_rounds;
+        const double t_round0 = f.phases ? be::host_ms() : 0.0;
+        if (++f.rounds > 1000000ull) { f.active = false; return fail("yr_frontier_solve: round loop did not terminate"); }
         const unsigned long long produced = n_res + 4 * n_sub;            // boxes the scalar step of this round may see
         for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) cur_lists[o][c] = a.lists[o][c];
         // capacities for everything this round can append
-        if (n_boxes + 4 * n_sub > cap_boxes) {
-            const size_t want = (size_t)((n_boxes + 4 * n_sub) * 2) + 4096;
-            F2_TRY(recs.reserve(want * sizeof(BoxRec<2>), n_boxes * sizeof(BoxRec<2>), stream, 1.0));
-            F2_TRY(work.reserve(want * sizeof(Work), n_boxes * sizeof(Work), stream, 1.0));
-            cap_boxes = want;
+        if (f.n_boxes + 4 * n_sub > f.cap_boxes) {
+            const size_t want = (size_t)((f.n_boxes + 4 * n_sub) * 2) + 4096;
+            F2_TRY(ws.recs.reserve(want * sizeof(BoxRec<2>), f.n_boxes * sizeof(BoxRec<2>), stream, 1.0));
+            F2_TRY(ws.work.reserve(want * sizeof(Work), f.n_boxes * sizeof(Work), stream, 1.0));
+            f.cap_boxes = want;
         }
-        if (n_results + produced > cap_results) {
-            const size_t want = (size_t)((n_results + produced) * 2) + 1024;
-            F2_TRY(results.reserve(want * sizeof(ResultRec<2>), n_results * sizeof(ResultRec<2>), stream, 1.0));
-            cap_results = want;
+        if (f.n_results + produced > f.cap_results) {
+            const size_t want = (size_t)((f.n_results + produced) * 2) + 1024;
+            F2_TRY(ws.results.reserve(want * sizeof(ResultRec<2>), f.n_results * sizeof(ResultRec<2>), stream, 1.0));
+            f.cap_results = want;
         }
-        if (n_nodes + produced > cap_nodes) {
-            const size_t want = (size_t)((n_nodes + produced) * 2) + 1024;
-            F2_TRY(nodes.reserve(want * sizeof(NodeRec<2>), n_nodes * sizeof(NodeRec<2>), stream, 1.0));
-            cap_nodes = want;
+        if (f.n_nodes + produced > f.cap_nodes) {
+            const size_t want = (size_t)((f.n_nodes + produced) * 2) + 1024;
+            F2_TRY(ws.nodes.reserve(want * sizeof(NodeRec<2>), f.n_nodes * sizeof(NodeRec<2>), stream, 1.0));
+            f.cap_nodes = want;
         }
-        F2_TRY(arena[out_arena].reserve((size_t)(h.out_bound + 16) * 8, 0, stream, 1.25));
-        F2_TRY(carve_lists(lists[cur ^ 1], (size_t)produced));
-        bind_tables();
-        a.results = static_cast<ResultRec<2>*>(results.p) + n_results; a.cap_results = cap_results - n_results;
-        a.nodes = static_cast<NodeRec<2>*>(nodes.p) + n_nodes; a.cap_nodes = cap_nodes - n_nodes;
-        a.result_base = d->result_base + n_results; a.node_base = d->node_base + n_nodes;
+        F2_TRY(ws.arena[f.out_arena].reserve((size_t)(h.out_bound + 16) * 8, 0, stream, 1.25));
+        f.per_list[f.cur ^ 1] = (size_t)produced;
+        F2_TRY(ws.lists[f.cur ^ 1].reserve((size_t)kOps * kClasses * f.per_list[f.cur ^ 1] * 4 + 64, 0, stream, 1.25));
+        carve(f, ws.lists[f.cur ^ 1], f.per_list[f.cur ^ 1]);
+        bind_tables(f);
+        a.results = static_cast<ResultRec<2>*>(ws.results.p) + f.n_results; a.cap_results = f.cap_results - f.n_results;
+        a.nodes = static_cast<NodeRec<2>*>(ws.nodes.p) + f.n_nodes; a.cap_nodes = f.cap_nodes - f.n_nodes;
+        a.result_base = f.result_base0 + f.n_results; a.node_base = f.node_base0 + f.n_nodes;
         a.coarse = (produced < 8192ull) ? 1 : 0;
-        a.data_in = data_in; a.data_out = static_cast<double*>(arena[out_arena].p); a.cap_data_out = arena[out_arena].cap / 8;
+        a.data_in = f.data_in; a.data_out = static_cast<double*>(ws.arena[f.out_arena].p); a.cap_data_out = ws.arena[f.out_arena].cap / 8;
         // per-round part of the control block: queues, bounds, arena cursor; slot counters restart at their totals
-        F2_TRY(be::dev_zero(ctlbuf.p, offsetof(Ctl, n_boxes), stream));
+        F2_TRY(be::dev_zero(ws.ctlbuf.p, offsetof(Ctl, n_boxes), stream));
         F2_TRY(be::dev_zero(&a.ctl->n_results, 2 * sizeof(unsigned long long), stream));
-        if (trace) fprintf(stderr, "f2 round %3llu: host %.3f ms |", rounds, be::trace_sync_ms(stream));
+        if (f.trace) fprintf(stderr, "f2 round %3llu: host %.3f ms |", f.rounds, be::trace_sync_ms(stream));
         be::timer_mark(0, 1, stream);
         be::round_fork(stream);
         for (int o = kOps - 1; o >= 0; --o)
             for (int c = 0; c < kClasses; ++c) {
                 if (!h.n_list[o][c]) continue;
-                if (h.need_max[o][c] + (o ? 2ull * panel_doubles((int)(h.ext_max[c] < 4 ? 4 : h.ext_max[c])) : 0ull) > kMaxNeed) { cleanup(false); return fail("yr_frontier_solve: a box exceeds the shared-memory budget"); }
+                if (h.need_max[o][c] + (o ? 2ull * panel_doubles((int)(h.ext_max[c] < 4 ? 4 : h.ext_max[c])) : 0ull) > kMaxNeed) { f.active = false; return fail("yr_frontier_solve: a box exceeds the shared-memory budget"); }
                 F2_TRY(be::launch_tensor(a, o == 0 ? (int)kTRestrict : (int)kTSubdivide, c, cur_lists[o][c], h.n_list[o][c],
                                          h.need_max[o][c], (int)(o ? h.ext_max[c] : 0), stream));
-                ++launches;
-                if (trace) fprintf(stderr, " %s%d n=%llu need=%llu ext=%llu %.3f ms |", o ? "S" : "R", c, h.n_list[o][c], h.need_max[o][c], o ? h.ext_max[c] : 0ull, be::trace_sync_ms(stream));
+                ++f.launches;
+                if (f.trace) fprintf(stderr, " %s%d n=%llu need=%llu ext=%llu %.3f ms |", o ? "S" : "R", c, h.n_list[o][c], h.need_max[o][c], o ? h.ext_max[c] : 0ull, be::trace_sync_ms(stream));
             }
         be::round_join(stream);
         be::timer_mark(0, 0, stream);
         be::Segments sg;
         for (int c = 0; c < kClasses; ++c) { sg.list[c] = cur_lists[0][c]; sg.n[c] = h.n_list[0][c]; }
-        sg.child_lo = n_boxes; sg.child_bound = 4 * n_sub;
+        sg.child_lo = f.n_boxes; sg.child_bound = 4 * n_sub;
         be::timer_mark(1, 1, stream);
         F2_TRY(be::launch_scalar(a, sg, stream));
         be::timer_mark(1, 0, stream);
-        ++launches;
-        if (trace) fprintf(stderr, " scalar %.3f ms\n", be::trace_sync_ms(stream));
-        const double t_issue = phases ? be::host_ms() : 0.0;
-        F2_TRY(be::to_host(&h, ctlbuf.p, sizeof(Ctl), stream));
-        if (phases) { const double t_done = be::host_ms(); fprintf(stderr, " r%llu:%.2f+%.2f", rounds, t_issue - t_round0, t_done - t_issue); }
-        if (h.overflow) { cleanup(false); return fail("yr_frontier_solve: internal buffer overflow"); }
-        if (h.bad_mid) { cleanup(false); return fail("yr_frontier_solve: unexpected split point (nextTransformPoints)"); }
-        n_boxes = h.n_boxes; n_results += h.n_results; n_nodes += h.n_nodes;
-        data_in = a.data_out;
-        out_arena ^= 1; cur ^= 1;
+        ++f.launches;
+        if (f.trace) fprintf(stderr, " scalar %.3f ms\n", be::trace_sync_ms(stream));
+        const double t_issue = f.phases ? be::host_ms() : 0.0;
+        F2_TRY(be::to_host(&h, ws.ctlbuf.p, sizeof(Ctl), stream));
+        if (f.phases) { const double t_done = be::host_ms(); fprintf(stderr, " r%llu:%.2f+%.2f", f.rounds, t_issue - t_round0, t_done - t_issue); }
+        if (h.overflow) { f.active = false; return fail("yr_frontier_solve: internal buffer overflow"); }
+        if (h.bad_mid) { f.active = false; return fail("yr_frontier_solve: unexpected split point (nextTransformPoints)"); }
+        f.n_boxes = h.n_boxes; f.n_results += h.n_results; f.n_nodes += h.n_nodes;
+        f.data_in = a.data_out; f.own_input = true; f.in_arena = f.out_arena; f.in_used = h.data_used;
+        f.out_arena ^= 1; f.cur ^= 1;
     }
-    out->order = n_results ? be::sort_results(results.p, n_results, stream) : nullptr;
-    if (phases) { ph[2] = be::trace_sync_ms(stream); fprintf(stderr, "f2 phases: setup %.2f ms, sort %.2f ms (%llu rounds, %llu launches)\n", ph[0], ph[2], rounds, launches); }
+    return 0;
+}
+
+inline int finish(yr_frontier_out* out, void* stream) {
+    namespace be = yr_f2_backend;
+    Frontier& f = frontier();
+    memset(out, 0, sizeof(*out));
+    if (!f.active) return fail("yr_frontier_finish: no frontier solve in progress");
+    Workspace& ws = workspace();
+    f.active = false;
+    const unsigned long long n_results = f.n_results, n_nodes = f.n_nodes;
+    double ph2 = 0.0;
+    out->order = n_results ? be::sort_results(ws.results.p, n_results, stream) : nullptr;
+    if (f.phases) { ph2 = be::trace_sync_ms(stream); fprintf(stderr, "f2 phases: sort %.2f ms (%llu rounds, %llu launches)\n", ph2, f.rounds, f.launches); }
     if (n_results) {
         out->results = be::dev_alloc((size_t)n_results * sizeof(ResultRec<2>), stream);
-        if (!out->results || be::dev_copy(out->results, results.p, (size_t)n_results * sizeof(ResultRec<2>), stream)) { release(out, stream); return fail("device allocation failed (results)"); }
+        if (!out->results || be::dev_copy(out->results, ws.results.p, (size_t)n_results * sizeof(ResultRec<2>), stream)) { release(out, stream); return fail("device allocation failed (results)"); }
     }
     if (n_nodes) {
         out->nodes = be::dev_alloc((size_t)n_nodes * sizeof(NodeRec<2>), stream);
-        if (!out->nodes || be::dev_copy(out->nodes, nodes.p, (size_t)n_nodes * sizeof(NodeRec<2>), stream)) { release(out, stream); return fail("device allocation failed (nodes)"); }
+        if (!out->nodes || be::dev_copy(out->nodes, ws.nodes.p, (size_t)n_nodes * sizeof(NodeRec<2>), stream)) { release(out, stream); return fail("device allocation failed (nodes)"); }
     }
     out->n_results = n_results; out->n_nodes = n_nodes;
-    out->rounds = rounds; out->launches = launches; out->slots = n_boxes;
+    out->rounds = f.rounds; out->launches = f.launches; out->slots = f.n_boxes;
     yr_counters& c = out->counters;
+    const Ctl& h = f.h;
     c.n_results = n_results; c.n_nodes = n_nodes; c.boxes = h.boxes; c.zooms = h.zooms; c.subdivisions = h.subdivisions;
     c.discard_const = h.dconst; c.discard_quad = h.dquad; c.discard_zoom = h.dzoom; c.entry_coeffs = h.entry_coeffs;
     c.restrict_macs = h.restrict_macs; c.max_level = h.max_level;
     be::timer_collect(&out->tensor_ms, &out->scalar_ms);
-    cleanup(true);
     return 0;
-#undef F2_TRY
 }
+
+inline int solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) {
+    memset(out, 0, sizeof(*out));
+    if (d->n_in == 0) return 0;
+    if (begin(d, stream)) return -1;
+    if (advance(0, stream)) return -1;
+    return finish(out, stream);
+}
+
+// ---- moving queued boxes between frontiers (multi-GPU load rebalancing) ------------------------------------
+inline unsigned long long xbuf_bytes_bound(unsigned long long n_take) {
+    const Frontier& f = frontier();
+    // every exported tensor lives in the input arena: its used size bounds the data section
+    return (unsigned long long)xbuf_data_off(n_take) + (f.in_used + 2 * n_take + 16) * 8;
+}
+
+// Removes up to n_take queued boxes (the tails of the pending lists, every (op, class) in proportion) and packs them
+// into xbuf.  *n_taken / *bytes: what was written.
+inline int export_boxes(unsigned long long n_take, void* xbuf, unsigned long long cap_bytes, unsigned long long* n_taken,
+                        unsigned long long* bytes, void* stream) {
+    namespace be = yr_f2_backend;
+    Frontier& f = frontier();
+    *n_taken = 0; *bytes = 0;
+    if (!f.active) return fail("yr_frontier_export: no frontier solve in progress");
+    Ctl& h = f.h;
+    const unsigned long long total = pending(h);
+    if (n_take > total) n_take = total;
+    if (!n_take) return 0;
+    if (!f.own_input) return fail("yr_frontier_export: run at least one round first (the level-0 pool belongs to the caller)");
+    if (cap_bytes < xbuf_bytes_bound(n_take)) return fail("yr_frontier_export: exchange buffer too small (yr_frontier_export_bound)");
+    XTake take;
+    unsigned long long got = 0;
+    for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) {
+        take.count[o][c] = (unsigned long long)((long double)h.n_list[o][c] * n_take / total);
+        got += take.count[o][c];
+    }
+    for (int o = 0; o < kOps && got < n_take; ++o) for (int c = 0; c < kClasses && got < n_take; ++c) {
+        const unsigned long long room = h.n_list[o][c] - take.count[o][c];
+        const unsigned long long add = room < n_take - got ? room : n_take - got;
+        take.count[o][c] += add; got += add;
+    }
+    for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) take.first[o][c] = h.n_list[o][c] - take.count[o][c];
+    XHeader hdr = {kXMagic, n_take, 0ull, 0ull};
+    F2_TRY(be::to_device(xbuf, &hdr, sizeof(hdr), stream));
+    F2_TRY(be::launch_export(f.a, take, n_take, static_cast<unsigned char*>(xbuf), f.data_in, stream));
+    F2_TRY(be::to_host(&hdr, xbuf, sizeof(hdr), stream));
+    for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) h.n_list[o][c] -= take.count[o][c];
+    F2_TRY(be::to_device(&f.a.ctl->n_list[0][0], &h.n_list[0][0], sizeof(h.n_list), stream));
+    *n_taken = n_take;
+    *bytes = (unsigned long long)xbuf_data_off(n_take) + hdr.data_doubles * 8;
+    return 0;
+}
+
+// Adopts the boxes of an exchange buffer written by yr_frontier_export (of this or another process).
+inline int import_boxes(const void* xbuf, unsigned long long bytes, void* stream) {
+    namespace be = yr_f2_backend;
+    Frontier& f = frontier();
+    if (!f.active) return fail("yr_frontier_import: no frontier solve in progress");
+    if (bytes < sizeof(XHeader)) return fail("yr_frontier_import: truncated exchange buffer");
+    Workspace& ws = workspace();
+    XHeader hdr;
+    F2_TRY(be::to_host(&hdr, xbuf, sizeof(hdr), stream));
+    if (hdr.magic != kXMagic) return fail("yr_frontier_import: not an exchange buffer");
+    const unsigned long long n = hdr.n_boxes, nd = hdr.data_doubles;
+    if (!n) return 0;
+    if (bytes < xbuf_data_off(n) + nd * 8) return fail("yr_frontier_import: truncated exchange buffer");
+    Ctl& h = f.h;
+    // the imported tensors join the input arena of the next round
+    if (!f.own_input) {
+        // nothing has run here yet: the (possibly empty) level-0 pool is the caller's -- move it into an arena of ours
+        if (f.n0) return fail("yr_frontier_import: run at least one round before importing into a frontier that has level-0 boxes");
+        f.in_arena = f.out_arena ^ 1; f.in_used = 0; f.own_input = true;
+    }
+    DevBuf& ar = ws.arena[f.in_arena];
+    F2_TRY(ar.reserve((size_t)(f.in_used + nd + 16) * 8, (size_t)f.in_used * 8, stream, 1.25));
+    f.data_in = static_cast<const double*>(ar.p);
+    F2_TRY(be::dev_copy(static_cast<double*>(ar.p) + f.in_used, static_cast<const unsigned char*>(xbuf) + xbuf_data_off(n), (size_t)nd * 8, stream));
+    // slots
+    if (f.n_boxes + n > f.cap_boxes) {
+        const size_t want = (size_t)((f.n_boxes + n) * 2) + 4096;
+        F2_TRY(ws.recs.reserve(want * sizeof(BoxRec<2>), f.n_boxes * sizeof(BoxRec<2>), stream, 1.0));
+        F2_TRY(ws.work.reserve(want * sizeof(Work), f.n_boxes * sizeof(Work), stream, 1.0));
+        f.cap_boxes = want;
+    }
+    // queues: every pending list must have room for all incoming boxes
+    unsigned long long longest = 0;
+    for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c) if (h.n_list[o][c] > longest) longest = h.n_list[o][c];
+    if (longest + n > f.per_list[f.cur]) {
+        const size_t per = (size_t)((longest + n) * 3 / 2 + 64);
+        DevBuf fresh;
+        F2_TRY(fresh.reserve((size_t)kOps * kClasses * per * 4 + 64, 0, stream, 1.0));
+        unsigned int* base = static_cast<unsigned int*>(fresh.p);
+        for (int o = 0; o < kOps; ++o) for (int c = 0; c < kClasses; ++c)
+            if (h.n_list[o][c]) F2_TRY(be::dev_copy(base + (size_t)(o * kClasses + c) * per, f.a.lists[o][c], (size_t)h.n_list[o][c] * 4, stream));
+        ws.lists[f.cur].release(stream);
+        ws.lists[f.cur] = fresh;
+        f.per_list[f.cur] = per;
+        carve(f, ws.lists[f.cur], per);
+    }
+    bind_tables(f);
+    f.a.coarse = 0;
+    f.a.data_in = f.data_in;
+    F2_TRY(be::launch_import_x(f.a, n, static_cast<const unsigned char*>(xbuf), f.n_boxes, f.in_used, stream));
+    Ctl now;
+    F2_TRY(be::to_host(&now, ws.ctlbuf.p, sizeof(Ctl), stream));
+    memcpy(h.n_list, now.n_list, sizeof(h.n_list)); memcpy(h.need_max, now.need_max, sizeof(h.need_max));
+    memcpy(h.ext_max, now.ext_max, sizeof(h.ext_max)); h.out_bound = now.out_bound;
+    f.n_boxes += n; f.in_used += nd;
+    // the slot counter on the device is what the next round's subdivisions allocate from
+    F2_TRY(be::to_device(&f.a.ctl->n_boxes, &f.n_boxes, sizeof(unsigned long long), stream));
+    h.n_boxes = f.n_boxes;
+    return 0;
+}
+#undef F2_TRY
 
 }  // namespace yr_f2_host

@@ -385,6 +385,32 @@ __global__ void __launch_bounds__(128) f2_import_kernel(const Args a, unsigned l
     commit_warp(a, (unsigned int)i, dc);
 }
 
+// ---- moving queued boxes between frontiers (yr_frontier_export / _import) ----
+__global__ void __launch_bounds__(128) f2_export_kernel(const Args a, const yr_f2_host::XTake take, unsigned long long n, unsigned char* xbuf,
+                                                        const double* __restrict__ data_in) {
+    const unsigned long long j = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // warp per box
+    const int lane = threadIdx.x & 31;
+    if (j >= n) return;
+    const unsigned int b = yr_f2_host::export_box_of(a, take, j);
+    int sz0;
+    const int tot = yr_f2_host::export_doubles(a, b, sz0);
+    unsigned long long at = 0;
+    if (lane == 0) at = atomicAdd(&reinterpret_cast<yr_f2_host::XHeader*>(xbuf)->data_doubles, (unsigned long long)tot);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    yr_f2_host::export_one(a, b, j, n, xbuf, data_in, lane, 32, at);
+    __syncwarp();
+    if (lane == 0) yr_f2_host::export_fix_offsets(j, n, xbuf, at, sz0);
+}
+
+__global__ void __launch_bounds__(128) f2_import_x_kernel(const Args a, unsigned long long n, const unsigned char* __restrict__ xbuf,
+                                                          unsigned long long slot_base, unsigned long long data_base) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Decision dc;
+    memset(&dc, 0, sizeof(dc));
+    if (i < n) yr_f2_host::import_one(a, i, n, xbuf, (unsigned int)(slot_base + i), data_base, dc, DevAt());
+    commit_warp(a, (unsigned int)(slot_base + i), dc);
+}
+
 // the four level-independent matrices: CTA m builds (mid, half) = (m >> 1, m & 1)
 __global__ void __launch_bounds__(256) f2_tables_kernel(double* mats, int* rows, int nt) {
     __shared__ CtaShared cta_sh;
@@ -522,6 +548,24 @@ int to_host(void* dst, const void* src, size_t bytes, void* stream) {
     cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "device -> host copy");
+}
+
+int to_device(void* dst, const void* src, size_t bytes, void* stream) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "host -> device copy");
+}
+
+int launch_export(const Args& a, const yr_f2_host::XTake& take, unsigned long long n, unsigned char* xbuf, const double* data_in, void* stream) {
+    f2_export_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, take, n, xbuf, data_in);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "f2_export_kernel launch");
+}
+
+int launch_import_x(const Args& a, unsigned long long n, const unsigned char* xbuf, unsigned long long slot_base, unsigned long long data_base, void* stream) {
+    f2_import_x_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, n, xbuf, slot_base, data_base);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "f2_import_x_kernel launch");
 }
 
 int launch_tables(double* mats, int* rows, int nt, void* stream) {
@@ -678,6 +722,7 @@ int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* str
 }
 
 int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
+#include "yr_f2_abi.inc"
 int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
 int yr_frontier_trim(void* stream) { return yr_f2_host::trim_workspace(stream); }
 

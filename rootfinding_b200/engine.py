@@ -328,6 +328,8 @@ class SolveSession:
         # 2-D, plain arithmetic, tensors that fit shared memory: the round-based frontier pipeline serves the session
         self.use_frontier = bool(engine.pipeline == 2 and D == 2 and not prm.exact and self.nsys > 0)
         self._segments = []               # record ranges in production order: ("level", start, count) / ("frontier", start, count, out)
+        self.index_base = 0               # added to every record index the device links with (box-level multi-GPU: rank << 27)
+        self.frontier_runner = None       # replaces _run_frontier (distributed.ShardedFrontier)
 
     # -- growable append-only device arrays ------------------------------------------------
     def _reserve(self, which, want):
@@ -399,9 +401,12 @@ class SolveSession:
         """Solve the given level-0 jobs to completion. Returns (first new result index, count)."""
         D, m, eng = self.dim, self.mem, self.eng
         first_result = self.n_results
+        run_frontier = self.frontier_runner or self._run_frontier
+        if len(jobs["system"]) == 0:                              # a rank that only receives boxes (sharded frontier)
+            return run_frontier(None, None, dict(n_children=0, max_child_extent=0), first_result)
         recs, data, c = self._init_boxes(jobs)
         if self.use_frontier and self.lib.yr_frontier_fits(int(c["max_child_extent"])):
-            return self._run_frontier(recs, data, c, first_result)
+            return run_frontier(recs, data, c, first_result)
         n_in, data_used = c["n_children"], c["data_used"]
         big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
         fan = 1 << D
@@ -434,7 +439,7 @@ class SolveSession:
                 d.cap_results = self.cap_results - self.n_results
                 d.nodes = self.d_nodes.ptr + self.n_nodes * self.ndt.itemsize
                 d.cap_nodes = self.cap_nodes - self.n_nodes
-                d.result_base, d.node_base = self.n_results, self.n_nodes
+                d.result_base, d.node_base = self.index_base + self.n_results, self.index_base + self.n_nodes
                 d.counters, d.prm, d.launch = self.d_counters.ptr, self.prm, L
                 d.pipeline = pipeline
                 d.max_box_doubles, d.max_tensor_doubles, d.max_extent = int(big_box), int(big_tensor), int(big_extent)
@@ -484,22 +489,31 @@ class SolveSession:
             big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
             if self.use_frontier and n_in > 0 and self.lib.yr_frontier_fits(int(big_extent)):
                 # large 2-D systems: the first levels run here, the rest of the search on the frontier pipeline
-                self._run_frontier(recs, data, c, first_result)
+                run_frontier(recs, data, c, first_result)
                 break
         return first_result, self.n_results - first_result
+
+    def frontier_desc(self, recs, data, c, max_extent=None):
+        d = _lib.YrFrontierDesc()
+        d.dim, d.time_kernels = 2, int(bool(self.time_kernels))
+        if recs is not None:
+            d.recs_in, d.data_in = recs.ptr, data.ptr
+        d.n_in = int(c["n_children"])
+        d.max_extent = int(c["max_child_extent"] if max_extent is None else max_extent)
+        d.result_base, d.node_base = self.index_base + self.n_results, self.index_base + self.n_nodes
+        d.prm = self.prm
+        return d
 
     def _run_frontier(self, recs, data, c, first_result):
         """2-D systems: the whole search in one call (include/yroots_b200.h: yr_frontier_solve)."""
         m, lib = self.mem, self.lib
-        d = _lib.YrFrontierDesc()
-        d.dim, d.time_kernels = 2, int(bool(self.time_kernels))
-        d.recs_in, d.data_in, d.n_in = recs.ptr, data.ptr, int(c["n_children"])
-        d.max_extent = int(c["max_child_extent"])
-        d.result_base, d.node_base = self.n_results, self.n_nodes
-        d.prm = self.prm
+        d = self.frontier_desc(recs, data, c)
         out = _lib.YrFrontierOut()
         stream = m.stream()
         _lib.check(lib, lib.yr_frontier_solve(C.byref(d), C.byref(out), stream), "yr_frontier_solve")
+        return self.adopt_frontier_out(out, first_result)
+
+    def adopt_frontier_out(self, out, first_result):
         nres, nnod = int(out.n_results), int(out.n_nodes)
         self._pending.append(out)                                 # records stay on the device until results() / nodes()
         self._segments.append(("frontier", self.n_results, nres, self.n_nodes, nnod, out))

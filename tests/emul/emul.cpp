@@ -401,6 +401,30 @@ int dev_copy(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src,
 int dev_zero(void* p, size_t bytes, void*) { memset(p, 0, bytes); return 0; }
 int to_host(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
 
+int to_device(void* dst, const void* src, size_t bytes, void*) { memcpy(dst, src, bytes); return 0; }
+
+int launch_export(const yr::f2::Args& a, const yr_f2_host::XTake& take, unsigned long long n, unsigned char* xbuf, const double* data_in, void*) {
+    yr_f2_host::XHeader* hdr = reinterpret_cast<yr_f2_host::XHeader*>(xbuf);
+    for (unsigned long long j = 0; j < n; ++j) {
+        const unsigned int b = yr_f2_host::export_box_of(a, take, j);
+        int sz0;
+        const int tot = yr_f2_host::export_doubles(a, b, sz0);
+        const unsigned long long at = hdr->data_doubles; hdr->data_doubles += (unsigned long long)tot;
+        yr_f2_host::export_one(a, b, j, n, xbuf, data_in, 0, 1, at);
+        yr_f2_host::export_fix_offsets(j, n, xbuf, at, sz0);
+    }
+    return 0;
+}
+
+int launch_import_x(const yr::f2::Args& a, unsigned long long n, const unsigned char* xbuf, unsigned long long slot_base, unsigned long long data_base, void*) {
+    for (unsigned long long i = 0; i < n; ++i) {
+        yr::f2::Decision dc; memset(&dc, 0, sizeof(dc));
+        yr_f2_host::import_one(a, i, n, xbuf, (unsigned int)(slot_base + i), data_base, dc, F2At());
+        yr::f2::commit_decision(a, (unsigned int)(slot_base + i), dc, F2At());
+    }
+    return 0;
+}
+
 int launch_tables(double* mats, int* rows, int nt, void*) {
     const int P = yr::f2::panel_doubles(nt);
     for (int m = 0; m < 4; ++m) {
@@ -502,6 +526,7 @@ int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* str
     return yr_f2_host::solve(d, out, stream);
 }
 int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
+#include "../../rootfinding_b200/csrc/yr_f2_abi.inc"
 int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
 int yr_frontier_trim(void* stream) { return yr_f2_host::trim_workspace(stream); }
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void*) { memcpy(host_dst, dev_src, bytes); return 0; }

@@ -136,3 +136,11 @@ def match_boxes(want_roots, want_boxes, got_roots, got_boxes, tol, rel=0.05):
         assert diff < lim, f"bounding box {bx.tolist()} differs by {diff} (limit {lim})"
         worst = max(worst, diff)
     return worst
+
+
+def sharded_cases():
+    """(name, systems) inputs of the box-level multi-GPU tests (tests/test_distributed_gloo.py, test_gpu_parity)."""
+    rs = np.random.RandomState(5)
+    return [("one30", seeded_systems(2, 30, 1)),
+            ("corners", seeded_systems(2, 12, 3) + [corner_system(s, 2, 3) for s in range(6)]),
+            ("extent80", [[rs.randn(80, 3), rs.randn(3, 80)]])]

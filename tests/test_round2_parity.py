@@ -233,3 +233,67 @@ def test_chebfun_bounding_boxes_gpu(gpu_yr, tid):
     boxes = np.asarray(boxes, float)
     for r in roots:                                            # every root lies in one of the reported boxes
         assert np.any(np.all((boxes[:, :, 0] <= r) & (r <= boxes[:, :, 1]), axis=1))
+
+
+# ---- box-level multi-GPU primitives: export / import of queued boxes (include/yroots_b200.h) ----------------------
+def _export_import_roundtrip(yr, engine, systems):
+    """begin -> a few rounds -> export half of the queue -> import it back -> finish: the same roots, the same number
+    of solvePolyRecursive invocations as the plain solve (the moved boxes got new slots and new arena offsets)."""
+    import ctypes as C
+    from rootfinding_b200 import _lib, postpass
+    from rootfinding_b200.distributed import _bytes_tensor
+    S = yr.ChebyshevSubdivisionSolver
+    errs = [np.full(2, 2.0 ** -52)] * len(systems)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, ref = S.solve_batch(systems, errs, engine=engine, return_session=True)
+    sess = engine.session(systems, errs)
+    moved = []
+
+    def runner(recs, data, c, first_result):
+        lib, mem = sess.lib, sess.mem
+        d = sess.frontier_desc(recs, data, c)
+        _lib.check(lib, lib.yr_frontier_begin(C.byref(d), mem.stream()), "begin")
+        prog = _lib.YrFrontierProgress()
+        for _ in range(64):
+            _lib.check(lib, lib.yr_frontier_advance(3, C.byref(prog), mem.stream()), "advance")
+            if not prog.pending:
+                break
+            n = int(prog.pending) // 2
+            if n:
+                cap = int(lib.yr_frontier_export_bound(n))
+                t, ptr, keep = _bytes_tensor(mem, cap)
+                taken, nbytes = C.c_uint64(0), C.c_uint64(0)
+                _lib.check(lib, lib.yr_frontier_export(n, ptr, cap, C.byref(taken), C.byref(nbytes), mem.stream()), "export")
+                assert taken.value == n and 0 < nbytes.value <= cap
+                _lib.check(lib, lib.yr_frontier_import(ptr, nbytes.value, mem.stream()), "import")
+                mem.synchronize()
+                moved.append(n)
+        out = _lib.YrFrontierOut()
+        _lib.check(lib, lib.yr_frontier_finish(C.byref(out), mem.stream()), "finish")
+        return sess.adopt_frontier_out(out, first_result)
+
+    sess.frontier_runner = runner
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sess.run_jobs(sess.unit_jobs())
+        res, keep, dup, extra = postpass.assemble(sess)
+        got, _ = postpass.per_system_roots(res, keep, dup, extra, sess.nsys, sess.dim, sorted_fields=getattr(sess, "sorted_fields", None),
+                                           late_by_system=getattr(sess, "late_by_system", None),
+                                           redo_systems=getattr(sess, "redo_systems", None), alive=getattr(sess, "alive", None))
+    assert moved and sum(moved) > 0
+    assert sess.stats.boxes == ref.stats.boxes
+    for g, w in zip(got, want):
+        assert np.array_equal(np.asarray(g).reshape(-1, 2), np.asarray(w).reshape(-1, 2))
+
+
+def test_frontier_export_import_emulated(emu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _export_import_roundtrip(emu_yr, get_engine(), H.seeded_systems(2, 14, 3))
+
+
+@pytest.mark.gpu
+def test_frontier_export_import_gpu(gpu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _export_import_roundtrip(gpu_yr, get_engine(), H.seeded_systems(2, 50, 6))
+    _export_import_roundtrip(gpu_yr, get_engine(), H.seeded_systems(2, 20, 64))
