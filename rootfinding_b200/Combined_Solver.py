@@ -16,8 +16,24 @@ from .polynomial import MultiCheb, MultiPower
 _RESPLIT = 0.51234912839471234      # :146
 
 
-def solve(funcs, a=-1, b=1, verbose=False, returnBoundingBoxes=False, exact=False, minBoundingIntervalSize=1e-5):
-    """Roots of the system `funcs` on the box [a, b] (and optionally a bounding box per root)."""
+class _Region:
+    """One search box of the recursion of /root/reference/yroots/Combined_Solver.py:138-190.  `parts` lists, in the
+    reference's reporting order, what the region contributes: finished (roots, boxes) pairs and sub-regions."""
+    __slots__ = ("a", "b", "parts")
+
+    def __init__(self, a, b):
+        self.a, self.b, self.parts = a, b, []
+
+    def collect(self, roots, boxes):
+        for part in self.parts:
+            if isinstance(part, _Region):
+                part.collect(roots, boxes)
+            else:
+                roots.append(part[0])
+                boxes.append(part[1])
+
+
+def _validated(funcs, a, b):
     if type(funcs) != list and type(funcs) != np.ndarray:
         funcs = [funcs]
     for i in range(len(funcs)):
@@ -36,62 +52,82 @@ def solve(funcs, a=-1, b=1, verbose=False, returnBoundingBoxes=False, exact=Fals
         raise ValueError(f"Invalid input: {len(a)} lower bounds were given but {len(b)} upper bounds were given")
     if (b < a).any():
         raise ValueError("Invalid input: at least one lower bound is greater than the corresponding upper bound.")
+    return funcs, a, b
+
+
+def _approximate(funcs, a, b, verbose):
+    """Chebyshev tensors + error bounds of every function on [a, b] (:108-129)."""
+    dim = len(funcs)
     unit_box = np.allclose(a, -np.ones_like(a)) and np.allclose(b, np.ones_like(b))
     polys, errs = [None] * dim, np.zeros(dim)
-    if verbose:
-        print("Approximation shapes:", end=" ")
-    for i in range(dim):                                                  # :117-129
+    for i in range(dim):
         if unit_box and isinstance(funcs[i], MultiPower):
             polys[i], errs[i] = funcs[i].to_cheb(), 2.0 ** -52
         elif unit_box and isinstance(funcs[i], MultiCheb):
             polys[i], errs[i] = funcs[i].coeff, 2.0 ** -52
         else:
             polys[i], errs[i] = ChebyshevApproximator.chebApproximate(funcs[i], a, b)
-        if verbose:
-            print(f"{i}: {polys[i].shape}", end=" " if i != dim - 1 else '\n')
     if verbose:
+        print("Approximation shapes:", " ".join(f"{i}: {polys[i].shape}" for i in range(dim)))
         print(f"Searching on interval {[[a[i], b[i]] for i in range(dim)]}")
+    return polys, errs
 
-    roots, boxes = ChebyshevSubdivisionSolver.solveChebyshevSubdivision(
-        polys, errs, verbose, True, exact, constant_check=True, low_dim_quadratic_check=True,
-        all_dim_quadratic_check=False)
-    again = dict(verbose=verbose, returnBoundingBoxes=True, exact=exact, minBoundingIntervalSize=minBoundingIntervalSize)
 
-    may_split = np.all(b - a > minBoundingIntervalSize)
-    if len(boxes) == 1 and np.all(boxes[0].finalDimSize() == 2) and may_split:       # :138-162
-        all_roots, all_boxes = [], []
-        for upper in itertools.product([False, True], repeat=len(a)):
-            mid = (a + b) * _RESPLIT
-            lo, hi = np.where(upper, mid, a), np.where(upper, b, mid)
-            if verbose:
-                print("Re-solving on:", lo, hi)
-            r, bx = solve(funcs, a=lo, b=hi, **again)
-            if len(r) != 0:
-                all_boxes.append(bx)
-                all_roots.append(r)
-        if len(all_roots) > 0:
-            all_roots, all_boxes = np.vstack(all_roots), np.vstack(all_boxes)
-        return (all_roots, all_boxes) if returnBoundingBoxes else all_roots
+def solve(funcs, a=-1, b=1, verbose=False, returnBoundingBoxes=False, exact=False, minBoundingIntervalSize=1e-5):
+    """Roots of the system `funcs` on the box [a, b] (and optionally a bounding box per root).
 
-    final_roots, final_boxes = [], []
-    for box in boxes:                                                     # :170-190
-        lo, hi = ChebyshevApproximator.transform(box.finalInterval.T, a, b)
-        limit = minBoundingIntervalSize * functools.reduce(np.maximum, [np.abs(a), np.abs(b), 1])
-        if np.all(hi - lo > limit):
-            if verbose:
-                print("Re-solving on:", lo, hi)
-            r, bx = solve(funcs, a=lo, b=hi, **again)
-            if len(r) > 0:
-                final_roots.append(r)
-                final_boxes.append(bx)
-        else:
-            final_boxes.append([ChebyshevApproximator.transform(box.finalInterval.T, a, b).T])
-            if len(box.possibleDuplicateRoots) > 0:
-                final_roots.append(ChebyshevApproximator.transform(np.array(box.possibleDuplicateRoots), a, b))
-            else:
-                final_roots.append(ChebyshevApproximator.transform(box.getFinalPoint(), a, b))
-    if len(final_boxes) != 0:
-        final_boxes = np.vstack(final_boxes)
-    if len(final_roots) != 0:
-        final_roots = np.vstack(final_roots)
-    return (final_roots, final_boxes) if returnBoundingBoxes else final_roots
+    The reference recurses: a result box still wider than minBoundingIntervalSize is re-approximated and re-solved on its
+    own (:170-183), and a solve that only returns the whole search box is split into 2^dim pieces (:138-162) -- one
+    approximation and one device solve per box, depth first.  Here the recursion runs LEVEL BY LEVEL: every region of a
+    level is approximated, all of them are solved in ONE device batch (solve_batch), and their oversized boxes become
+    the regions of the next level; a solve makes O(depth) device calls instead of O(roots).  Regions keep their place in
+    a tree, so roots and boxes come back in the reference's (depth-first) order.
+    """
+    funcs, a, b = _validated(funcs, a, b)
+    dim = len(funcs)
+    top = _Region(a, b)
+    level = [top]
+    while level:
+        systems, errors = [], []
+        for reg in level:
+            if verbose and reg is not top:
+                print("Re-solving on:", reg.a, reg.b)
+            polys, errs = _approximate(funcs, reg.a, reg.b, verbose)
+            ChebyshevSubdivisionSolver._check_system(polys, errs)
+            systems.append(polys)
+            errors.append(errs)
+        if verbose:
+            print(f"Finding roots on {len(level)} region(s)...")
+        found, boxes_all = ChebyshevSubdivisionSolver.solve_batch(systems, errors, True, exact, True, True, False)
+        nxt = []
+        for reg, boxes in zip(level, boxes_all):
+            lo0, hi0 = reg.a, reg.b
+            if len(boxes) == 1 and np.all(boxes[0].finalDimSize() == 2) and np.all(hi0 - lo0 > minBoundingIntervalSize):
+                # the whole region came back as one box: cut it (almost) in half along every axis and solve the pieces
+                mid = (lo0 + hi0) * _RESPLIT
+                for upper in itertools.product([False, True], repeat=dim):
+                    sub = _Region(np.where(upper, mid, lo0), np.where(upper, hi0, mid))
+                    reg.parts.append(sub)
+                    nxt.append(sub)
+                continue
+            limit = minBoundingIntervalSize * functools.reduce(np.maximum, [np.abs(lo0), np.abs(hi0), 1])
+            for box in boxes:
+                lo, hi = ChebyshevApproximator.transform(box.finalInterval.T, lo0, hi0)
+                if np.all(hi - lo > limit):
+                    sub = _Region(lo, hi)                              # still too wide: its own approximation and solve
+                    reg.parts.append(sub)
+                    nxt.append(sub)
+                    continue
+                pts = np.array(box.possibleDuplicateRoots) if len(box.possibleDuplicateRoots) > 0 else box.getFinalPoint()
+                reg.parts.append((np.atleast_2d(ChebyshevApproximator.transform(pts, lo0, hi0)),
+                                  [np.stack([lo, hi], axis=1)]))
+        if verbose:
+            print(f"Found {sum(len(r) for r in found)} roots; {len(nxt)} region(s) to re-solve")
+        level = nxt
+    roots, boxes = [], []
+    top.collect(roots, boxes)
+    if len(boxes) != 0:
+        boxes = np.vstack(boxes)
+    if len(roots) != 0:
+        roots = np.vstack(roots)
+    return (roots, boxes) if returnBoundingBoxes else roots

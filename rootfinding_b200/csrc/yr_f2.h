@@ -513,39 +513,18 @@ YR_HD void store_epilogue(Work& w, int p, const Epilogue& ep, double sumabs) {
         if (rem > 3) { dl[3 * (STRIDE_OUT_L)] = l3; du[3 * (STRIDE_OUT_U)] = u3; asl += fabs(l3); asu += fabs(u3); } \
     }
 
-// warp teams: items (row block, fiber) handed to the lanes in waves, block-major.  Either output may be src (in place):
-// within a wave every lane finishes its loads before any lane stores (team barrier), and a later wave only reads rows
-// >= 4b' of its own fiber, which earlier waves (blocks b <= b') have not written.  dstL != dstU; same strides everywhere.
+// warp teams: fiber per lane; either output may be src (in place: a block's stores follow all of its loads);
+// dstL != dstU; same strides everywhere
 template <bool FMA, class Team>
 YR_DEV void pass_fiber_dual(Team& tm, const double* src, double* dstL, double* dstU, int sk, int sf, int n, int r, int F,
                             const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
     const int B = (r + 3) >> 2;
-    const int items = B * F, W = tm.nthreads;
     double asl = 0.0, asu = 0.0;
-    int b = 0, f = tm.tid;
-    while (f >= F && b < B) { f -= F; ++b; }
-    for (int w0 = 0; w0 < items; w0 += W) {
-        const bool have = b < B;
-        const int i0 = b << 2;
-        double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0, u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
-        if (have) {
-            const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));
-            const double* s = src + f * sf + i0 * sk;
-            int k = i0;
-            for (; k + 1 < n; k += 2) { YR_F2_DUAL_STEP(1.0) YR_F2_DUAL_STEP(-1.0) }
-            if (k < n) YR_F2_DUAL_STEP(1.0)
+    for (int f = tm.tid; f < F; f += tm.nthreads) {
+        for (int b = 0; b < B; ++b) {
+            const int i0 = b << 2;
+            YR_F2_DUAL_BLOCK(src + f * sf + i0 * sk, dstL + f * sf + i0 * sk, dstU + f * sf + i0 * sk, sk, sk)
         }
-        tm.wsync();
-        if (have) {
-            const int rem = r - i0;
-            double* dl = dstL + f * sf + i0 * sk; double* du = dstU + f * sf + i0 * sk;
-            dl[0] = l0; du[0] = u0; asl += fabs(l0); asu += fabs(u0);
-            if (rem > 1) { dl[sk] = l1; du[sk] = u1; asl += fabs(l1); asu += fabs(u1); }
-            if (rem > 2) { dl[2 * sk] = l2; du[2 * sk] = u2; asl += fabs(l2); asu += fabs(u2); }
-            if (rem > 3) { dl[3 * sk] = l3; du[3 * sk] = u3; asl += fabs(l3); asu += fabs(u3); }
-        }
-        f += W;
-        while (f >= F && b < B) { f -= F; ++b; }
     }
     if (tm.tid == 0) macs += 2ull * (unsigned)(F * (r * n - r * (r - 1) / 2));
     tm.sum2_sync(asl, asu, sumL, sumU);
@@ -865,28 +844,24 @@ YR_DEV void subdivide_box(Team& tm, const Args& a, unsigned int b, double* slice
     }
 }
 
-// ---- warp teams: in-place, items (row block, fiber) in waves ------------------------------------------------------
-// Block b of a fiber reads source rows >= 4b and then overwrites rows 4b..4b+3, which no later block reads -- so a
-// pass can run in place (dst == src) and a box needs one tensor region instead of three.  Items are handed to the lanes
-// block-major, one wave of `lanes` items at a time: every lane of a wave finishes its loads before any lane stores
-// (team barrier), later waves never read what earlier waves wrote.  A tensor with fewer fibers than lanes (the
-// typical restricted box) still fills the team.  dst may also be another region (same strides).  Returns the team-wide
-// sum|dst|; ends with the team barrier.
+// ---- warp teams: in-place, fiber per lane -----------------------------------------------------------------
+// Lane f owns fiber f and walks its row blocks in ascending order: block b reads source rows >= 4b and then
+// overwrites rows 4b..4b+3, which no later block reads -- so a pass can run in place (dst == src), every lane
+// has the same trip count, and a box needs one tensor region instead of three.  dst may also be another region
+// (same strides).  Returns the team-wide sum|dst|; ends with the team barrier.
 template <bool FMA, class Team>
 YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int sf, int n, int r, int F,
                          const double* Cp, int nt, unsigned long long& macs) {
     const int B = (r + 3) >> 2;
-    const int items = B * F, W = tm.nthreads;
     double asum = 0.0;
-    int b = 0, f = tm.tid;
-    while (f >= F && b < B) { f -= F; ++b; }
-    for (int w0 = 0; w0 < items; w0 += W) {
-        const bool have = b < B;
-        const int i0 = b << 2;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        if (have) {
+    for (int f = tm.tid; f < F; f += tm.nthreads) {
+        const double* sc = src + f * sf;
+        double* dc = dst + f * sf;
+        for (int b = 0; b < B; ++b) {
+            const int i0 = b << 2;
             const pair_t* cp = reinterpret_cast<const pair_t*>(Cp + panel_off(b, nt));
-            const double* s = src + f * sf + i0 * sk;
+            const double* s = sc + i0 * sk;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 2
             for (int k = i0; k < n; ++k) {
                 const double x = *s; s += sk;
@@ -894,18 +869,13 @@ YR_DEV double pass_fiber(Team& tm, const double* src, double* dst, int sk, int s
                 if (FMA) { a0 = fma(c01.x, x, a0); a1 = fma(c01.y, x, a1); a2 = fma(c23.x, x, a2); a3 = fma(c23.y, x, a3); }
                 else { a0 = a0 + c01.x * x; a1 = a1 + c01.y * x; a2 = a2 + c23.x * x; a3 = a3 + c23.y * x; }
             }
-        }
-        tm.wsync();
-        if (have) {
-            double* d = dst + f * sf + i0 * sk;
+            double* d = dc + i0 * sk;
             const int rem = r - i0;
             d[0] = a0; asum += fabs(a0);
             if (rem > 1) { d[sk] = a1; asum += fabs(a1); }
             if (rem > 2) { d[2 * sk] = a2; asum += fabs(a2); }
             if (rem > 3) { d[3 * sk] = a3; asum += fabs(a3); }
         }
-        f += W;
-        while (f >= F && b < B) { f -= F; ++b; }
     }
     if (tm.tid == 0) macs += (unsigned long long)(unsigned)(F * (r * n - r * (r - 1) / 2));
     return tm.sum_sync(asum);
