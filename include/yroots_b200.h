@@ -228,6 +228,20 @@ int yr_poly_eval_axis(const double* coef, const double* x, double* out, int64_t 
 /* mean of |t| over all axes but one: in [outer][n][inner] -> out [n]; also max|t| -> *supnorm. */
 int yr_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream);
 
+/* One probe of getChebyshevDegrees' doubling search decided on the device (ChebyshevApproximator.py:228-311): the host
+ * reads back this 64-byte struct instead of the coefficient tensors.
+ *   mode 0  first probe of an iteration (degree guess g along `axis`): supnorm = max|values| (:72), tol = abs_tol +
+ *           supnorm * rel_tol (:290), started = startedConverging(axis means of |coeff|, tol) (:91-106, :288)
+ *   mode 1  second probe (degree 2g+1): supnorm of ITS values, tol from max(prev_supnorm, supnorm) (:300), converged =
+ *           hasConverged(prev_coeff, coeff, tol) (:108-129), and (degree, eps, rho) = getFinalDegree(axis means, tol) (:131-172)
+ * coeff / prev_coeff: full coefficient tensors on the device, row-major with extents shape[] / prev_shape[]; keep[] <= shape[]
+ * is the sub-box the reference's sliced tensor covers (axes the function is constant along keep one plane, :57,:85).
+ * scratch: keep[axis] + 128 doubles of device memory. */
+typedef struct yr_decay_out { double supnorm, tol, started, converged, degree, eps, rho, reserved; } yr_decay_out;
+int yr_decay_probe(int32_t mode, int32_t dim, int32_t axis, const double* coeff, const int64_t* shape, const int64_t* keep,
+                   const double* prev_coeff, const int64_t* prev_shape, const int64_t* prev_keep, const double* values, int64_t nvalues,
+                   double prev_supnorm, double rel_tol, double abs_tol, double* scratch, yr_decay_out* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,7 +140,7 @@ class _DeviceGrid:
         return m.download(mean, n * 8).view(np.float64).copy()
 
 
-def interval_approximate_nd(f, degs, a, b, retSupNorm=False, engine=None, _want_chunk_axis=None):
+def interval_approximate_nd(f, degs, a, b, retSupNorm=False, engine=None):
     """Chebyshev interpolant of f on [a,b] with the given degrees (:28-89)."""
     eng = get_engine() if engine is None else engine
     originalDegs = degs.copy()
@@ -148,13 +148,8 @@ def interval_approximate_nd(f, degs, a, b, retSupNorm=False, engine=None, _want_
     grid = _DeviceGrid(eng, f, degs, a, b)
     supNorm = grid.sup_norm() if retSupNorm else None
     buf = grid.coefficients()
-    chunk = None
-    if _want_chunk_axis is not None and np.all(originalDegs >= 1):
-        chunk = grid.axis_mean_abs(buf, _want_chunk_axis)
     full = eng.mem.download(buf, grid.size * 8).view(np.float64).reshape(grid.npts)
     coeffs = full[tuple(slice(0, d + 1) for d in originalDegs)]
-    if _want_chunk_axis is not None:
-        return coeffs, supNorm, chunk
     return (coeffs, supNorm) if retSupNorm else coeffs
 
 
@@ -206,8 +201,43 @@ def checkConstantInDimension(f, a, b, currDim, relApproxTol, absApproxTol=0):
     return True
 
 
-def getChebyshevDegrees(f, a, b, relApproxTol, absApproxTol=0, engine=None):
-    """Degree search per axis by doubling (:228-311) -> (degrees, epsilons, rhos)."""
+DECAY_DTYPE = np.dtype([(k, np.float64) for k in ("supnorm", "tol", "started", "converged", "degree", "eps", "rho", "reserved")])
+
+
+class _Probe:
+    """One evaluation of the doubling search: the grid of a degree guess, its coefficient tensor (both on the device) and
+    the sub-box of it the reference would keep (:57,:85)."""
+
+    def __init__(self, eng, f, degs, a, b):
+        self.keep = [int(d) + 1 for d in degs]                  # extents of the tensor interval_approximate_nd returns
+        # The reference turns degree-0 axes into degree 1 IN THE CALLER'S ARRAY (:57), so within one axis' search only the
+        # first probe is sliced back to one plane (:85); later probes keep both planes.  Reproduced: the axis means that
+        # drive the decisions are averages over exactly the tensors the reference averages over.
+        degs[degs == 0] = 1
+        self.grid = _DeviceGrid(eng, f, degs, a, b)
+        self.coeff = self.grid.coefficients()
+        self.shape = list(self.grid.npts)
+
+
+def _decide(eng, mode, axis, probe, prev, prev_sup, rel, abs_, out_buf, slot):
+    """Queues yr_decay_probe for `probe`; its 64-byte answer lands in slot `slot` of out_buf (read later, with the others)."""
+    m, lib = eng.mem, eng.lib
+    dim = len(probe.shape)
+    i64 = lambda v: np.ascontiguousarray(v, dtype=np.int64)
+    shape, keep = i64(probe.shape), i64(probe.keep)
+    pshape, pkeep = (i64(prev.shape), i64(prev.keep)) if prev is not None else (shape, keep)
+    scratch = m.empty((probe.keep[axis] + 128) * 8)
+    _lib.check(lib, lib.yr_decay_probe(mode, dim, axis, probe.coeff.ptr, shape.ctypes.data, keep.ctypes.data,
+                                       prev.coeff.ptr if prev is not None else None, pshape.ctypes.data, pkeep.ctypes.data,
+                                       probe.grid.values.ptr, probe.grid.size, float(prev_sup), float(rel), float(abs_),
+                                       scratch.ptr, out_buf.ptr + slot * DECAY_DTYPE.itemsize, m.stream()), "yr_decay_probe")
+    probe._scratch = scratch                                     # alive until the answer has been read
+
+
+def _degree_search(eng, f, a, b, relApproxTol, absApproxTol, out_buf, slot):
+    """getChebyshevDegrees (:228-311) as a coroutine: every `yield` is one probe whose decision -- startedConverging,
+    hasConverged, getFinalDegree, all evaluated on the device -- the driver hands back as a DECAY_DTYPE record.  Returns
+    (degrees, epsilons, rhos)."""
     dim = len(a)
     chebDegrees = [np.inf] * dim
     epsilons, rhos = [], []
@@ -223,40 +253,61 @@ def getChebyshevDegrees(f, a, b, relApproxTol, absApproxTol=0, engine=None):
         for i in range(dim):
             if chebDegrees[i] < degs[i]:
                 degs[i] = chebDegrees[i]
-        currGuess = 8
+        guess = 8
         while True:
-            if currGuess > 1e5:
+            if guess > 1e5:
                 warnings.warn(f"Approximation bound exceeded!\n\nApproximation degree in dimension {currDim} "
                               "has exceeded 1e5, so the process may not finish.\n\nConsider interrupting "
                               "and restarting the process after ensuring that the function(s) inputted are "
                               "continuous and smooth on the approximation interval.\n\n")
-            degs[currDim] = currGuess
-            coeff, supNorm, chunk = interval_approximate_nd(f, degs, a, b, True, engine, _want_chunk_axis=currDim)
-            chunk = _sliced_chunk(coeff, chunk, currDim)
-            tol = absApproxTol + supNorm * relApproxTol
-            currGuess *= 2
-            if not startedConverging(chunk, tol):
+            degs[currDim] = guess
+            first = _Probe(eng, f, degs, a, b)
+            _decide(eng, 0, currDim, first, None, 0.0, relApproxTol, absApproxTol, out_buf, slot)
+            ans = yield
+            guess *= 2
+            if not ans["started"]:
                 continue
-            degs[currDim] = currGuess + 1
-            coeff2, supNorm2, chunk2 = interval_approximate_nd(f, degs, a, b, True, engine, _want_chunk_axis=currDim)
-            tol = absApproxTol + max(supNorm, supNorm2) * relApproxTol
-            if not hasConverged(coeff, coeff2, tol):
+            degs[currDim] = guess + 1
+            second = _Probe(eng, f, degs, a, b)
+            _decide(eng, 1, currDim, second, first, ans["supnorm"], relApproxTol, absApproxTol, out_buf, slot)
+            ans = yield
+            if not ans["converged"]:
                 continue
-            chunk2 = _sliced_chunk(coeff2, chunk2, currDim)
-            deg, eps, rho = getFinalDegree(chunk2, tol)
-            chebDegrees[currDim] = deg
-            epsilons.append(eps)
-            rhos.append(rho)
+            chebDegrees[currDim] = int(ans["degree"])
+            epsilons.append(float(ans["eps"]))
+            rhos.append(float(ans["rho"]))
             break
     return np.array(chebDegrees), np.array(epsilons), np.array(rhos)
 
 
-def _sliced_chunk(coeff, device_chunk, axis):
-    """Axis means of |coeff| (:288): the device's when it covers exactly the returned tensor, else
-    (degree-0 axes are sampled as degree 1 and sliced away, :57,:85) recomputed on the sliced tensor."""
-    if device_chunk is not None:
-        return device_chunk
-    return np.average(np.abs(coeff), axis=tuple(i for i in range(coeff.ndim) if i != axis))
+def _run_searches(eng, jobs, relApproxTol, absApproxTol=0):
+    """Runs the degree searches of several (f, a, b) in lock step: per round every unfinished search queues one probe on
+    the device and ONE small download brings all their decisions back.  Returns [(degrees, epsilons, rhos)]."""
+    m = eng.mem
+    out_buf = m.zeros(len(jobs) * DECAY_DTYPE.itemsize)
+    gens = [_degree_search(eng, f, a, b, relApproxTol, absApproxTol, out_buf, i) for i, (f, a, b) in enumerate(jobs)]
+    results, live = [None] * len(jobs), {}
+    for i, g in enumerate(gens):
+        try:
+            next(g)
+            live[i] = g
+        except StopIteration as done:
+            results[i] = done.value
+    while live:
+        answers = m.download(out_buf, len(jobs) * DECAY_DTYPE.itemsize).view(DECAY_DTYPE)     # the round's only read-back
+        for i in list(live):
+            try:
+                live[i].send(answers[i].copy())
+            except StopIteration as done:
+                results[i] = done.value
+                del live[i]
+    return results
+
+
+def getChebyshevDegrees(f, a, b, relApproxTol, absApproxTol=0, engine=None):
+    """Degree search per axis by doubling (:228-311) -> (degrees, epsilons, rhos)."""
+    eng = get_engine() if engine is None else engine
+    return _run_searches(eng, [(f, a, b)], relApproxTol, absApproxTol)[0]
 
 
 def getApproxError(degs, epsilons, rhos):
@@ -276,8 +327,7 @@ def getApproxError(degs, epsilons, rhos):
     return total
 
 
-def chebApproximate(f, a, b, relApproxTol=1e-10, engine=None):
-    """(coefficient tensor, error bound) of f on [a,b] (:358-450)."""
+def _checked_bounds(f, a, b):
     if not hasattr(f, '__call__'):
         raise ValueError("Invalid input: input function is not callable")
     if type(a) == list:
@@ -297,5 +347,19 @@ def chebApproximate(f, a, b, relApproxTol=1e-10, engine=None):
         f(mid) if _is_poly(f) else f(*mid)
     except TypeError:
         raise ValueError("Invalid input: length of the upper/lower bound lists must match the dimension of the function")
-    degs, epsilons, rhos = getChebyshevDegrees(f, a, b, relApproxTol, engine=engine)
-    return interval_approximate_nd(f, degs, a, b, engine=engine), getApproxError(degs, epsilons, rhos)
+    return a, b
+
+
+def chebApproximate_batch(jobs, relApproxTol=1e-10, engine=None):
+    """chebApproximate for a list of (f, a, b): the degree searches advance together (one read-back per round for all of
+    them), then every final interpolant is computed.  Returns [(coefficient tensor, error bound)]."""
+    eng = get_engine() if engine is None else engine
+    jobs = [(f,) + _checked_bounds(f, a, b) for f, a, b in jobs]
+    found = _run_searches(eng, jobs, relApproxTol)
+    return [(interval_approximate_nd(f, degs, a, b, engine=eng), getApproxError(degs, eps, rhos))
+            for (f, a, b), (degs, eps, rhos) in zip(jobs, found)]
+
+
+def chebApproximate(f, a, b, relApproxTol=1e-10, engine=None):
+    """(coefficient tensor, error bound) of f on [a,b] (:358-450)."""
+    return chebApproximate_batch([(f, a, b)], relApproxTol, engine)[0]

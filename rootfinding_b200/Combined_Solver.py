@@ -55,22 +55,32 @@ def _validated(funcs, a, b):
     return funcs, a, b
 
 
-def _approximate(funcs, a, b, verbose):
-    """Chebyshev tensors + error bounds of every function on [a, b] (:108-129)."""
+def _approximate_level(funcs, level, verbose):
+    """Chebyshev tensors + error bounds of every function on every region of a recursion level (:108-129).  Polynomial
+    objects on the unit box are used as they are; everything else goes through ONE batched approximation whose degree
+    searches advance in lock step on the device (ChebyshevApproximator.chebApproximate_batch)."""
     dim = len(funcs)
-    unit_box = np.allclose(a, -np.ones_like(a)) and np.allclose(b, np.ones_like(b))
-    polys, errs = [None] * dim, np.zeros(dim)
-    for i in range(dim):
-        if unit_box and isinstance(funcs[i], MultiPower):
-            polys[i], errs[i] = funcs[i].to_cheb(), 2.0 ** -52
-        elif unit_box and isinstance(funcs[i], MultiCheb):
-            polys[i], errs[i] = funcs[i].coeff, 2.0 ** -52
-        else:
-            polys[i], errs[i] = ChebyshevApproximator.chebApproximate(funcs[i], a, b)
+    out, jobs, where = [], [], []
+    for r, reg in enumerate(level):
+        unit_box = np.allclose(reg.a, -np.ones_like(reg.a)) and np.allclose(reg.b, np.ones_like(reg.b))
+        polys, errs = [None] * dim, np.zeros(dim)
+        for i in range(dim):
+            if unit_box and isinstance(funcs[i], MultiPower):
+                polys[i], errs[i] = funcs[i].to_cheb(), 2.0 ** -52
+            elif unit_box and isinstance(funcs[i], MultiCheb):
+                polys[i], errs[i] = funcs[i].coeff, 2.0 ** -52
+            else:
+                jobs.append((funcs[i], reg.a, reg.b))
+                where.append((r, i))
+        out.append((polys, errs))
+    if jobs:
+        for (r, i), (coeff, err) in zip(where, ChebyshevApproximator.chebApproximate_batch(jobs)):
+            out[r][0][i], out[r][1][i] = coeff, err
     if verbose:
-        print("Approximation shapes:", " ".join(f"{i}: {polys[i].shape}" for i in range(dim)))
-        print(f"Searching on interval {[[a[i], b[i]] for i in range(dim)]}")
-    return polys, errs
+        for reg, (polys, errs) in zip(level, out):
+            print("Approximation shapes:", " ".join(f"{i}: {polys[i].shape}" for i in range(dim)))
+            print(f"Searching on interval {[[reg.a[i], reg.b[i]] for i in range(dim)]}")
+    return out
 
 
 def solve(funcs, a=-1, b=1, verbose=False, returnBoundingBoxes=False, exact=False, minBoundingIntervalSize=1e-5):
@@ -89,10 +99,11 @@ def solve(funcs, a=-1, b=1, verbose=False, returnBoundingBoxes=False, exact=Fals
     level = [top]
     while level:
         systems, errors = [], []
-        for reg in level:
-            if verbose and reg is not top:
-                print("Re-solving on:", reg.a, reg.b)
-            polys, errs = _approximate(funcs, reg.a, reg.b, verbose)
+        if verbose:
+            for reg in level:
+                if reg is not top:
+                    print("Re-solving on:", reg.a, reg.b)
+        for polys, errs in _approximate_level(funcs, level, verbose):
             ChebyshevSubdivisionSolver._check_system(polys, errs)
             systems.append(polys)
             errors.append(errs)

@@ -10,6 +10,7 @@
 #include "yr_box.h"
 #include "yr_phases.h"
 #include "yr_items.h"
+#include "yr_approx.h"
 
 // Hooks every backend defines after including this header.
 namespace yr_backend {
@@ -31,6 +32,8 @@ template <int D> int launch_bils(int64_t n, const double* lin, const double* c0,
 template <int D> int launch_quad(int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes,
                                  const double* tol, int32_t nd_check, int32_t* out, void* stream);
 int launch_dct1(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void* stream);
+int launch_decay(int mode, int dim, int axis, const yr::DecayTensor& t, const yr::DecayTensor* prev, const double* values, int64_t nvalues,
+                 double prev_supnorm, double rel_tol, double abs_tol, double* scratch, yr::DecayOut* out, void* stream);
 int launch_poly_eval(const double* coef, const double* x, double* out, int64_t outer, int64_t ncoef, int64_t npts,
                      int64_t inner, int32_t basis, void* stream);
 int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream);
@@ -277,6 +280,25 @@ int yr_poly_eval_axis(const double* coef, const double* x, double* out, int64_t 
 
 int yr_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream) {
     return yr_backend::launch_abs_axis_mean(t, out, supnorm, outer, n, inner, stream);
+}
+
+int yr_decay_probe(int32_t mode, int32_t dim, int32_t axis, const double* coeff, const int64_t* shape, const int64_t* keep,
+                   const double* prev_coeff, const int64_t* prev_shape, const int64_t* prev_keep, const double* values, int64_t nvalues,
+                   double prev_supnorm, double rel_tol, double abs_tol, double* scratch, yr_decay_out* out, void* stream) {
+    if (dim < 1 || dim > yr::kMaxApproxDim || axis < 0 || axis >= dim) return yr_api::fail("yr_decay_probe: bad dimension / axis");
+    if (mode != 0 && mode != 1) return yr_api::fail("yr_decay_probe: mode must be 0 or 1");
+    if (mode == 1 && !prev_coeff) return yr_api::fail("yr_decay_probe: mode 1 needs the previous probe");
+    yr::DecayTensor t, p;
+    memset(&t, 0, sizeof(t)); memset(&p, 0, sizeof(p));
+    t.c = coeff; p.c = prev_coeff;
+    for (int d = 0; d < dim; ++d) {
+        t.shape[d] = shape[d]; t.keep[d] = keep[d];
+        if (keep[d] < 1 || keep[d] > shape[d]) return yr_api::fail("yr_decay_probe: keep must be in 1..shape");
+        if (mode == 1) { p.shape[d] = prev_shape[d]; p.keep[d] = prev_keep[d]; }
+    }
+    static_assert(sizeof(yr::DecayOut) == sizeof(yr_decay_out), "yr_decay_out layout");
+    return yr_backend::launch_decay(mode, dim, axis, t, mode == 1 ? &p : nullptr, values, nvalues, prev_supnorm, rel_tol, abs_tol, scratch,
+                                    reinterpret_cast<yr::DecayOut*>(out), stream);
 }
 
 }  // extern "C"

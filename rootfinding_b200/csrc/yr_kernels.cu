@@ -74,6 +74,16 @@ struct DeviceCtx {
         __syncthreads();
         return t;
     }
+    // maximum of non-negative values that keeps a NaN (numpy's max propagates it)
+    __device__ __forceinline__ double block_max_nan(double v) {
+        for (int off = 16; off > 0; off >>= 1) { const double o = __shfl_down_sync(0xffffffffu, v, off); v = (v != v || o != o) ? NAN : fmax(v, o); }
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        double t = red[0];
+        for (int w = 1; w < nwarps; ++w) t = (t != t || red[w] != red[w]) ? NAN : fmax(t, red[w]);
+        __syncthreads();
+        return t;
+    }
     __device__ __forceinline__ double warp_sum(double v) {
         v = warp_tree(v);
         return __shfl_sync(0xffffffffu, v, 0);
@@ -325,6 +335,17 @@ __global__ void dct1_kernel(yr::Dct1Args a) {
     yr::dct1_worker(cx, a, table, blockIdx.x, gridDim.x);
 }
 
+__global__ void dct1_table_kernel(double* table, long long N) {
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < 2 * N; m += (long long)gridDim.x * blockDim.x)
+        table[m] = cospi((double)m / (double)N);
+}
+__global__ void dct1_kernel_gtable(yr::Dct1Args a, double* table) {
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::dct1_worker(cx, a, table, blockIdx.x, gridDim.x, false);
+}
+
 __global__ void poly_eval_kernel(yr::PolyEvalArgs a) {
     __shared__ double red[32];
     __shared__ __align__(8) uint64_t mbar;
@@ -337,6 +358,29 @@ __global__ void abs_mean_kernel(yr::AbsMeanArgs a) {
     __shared__ __align__(8) uint64_t mbar;
     DeviceCtx cx = make_ctx(red, &mbar, 0);
     yr::abs_mean_worker(cx, a, blockIdx.x);
+}
+
+__global__ void subbox_mean_kernel(yr::DecayTensor t, int dim, int axis, double* chunk) {
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::subbox_axis_mean_worker(cx, t, dim, axis, chunk, blockIdx.x);
+}
+__global__ void maxdiff_kernel(yr::DecayTensor t2, yr::DecayTensor t1, int dim, double* part) {
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::maxdiff_worker(cx, t2, t1, dim, part, blockIdx.x, gridDim.x);
+}
+__global__ void absmax_kernel(const double* v, long long n, double* part) {
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::absmax_worker(cx, v, n, part, blockIdx.x, gridDim.x);
+}
+__global__ void decay_decide_kernel(int mode, const double* chunk, long long n, const double* sup_part, long long nsup, const double* diff_part,
+                                    long long ndiff, double prev_supnorm, double rel_tol, double abs_tol, yr::DecayOut* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) yr::decay_decide(mode, chunk, n, sup_part, nsup, diff_part, ndiff, prev_supnorm, rel_tol, abs_tol, out);
 }
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -539,7 +583,17 @@ static unsigned grid_for(long long total, int threads) {
 int launch_dct1(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void* stream) {
     yr::Dct1Args a{values, coeffs, outer, npts, inner};
     const size_t smem = (size_t)(2 * (npts - 1)) * 8;
-    if (smem > 200 * 1024) return yr_api::fail("DCT axis too long for the shared-memory cosine table");
+    if (smem > 200 * 1024) {
+        // an axis beyond 12 800 points (the degree search doubles its guess up to 1e5, :280): cosine table in global memory
+        double* table = nullptr;
+        cudaError_t e0 = cudaMallocAsync(&table, smem, (cudaStream_t)stream);
+        if (e0 != cudaSuccess) return cuda_fail(e0, "cudaMallocAsync (DCT table)");
+        dct1_table_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(table, npts - 1);
+        dct1_kernel_gtable<<<grid_for(outer * npts * inner, 256), 256, 0, (cudaStream_t)stream>>>(a, table);
+        cudaError_t e1 = cudaGetLastError();
+        cudaFreeAsync(table, (cudaStream_t)stream);
+        return e1 == cudaSuccess ? 0 : cuda_fail(e1, "dct1_kernel_gtable launch");
+    }
     if (smem > 48 * 1024 && set_smem(dct1_kernel, smem)) return -1;
     dct1_kernel<<<grid_for(outer * npts * inner, 256), 256, smem, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
@@ -559,6 +613,20 @@ int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t 
     abs_mean_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "abs_mean_kernel launch");
+}
+
+// Degree-selection probe: scratch = [chunk: n][sup partials: 64][diff partials: 64] doubles (device), out on the device.
+int launch_decay(int mode, int dim, int axis, const yr::DecayTensor& t, const yr::DecayTensor* prev, const double* values, int64_t nvalues,
+                 double prev_supnorm, double rel_tol, double abs_tol, double* scratch, yr::DecayOut* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = t.keep[axis];
+    double* chunk = scratch; double* sup_part = scratch + n; double* diff_part = sup_part + 64;
+    subbox_mean_kernel<<<(unsigned)n, 128, 0, st>>>(t, dim, axis, chunk);
+    absmax_kernel<<<64, 256, 0, st>>>(values, nvalues, sup_part);
+    if (mode == 1) maxdiff_kernel<<<64, 256, 0, st>>>(t, *prev, dim, diff_part);
+    decay_decide_kernel<<<1, 32, 0, st>>>(mode, chunk, n, sup_part, 64, diff_part, mode == 1 ? 64 : 0, prev_supnorm, rel_tol, abs_tol, out);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "decay kernels launch");
 }
 
 }  // namespace yr_backend

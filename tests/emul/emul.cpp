@@ -82,6 +82,12 @@ struct HostCtxT {
         double m = team->scratch[0]; for (int t = 1; t < nthreads; ++t) m = team->scratch[t] > m ? team->scratch[t] : m;
         sync(); return m;
     }
+    double block_max_nan(double v) {
+        team->scratch[tid] = v; sync();
+        double m = team->scratch[0];
+        for (int t = 1; t < nthreads; ++t) { const double o = team->scratch[t]; m = (m != m || o != o) ? NAN : (o > m ? o : m); }
+        sync(); return m;
+    }
     double warp_sum(double v) {
         team->scratch[tid] = v; sync();
         const double r = tree(warp);
@@ -298,6 +304,17 @@ int launch_poly_eval(const double* coef, const double* x, double* out, int64_t o
                      int64_t inner, int32_t basis, void*) {
     yr::PolyEvalArgs a{coef, x, out, outer, ncoef, npts, inner, basis};
     run_team(4, 4, [&](HostCtx& cx) { yr::poly_eval_worker(cx, a, 0, 1); });
+    return 0;
+}
+
+int launch_decay(int mode, int dim, int axis, const yr::DecayTensor& t, const yr::DecayTensor* prev, const double* values, int64_t nvalues,
+                 double prev_supnorm, double rel_tol, double abs_tol, double* scratch, yr::DecayOut* out, void*) {
+    const long long n = t.keep[axis];
+    double* chunk = scratch; double* sup_part = scratch + n; double* diff_part = sup_part + 64;
+    run_team(4, 4, [&](HostCtx& cx) { for (long long j = 0; j < n; ++j) yr::subbox_axis_mean_worker(cx, t, dim, axis, chunk, j); });
+    run_team(4, 4, [&](HostCtx& cx) { yr::absmax_worker(cx, values, nvalues, sup_part, 0, 1); });
+    if (mode == 1) run_team(4, 4, [&](HostCtx& cx) { yr::maxdiff_worker(cx, t, *prev, dim, diff_part, 0, 1); });
+    yr::decay_decide(mode, chunk, n, sup_part, 1, diff_part, mode == 1 ? 1 : 0, prev_supnorm, rel_tol, abs_tol, out);
     return 0;
 }
 

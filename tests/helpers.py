@@ -144,3 +144,28 @@ def sharded_cases():
     return [("one30", seeded_systems(2, 30, 1)),
             ("corners", seeded_systems(2, 12, 3) + [corner_system(s, 2, 3) for s in range(6)]),
             ("extent80", [[rs.randn(80, 3), rs.randn(3, 80)]])]
+
+
+APPROX_FUNCS = {
+    "cos": lambda x: np.cos(x),
+    "exp_sin": lambda x, y: np.exp(x) * np.sin(3 * y),
+    "readme_f": lambda x, y: np.sin(x * y) + x * np.log(y + 3) - x ** 2 + 1 / (y - 4),
+    "readme_g": lambda x, y: np.cos(3 * x * y) + np.exp(3 * y / (x - 2)) - x - 6,
+    "const_dim": lambda x, y, z: x ** 2 - y ** 2 + 3 * x * y,
+    "poly3": lambda x, y, z: np.sin(5 * x + y + z),
+}
+
+
+def check_approx_error(err, z, name):
+    """getApproxError (:313-356) against the reference's value.  The bound is built from epsVal = 2 max(2^-52, noise floor
+    of the trailing axis means) and rho = (peak / epsVal)^(1/(deg - peak + 1)) (:131-172).  When the reference's epsVal sits
+    on the 2^-52 floor on every axis the bound depends only on the peak means and must agree to 1e-9 (relative); when the
+    rounding noise of the DCT itself sets epsVal (scipy's FFT vs the device's summation) only its size is comparable:
+    within a factor 1.5."""
+    want = float(z[f"{name}_err"])
+    eps = np.asarray(z[f"{name}_eps"], dtype=float)
+    on_floor = np.all((eps == 0) | (eps == 2.0 ** -51))
+    if on_floor:
+        assert abs(err - want) <= 1e-9 * abs(want), (name, err, want)
+    else:
+        assert 1 / 1.5 < (err + 1e-300) / (want + 1e-300) < 1.5, (name, err, want)

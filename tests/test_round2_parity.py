@@ -297,3 +297,52 @@ def test_frontier_export_import_gpu(gpu_yr):
     from rootfinding_b200.runtime import get_engine
     _export_import_roundtrip(gpu_yr, get_engine(), H.seeded_systems(2, 50, 6))
     _export_import_roundtrip(gpu_yr, get_engine(), H.seeded_systems(2, 20, 64))
+
+
+# ---- approximator: degree selection decided on the device (yr_decay_probe), searches in lock step ---------------------
+def _approximator(yr, engine):
+    A = yr.ChebyshevApproximator
+    z = H.load("approx.npz")
+    names = [str(s) for s in z["names"]]
+    reads = [0]
+    orig = engine.mem.download
+
+    def counted(*a, **k):
+        reads[0] += 1
+        return orig(*a, **k)
+    engine.mem.download = counted
+    try:
+        for name in names:
+            f, a, b = H.APPROX_FUNCS[name], z[f"{name}_a"], z[f"{name}_b"]
+            reads[0] = 0
+            degs, eps, rhos = A.getChebyshevDegrees(f, a, b, 1e-10)
+            assert np.array_equal(degs, z[f"{name}_degs"]), name                      # same numerical degrees
+            assert reads[0] <= 4 * len(a) + 1, (name, reads[0])                       # one 64-byte read-back per probe, nothing else
+            coeff, err = A.chebApproximate(f, a, b)
+            want = z[f"{name}_coeff"]
+            assert coeff.shape == want.shape
+            assert np.max(np.abs(coeff - want)) < 64 * 2.0 ** -52 * np.max(np.abs(want)), name
+            H.check_approx_error(err, z, name)
+        # all functions of a system together: as many read-back rounds as the slowest search needs, not the sum
+        jobs = [(H.APPROX_FUNCS[n], z[f"{n}_a"], z[f"{n}_b"]) for n in ("readme_f", "readme_g")]
+        reads[0] = 0
+        A.chebApproximate(*jobs[0]); A.chebApproximate(*jobs[1])
+        separate = reads[0]
+        reads[0] = 0
+        both = A.chebApproximate_batch(jobs)
+        assert reads[0] < separate
+        for (c, e), n in zip(both, ("readme_f", "readme_g")):
+            assert c.shape == z[f"{n}_coeff"].shape
+    finally:
+        engine.mem.download = orig
+
+
+def test_device_degree_selection_emulated(emu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _approximator(emu_yr, get_engine())
+
+
+@pytest.mark.gpu
+def test_device_degree_selection_gpu(gpu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _approximator(gpu_yr, get_engine())
