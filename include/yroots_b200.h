@@ -228,6 +228,11 @@ int yr_poly_eval_axis(const double* coef, const double* x, double* out, int64_t 
 /* mean of |t| over all axes but one: in [outer][n][inner] -> out [n]; also max|t| -> *supnorm. */
 int yr_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream);
 
+/* out[o][i][in] = sum_{k >= i} P[i][k] * coef[o][k][in] (P row-major n x n, upper triangular part used), accumulated from
+ * zero in ascending k with separately rounded multiply and add: MultiPower.to_cheb along one axis (polynomial.py:587-640,
+ * P[i][k] = T_i coefficient of x^k), bit-identical to the reference's loop. */
+int yr_upper_axis_apply(const double* coef, const double* P, double* out, int64_t outer, int64_t n, int64_t inner, void* stream);
+
 /* One probe of getChebyshevDegrees' doubling search decided on the device (ChebyshevApproximator.py:228-311): the host
  * reads back this 64-byte struct instead of the coefficient tensors.
  *   mode 0  first probe of an iteration (degree guess g along `axis`): supnorm = max|values| (:72), tol = abs_tol +

@@ -12,6 +12,7 @@ import numpy as np
 
 from . import ChebyshevApproximator, ChebyshevSubdivisionSolver
 from .polynomial import MultiCheb, MultiPower
+from .runtime import get_engine
 
 _RESPLIT = 0.51234912839471234      # :146
 
@@ -66,7 +67,7 @@ def _approximate_level(funcs, level, verbose):
         polys, errs = [None] * dim, np.zeros(dim)
         for i in range(dim):
             if unit_box and isinstance(funcs[i], MultiPower):
-                polys[i], errs[i] = funcs[i].to_cheb(), 2.0 ** -52
+                polys[i], errs[i] = funcs[i].to_cheb(engine=get_engine()), 2.0 ** -52
             elif unit_box and isinstance(funcs[i], MultiCheb):
                 polys[i], errs[i] = funcs[i].coeff, 2.0 ** -52
             else:

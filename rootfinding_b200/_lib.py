@@ -87,7 +87,7 @@ EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_param
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
            "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch",
            "yr_frontier_begin", "yr_frontier_advance", "yr_frontier_export_bound", "yr_frontier_export",
-           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe"]
+           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -137,6 +137,8 @@ def bind(lib):
     lib.yr_frontier_fits.restype = C.c_int
     lib.yr_fetch.argtypes = [vp, vp, u64, vp]
     lib.yr_fetch.restype = C.c_int
+    lib.yr_upper_axis_apply.argtypes = [dp, dp, dp, i64, i64, i64, vp]
+    lib.yr_upper_axis_apply.restype = C.c_int
     lib.yr_decay_probe.argtypes = [i32, i32, i32, dp, vp, vp, dp, vp, vp, dp, i64, C.c_double, C.c_double, C.c_double, dp, vp, vp]
     lib.yr_decay_probe.restype = C.c_int
     lib.yr_frontier_begin.argtypes = [C.POINTER(YrFrontierDesc), vp]

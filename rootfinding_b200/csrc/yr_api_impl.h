@@ -32,6 +32,7 @@ template <int D> int launch_bils(int64_t n, const double* lin, const double* c0,
 template <int D> int launch_quad(int64_t n, const double* coeffs, const int64_t* off, const int32_t* shapes,
                                  const double* tol, int32_t nd_check, int32_t* out, void* stream);
 int launch_dct1(const double* values, double* coeffs, int64_t outer, int64_t npts, int64_t inner, void* stream);
+int launch_upper_axis(const double* coef, const double* P, double* out, int64_t outer, int64_t n, int64_t inner, void* stream);
 int launch_decay(int mode, int dim, int axis, const yr::DecayTensor& t, const yr::DecayTensor* prev, const double* values, int64_t nvalues,
                  double prev_supnorm, double rel_tol, double abs_tol, double* scratch, yr::DecayOut* out, void* stream);
 int launch_poly_eval(const double* coef, const double* x, double* out, int64_t outer, int64_t ncoef, int64_t npts,
@@ -280,6 +281,11 @@ int yr_poly_eval_axis(const double* coef, const double* x, double* out, int64_t 
 
 int yr_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream) {
     return yr_backend::launch_abs_axis_mean(t, out, supnorm, outer, n, inner, stream);
+}
+
+int yr_upper_axis_apply(const double* coef, const double* P, double* out, int64_t outer, int64_t n, int64_t inner, void* stream) {
+    if (n < 1) return yr_api::fail("yr_upper_axis_apply: empty axis");
+    return yr_backend::launch_upper_axis(coef, P, out, outer, n, inner, stream);
 }
 
 int yr_decay_probe(int32_t mode, int32_t dim, int32_t axis, const double* coeff, const int64_t* shape, const int64_t* keep,

@@ -90,6 +90,26 @@ YR_DEV void poly_eval_worker(Ctx& cx, const PolyEvalArgs& a, long long cta, long
     }
 }
 
+// out[o][i][in] = sum_{k >= i} P[i][k] * c[o][k][in], accumulated from zero in ascending k with separately rounded
+// multiply and add: the power -> Chebyshev basis change of MultiPower.to_cheb along one axis (polynomial.py:587-640,
+// P[i][k] = coefficient of T_i in x^k), bit-identical to the reference's `cheb_coeffs[:k+1] += As * coeff[k]` loop.
+struct UpperAxisArgs { const double* coef; const double* P; double* out; long long outer, n, inner; };
+
+template <class Ctx>
+YR_DEV void upper_axis_worker(Ctx& cx, const UpperAxisArgs& a, long long cta, long long nctas) {
+    const long long per_o = a.n * a.inner;
+    const long long total = a.outer * per_o;
+    for (long long id = cta * cx.nthreads + cx.tid; id < total; id += nctas * cx.nthreads) {
+        const long long o = id / per_o, r = id - o * per_o;
+        const long long i = r / a.inner, in = r - i * a.inner;
+        const double* c = a.coef + o * per_o + in;
+        const double* p = a.P + i * a.n;
+        double acc = 0.0;
+        for (long long k = i; k < a.n; ++k) acc = acc + p[k] * c[k * a.inner];
+        a.out[id] = acc;
+    }
+}
+
 struct AbsMeanArgs { const double* t; double* mean; double* maxabs; long long outer, n, inner; };
 
 // one CTA per index j of the middle axis

@@ -353,6 +353,13 @@ __global__ void poly_eval_kernel(yr::PolyEvalArgs a) {
     yr::poly_eval_worker(cx, a, blockIdx.x, gridDim.x);
 }
 
+__global__ void upper_axis_kernel(yr::UpperAxisArgs a) {
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar;
+    DeviceCtx cx = make_ctx(red, &mbar, 0);
+    yr::upper_axis_worker(cx, a, blockIdx.x, gridDim.x);
+}
+
 __global__ void abs_mean_kernel(yr::AbsMeanArgs a) {
     __shared__ double red[32];
     __shared__ __align__(8) uint64_t mbar;
@@ -606,6 +613,13 @@ int launch_poly_eval(const double* coef, const double* x, double* out, int64_t o
     poly_eval_kernel<<<grid_for(outer * npts * inner, 256), 256, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : cuda_fail(e, "poly_eval_kernel launch");
+}
+
+int launch_upper_axis(const double* coef, const double* P, double* out, int64_t outer, int64_t n, int64_t inner, void* stream) {
+    yr::UpperAxisArgs a{coef, P, out, outer, n, inner};
+    upper_axis_kernel<<<grid_for(outer * n * inner, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "upper_axis_kernel launch");
 }
 
 int launch_abs_axis_mean(const double* t, double* out, double* supnorm, int64_t outer, int64_t n, int64_t inner, void* stream) {

@@ -157,9 +157,15 @@ class MultiPower(Polynomial):
             self.jac = [poly.polyder(self.coeff, axis=i) for i in range(self.dim)]
         return np.array([MultiPower(j, clean_zeros=False)(point) for j in self.jac], dtype=complex)
 
-    def to_cheb(self):
+    def to_cheb(self, engine=None):
         """Chebyshev coefficient tensor of the same polynomial (:587-640): per axis, the T-expansion
-        of x^k is built from that of x^(k-1) by x T_0 = T_1, x T_j = (T_{j+1} + T_{j-1}) / 2."""
+        of x^k is built from that of x^(k-1) by x T_0 = T_1, x T_j = (T_{j+1} + T_{j-1}) / 2.
+
+        With an `engine` the tensor is transformed on the device (yr_upper_axis_apply, one launch per axis; the small
+        power -> Chebyshev matrices are built here with the same recurrence): same operations in the same order, so the
+        result is bit-identical to the host loop."""
+        if engine is not None:
+            return _to_cheb_device(np.ascontiguousarray(self.coeff, dtype=np.float64), engine)
         out = self.coeff
         for axis in range(out.ndim):
             moved = np.moveaxis(out, axis, 0)
@@ -170,6 +176,31 @@ class MultiPower(Polynomial):
                 acc[:k + 1] += np.einsum("i,...->i...", row, slab)
             out = np.moveaxis(acc, 0, axis)
         return out
+
+
+def _power_to_cheb_matrix(n):
+    """P[i][k] = coefficient of T_i in x^k, k < n (upper triangular), from the recurrence of _times_x."""
+    P = np.zeros((n, n))
+    row = np.array([])
+    for k in range(n):
+        row = _times_x(row)
+        P[:k + 1, k] = row
+    return P
+
+
+def _to_cheb_device(coeff, eng):
+    from . import _lib
+    m, lib = eng.mem, eng.lib
+    shape = coeff.shape
+    cur = m.upload(coeff)
+    for axis, n in enumerate(shape):
+        outer = int(np.prod(shape[:axis], dtype=np.int64))
+        inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+        P = m.upload(_power_to_cheb_matrix(n))
+        out = m.empty(coeff.size * 8)
+        _lib.check(lib, lib.yr_upper_axis_apply(cur.ptr, P.ptr, out.ptr, outer, n, inner, m.stream()), "yr_upper_axis_apply")
+        cur = out
+    return m.download(cur, coeff.size * 8).view(np.float64).reshape(shape).copy()
 
 
 def _times_x(A):

@@ -307,6 +307,12 @@ int launch_poly_eval(const double* coef, const double* x, double* out, int64_t o
     return 0;
 }
 
+int launch_upper_axis(const double* coef, const double* P, double* out, int64_t outer, int64_t n, int64_t inner, void*) {
+    yr::UpperAxisArgs a{coef, P, out, outer, n, inner};
+    run_team(4, 4, [&](HostCtx& cx) { yr::upper_axis_worker(cx, a, 0, 1); });
+    return 0;
+}
+
 int launch_decay(int mode, int dim, int axis, const yr::DecayTensor& t, const yr::DecayTensor* prev, const double* values, int64_t nvalues,
                  double prev_supnorm, double rel_tol, double abs_tol, double* scratch, yr::DecayOut* out, void*) {
     const long long n = t.keep[axis];

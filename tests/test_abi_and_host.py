@@ -387,6 +387,25 @@ def test_workload_generator_matches_reference_stream():
     assert systems[0][0][6, 1] == 0.0 and systems[0][0][5, 1] != 0.0          # zero beyond total degree
 
 
+def test_npy_test_files_round_trip(tmp_path):
+    """The reference's random-test harness stores systems as .npy arrays [N, dim, deg+1, ...] (tests/random_tests.py:27-44);
+    workloads.save_tests / load_tests / load_systems read and write the same files."""
+    from rootfinding_b200 import workloads as W, MultiCheb, MultiPower
+    fmt = str(tmp_path / "dim{dim}_deg{deg}_{kind}.npy")
+    np.random.seed(2)
+    W.save_tests(2, [3, 5], 4, "randint", filefmt=fmt)
+    np.random.seed(2)
+    want = W.gen_tests(2, [3, 5], 4, "randint")
+    for deg, arr in zip([3, 5], want):
+        assert np.array_equal(np.load(fmt.format(dim=2, deg=deg, kind="randint")), arr)
+        tests = W.load_tests(2, deg, "power", "randint", N=3, filefmt=fmt)
+        assert len(tests) == 3 and all(isinstance(p, MultiPower) for t in tests for p in t)
+        cheb = W.load_tests(2, deg, "cheb", "randint", filefmt=fmt)
+        assert len(cheb) == 4 and isinstance(cheb[0][0], MultiCheb)
+        systems, errs = W.load_systems(2, deg, "randint", filefmt=fmt)
+        assert len(systems) == 4 and np.array_equal(systems[1][0], arr[1][0]) and errs[0][0] == 2.0 ** -52
+
+
 def test_batch_that_does_not_fit_is_solved_in_halves(monkeypatch):
     """A device out-of-memory failure of a batch falls back to solving its halves one after the other (systems never
     interact); a single system that does not fit still raises."""

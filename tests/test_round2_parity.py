@@ -346,3 +346,25 @@ def test_device_degree_selection_emulated(emu_yr):
 def test_device_degree_selection_gpu(gpu_yr):
     from rootfinding_b200.runtime import get_engine
     _approximator(gpu_yr, get_engine())
+
+
+# ---- MultiPower.to_cheb on the device ------------------------------------------------------------------
+def _to_cheb(yr, engine):
+    import oracle
+    rng = np.random.RandomState(3)
+    for shp in [(7,), (4, 9), (6, 6), (3, 5, 4), (2, 3, 2, 3), (41, 37)]:
+        c = rng.randn(*shp)
+        got = yr.MultiPower(c, clean_zeros=False).to_cheb(engine=engine)
+        assert np.array_equal(got, oracle.MultiPower(c, clean_zeros=False).to_cheb()), shp       # bit for bit
+        assert np.array_equal(got, yr.MultiPower(c, clean_zeros=False).to_cheb())
+
+
+def test_to_cheb_device_emulated(emu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _to_cheb(emu_yr, get_engine())
+
+
+@pytest.mark.gpu
+def test_to_cheb_device_gpu(gpu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _to_cheb(gpu_yr, get_engine())
