@@ -205,6 +205,31 @@ int yr_frontier_trim(void* stream);
 /* device -> host copy of `bytes` bytes on `stream`, synchronous (host_dst is a HOST pointer) */
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void* stream);
 
+/* The frontier pipeline's TENSOR kernels on caller-supplied 2-D boxes -- the batched forms of transformChebToInterval
+ * (ChebyshevSubdivisionSolver.py:864-894, op = 1) and getSubdivisionIntervals (:1051-1129 with getSubdivisionDims :1013-1049,
+ * op = 2) -- through exactly the launches yr_frontier_solve makes (same size classes, teams and code).  Every pointer is
+ * a HOST pointer (an operator-level / test entry, not the solve path).  Box b has two tensors, row-major at coeffs +
+ * off[b][p] with extents shape[b][p][2], and error bounds err[b][p].
+ *   op 1: alpha / beta [n][2] per axis.  One output box per input box.
+ *   op 2: iv [n][2][2] tracked interval, next_mid [n][2] (nextTransformPoints), level [n] (solverOptions.level of the
+ *         calling solvePolyRecursive).  2^k output boxes per input box, children of one box consecutive, in the
+ *         reference's order; out_parent names the input box.
+ * Outputs per output box q and polynomial p: tensor (row-major packed at out_coeffs + out_off[q][p]), out_shape, out_err
+ * (error after the transformation charges :831), out_sumabs (sum|M|), the outcome trimMs (:1131-1171) would have on it
+ * (out_trim_shape, out_trim_err), and the box's tracked interval / nextTransformPoints (out_iv, out_next_mid). */
+typedef struct yr_f2_ops_desc {
+    int32_t op, flat;            /* op 1, flat = 0: inputs packed like level-0 boxes (even row strides possible); otherwise like arena tensors (odd row stride) */
+    uint64_t n;
+    const double* coeffs; const uint64_t* off; const int32_t* shape; const double* err;
+    const double* alpha; const double* beta;
+    const double* iv; const double* next_mid; const int32_t* level;
+    yr_params prm;
+    uint64_t cap_out, cap_coeffs; uint64_t* n_out;
+    double* out_coeffs; uint64_t* out_off; int32_t* out_shape; double* out_err; double* out_sumabs;
+    int32_t* out_trim_shape; double* out_trim_err; double* out_iv; double* out_next_mid; int32_t* out_parent;
+} yr_f2_ops_desc;
+int yr_f2_tensor_ops(const yr_f2_ops_desc* d, void* stream);
+
 /* BoundingIntervalLinearSystem on n independent dim x dim problems (thread per problem).
  *   lin [n][dim][dim], c0 [n][dim], sumabs [n][dim], errs [n][dim], final_step [n]
  *   -> interval [n][dim][2], flags [n][3] = (changed, should_stop, throwOut) */

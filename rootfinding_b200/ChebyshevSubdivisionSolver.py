@@ -289,3 +289,55 @@ def BoundingIntervalLinearSystem(Ms, errors, finalStep, macheps=2 ** -52):
     """:628-753 -> (interval, changed, should_stop, throwOut)."""
     iv, fl = bils_batched([Ms], [errors], [int(bool(finalStep))])
     return iv[0], bool(fl[0][0]), bool(fl[0][1]), bool(fl[0][2])
+
+
+def frontier_tensor_ops(op, systems, errors, alphas=None, betas=None, intervals=None, next_mids=None, levels=None,
+                        flat=True, use_fma=False, engine=None):
+    """The 2-D frontier pipeline's tensor kernels on caller-supplied boxes (include/yroots_b200.h: yr_f2_tensor_ops):
+    op = "restrict" -- transformChebToInterval (:864-894) with alphas / betas [n][2];
+    op = "subdivide" -- getSubdivisionIntervals (:1051-1129) with the boxes' tracked `intervals` [n][2][2], `next_mids` [n][2]
+    and `levels` [n].  Returns one dict per output box: Ms (two tensors), errors, sumabs, trim_shapes, trim_errors
+    (what trimMs :1131-1171 would leave), interval, next_mid, parent (index of the input box)."""
+    eng = get_engine() if engine is None else engine
+    n = len(systems)
+    code = {"restrict": 1, "subdivide": 2}[op]
+    shape = np.array([[M.shape for M in Ms] for Ms in systems], dtype=np.int32).reshape(n, 2, 2)
+    sizes = shape.prod(axis=2).reshape(-1).astype(np.uint64)
+    off = np.ascontiguousarray(np.cumsum(sizes) - sizes, dtype=np.uint64)
+    coeffs = np.concatenate([np.ascontiguousarray(M, dtype=np.float64).reshape(-1) for Ms in systems for M in Ms])
+    err = np.ascontiguousarray(errors, dtype=np.float64).reshape(n, 2)
+    d = _lib.YrF2OpsDesc()
+    d.op, d.flat, d.n = code, int(bool(flat)), n
+    keep = [coeffs, off, shape, err]
+    d.coeffs, d.off, d.shape, d.err = coeffs.ctypes.data, off.ctypes.data, shape.ctypes.data, err.ctypes.data
+    for name, arr, dt, shp in (("alpha", alphas, np.float64, (n, 2)), ("beta", betas, np.float64, (n, 2)),
+                               ("iv", intervals, np.float64, (n, 2, 2)), ("next_mid", next_mids, np.float64, (n, 2)),
+                               ("level", levels, np.int32, (n,))):
+        if arr is not None:
+            a = np.ascontiguousarray(arr, dtype=dt).reshape(shp)
+            keep.append(a)
+            setattr(d, name, a.ctypes.data)
+    d.prm = eng.params(use_fma=int(bool(use_fma)))
+    cap = n * (4 if code == 2 else 1)
+    total = int(sizes.sum()) * (4 if code == 2 else 1) + 16
+    n_out = np.zeros(1, dtype=np.uint64)
+    out = dict(coeffs=np.zeros(total), off=np.zeros((cap, 2), np.uint64), shape=np.zeros((cap, 2, 2), np.int32), err=np.zeros((cap, 2)),
+               sumabs=np.zeros((cap, 2)), tshape=np.zeros((cap, 2, 2), np.int32), terr=np.zeros((cap, 2)), iv=np.zeros((cap, 2, 2)),
+               mid=np.zeros((cap, 2)), parent=np.zeros(cap, np.int32))
+    d.cap_out, d.cap_coeffs, d.n_out = cap, total, n_out.ctypes.data
+    d.out_coeffs, d.out_off, d.out_shape, d.out_err = (out[k].ctypes.data for k in ("coeffs", "off", "shape", "err"))
+    d.out_sumabs, d.out_trim_shape, d.out_trim_err = (out[k].ctypes.data for k in ("sumabs", "tshape", "terr"))
+    d.out_iv, d.out_next_mid, d.out_parent = (out[k].ctypes.data for k in ("iv", "mid", "parent"))
+    import ctypes as C
+    _lib.check(eng.lib, eng.lib.yr_f2_tensor_ops(C.byref(d), eng.mem.stream()), "yr_f2_tensor_ops")
+    boxes = []
+    for q in range(int(n_out[0])):
+        Ms = []
+        for p in range(2):
+            shp = tuple(int(v) for v in out["shape"][q, p])
+            o = int(out["off"][q, p])
+            Ms.append(out["coeffs"][o:o + shp[0] * shp[1]].reshape(shp).copy())
+        boxes.append(dict(Ms=Ms, errors=out["err"][q].copy(), sumabs=out["sumabs"][q].copy(), trim_shapes=out["tshape"][q].copy(),
+                          trim_errors=out["terr"][q].copy(), interval=out["iv"][q].copy(), next_mid=out["mid"][q].copy(),
+                          parent=int(out["parent"][q])))
+    return boxes

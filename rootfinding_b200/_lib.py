@@ -66,6 +66,14 @@ class YrFrontierOut(C.Structure):
                 ("rounds", u64), ("launches", u64), ("slots", u64), ("tensor_ms", C.c_double), ("scalar_ms", C.c_double)]
 
 
+class YrF2OpsDesc(C.Structure):
+    _fields_ = [("op", i32), ("flat", i32), ("n", u64), ("coeffs", vp), ("off", vp), ("shape", vp), ("err", vp),
+                ("alpha", vp), ("beta", vp), ("iv", vp), ("next_mid", vp), ("level", vp), ("prm", YrParams),
+                ("cap_out", u64), ("cap_coeffs", u64), ("n_out", vp),
+                ("out_coeffs", vp), ("out_off", vp), ("out_shape", vp), ("out_err", vp), ("out_sumabs", vp),
+                ("out_trim_shape", vp), ("out_trim_err", vp), ("out_iv", vp), ("out_next_mid", vp), ("out_parent", vp)]
+
+
 class YrFrontierProgress(C.Structure):
     _fields_ = [("pending", u64), ("pending_restrict", u64), ("pending_subdivide", u64), ("rounds", u64), ("boxes", u64),
                 ("arena_doubles", u64)]
@@ -87,7 +95,7 @@ EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_param
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
            "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch",
            "yr_frontier_begin", "yr_frontier_advance", "yr_frontier_export_bound", "yr_frontier_export",
-           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply"]
+           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply", "yr_f2_tensor_ops"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -137,6 +145,8 @@ def bind(lib):
     lib.yr_frontier_fits.restype = C.c_int
     lib.yr_fetch.argtypes = [vp, vp, u64, vp]
     lib.yr_fetch.restype = C.c_int
+    lib.yr_f2_tensor_ops.argtypes = [C.POINTER(YrF2OpsDesc), vp]
+    lib.yr_f2_tensor_ops.restype = C.c_int
     lib.yr_upper_axis_apply.argtypes = [dp, dp, dp, i64, i64, i64, vp]
     lib.yr_upper_axis_apply.restype = C.c_int
     lib.yr_decay_probe.argtypes = [i32, i32, i32, dp, vp, vp, dp, vp, vp, dp, i64, C.c_double, C.c_double, C.c_double, dp, vp, vp]

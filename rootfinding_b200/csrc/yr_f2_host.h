@@ -504,6 +504,149 @@ inline int import_boxes(const void* xbuf, unsigned long long bytes, void* stream
     h.n_boxes = f.n_boxes;
     return 0;
 }
+// ---- operator-level entry: the frontier pipeline's tensor kernels on caller-supplied boxes -----------------------
+// yr_f2_tensor_ops (include/yroots_b200.h).  Everything crosses the boundary through HOST arrays: this is the batched
+// form of transformChebToInterval (:864-894) / getSubdivisionIntervals (:1051-1129) for callers and parity tests, not
+// the solve path.  The boxes go through exactly the kernels yr_frontier_solve launches (same classes, same teams).
+inline int tensor_ops(const yr_f2_ops_desc* d, void* stream) {
+    namespace be = yr_f2_backend;
+    Frontier& f = frontier();
+    if (f.active) return fail("yr_f2_tensor_ops: a frontier solve is in progress");
+    const unsigned long long n = d->n;
+    if (!n) return 0;
+    const bool sub = d->op == (int)kTSubdivide;
+    if (!sub && d->op != (int)kTRestrict) return fail("yr_f2_tensor_ops: op must be 1 (restrict) or 2 (subdivide)");
+    int ext = 4;
+    for (unsigned long long b = 0; b < n; ++b) for (int p = 0; p < 2; ++p) for (int a = 0; a < 2; ++a) {
+        const int e = d->shape[(b * 2 + p) * 2 + a];
+        if (e < 1) return fail("yr_f2_tensor_ops: extents must be >= 1");
+        if (e > ext) ext = e;
+    }
+    if (!fits((unsigned long long)ext)) return fail("yr_f2_tensor_ops: tensors too large for the shared-memory pipeline");
+    yr_frontier_desc fd;
+    memset(&fd, 0, sizeof(fd));
+    fd.dim = 2; fd.n_in = 0; fd.max_extent = (unsigned long long)ext; fd.prm = d->prm;
+    fd.prm.constant_check = 0;          // every output tensor is wanted here (a solve does not write children the check discards)
+    if (begin(&fd, stream)) return -1;
+    Workspace& ws = workspace();
+    Args& a = f.a;
+    // ---- host images of the records and of the input arena ----
+    std::vector<BoxRec<2>> recs(n);
+    std::vector<Work> work(n);
+    std::vector<double> arena;
+    std::vector<std::vector<unsigned int>> lists((size_t)kClasses);
+    unsigned long long need_max[kClasses], ext_max[kClasses], out_bound = 0;
+    for (int c = 0; c < kClasses; ++c) need_max[c] = ext_max[c] = 0;
+    const int slot = sub ? 1 : 0;
+    for (unsigned long long b = 0; b < n; ++b) {
+        BoxRec<2>& rec = recs[b]; Work& w = work[b];
+        memset(&rec, 0, sizeof(rec)); memset(&w, 0, sizeof(w));
+        rec.st.init_unit();
+        rec.system = (int32_t)b; rec.parent_node = -1; rec.collector = -1; rec.level = d->level ? d->level[b] : 0;
+        for (int p = 0; p < 2; ++p) {
+            const int n0 = d->shape[(b * 2 + p) * 2], n1 = d->shape[(b * 2 + p) * 2 + 1];
+            rec.shape[p][0] = n0; rec.shape[p][1] = n1; rec.err[p] = d->err[b * 2 + p];
+            const int ld = (d->flat || sub) ? odd_ld(n1) : n1;          // (a subdivision only ever sees arena tensors: odd row stride)
+            if (arena.size() & 1) arena.push_back(0.0);
+            w.off[p] = arena.size(); w.ld[p] = ld;
+            const double* src = d->coeffs + d->off[b * 2 + p];
+            double sum = 0.0;
+            const size_t base = arena.size();
+            arena.resize(base + (size_t)tensor_doubles(n0, ld), 0.0);
+            for (int i = 0; i < n0; ++i) for (int j = 0; j < n1; ++j) { const double v = src[(size_t)i * n1 + j]; arena[base + (size_t)i * ld + j] = v; sum += fabs(v); }
+            w.sumabs[p] = sum; w.tsumabs[p] = sum; w.terr[p] = rec.err[p];
+            w.tshape[p][0] = n0; w.tshape[p][1] = n1;
+            w.low[p][0] = src[0];
+        }
+        if (d->iv) for (int ax = 0; ax < 2; ++ax) { rec.st.iv[ax][0] = d->iv[(b * 2 + ax) * 2]; rec.st.iv[ax][1] = d->iv[(b * 2 + ax) * 2 + 1]; }
+        if (d->next_mid) for (int ax = 0; ax < 2; ++ax) rec.st.next_mid[ax] = d->next_mid[b * 2 + ax];
+        for (int ax = 0; ax < 2; ++ax) { w.cell_iv[ax][0] = rec.st.iv[ax][0]; w.cell_iv[ax][1] = rec.st.iv[ax][1]; }
+        w.node_level = rec.level + 1; w.result_index = -1; w.node_index = (int32_t)b;      // children report parent_node = b
+        w.trim_valid = 1; w.changed = 1;
+        int T, n0m, n1m; unsigned long long total, need; int cls;
+        box_sizes(rec, w, T, n0m, n1m, total);
+        if (!sub) {
+            w.op = kTRestrict;
+            for (int ax = 0; ax < 2; ++ax) { w.alpha[ax] = d->alpha[b * 2 + ax]; w.beta[ax] = d->beta[b * 2 + ax]; }
+            pick_team(need_restrict_w(T, n0m, n1m), need_restrict(T, n0m, n1m), 0, a.pol, 0, need, cls);
+            out_bound += total;
+        } else {
+            w.op = kTSubdivide;
+            int shape[2][2] = {{rec.shape[0][0], rec.shape[0][1]}, {rec.shape[1][0], rec.shape[1][1]}};
+            int order[2][2];
+            const int k = subdivision_axes<2>(shape, rec.st.iv, w.node_level, order);     // getSubdivisionDims :1013-1049
+            w.nsplit = k;
+            for (int p = 0; p < 2; ++p) { w.order[p][0] = order[p][0]; w.order[p][1] = (k > 1) ? order[p][1] : order[p][0]; }
+            pick_team(need_subdivide_w(T), need_subdivide(T), 0, a.pol, 1, need, cls);
+            out_bound += total << k;
+        }
+        lists[(size_t)cls].push_back((unsigned int)b);
+        if (need > need_max[cls]) need_max[cls] = need;
+        const unsigned long long e = (unsigned long long)(n0m > n1m ? n0m : n1m);
+        if (e > ext_max[cls]) ext_max[cls] = e;
+    }
+    // ---- device buffers ----
+#define F2_TRY2(expr) do { if (expr) { f.active = false; return -1; } } while (0)
+    f.cap_boxes = (size_t)(n * 5 + 64);
+    F2_TRY2(ws.recs.reserve(f.cap_boxes * sizeof(BoxRec<2>), 0, stream, 1.0));
+    F2_TRY2(ws.work.reserve(f.cap_boxes * sizeof(Work), 0, stream, 1.0));
+    F2_TRY2(be::to_device(ws.recs.p, recs.data(), n * sizeof(BoxRec<2>), stream));
+    F2_TRY2(be::to_device(ws.work.p, work.data(), n * sizeof(Work), stream));
+    F2_TRY2(ws.arena[0].reserve((arena.size() + 16) * 8, 0, stream, 1.0));
+    F2_TRY2(be::to_device(ws.arena[0].p, arena.data(), arena.size() * 8, stream));
+    F2_TRY2(ws.arena[1].reserve((size_t)(out_bound + 16) * 8, 0, stream, 1.0));
+    F2_TRY2(ws.lists[0].reserve((size_t)n * 4 + 64, 0, stream, 1.0));
+    bind_tables(f);
+    a.data_in = static_cast<const double*>(ws.arena[0].p);
+    a.data_out = static_cast<double*>(ws.arena[1].p); a.cap_data_out = ws.arena[1].cap / 8;
+    unsigned long long nb = n;
+    F2_TRY2(be::to_device(&a.ctl->n_boxes, &nb, sizeof(nb), stream));
+    unsigned int* dl = static_cast<unsigned int*>(ws.lists[0].p);
+    size_t pos = 0;
+    for (int c = 0; c < kClasses; ++c) {
+        if (lists[(size_t)c].empty()) continue;
+        F2_TRY2(be::to_device(dl + pos, lists[(size_t)c].data(), lists[(size_t)c].size() * 4, stream));
+        F2_TRY2(be::launch_tensor(a, d->op, c, dl + pos, lists[(size_t)c].size(), need_max[c], (int)(sub ? ext_max[c] : 0), stream));
+        pos += lists[(size_t)c].size();
+    }
+    // ---- read everything back and unpack on the host ----
+    Ctl h;
+    F2_TRY2(be::to_host(&h, ws.ctlbuf.p, sizeof(Ctl), stream));
+    if (h.overflow) { f.active = false; return fail("yr_f2_tensor_ops: internal buffer overflow"); }
+    const unsigned long long slots = h.n_boxes;
+    recs.resize(slots); work.resize(slots);
+    F2_TRY2(be::to_host(recs.data(), ws.recs.p, slots * sizeof(BoxRec<2>), stream));
+    F2_TRY2(be::to_host(work.data(), ws.work.p, slots * sizeof(Work), stream));
+    std::vector<double> outd((size_t)h.data_used + 2);
+    if (h.data_used) F2_TRY2(be::to_host(outd.data(), ws.arena[1].p, (size_t)h.data_used * 8, stream));
+#undef F2_TRY2
+    f.active = false;
+    const unsigned long long first = sub ? n : 0, count = sub ? slots - n : n;
+    if (count > d->cap_out) return fail("yr_f2_tensor_ops: output arrays too small (cap_out)");
+    unsigned long long used = 0;
+    for (unsigned long long q = 0; q < count; ++q) {
+        const BoxRec<2>& rec = recs[first + q]; const Work& w = work[first + q];
+        d->out_parent[q] = sub ? rec.parent_node : (int32_t)q;
+        for (int p = 0; p < 2; ++p) {
+            const int n0 = rec.shape[p][0], n1 = rec.shape[p][1];
+            d->out_shape[(q * 2 + p) * 2] = n0; d->out_shape[(q * 2 + p) * 2 + 1] = n1;
+            d->out_err[q * 2 + p] = rec.err[p]; d->out_sumabs[q * 2 + p] = w.sumabs[p];
+            d->out_trim_shape[(q * 2 + p) * 2] = w.tshape[p][0]; d->out_trim_shape[(q * 2 + p) * 2 + 1] = w.tshape[p][1];
+            d->out_trim_err[q * 2 + p] = w.terr[p];
+            if (used + (unsigned long long)n0 * n1 > d->cap_coeffs) return fail("yr_f2_tensor_ops: output arrays too small (cap_coeffs)");
+            d->out_off[q * 2 + p] = used;
+            for (int i = 0; i < n0; ++i) for (int j = 0; j < n1; ++j) d->out_coeffs[used + (size_t)i * n1 + j] = outd[(size_t)w.off[p] + (size_t)i * w.ld[p] + j];
+            used += (unsigned long long)n0 * n1;
+        }
+        for (int ax = 0; ax < 2; ++ax) {
+            d->out_iv[(q * 2 + ax) * 2] = rec.st.iv[ax][0]; d->out_iv[(q * 2 + ax) * 2 + 1] = rec.st.iv[ax][1];
+            d->out_next_mid[q * 2 + ax] = rec.st.next_mid[ax];
+        }
+    }
+    *d->n_out = count;
+    return 0;
+}
+
 #undef F2_TRY
 
 }  // namespace yr_f2_host

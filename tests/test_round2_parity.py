@@ -368,3 +368,92 @@ def test_to_cheb_device_emulated(emu_yr):
 def test_to_cheb_device_gpu(gpu_yr):
     from rootfinding_b200.runtime import get_engine
     _to_cheb(gpu_yr, get_engine())
+
+
+# ---- the f2 tensor kernels themselves against the reference's tensors --------------------------
+def _f2_restrict_tensor_level(yr, engine):
+    """TransformChebInPlaceND goldens (restrict_axis.npz, 2-D, plain arithmetic) through the frontier pipeline's RESTRICT
+    kernels: output tensor bit for bit (array_equal, row counts included), sum|M| to 1e-13 relative, the error charged for the
+    transformation (:831, n_axis * 2^-52 * sum|M| before each axis) to 1e-12 relative.  Both the flat (arena) and the packed
+    (level-0) input layouts, a batch large enough to reach the 16-lane, 32-lane and CTA teams."""
+    S = yr.ChebyshevSubdivisionSolver
+    z = H.load("restrict_axis.npz")
+    cases = []
+    for i in range(int(z["n"])):
+        M = z[f"in_{i}"]
+        axis, al, be, exact = z[f"par_{i}"]
+        if M.ndim == 2 and not exact:
+            cases.append((M, int(axis), float(al), float(be), z[f"out_{i}"]))
+    assert len(cases) >= 20
+    rng = np.random.RandomState(0)
+    for flat in (True, False):
+        systems, errs, alphas, betas = [], [], [], []
+        for M, axis, al, be, want in cases:
+            other = rng.randn(rng.randint(1, 6), rng.randint(1, 6))
+            systems.append([M, other])
+            errs.append([1e-9, 2e-9])
+            a, b = [1.0, 1.0], [0.0, 0.0]
+            a[axis], b[axis] = al, be
+            alphas.append(a); betas.append(b)
+        out = S.frontier_tensor_ops("restrict", systems, errs, alphas=alphas, betas=betas, flat=flat, engine=engine)
+        assert len(out) == len(cases)
+        for (M, axis, al, be, want), box, other in zip(cases, out, [s[1] for s in systems]):
+            got = box["Ms"][0]
+            assert got.shape == want.shape, (M.shape, axis, al, be, got.shape, want.shape)
+            assert np.array_equal(got, want), (M.shape, axis, al, be)
+            from oracle import kernels as okern                              # (pinned bit for bit to the reference)
+            assert np.array_equal(box["Ms"][1], okern.restrict_axis(other, axis, al, be)), (other.shape, axis)   # same (alpha, beta) for both
+            assert abs(box["sumabs"][0] - np.sum(np.abs(want))) <= 1e-13 * np.sum(np.abs(want))
+            # errors: n0 * eps * sum|M| before axis 0, n1 * eps * sum|M'| before axis 1 (identity axes are charged too)
+            s0 = np.sum(np.abs(M))
+            mid = want if axis == 0 else M
+            e = 1e-9 + M.shape[0] * 2.0 ** -52 * s0 + M.shape[1] * 2.0 ** -52 * np.sum(np.abs(mid))
+            assert abs(box["errors"][0] - e) <= 1e-12 * e
+
+
+def _f2_subdivide_tensor_level(yr, engine):
+    """getSubdivisionIntervals goldens (trim_subdivide.npz, 2-D, plain arithmetic) through the SUBDIVIDE kernels: every child
+    tensor bit for bit, child errors to 1e-12 relative, child intervals and nextTransformPoints exactly; plus the trimMs
+    outcome the kernels attach to each child against the reference's trimMs run on the reference's child."""
+    S = yr.ChebyshevSubdivisionSolver
+    from oracle import subdivision as osub
+    z = H.load("trim_subdivide.npz")
+    done = 0
+    for i in range(int(z["n"])):
+        Ms = H.unpack(z, f"trimM_{i}")
+        if Ms[0].ndim != 2:
+            continue
+        errs = z[f"trimE_{i}"]
+        tag = f"sub0_{i}"
+        nchild = int(z[f"{tag}_nchild"])
+        for flat in (True,):
+            out = S.frontier_tensor_ops("subdivide", [Ms], [errs], intervals=[z[f"box_iv_{i}"]], next_mids=[z[f"box_next_{i}"]],
+                                        levels=[int(z[f"level_{i}"]) - 1], flat=flat, engine=engine)
+            assert len(out) == nchild, (i, len(out), nchild)
+            for c, box in enumerate(out):
+                want_M = H.unpack(z, f"{tag}_c{c}_M")
+                for p in range(2):
+                    assert np.array_equal(box["Ms"][p], want_M[p]), (i, c, p)
+                want_E = z[f"{tag}_c{c}_E"]
+                assert np.all(np.abs(box["errors"] - want_E) <= 1e-12 * np.abs(want_E)), (i, c)
+                assert np.array_equal(box["interval"], z[f"{tag}_c{c}_iv"]), (i, c)
+                assert np.array_equal(box["next_mid"], z[f"{tag}_c{c}_next"]), (i, c)
+                tM, tE = [m.copy() for m in want_M], np.array(want_E, dtype=float).copy()
+                osub.trim_system(tM, tE)
+                assert [tuple(s) for s in box["trim_shapes"]] == [m.shape for m in tM], (i, c)
+                assert np.all(np.abs(box["trim_errors"] - tE) <= 1e-12 * np.abs(tE)), (i, c)
+        done += 1
+    assert done >= 8
+
+
+def test_f2_tensor_kernels_emulated(emu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _f2_restrict_tensor_level(emu_yr, get_engine())
+    _f2_subdivide_tensor_level(emu_yr, get_engine())
+
+
+@pytest.mark.gpu
+def test_f2_tensor_kernels_gpu(gpu_yr):
+    from rootfinding_b200.runtime import get_engine
+    _f2_restrict_tensor_level(gpu_yr, get_engine())
+    _f2_subdivide_tensor_level(gpu_yr, get_engine())
