@@ -150,7 +150,7 @@ int yr_process_level(const yr_level_desc* d, void* stream);
  * The library owns every buffer of the solve; result and node records (yr_record_layout kinds 1, 2)
  * stay on the device until yr_frontier_release and are read with yr_fetch.  exact = 0 only. */
 typedef struct yr_frontier_desc {
-    int32_t dim;                 /* must be 2 */
+    int32_t dim;                 /* 2, 3 or 4 (the resumable pieces below and yr_f2_tensor_ops: 2 only) */
     int32_t time_kernels;        /* 1: CUDA-event timing of the tensor / scalar launches (out->tensor_ms, scalar_ms) */
     const void*   recs_in;  const double* data_in;  uint64_t n_in;   /* level-0 boxes (yr_init_boxes) */
     uint64_t      max_extent;    /* largest extent of any of their tensors */
@@ -158,7 +158,7 @@ typedef struct yr_frontier_desc {
     yr_params     prm;
 } yr_frontier_desc;
 
-/* one entry of yr_frontier_out.order */
+/* one entry of yr_frontier_out.order for dim = 2; for dim = 3, 4 the entry has root[dim] (16 + 8 * dim bytes) */
 typedef struct yr_sorted_rec { uint32_t index; int32_t system; uint32_t flags; int32_t collector; double root[2]; } yr_sorted_rec;
 
 typedef struct yr_frontier_out {
@@ -199,6 +199,8 @@ int yr_frontier_import(const void* xbuf, uint64_t bytes, void* stream);
 int yr_frontier_finish(yr_frontier_out* out, void* stream);
 /* 1 when 2-D boxes with extents up to max_extent fit the pipeline's shared-memory budget (else use yr_process_level) */
 int yr_frontier_fits(uint64_t max_extent);
+/* the same for dim = 2, 3, 4 (0 for other dimensions): max_tensor = coefficients of the largest single tensor */
+int yr_frontier_fits_dim(int32_t dim, uint64_t max_extent, uint64_t max_tensor);
 int yr_frontier_release(yr_frontier_out* out, void* stream);
 /* the pipeline keeps its box tables, arenas and queues between solves (grow-only); this frees them */
 int yr_frontier_trim(void* stream);

@@ -79,9 +79,13 @@ class YrFrontierProgress(C.Structure):
                 ("arena_doubles", u64)]
 
 
-# yr_sorted_rec (include/yroots_b200.h)
-SORTED_DTYPE = np.dtype([("index", np.uint32), ("system", np.int32), ("flags", np.uint32), ("collector", np.int32),
-                         ("root", np.float64, (2,))])
+# yr_sorted_rec (include/yroots_b200.h): root[dim]
+def sorted_dtype(dim):
+    return np.dtype([("index", np.uint32), ("system", np.int32), ("flags", np.uint32), ("collector", np.int32),
+                     ("root", np.float64, (dim,))])
+
+
+SORTED_DTYPE = sorted_dtype(2)
 
 COUNTER_FIELDS = ["next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms", "subdivisions",
                   "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "restrict_macs",
@@ -95,7 +99,7 @@ EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_param
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
            "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch",
            "yr_frontier_begin", "yr_frontier_advance", "yr_frontier_export_bound", "yr_frontier_export",
-           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply", "yr_f2_tensor_ops"]
+           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply", "yr_f2_tensor_ops", "yr_frontier_fits_dim"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -145,6 +149,8 @@ def bind(lib):
     lib.yr_frontier_fits.restype = C.c_int
     lib.yr_fetch.argtypes = [vp, vp, u64, vp]
     lib.yr_fetch.restype = C.c_int
+    lib.yr_frontier_fits_dim.argtypes = [i32, u64, u64]
+    lib.yr_frontier_fits_dim.restype = C.c_int
     lib.yr_f2_tensor_ops.argtypes = [C.POINTER(YrF2OpsDesc), vp]
     lib.yr_f2_tensor_ops.restype = C.c_int
     lib.yr_upper_axis_apply.argtypes = [dp, dp, dp, i64, i64, i64, vp]

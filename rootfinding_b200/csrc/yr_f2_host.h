@@ -25,6 +25,7 @@ int launch_tensor(const yr::f2::Args& a, int op, int cls, const unsigned int* li
 // the tensor launches of a round are independent: the backend may spread them over several streams between these
 void round_fork(void* stream);
 void round_join(void* stream);
+void* fan_stream(void* stream);          // the stream the next tensor launch of the round should use
 struct Segments { const unsigned int* list[yr::f2::kClasses]; unsigned long long n[yr::f2::kClasses];
                   unsigned long long child_lo, child_bound; };
 int launch_scalar(const yr::f2::Args& a, const Segments& s, void* stream);

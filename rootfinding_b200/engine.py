@@ -326,7 +326,9 @@ class SolveSession:
         self._reserve("results", max(256, 4 * self.nsys))
         self._reserve("nodes", max(256, 4 * self.nsys))
         # 2-D, plain arithmetic, tensors that fit shared memory: the round-based frontier pipeline serves the session
-        self.use_frontier = bool(engine.pipeline == 2 and D == 2 and not prm.exact and self.nsys > 0)
+        # 2-D, 3-D and 4-D systems in plain arithmetic: the round-based frontier pipelines serve the session
+        self.use_frontier = bool(engine.pipeline == 2 and D in (2, 3, 4) and not prm.exact and self.nsys > 0)
+        self.sorted_dt = _lib.sorted_dtype(D)
         self._segments = []               # record ranges in production order: ("level", start, count) / ("frontier", start, count, out)
         self.index_base = 0               # added to every record index the device links with (box-level multi-GPU: rank << 27)
         self.frontier_runner = None       # replaces _run_frontier (distributed.ShardedFrontier)
@@ -405,7 +407,7 @@ class SolveSession:
         if len(jobs["system"]) == 0:                              # a rank that only receives boxes (sharded frontier)
             return run_frontier(None, None, dict(n_children=0, max_child_extent=0), first_result)
         recs, data, c = self._init_boxes(jobs)
-        if self.use_frontier and self.lib.yr_frontier_fits(int(c["max_child_extent"])):
+        if self.use_frontier and self.lib.yr_frontier_fits_dim(D, int(c["max_child_extent"]), int(c["max_child_tensor"])):
             return run_frontier(recs, data, c, first_result)
         n_in, data_used = c["n_children"], c["data_used"]
         big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
@@ -487,7 +489,7 @@ class SolveSession:
             recs, data = out_recs, out_data
             n_in, data_used = c["n_children"], c["data_used"]
             big_box, big_tensor, big_extent = c["max_child_doubles"], c["max_child_tensor"], c["max_child_extent"]
-            if self.use_frontier and n_in > 0 and self.lib.yr_frontier_fits(int(big_extent)):
+            if self.use_frontier and n_in > 0 and self.lib.yr_frontier_fits_dim(D, int(big_extent), int(big_tensor)):
                 # large 2-D systems: the first levels run here, the rest of the search on the frontier pipeline
                 run_frontier(recs, data, c, first_result)
                 break
@@ -495,7 +497,7 @@ class SolveSession:
 
     def frontier_desc(self, recs, data, c, max_extent=None):
         d = _lib.YrFrontierDesc()
-        d.dim, d.time_kernels = 2, int(bool(self.time_kernels))
+        d.dim, d.time_kernels = self.dim, int(bool(self.time_kernels))
         if recs is not None:
             d.recs_in, d.data_in = recs.ptr, data.ptr
         d.n_in = int(c["n_children"])
@@ -570,7 +572,7 @@ class SolveSession:
                         _lib.check(lib, lib.yr_fetch(dst.ctypes.data, ptr, dst.nbytes, stream), "yr_fetch")
                         self.mem.d2h_bytes += dst.nbytes
                 if self._order_host is None and rn and out.order:
-                    order = np.empty(rn, dtype=_lib.SORTED_DTYPE)
+                    order = np.empty(rn, dtype=self.sorted_dt)
                     _lib.check(lib, lib.yr_fetch(order.ctypes.data, out.order, order.nbytes, stream), "yr_fetch")
                     self.mem.d2h_bytes += order.nbytes
                     self._order_host, self._order_base = order, r0
@@ -609,12 +611,12 @@ class SolveSession:
         if r0 != 0 or rn != self.n_results or not rn or not out.order:
             return None
         alloc = getattr(self.mem, "host_bytes", None)
-        nbytes = rn * _lib.SORTED_DTYPE.itemsize
+        nbytes = rn * self.sorted_dt.itemsize
         raw = alloc(nbytes, self, 2) if alloc is not None else np.empty(nbytes, dtype=np.uint8)
         _lib.check(self.lib, self.lib.yr_fetch(raw.ctypes.data, out.order, nbytes, self.mem.stream()), "yr_fetch")
         self.mem.d2h_bytes += nbytes
         self._order_raw = raw
-        self._order_host, self._order_base = raw.view(_lib.SORTED_DTYPE), 0
+        self._order_host, self._order_base = raw.view(self.sorted_dt), 0
         return self._order_host
 
     def dfs_order(self):

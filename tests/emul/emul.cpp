@@ -16,6 +16,7 @@
 #include "../../rootfinding_b200/csrc/yr_api_impl.h"
 #include "../../rootfinding_b200/csrc/yr_approx.h"
 #include "../../rootfinding_b200/csrc/yr_f2_host.h"
+#include "../../rootfinding_b200/csrc/yr_fd_host.h"
 
 namespace {
 
@@ -538,19 +539,112 @@ double trace_sync_ms(void*) { return 0.0; }
 double host_ms() { return 0.0; }
 void round_fork(void*) {}
 void round_join(void*) {}
+void* fan_stream(void* s) { return s; }
 void timer_reset(int) {}
 void timer_mark(int, int, void*) {}
 void timer_collect(double* t, double* s) { *t = 0; *s = 0; }
 }  // namespace yr_f2_backend
 
+// ---- D-dimensional frontier pipeline (yr_fd.h) on pthreads ----------------------------------------
+namespace yr_fd_backend {
+void* fan_unused = nullptr;
+
+template <int D>
+int launch_import(const yr::fd::Args<D>& a, unsigned long long n, void*) {
+    for (unsigned long long i = 0; i < n; ++i) {
+        yr::f2::Decision dc; memset(&dc, 0, sizeof(dc));
+        yr::fd::import_box<D>(a, (unsigned int)i, dc, F2At());
+        yr::fd::commit_decision<D>(a, (unsigned int)i, dc, F2At());
+    }
+    return 0;
+}
+
+template <int D>
+int launch_tensor(const yr::fd::Args<D>& a, int op, int cls, const unsigned int* list, unsigned long long n,
+                  unsigned long long need, int ext, void*) {
+    const int T = cls < yr::f2::kWarpClasses ? env_int("YR_EMUL_LANES", 4) : env_int("YR_EMUL_THREADS", 8);
+    std::vector<double> smat;
+    int snt = 0;
+    if (op == yr::f2::kTSubdivide) {
+        snt = ext < 4 ? 4 : ext;
+        const int P = yr::f2::panel_doubles(snt), B = (snt + 3) >> 2;
+        smat.assign(2 * (size_t)P, 0.0);
+        for (int h = 0; h < 2; ++h)
+            for (int b = 0; b < B; ++b)
+                memcpy(&smat[(size_t)h * P + yr::f2::panel_off(b, snt)], a.tab.mat[0][h] + yr::f2::panel_off(b, a.tab.nt), (size_t)(snt - 4 * b) * 4 * 8);
+    }
+    std::vector<double> slice((size_t)need + 8, 0.0);
+    const bool fma = a.prm.use_fma != 0;
+    unsigned long long macs_total = 0;
+    f2_run_team(T, [&](F2Team& tm) {
+        unsigned long long macs = 0;
+        for (unsigned long long i = 0; i < n; ++i) {
+            const unsigned int b = list[i];
+            const double* lo = smat.data(); const double* hi = smat.data() + yr::f2::panel_doubles(snt);
+            if (op == yr::f2::kTRestrict) { if (fma) yr::fd::restrict_box<D, true>(tm, a, b, slice.data(), macs); else yr::fd::restrict_box<D, false>(tm, a, b, slice.data(), macs); }
+            else if (fma) yr::fd::subdivide_box<D, true>(tm, a, b, slice.data(), lo, hi, snt, macs); else yr::fd::subdivide_box<D, false>(tm, a, b, slice.data(), lo, hi, snt, macs);
+            tm.sync();
+        }
+        if (tm.tid == 0) macs_total = macs;
+    });
+    a.ctl->restrict_macs += macs_total;
+    return 0;
+}
+
+template <int D>
+int launch_scalar(const yr::fd::Args<D>& a, const Segments& s, void*) {
+    auto one = [&](unsigned int b) {
+        yr::f2::Decision dc; memset(&dc, 0, sizeof(dc));
+        yr::fd::scalar_step<D>(a, b, dc, F2At());
+        yr::fd::commit_decision<D>(a, b, dc, F2At());
+        yr::f2::Ctl* c = a.ctl;
+        c->boxes += dc.boxes; c->zooms += dc.zooms; c->dconst += dc.dconst; c->dquad += dc.dquad; c->dzoom += dc.dzoom;
+        c->entry_coeffs += dc.coeffs; c->subdivisions += dc.subdiv;
+        if (dc.maxlevel > c->max_level) c->max_level = dc.maxlevel;
+    };
+    for (int c = 0; c < yr::f2::kClasses; ++c) for (unsigned long long i = 0; i < s.n[c]; ++i) one(s.list[c][i]);
+    const unsigned long long hi = a.ctl->n_boxes;
+    for (unsigned long long b = s.child_lo; b < hi; ++b) one((unsigned int)b);
+    return 0;
+}
+
+template <int D> struct SortedRec { uint32_t index; int32_t system; uint32_t flags; int32_t collector; double root[D]; };
+
+template <int D>
+void* sort_results(const void* results, unsigned long long n, void*) {
+    const yr::ResultRec<D>* res = static_cast<const yr::ResultRec<D>*>(results);
+    std::vector<unsigned int> v((size_t)n);
+    for (size_t i = 0; i < v.size(); ++i) v[i] = (unsigned int)i;
+    std::stable_sort(v.begin(), v.end(), [&](unsigned int a, unsigned int b) {
+        if (res[a].system != res[b].system) return res[a].system < res[b].system;
+        if (res[a].path_hi != res[b].path_hi) return res[a].path_hi < res[b].path_hi;
+        return res[a].path_lo < res[b].path_lo;
+    });
+    SortedRec<D>* order = static_cast<SortedRec<D>*>(malloc((size_t)n * sizeof(SortedRec<D>) + 16));
+    for (size_t i = 0; i < v.size(); ++i) {
+        order[i].index = v[i]; order[i].system = res[v[i]].system; order[i].flags = res[v[i]].flags; order[i].collector = res[v[i]].collector;
+        for (int d = 0; d < D; ++d) order[i].root[d] = res[v[i]].root[d];
+    }
+    return order;
+}
+}  // namespace yr_fd_backend
+
 extern "C" {
 int yr_frontier_solve(const yr_frontier_desc* d, yr_frontier_out* out, void* stream) {
     if (!d || !out) return yr_api::fail("null descriptor");
+    if (d->dim == 3) return yr_fd_host::solve<3>(d, out, stream);
+    if (d->dim == 4) return yr_fd_host::solve<4>(d, out, stream);
     return yr_f2_host::solve(d, out, stream);
+}
+int yr_frontier_fits_dim(int32_t dim, uint64_t max_extent, uint64_t max_tensor) {
+    if (dim == 2) return yr_f2_host::fits(max_extent);
+    if (dim == 3) return yr_fd_host::fits<3>(max_extent, max_tensor);
+    if (dim == 4) return yr_fd_host::fits<4>(max_extent, max_tensor);
+    return 0;
 }
 int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
 #include "../../rootfinding_b200/csrc/yr_f2_abi.inc"
 int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
-int yr_frontier_trim(void* stream) { return yr_f2_host::trim_workspace(stream); }
+int yr_frontier_trim(void* stream) { yr_fd_host::trim_workspace<3>(stream); yr_fd_host::trim_workspace<4>(stream); return yr_f2_host::trim_workspace(stream); }
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void*) { memcpy(host_dst, dev_src, bytes); return 0; }
 }

@@ -299,8 +299,8 @@ def test_emulated_hybrid_level_then_frontier(emu):
             self.lib, self.asked = lib, 0
 
         def __getattr__(self, k):
-            if k == "yr_frontier_fits":
-                def fits(extent):                      # "too large" for the first three levels of every run
+            if k == "yr_frontier_fits_dim":
+                def fits(dim, extent, tensor):          # "too large" for the first three levels of every run
                     self.asked += 1
                     return int(self.asked % 4 == 0)
                 return fits

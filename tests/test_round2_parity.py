@@ -457,3 +457,52 @@ def test_f2_tensor_kernels_gpu(gpu_yr):
     from rootfinding_b200.runtime import get_engine
     _f2_restrict_tensor_level(gpu_yr, get_engine())
     _f2_subdivide_tensor_level(gpu_yr, get_engine())
+
+
+# ---- the D-dimensional frontier pipeline (csrc/yr_fd.h: dimension 3 and 4) -------------------------------------------
+def _fd_vs_oracle_and_level(yr, engine, cases):
+    """Same search tree as the oracle box for box (and therefore as the reference), roots within 1e-13; the frontier
+    pipeline really ran (rounds > 0); and the level pipeline on the same inputs visits the same boxes."""
+    S = yr.ChebyshevSubdivisionSolver
+    for dim, deg, N, kw in cases:
+        systems = H.seeded_systems(dim, deg, N)
+        errs = [np.full(dim, 2.0 ** -52)] * N
+        sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=engine, **kw)
+        assert sess.stats.boxes == boxes, (dim, deg, sess.stats.boxes, boxes)
+        assert worst < 1e-13
+        assert getattr(sess.stats, "rounds", 0) > 0                    # the frontier pipeline, not the level pipeline
+        old = engine.pipeline
+        engine.pipeline = 1
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                got2, sess2 = S.solve_batch(systems, errs, engine=engine, return_session=True, **kw)
+        finally:
+            engine.pipeline = old
+        assert getattr(sess2.stats, "rounds", 0) == 0 and sess2.stats.boxes == sess.stats.boxes
+        assert (sess2.stats.zooms, sess2.stats.subdivisions) == (sess.stats.zooms, sess.stats.subdivisions)
+
+
+def test_fd_pipeline_emulated(emu_yr, monkeypatch):
+    from rootfinding_b200.runtime import get_engine
+    cases = [(3, 4, 2, {}), (3, 6, 1, {}), (4, 2, 2, {}), (4, 3, 1, {"all_dim_quadratic_check": True}), (3, 5, 1, {"use_fma": True})]
+    _fd_vs_oracle_and_level(emu_yr, get_engine(), cases[:4])
+    # one CTA per box instead of a warp team (boxes above the warp-team budget take this path on the device)
+    monkeypatch.setenv("YR_F2_WARP_MAX_R", "64")
+    monkeypatch.setenv("YR_F2_WARP_MAX_S", "64")
+    _fd_vs_oracle_and_level(emu_yr, get_engine(), [(3, 4, 1, {}), (4, 2, 1, {})])
+    monkeypatch.delenv("YR_F2_WARP_MAX_R"); monkeypatch.delenv("YR_F2_WARP_MAX_S")
+    S = emu_yr.ChebyshevSubdivisionSolver
+    systems = H.seeded_systems(3, 5, 1)
+    sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, [np.full(3, 2.0 ** -52)], engine=get_engine(), use_fma=True)
+    assert worst < H.ROOT_TOL
+
+
+@pytest.mark.gpu
+def test_fd_pipeline_gpu(gpu_yr, monkeypatch):
+    from rootfinding_b200.runtime import get_engine
+    _fd_vs_oracle_and_level(gpu_yr, get_engine(), [(3, 4, 3, {}), (3, 8, 2, {}), (3, 10, 1, {}), (4, 3, 2, {}), (4, 4, 1, {}),
+                                                  (4, 3, 1, {"all_dim_quadratic_check": True})])
+    monkeypatch.setenv("YR_F2_WARP_MAX_R", "64")
+    monkeypatch.setenv("YR_F2_WARP_MAX_S", "64")
+    _fd_vs_oracle_and_level(gpu_yr, get_engine(), [(3, 6, 2, {}), (4, 3, 1, {})])
