@@ -262,7 +262,7 @@ constexpr size_t kStaticReserve = 1024;
 template <class K>
 int ensure_smem(K kernel, size_t bytes) {
     static std::vector<const void*> done;
-    if (bytes <= 48 * 1024) return 0;
+    if (bytes + kStaticReserve <= 48 * 1024) return 0;          // (static shared memory counts against the default 48 KB limit)
     const void* key = reinterpret_cast<const void*>(kernel);
     for (const void* k : done) if (k == key) return 0;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev().smem_cta - (int)kStaticReserve);

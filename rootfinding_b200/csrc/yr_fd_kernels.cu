@@ -177,7 +177,7 @@ constexpr size_t kStaticReserve = 1024;
 template <class K>
 int ensure_smem(K kernel, size_t bytes) {
     static std::vector<const void*> done;
-    if (bytes <= 48 * 1024) return 0;
+    if (bytes + kStaticReserve <= 48 * 1024) return 0;          // (static shared memory counts against the default 48 KB limit)
     const void* key = reinterpret_cast<const void*>(kernel);
     for (const void* k : done) if (k == key) return 0;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev().smem_cta - (int)kStaticReserve);
@@ -224,7 +224,12 @@ int launch_tensor_t(const Args<D>& a, int cls, const unsigned int* list, unsigne
         }
     }
     cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : cuda_fail(e, "fd tensor launch");
+    if (e != cudaSuccess) {
+        char what[200];
+        snprintf(what, sizeof(what), "fd tensor launch (dim %d op %d class %d, %llu boxes, need %llu doubles, extent %d)", D, OP, cls, n, need, ext);
+        return cuda_fail(e, what);
+    }
+    return 0;
 }
 
 // ---- reporting order: stable LSD radix sort of the record indices by path_lo, path_hi, system (CUB) ----
