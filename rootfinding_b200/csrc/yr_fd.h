@@ -80,14 +80,28 @@ YR_HD int tensor_doubles(const int* full, int ld) {                // storage of
 template <int D>
 YR_HD int tight_doubles(const int* shape) { return tensor_doubles<D>(shape, odd_ld(shape[D - 1])); }
 
-// element e (row-major over `shape`) -> offset with `stride`
+// element e (row-major over `shape`) -> offset with `stride` (no division for the outermost axis)
 template <int D>
 YR_HD int view_offset(int e, const int* shape, const int* stride) {
     int off = 0;
-    for (int a = D - 1; a >= 0; --a) { const int q = e / shape[a]; off += (e - q * shape[a]) * stride[a]; e = q; }
-    return off;
+#pragma unroll
+    for (int a = D - 1; a >= 1; --a) { const int q = e / shape[a]; off += (e - q * shape[a]) * stride[a]; e = q; }
+    return off + e * stride[0];
 }
-// fiber f along `axis` (row-major over the other axes) -> offset of its first element
+// fiber f along AXIS (row-major over the other axes) -> offset of its first element
+template <int D, int AXIS>
+YR_HD int fiber_offset_t(int f, const int* shape, const int* stride) {
+    constexpr int kOuter = (AXIS == 0) ? 1 : 0;                 // the outermost axis that is not AXIS
+    int off = 0;
+#pragma unroll
+    for (int a = D - 1; a > kOuter; --a) {
+        if (a == AXIS) continue;
+        const int q = f / shape[a];
+        off += (f - q * shape[a]) * stride[a];
+        f = q;
+    }
+    return off + f * stride[kOuter];
+}
 template <int D>
 YR_HD int fiber_offset(int f, int axis, const int* shape, const int* stride) {
     int off = 0;
@@ -102,15 +116,19 @@ YR_HD int fiber_offset(int f, int axis, const int* shape, const int* stride) {
 template <int D>
 YR_HD int fibers_of(int axis, const int* shape) { int F = 1; for (int a = 0; a < D; ++a) if (a != axis) F *= shape[a]; return F; }
 
-// ---- one restriction pass along `axis`, in place or into another region with the same strides --------------------
-template <int D, bool FMA, class Team>
-YR_DEV double pass_axis(Team& tm, const double* src, double* dst, const int* shape, const int* stride, int axis, int r,
-                        const double* Cp, int nt, unsigned long long& macs) {
-    const int n = shape[axis], sk = stride[axis];
-    const int B = (r + 3) >> 2, F = fibers_of<D>(axis, shape);
+// ---- one restriction pass along AXIS, in place or into another region with the same strides --------------------
+// (AXIS is a template parameter: with every index into shape / stride a compile-time constant the arrays live in registers)
+template <int D, int AXIS, bool FMA, class Team>
+YR_DEV double pass_axis_t(Team& tm, const double* src, double* dst, const int* shape, const int* stride, int r,
+                          const double* Cp, int nt, unsigned long long& macs) {
+    const int n = shape[AXIS], sk = stride[AXIS];
+    int F = 1;
+#pragma unroll
+    for (int a = 0; a < D; ++a) if (a != AXIS) F *= shape[a];
+    const int B = (r + 3) >> 2;
     double asum = 0.0;
     for (int f = tm.tid; f < F; f += tm.nthreads) {
-        const int base = fiber_offset<D>(f, axis, shape, stride);
+        const int base = fiber_offset_t<D, AXIS>(f, shape, stride);
         const double* sc = src + base;
         double* dc = dst + base;
         for (int b = 0; b < B; ++b) {
@@ -136,17 +154,30 @@ YR_DEV double pass_axis(Team& tm, const double* src, double* dst, const int* sha
     if (tm.tid == 0) macs += (unsigned long long)(unsigned)(F * (r * n - r * (r - 1) / 2));
     return tm.sum_sync(asum);
 }
+template <int D, bool FMA, class Team>
+YR_DEV double pass_axis(Team& tm, const double* src, double* dst, const int* shape, const int* stride, int axis, int r,
+                        const double* Cp, int nt, unsigned long long& macs) {
+    switch (axis) {
+        case 0: return pass_axis_t<D, 0, FMA>(tm, src, dst, shape, stride, r, Cp, nt, macs);
+        case 1: return pass_axis_t<D, 1, FMA>(tm, src, dst, shape, stride, r, Cp, nt, macs);
+        case 2: return pass_axis_t<D, 2, FMA>(tm, src, dst, shape, stride, r, Cp, nt, macs);
+        default: return pass_axis_t<D, D - 1, FMA>(tm, src, dst, shape, stride, r, Cp, nt, macs);
+    }
+}
 
 // both halves of a subdivision at m = 0 in one sweep (mirror-image matrices, see yr_f2.h): lower -> dstL, upper -> dstU;
 // either may be src
-template <int D, bool FMA, class Team>
-YR_DEV void pass_axis_dual(Team& tm, const double* src, double* dstL, double* dstU, const int* shape, const int* stride, int axis,
-                           int r, const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
-    const int n = shape[axis], sk = stride[axis];
-    const int B = (r + 3) >> 2, F = fibers_of<D>(axis, shape);
+template <int D, int AXIS, bool FMA, class Team>
+YR_DEV void pass_axis_dual_t(Team& tm, const double* src, double* dstL, double* dstU, const int* shape, const int* stride,
+                             int r, const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
+    const int n = shape[AXIS], sk = stride[AXIS];
+    int F = 1;
+#pragma unroll
+    for (int a = 0; a < D; ++a) if (a != AXIS) F *= shape[a];
+    const int B = (r + 3) >> 2;
     double asl = 0.0, asu = 0.0;
     for (int f = tm.tid; f < F; f += tm.nthreads) {
-        const int base = fiber_offset<D>(f, axis, shape, stride);
+        const int base = fiber_offset_t<D, AXIS>(f, shape, stride);
         for (int b = 0; b < B; ++b) {
             const int i0 = b << 2;
             YR_F2_DUAL_BLOCK(src + base + i0 * sk, dstL + base + i0 * sk, dstU + base + i0 * sk, sk, sk)
@@ -154,6 +185,16 @@ YR_DEV void pass_axis_dual(Team& tm, const double* src, double* dstL, double* ds
     }
     if (tm.tid == 0) macs += 2ull * (unsigned)(F * (r * n - r * (r - 1) / 2));
     tm.sum2_sync(asl, asu, sumL, sumU);
+}
+template <int D, bool FMA, class Team>
+YR_DEV void pass_axis_dual(Team& tm, const double* src, double* dstL, double* dstU, const int* shape, const int* stride, int axis,
+                           int r, const double* Cp, int nt, unsigned long long& macs, double& sumL, double& sumU) {
+    switch (axis) {
+        case 0: pass_axis_dual_t<D, 0, FMA>(tm, src, dstL, dstU, shape, stride, r, Cp, nt, macs, sumL, sumU); break;
+        case 1: pass_axis_dual_t<D, 1, FMA>(tm, src, dstL, dstU, shape, stride, r, Cp, nt, macs, sumL, sumU); break;
+        case 2: pass_axis_dual_t<D, 2, FMA>(tm, src, dstL, dstU, shape, stride, r, Cp, nt, macs, sumL, sumU); break;
+        default: pass_axis_dual_t<D, D - 1, FMA>(tm, src, dstL, dstU, shape, stride, r, Cp, nt, macs, sumL, sumU); break;
+    }
 }
 
 template <int D, class Team>
@@ -177,7 +218,7 @@ YR_HD double coef_or_zero(const double* M, const int* shape, const int* stride, 
     return M[off];
 }
 
-// Collective over the team's LEAD warp (callers guard with tm.warp == 0); every lane gets the results.
+// Collective over the whole team; every thread gets the results.
 template <int D, class Team>
 YR_DEV void tensor_epilogue(Team& tm, const double* M, const int* shape, const int* stride, double sumabs, double err,
                             const SolverParams& prm, Epilogue<D>& ep) {
@@ -199,9 +240,8 @@ YR_DEV void tensor_epilogue(Team& tm, const double* M, const int* shape, const i
                 for (int a = 0; a < D; ++a) if (a != axis) cnt *= t[a];
                 const double* plane = M + (t[axis] - 1) * stride[axis];
                 double s = 0.0;
-                for (int e = tm.lane; e < cnt; e += tm.lanes) s += fabs(plane[fiber_offset<D>(e, axis, t, stride)]);
-                s = tm.wsum(s);
-                s = tm.wshfl_idx_d(s, 0);
+                for (int e = tm.tid; e < cnt; e += tm.nthreads) s += fabs(plane[fiber_offset<D>(e, axis, t, stride)]);
+                s = tm.sum(s);
                 if (s < budget) { budget -= s; err += s; removed += s; t[axis] -= 1; } else break;
             }
         }
@@ -219,14 +259,36 @@ YR_HD void store_epilogue(Work<D>& w, int p, const Epilogue<D>& ep, double sumab
     w.tsumabs[p] = ep.tsum; w.terr[p] = ep.terr;
 }
 
-// view (shape, stride) in shared memory -> arena, tight with last-axis stride ld_out
+// view (shape, stride) in shared memory -> arena, tight with last-axis stride ld_out.  When the view still has the
+// extents its strides were built from (`full`) and the same last-axis stride, the arena image is the shared-memory image:
+// one flat copy (the common case for the children of a subdivision).  Otherwise row by row: one decode per row.
 template <int D, class Team>
-YR_DEV void copy_out(Team& tm, double* dst, int ld_out, const double* M, const int* shape, const int* stride) {
-    int ostr[D];
+YR_DEV void copy_out(Team& tm, double* dst, int ld_out, const double* M, const int* shape, const int* full, const int* stride) {
+    bool same = (ld_out == stride[D - 2 >= 0 ? D - 2 : 0]);
+#pragma unroll
+    for (int a = 1; a < D; ++a) same = same && (shape[a] == full[a]);
+    if (same) {
+        const int n2 = tensor_doubles<D>(shape, ld_out) >> 1;
+        const pair_t* s2 = reinterpret_cast<const pair_t*>(M);
+        pair_t* d2 = reinterpret_cast<pair_t*>(dst);
+        for (int e = tm.tid; e < n2; e += tm.nthreads) d2[e] = s2[e];
+        return;
+    }
+    int ostr[D], rshape[D];
     strides_of<D>(shape, ld_out, ostr);
-    int cnt = 1;
-    for (int a = 0; a < D; ++a) cnt *= shape[a];
-    for (int e = tm.tid; e < cnt; e += tm.nthreads) dst[view_offset<D>(e, shape, ostr)] = M[view_offset<D>(e, shape, stride)];
+    int rows = 1;
+#pragma unroll
+    for (int a = 0; a < D - 1; ++a) { rows *= shape[a]; rshape[a] = shape[a]; }
+    rshape[D - 1] = 1;
+    const int len = shape[D - 1];
+    // four threads per row (rows are short), teams are powers of two
+    const int cg = tm.nthreads >= 4 ? 4 : tm.nthreads;
+    const int per = tm.nthreads / cg, r0 = tm.tid / cg, j0 = tm.tid - r0 * cg;
+    for (int r = r0; r < rows; r += per) {
+        const double* srow = M + view_offset<D>(r, rshape, stride);
+        double* drow = dst + view_offset<D>(r, rshape, ostr);
+        for (int j = j0; j < len; j += cg) drow[j] = srow[j];
+    }
 }
 
 // arena -> shared memory: flat when the arena layout can be used as it is (odd ld, even offset), else re-laid out
@@ -322,6 +384,7 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
         if (j0.nt > 0 || j1.nt > 0) f2::build_two(tm, j0, j1);
     }
     unsigned long long out_off = base;
+#pragma unroll 1
     for (int p = 0; p < D; ++p) {
         int stride[D], cur[D];
         strides_of<D>(full[p], lds[p], stride);
@@ -331,8 +394,8 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
         tm.sync();
         double s = copy_only ? view_abs_sum<D>(tm, A, cur, stride) : sum_in[p];
         double err = err_in[p];
-#pragma unroll 1
-        for (int axis = 0; axis < D; ++axis) {
+#pragma unroll
+        for (int axis = 0; axis < D; ++axis) {                       // unrolled: the axis of every pass is a compile-time constant
             const int n = cur[axis];
             if (!copy_only) err += n * kMachEps * s;                 // charged before the axis (:860)
             if (ident[axis] || n <= 1) continue;
@@ -342,7 +405,7 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
         }
         const int ld_out = odd_ld(cur[D - 1]);
         const int osz = tight_doubles<D>(cur);
-        if (tm.warp == 0) {
+        {
             Epilogue<D> ep;
             tensor_epilogue<D>(tm, A, cur, stride, s, err, prm, ep);
             if (tm.tid == 0) {
@@ -352,7 +415,7 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
                 wk.off[p] = out_off; wk.ld[p] = ld_out;
             }
         }
-        copy_out<D>(tm, a.data_out + out_off, ld_out, A, cur, stride);
+        copy_out<D>(tm, a.data_out + out_off, ld_out, A, cur, full[p], stride);
         out_off += (unsigned long long)osz;
         tm.sync();                                               // tensor p has left A before tensor p + 1 arrives
     }
@@ -456,8 +519,8 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
                 if (YR_F2_SKIP_DEAD && prm.constant_check && (fabs(c0) > sm[l] - fabs(c0) + er[l])) dead |= 1u << c;
                 const bool is_dead = (dead >> c) & 1u;
                 if (!is_dead) {
-                    if (tm.warp == 0) tensor_epilogue<D>(tm, M, shp[l], stride, sm[l], er[l], prm, ep);
-                    copy_out<D>(tm, a.data_out + off, ld_out, M, shp[l], stride);
+                    tensor_epilogue<D>(tm, M, shp[l], stride, sm[l], er[l], prm, ep);
+                    copy_out<D>(tm, a.data_out + off, ld_out, M, shp[l], wk.full[p], stride);
                 } else {
                     for (int q = 0; q < kLow<D>; ++q) ep.low[q] = 0.0;
                     ep.low[0] = c0; ep.tsum = sm[l]; ep.terr = er[l];
