@@ -218,6 +218,34 @@ YR_HD double coef_or_zero(const double* M, const int* shape, const int* stride, 
     return M[off];
 }
 
+// abs-sum of the hyperplane idx[AXIS] = j of a view with extents t, for a team of one warp: lanes take ROWS of the plane
+// (runs along the innermost axis that is not AXIS), one index decode per row instead of one per element.  (Measured: the
+// 4-D subdivide kernel spent 45 % of its instructions in the per-element decode; for the 128-thread CTA teams of the 3-D
+// boxes the per-element loop below stays faster -- too few rows for 128 threads.  profiles/r02_fd.txt)
+template <int D, int AXIS, class Team>
+YR_DEV double plane_abs_sum_rows(Team& tm, const double* M, const int* t, const int* stride, int j) {
+    constexpr int INNER = (AXIS == D - 1) ? D - 2 : D - 1;
+    constexpr int kOuter = (AXIS == 0 || INNER == 0) ? ((AXIS == 1 || INNER == 1) ? 2 : 1) : 0;   // outermost remaining axis
+    int rows = 1;
+#pragma unroll
+    for (int a = 0; a < D; ++a) if (a != AXIS && a != INNER) rows *= t[a];
+    const int len = t[INNER], si = stride[INNER];
+    const double* plane = M + j * stride[AXIS];
+    double s = 0.0;
+    for (int r = tm.tid; r < rows; r += tm.nthreads) {
+        int rem = r, off = 0;
+#pragma unroll
+        for (int a = D - 1; a >= 0; --a) {
+            if (a == AXIS || a == INNER) continue;
+            if (a == kOuter) off += rem * stride[a];
+            else { const int q = rem / t[a]; off += (rem - q * t[a]) * stride[a]; rem = q; }
+        }
+        const double* row = plane + off;
+        for (int i = 0; i < len; ++i) s += fabs(row[i * si]);
+    }
+    return tm.sum(s);
+}
+
 // Collective over the whole team; every thread gets the results.
 template <int D, class Team>
 YR_DEV void tensor_epilogue(Team& tm, const double* M, const int* shape, const int* stride, double sumabs, double err,
@@ -240,8 +268,17 @@ YR_DEV void tensor_epilogue(Team& tm, const double* M, const int* shape, const i
                 for (int a = 0; a < D; ++a) if (a != axis) cnt *= t[a];
                 const double* plane = M + (t[axis] - 1) * stride[axis];
                 double s = 0.0;
-                for (int e = tm.tid; e < cnt; e += tm.nthreads) s += fabs(plane[fiber_offset<D>(e, axis, t, stride)]);
-                s = tm.sum(s);
+                if (tm.nthreads <= 32 && D >= 4) {
+                    switch (axis) {
+                        case 0: s = plane_abs_sum_rows<D, 0>(tm, M, t, stride, t[axis] - 1); break;
+                        case 1: s = plane_abs_sum_rows<D, 1>(tm, M, t, stride, t[axis] - 1); break;
+                        case 2: s = plane_abs_sum_rows<D, 2>(tm, M, t, stride, t[axis] - 1); break;
+                        default: s = plane_abs_sum_rows<D, D - 1>(tm, M, t, stride, t[axis] - 1); break;
+                    }
+                } else {
+                    for (int e = tm.tid; e < cnt; e += tm.nthreads) s += fabs(plane[fiber_offset<D>(e, axis, t, stride)]);
+                    s = tm.sum(s);
+                }
                 if (s < budget) { budget -= s; err += s; removed += s; t[axis] -= 1; } else break;
             }
         }

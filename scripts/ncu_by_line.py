@@ -33,10 +33,13 @@ cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 # mangled-name match: strip template punctuation from the ncu name
 m0 = re.search(r"(\w+)<\(int\)(\d+), \(bool\)(\d)(?:, \(int\)(\d+))?>", blk["name"])
-if m0:
+mkey = os.environ.get("YR_MANGLED")            # explicit substring of the mangled name (kernels with other template lists)
+if mkey:
+    key = mkey
+elif m0:
     key = f"{m0.group(1)}ILi{m0.group(2)}ELb{m0.group(3)}E" + (f"Li{m0.group(4)}E" if m0.group(4) else "")
 else:
-    key = re.search(r"(\w+)\(", blk["name"]).group(1)
+    key = re.search(r"(\w+)[<(]", blk["name"]).group(1)
 line_of, infn, curline = {}, False, ("?", 0)
 for ln in dis.splitlines():
     if ln.startswith(".text.") and ln.rstrip().endswith(":"):
