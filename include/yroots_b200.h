@@ -60,8 +60,7 @@ typedef struct yr_launch {
     int32_t threads;             /* threads per CTA (multiple of 32) */
     int32_t ctas;                /* persistent CTAs */
     int32_t ws_in_smem;          /* 1: workspace in dynamic shared memory, 0: in gws */
-    int32_t warp_per_box;        /* 0: CTA per box; 1: every warp of a CTA owns a box of its own (small boxes);
-                                    2: same, and the warps of a CTA walk the pipeline phases in lock step */
+    int32_t warp_per_box;        /* 0: CTA per box; 1: every warp of a CTA owns a box of its own (small boxes) */
     uint64_t ws_doubles;         /* workspace capacity per CTA, in doubles */
     double*  gws;                /* [ctas][gws_stride] global scratch when ws_in_smem == 0 */
     uint64_t gws_stride;
@@ -82,7 +81,7 @@ typedef struct yr_level_desc {
      * alive, untouched, until the level has succeeded; recs_in / data_in are updated in place.
      * resume_subdivide = 1 re-runs only the subdivision step after an overflow (larger *_out buffers). */
     void*         work;          uint64_t work_bytes;
-    int32_t       pipeline;      /* 0: one fused kernel per level, 1: phase-split kernels */
+    int32_t       pipeline;      /* must be 1: phase-split kernels (tensor step / scalar step rounds, then the subdivision step) */
     int32_t       resume_subdivide;
     /* pipeline 1 plans its own launches from the size of the largest box of the level: */
     uint64_t      max_box_doubles; uint64_t max_tensor_doubles; uint64_t max_extent;
@@ -121,6 +120,9 @@ typedef struct yr_counters {
 
 int         yr_abi_version(void);
 const char* yr_last_error(void);
+/* class of the last failure on this thread: 0 none, 1 generic, 2 the DEVICE ran out of memory (a caller may retry with a
+ * smaller batch) */
+int         yr_last_error_code(void);
 const char* yr_build_info(void);                 /* "cuda sm_100a ..." */
 void        yr_default_params(yr_params* out);
 

@@ -95,8 +95,41 @@ def _check_system(Ms, errors):
 
 
 def _is_out_of_memory(exc):
-    msg = str(exc).lower()
-    return "out of memory" in msg or "allocation failed" in msg
+    """Device out of memory, by TYPE: the library reports it through yr_last_error_code (-> _lib.DeviceOutOfMemory), torch's
+    allocator through torch.OutOfMemoryError."""
+    if isinstance(exc, _lib.DeviceOutOfMemory):
+        return True
+    try:
+        import torch
+        return isinstance(exc, torch.OutOfMemoryError)
+    except Exception:
+        return False
+
+
+# Device memory a frontier holds at its widest, as a multiple of the bytes of the system's input coefficients.  Measured
+# high-water marks (scripts/profile_solve.py, library pools included): 2-D degree 20 / 50 / 100: 830 / 1050 / 1150 x,
+# 3-D degree 10: 6200 x, 4-D degree 4 / 6: 5500 / 25000 x (profiles/r02_configs.txt).  The table is deliberately on the
+# safe side; solve_batch uses it to cut a batch into sub-batches that fit BEFORE launching anything.
+_PEAK_FACTOR = {1: 400, 2: 1500, 3: 8000, 4: 30000, 5: 30000, 6: 30000}
+
+
+def _batch_ranges_for_memory(sizes, dim, eng):
+    """Consecutive sub-batches whose estimated peak frontier fits the free device memory (None: one batch is fine)."""
+    info = getattr(eng.mem, "free_bytes", None)
+    if info is None:
+        return None
+    budget = 0.6 * info()
+    need = sizes.astype(np.float64) * 8.0 * _PEAK_FACTOR.get(dim, 30000)
+    if need.sum() <= budget or len(sizes) < 2:
+        return None
+    ranges, lo, acc = [], 0, 0.0
+    for i, b in enumerate(need):
+        if acc + b > budget and i > lo:
+            ranges.append((lo, i))
+            lo, acc = i, 0.0
+        acc += b
+    ranges.append((lo, len(sizes)))
+    return ranges if len(ranges) > 1 else None
 
 
 def _solve_chunks(systems, errors, ranges, returnBoundingBoxes, exact, constant_check, low_dim_quadratic_check,
@@ -149,6 +182,10 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
             if len(bounds) > 2:
                 return _solve_chunks(systems, errors, list(zip(bounds[:-1], bounds[1:])), returnBoundingBoxes, exact,
                                      constant_check, low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, return_session)
+        ranges = _batch_ranges_for_memory(sizes, len(systems[0]), eng)
+        if ranges is not None:
+            return _solve_chunks(systems, errors, ranges, returnBoundingBoxes, exact, constant_check, low_dim_quadratic_check,
+                                 all_dim_quadratic_check, use_fma, eng, return_session)
     sess = None
     try:
         sess = eng.session(systems, errors,

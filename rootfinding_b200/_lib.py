@@ -94,7 +94,7 @@ COUNTER_FIELDS = ["next_box", "n_children", "data_used", "n_results", "n_nodes",
 COUNTER_BYTES = 8 * len(COUNTER_FIELDS)
 
 # every symbol include/yroots_b200.h declares
-EXPORTS = ["yr_abi_version", "yr_last_error", "yr_build_info", "yr_default_params", "yr_record_layout",
+EXPORTS = ["yr_abi_version", "yr_last_error", "yr_last_error_code", "yr_build_info", "yr_default_params", "yr_record_layout",
            "yr_workspace_doubles", "yr_level_work_bytes", "yr_static_smem_bytes", "yr_device_limits", "yr_init_boxes", "yr_process_level", "yr_bils_batched",
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
            "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch",
@@ -112,6 +112,7 @@ def bind(lib):
     """Attach prototypes to a loaded library and return it."""
     lib.yr_abi_version.restype = C.c_int
     lib.yr_last_error.restype = C.c_char_p
+    lib.yr_last_error_code.restype = C.c_int
     lib.yr_build_info.restype = C.c_char_p
     lib.yr_default_params.argtypes = [C.POINTER(YrParams)]
     lib.yr_default_params.restype = None
@@ -174,9 +175,14 @@ def bind(lib):
     return lib
 
 
+class DeviceOutOfMemory(RuntimeError):
+    """The device ran out of memory inside the library (yr_last_error_code() == 2): the batch can be retried in parts."""
+
+
 def check(lib, rc, what):
     if rc != 0:
-        raise RuntimeError(f"yroots_b200: {what} failed: {lib.yr_last_error().decode()}")
+        msg = f"yroots_b200: {what} failed: {lib.yr_last_error().decode()}"
+        raise (DeviceOutOfMemory if lib.yr_last_error_code() == 2 else RuntimeError)(msg)
 
 
 def default_params(lib):

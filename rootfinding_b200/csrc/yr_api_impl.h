@@ -16,7 +16,6 @@
 namespace yr_backend {
 const char* build_info();
 int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_per_sm);
-template <int D> int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream);
 template <int D> int launch_init(const yr::InitArgs<D>& a, const yr_launch& l, void* stream);
 // phase-split pipeline: one step over pa.list_in[0 .. pa.n_list)
 template <int D> int launch_tensor_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream);
@@ -45,7 +44,8 @@ static_assert(sizeof(yr_counters) == sizeof(yr::LevelCounters), "yr_counters / L
 
 namespace yr_api {
 static thread_local char g_err[512] = "";
-inline int fail(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); return -1; }
+static thread_local int g_err_code = 0;                // yr_last_error_code: 1 generic, 2 out of device memory
+inline int fail(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); g_err_code = 1; return -1; }
 
 inline yr::SolverParams to_params(const yr_params& p) {
     yr::SolverParams q;
@@ -128,8 +128,8 @@ int level_impl(const yr_level_desc* d, void* stream) {
     a.ctr = static_cast<yr::LevelCounters*>(d->counters);
     a.gws = d->launch.gws; a.gws_stride = d->launch.gws_stride; a.ws_doubles = d->launch.ws_doubles;
     a.prm = to_params(d->prm);
-    if (d->pipeline == 1) return run_level_phased<D>(a, d, stream);
-    return yr_backend::launch_level<D>(a, d->launch, stream);
+    if (d->pipeline != 1) return fail("yr_process_level: pipeline must be 1 (phase-split kernels)");
+    return run_level_phased<D>(a, d, stream);
 }
 
 template <int D>
@@ -198,6 +198,8 @@ extern "C" {
 int yr_abi_version(void) { return YR_ABI_VERSION; }
 const char* yr_last_error(void) { return yr_api::g_err; }
 void yr_set_error(const char* msg) { yr_api::fail(msg); }          /* used by the other translation units of the library */
+void yr_set_error_oom(const char* msg) { yr_api::fail(msg); yr_api::g_err_code = 2; }
+int yr_last_error_code(void) { return yr_api::g_err_code; }
 const char* yr_build_info(void) { return yr_backend::build_info(); }
 
 void yr_default_params(yr_params* p) {

@@ -840,217 +840,6 @@ YR_DEVN void restrict_system_inplace(Ctx& cx, BoxShared<D>& sh, double* ws, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// The life of one box inside the kernel, as a small state machine so that it can be run either
-// straight through (process_box: CTA-per-box kernel, emulator) or in lock step with the other
-// warps of a CTA (lockstep_worker: warp-per-box kernel).  Each step is collective over the team
-// `cx` that owns the box.
-enum BoxState : int { kStIdle = 0, kStNode, kStZoom, kStFinish, kStDone };
-
-template <int D, class Ctx>
-YR_DEV int team_state(Ctx& cx, BoxShared<D>& sh) {
-    cx.sync();
-    const int st = sh.state;
-    cx.sync();           // everybody has sampled the state before thread 0 may rewrite it
-    return st;
-}
-
-// stage the box: record, then its tensors (contiguous in the pool)
-template <int D, class Ctx>
-YR_DEVN void stage_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws, unsigned long long box_index) {
-    const SolverParams& prm = args.prm;
-    {   // the record is a few hundred bytes: all threads copy it, 8 bytes each
-        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&args.recs_in[box_index]);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh.rec);
-        for (int w = cx.tid; w < (int)(sizeof(BoxRec<D>) / 8); w += cx.nthreads) dst[w] = src[w];
-    }
-    cx.sync();
-    if (cx.tid == 0) {
-        for (int p = 0; p < D; ++p) {
-            int st = 1;
-            for (int a = D - 1; a >= 0; --a) { sh.shape[p][a] = sh.rec.shape[p][a]; sh.stride[p][a] = st; st *= sh.rec.shape[p][a]; }
-            sh.err[p] = sh.rec.err[p];
-        }
-        compute_layout<D>(sh, prm.exact != 0);
-        for (int d = 0; d < D; ++d) { sh.cell_iv[d][0] = sh.rec.st.iv[d][0]; sh.cell_iv[d][1] = sh.rec.st.iv[d][1]; }
-        sh.level = sh.rec.level;
-        sh.action = kActNone;
-        sh.state = kStNode;
-    }
-    cx.sync();
-    cx.copy_in(ws, args.data_in + sh.rec.data_off, sh.lay.total);      // TMA bulk copy on device
-    cx.sync();
-}
-
-// entry of one invocation of the reference's solvePolyRecursive: point test, checks, trim (:1202-1241)
-template <int D, class Ctx>
-YR_DEVN void node_start(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws) {
-    const SolverParams& prm = args.prm;
-    if (cx.tid == 0) {
-        sh.c_boxes += 1;
-        sh.action = kActNone;
-        sh.trimmed_any = 0;
-        if (sh.rec.st.is_point()) sh.action = kActEmit;                     // :1202-1203
-    }
-    cx.sync();
-    if (sh.action == kActEmit) {
-        emit_result<D>(cx, args, sh, kResPointAtEntry);
-        if (cx.tid == 0) sh.state = kStIdle;
-        cx.sync();
-        return;
-    }
-    for (int p = 0; p < D; ++p) {
-        const double s = tensor_abs_sum<D>(cx, ws + sh.lay.base[p], sh.shape[p], sh.stride[p]);
-        if (cx.tid == 0) sh.sumabs[p] = s;
-    }
-    if (cx.tid == 0) {
-        sh.level += 1;
-        if ((unsigned long long)sh.level > sh.c_maxlevel) sh.c_maxlevel = sh.level;
-        for (int p = 0; p < D; ++p) sh.c_coeffs += (unsigned long long)tensor_size<D>(sh.shape[p]);
-        if (prm.constant_check) {                                           // :1213-1217
-            for (int p = 0; p < D && sh.action == kActNone; ++p) {
-                const double c0 = ws[sh.lay.base[p]];
-                if (fabs(c0) > sh.sumabs[p] - fabs(c0) + sh.err[p]) { sh.action = kActDiscard; sh.c_dconst += 1; }
-            }
-        }
-        if (sh.action == kActNone && ((prm.low_dim_quad_check && D <= 3) || prm.all_dim_quad_check)) {   // :1221-1224
-            for (int p = 0; p < D && sh.action == kActNone; ++p)
-                if (quadratic_check_box<D>(sh, ws, p, sh.err[p])) { sh.action = kActDiscard; sh.c_dquad += 1; }
-        }
-        if (sh.action == kActDiscard) sh.state = kStIdle;
-    }
-    cx.sync();
-    if (sh.action == kActDiscard) return;
-
-    if (prm.trim) trim_box<D>(cx, sh, ws, prm);                             // :1232
-    if (sh.trimmed_any) {
-        for (int p = 0; p < D; ++p) {
-            const double s = tensor_abs_sum<D>(cx, ws + sh.lay.base[p], sh.shape[p], sh.stride[p]);
-            if (cx.tid == 0) sh.sumabs[p] = s;
-        }
-    }
-    if (cx.tid == 0) {
-        const IntervalState<D>& st = sh.rec.st;
-        for (int d = 0; d < D; ++d) {
-            sh.entry_iv[d][0] = st.final_step() ? st.pf_iv[d][0] : st.iv[d][0];
-            sh.entry_iv[d][1] = st.final_step() ? st.pf_iv[d][1] : st.iv[d][1];
-            sh.last_size[d] = st.iv[d][1] - st.iv[d][0];
-        }
-        sh.zoom_count = 0; sh.changed = 1; sh.should_stop = 0;
-        sh.state = kStZoom;
-    }
-    cx.sync();
-}
-
-// one pass of the zoom loop :1243-1252 (zoomInOnIntervalIter :896-956)
-template <int D, class Ctx>
-YR_DEVN void zoom_step(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws) {
-    const SolverParams& prm = args.prm;
-    const bool go = sh.changed && sh.zoom_count <= prm.max_zoom_count;
-    cx.sync();   // all threads have sampled the loop condition before thread 0 rewrites it
-    if (!go) {
-        if (cx.tid == 0) sh.state = kStFinish;
-        cx.sync();
-        return;
-    }
-    if (cx.tid == 0) {
-        IntervalState<D>& st = sh.rec.st;
-        sh.c_zooms += 1;
-        double lin[D][D], c0[D];
-        for (int p = 0; p < D; ++p) {
-            c0[p] = ws[sh.lay.base[p]];
-            for (int d = 0; d < D; ++d) lin[p][d] = (sh.shape[p][d] == 1) ? 0.0 : ws[sh.lay.base[p] + sh.stride[p][d]];
-        }
-        double sub[D][2];
-        BilsOut b = bounding_interval<D>(lin, c0, sh.sumabs, sh.err, st.final_step(), sub);
-        for (int d = 0; d < D; ++d)                                       // frozen axes :932-935
-            if (st.iv[d][0] == st.iv[d][1]) { sub[d][0] = -1.0; sub[d][1] = 1.0; }
-        bool changed = b.changed, should_stop = b.should_stop, thr = b.throw_out;
-        if (thr && !st.can_throw_out()) { thr = false; should_stop = true; changed = true; }   // :937-940
-        sh.action = kActZoomStop;
-        if (thr) { sh.action = kActDiscard; sh.c_dzoom += 1; }
-        else if (changed) {
-            double al[D], be[D];
-            if (!add_transform<D>(st, sub, al, be)) { sh.action = kActDiscard; sh.c_dzoom += 1; }
-            else {
-                sh.action = kActZoomTransform;
-                int nm = 0;
-                for (int d = 0; d < D; ++d) {
-                    sh.alpha[d] = al[d]; sh.beta[d] = be[d];
-                    int n = 1;
-                    for (int p = 0; p < D; ++p) n = sh.shape[p][d] > n ? sh.shape[p][d] : n;
-                    sh.mat_axis[d] = d; sh.mat_n[d] = n; nm = d + 1;
-                }
-                sh.nmat = nm;
-            }
-        }
-        sh.changed = changed ? 1 : 0; sh.should_stop = should_stop ? 1 : 0;
-        if (sh.action == kActDiscard) sh.state = kStIdle;
-    }
-    cx.sync();
-    if (sh.action == kActDiscard) return;
-    if (sh.action == kActZoomTransform) {
-        restrict_system_inplace<D>(cx, sh, ws, prm);
-        if (cx.tid == 0) {
-            IntervalState<D>& st = sh.rec.st;
-            if (st.final_step() && st.is_point()) { sh.should_stop = 1; sh.changed = 0; }   // :952-954
-        }
-    }
-    if (cx.tid == 0) {                                                    // :1249-1252
-        const IntervalState<D>& st = sh.rec.st;
-        bool all_big = true;
-        for (int d = 0; d < D; ++d) {
-            const double now = st.iv[d][1] - st.iv[d][0];
-            all_big = all_big && (now >= sh.last_size[d] / 2);
-            sh.last_size[d] = now;
-        }
-        if (all_big) sh.zoom_count += 1;
-    }
-    cx.sync();
-}
-
-// what next? :1254-1317 -- final-step re-entry, emit, or subdivide
-template <int D, class Ctx>
-YR_DEVN void finish_node(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws) {
-    if (cx.tid == 0) {
-        IntervalState<D>& st = sh.rec.st;
-        if (sh.should_stop) {
-            if (st.final_step()) sh.action = kActEmit;
-            else { st.start_final_step(); sh.action = kActReenterFinal; }
-        } else if (st.final_step()) {
-            st.flags |= kFlagCanThrowFinal;
-            sh.action = kActSubdivideFinal;
-        } else sh.action = kActSubdivide;
-        sh.state = (sh.action == kActReenterFinal) ? kStNode : kStIdle;
-    }
-    cx.sync();
-    const int action = sh.action;
-    cx.sync();
-    if (action == kActReenterFinal) return;
-    if (action == kActEmit) { emit_result<D>(cx, args, sh, 0u); cx.sync(); return; }
-    if (action == kActSubdivideFinal) {
-        emit_result<D>(cx, args, sh, kResCollector);       // the parent reports; its subtree supplies the points
-        cx.sync();
-        subdivide_box<D>(cx, args, sh, ws, true);
-        cx.sync();
-        return;
-    }
-    subdivide_box<D>(cx, args, sh, ws, false);
-    cx.sync();
-}
-
-template <int D, class Ctx>
-YR_DEV void process_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws, unsigned long long box_index) {
-    stage_box<D>(cx, args, sh, ws, box_index);
-    for (;;) {
-        const int st = team_state<D>(cx, sh);
-        if (st == kStNode) node_start<D>(cx, args, sh, ws);
-        else if (st == kStZoom) zoom_step<D>(cx, args, sh, ws);
-        else if (st == kStFinish) finish_node<D>(cx, args, sh, ws);
-        else break;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Level-0 boxes.  A job is (system, optional restriction alpha/beta per axis, tracked interval,
 // level, next split points): the whole unit cube for a fresh solve, a sub-box when the host
 // re-solves merged exterior boxes (ChebyshevSubdivisionSolver.py:1376-1377) -- and, used on its
@@ -1156,80 +945,6 @@ YR_DEV void init_worker(Ctx& cx, const InitArgs<D>& args, BoxShared<D>& sh, doub
         }
     }
     if (cx.tid == 0) cx.atomic_add(&args.ctr->restrict_macs, sh.c_macs);
-}
-
-template <int D, class Ctx>
-YR_DEV void level_worker(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws) {
-    if (cx.tid == 0) {
-        sh.c_boxes = sh.c_zooms = sh.c_subdiv = sh.c_dconst = sh.c_dquad = sh.c_dzoom = 0;
-        sh.c_coeffs = sh.c_macs = sh.c_maxlevel = 0;
-        sh.trimmed_any = 0;
-    }
-    for (;;) {
-        cx.sync();
-        if (cx.tid == 0) sh.work_index = cx.atomic_add(&args.ctr->next_box, 1ull);
-        cx.sync();
-        const unsigned long long b = sh.work_index;
-        if (b >= args.n_in) break;
-        process_box<D>(cx, args, sh, ws, b);
-    }
-    if (cx.tid == 0) {
-        cx.atomic_add(&args.ctr->boxes, sh.c_boxes);
-        cx.atomic_add(&args.ctr->zooms, sh.c_zooms);
-        cx.atomic_add(&args.ctr->subdivisions, sh.c_subdiv);
-        cx.atomic_add(&args.ctr->discard_const, sh.c_dconst);
-        cx.atomic_add(&args.ctr->discard_quad, sh.c_dquad);
-        cx.atomic_add(&args.ctr->discard_zoom, sh.c_dzoom);
-        cx.atomic_add(&args.ctr->entry_coeffs, sh.c_coeffs);
-        cx.atomic_add(&args.ctr->restrict_macs, sh.c_macs);
-        cx.atomic_max(&args.ctr->max_level, sh.c_maxlevel);
-    }
-}
-
-// Warp-per-box kernels: every warp-team of a CTA owns a box, and the CTA walks the phases
-// (start / zoom pass / finish) in lock step.  All warps of an SM then execute the same few KB of
-// code at any time -- the kernel is instruction-fetch bound when every warp is somewhere else in
-// it (profiles/) -- at the price of idling in phases a warp's box does not need this round.
-template <int D, class Ctx>
-YR_DEV void lockstep_worker(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, double* ws) {
-    if (cx.tid == 0) {
-        sh.c_boxes = sh.c_zooms = sh.c_subdiv = sh.c_dconst = sh.c_dquad = sh.c_dzoom = 0;
-        sh.c_coeffs = sh.c_macs = sh.c_maxlevel = 0;
-        sh.trimmed_any = 0;
-        sh.state = kStIdle;
-    }
-    for (;;) {
-        cx.cta_sync();                                      // ---- phase A: new boxes, node entry
-        int st = team_state<D>(cx, sh);
-        if (st == kStIdle) {
-            if (cx.tid == 0) {
-                sh.work_index = cx.atomic_add(&args.ctr->next_box, 1ull);
-                if (sh.work_index >= args.n_in) sh.state = kStDone;
-            }
-            cx.sync();
-            const unsigned long long b = sh.work_index;
-            cx.sync();
-            if (b < args.n_in) stage_box<D>(cx, args, sh, ws, b);
-            st = team_state<D>(cx, sh);
-        }
-        if (st == kStNode) node_start<D>(cx, args, sh, ws);
-        cx.cta_sync();                                      // ---- phase B: one zoom pass
-        if (team_state<D>(cx, sh) == kStZoom) zoom_step<D>(cx, args, sh, ws);
-        cx.cta_sync();                                      // ---- phase C: emit / re-enter / subdivide
-        if (team_state<D>(cx, sh) == kStFinish) finish_node<D>(cx, args, sh, ws);
-        if (cx.cta_all(team_state<D>(cx, sh) == kStDone)) break;
-    }
-    if (cx.tid == 0) {
-        cx.atomic_add(&args.ctr->boxes, sh.c_boxes);
-        cx.atomic_add(&args.ctr->zooms, sh.c_zooms);
-        cx.atomic_add(&args.ctr->subdivisions, sh.c_subdiv);
-        cx.atomic_add(&args.ctr->discard_const, sh.c_dconst);
-        cx.atomic_add(&args.ctr->discard_quad, sh.c_dquad);
-        cx.atomic_add(&args.ctr->discard_zoom, sh.c_dzoom);
-        cx.atomic_add(&args.ctr->entry_coeffs, sh.c_coeffs);
-        cx.atomic_add(&args.ctr->restrict_macs, sh.c_macs);
-        cx.atomic_max(&args.ctr->max_level, sh.c_maxlevel);
-    }
 }
 
 }  // namespace yr

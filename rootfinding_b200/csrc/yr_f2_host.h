@@ -10,6 +10,7 @@
 #include "yr_f2.h"
 
 extern "C" void yr_set_error(const char* msg);       // defined next to yr_last_error (yr_api_impl.h)
+extern "C" void yr_set_error_oom(const char* msg);   // ... marks the failure as "out of device memory"
 
 namespace yr_f2_backend {
 void* dev_alloc(size_t bytes, void* stream);
@@ -52,7 +53,7 @@ struct DevBuf {
         if (bytes <= cap) return 0;
         size_t want = (size_t)(bytes * slack) + 256;
         void* q = yr_f2_backend::dev_alloc(want, stream);
-        if (!q) return fail("device allocation failed (frontier buffers)");
+        if (!q) { yr_set_error_oom("device allocation failed (frontier buffers)"); return -1; }
         if (p && keep) { if (yr_f2_backend::dev_copy(q, p, keep, stream)) return -1; }
         if (p) yr_f2_backend::dev_free(p, stream);
         p = q; cap = want;
@@ -376,11 +377,11 @@ inline int finish(yr_frontier_out* out, void* stream) {
     if (f.phases) { ph2 = be::trace_sync_ms(stream); fprintf(stderr, "f2 phases: sort %.2f ms (%llu rounds, %llu launches)\n", ph2, f.rounds, f.launches); }
     if (n_results) {
         out->results = be::dev_alloc((size_t)n_results * sizeof(ResultRec<2>), stream);
-        if (!out->results || be::dev_copy(out->results, ws.results.p, (size_t)n_results * sizeof(ResultRec<2>), stream)) { release(out, stream); return fail("device allocation failed (results)"); }
+        if (!out->results || be::dev_copy(out->results, ws.results.p, (size_t)n_results * sizeof(ResultRec<2>), stream)) { release(out, stream); yr_set_error_oom("device allocation failed (results)"); return -1; }
     }
     if (n_nodes) {
         out->nodes = be::dev_alloc((size_t)n_nodes * sizeof(NodeRec<2>), stream);
-        if (!out->nodes || be::dev_copy(out->nodes, ws.nodes.p, (size_t)n_nodes * sizeof(NodeRec<2>), stream)) { release(out, stream); return fail("device allocation failed (nodes)"); }
+        if (!out->nodes || be::dev_copy(out->nodes, ws.nodes.p, (size_t)n_nodes * sizeof(NodeRec<2>), stream)) { release(out, stream); yr_set_error_oom("device allocation failed (nodes)"); return -1; }
     }
     out->n_results = n_results; out->n_nodes = n_nodes;
     out->rounds = f.rounds; out->launches = f.launches; out->slots = f.n_boxes;

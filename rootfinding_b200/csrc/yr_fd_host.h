@@ -244,11 +244,11 @@ inline int finish(yr_frontier_out* out, void* stream) {
     if (f.phases) { ph2 = be::trace_sync_ms(stream); fprintf(stderr, "f2 phases: sort %.2f ms (%llu rounds, %llu launches)\n", ph2, f.rounds, f.launches); }
     if (n_results) {
         out->results = be::dev_alloc((size_t)n_results * sizeof(ResultRec<D>), stream);
-        if (!out->results || be::dev_copy(out->results, ws.results.p, (size_t)n_results * sizeof(ResultRec<D>), stream)) { release(out, stream); return fail("device allocation failed (results)"); }
+        if (!out->results || be::dev_copy(out->results, ws.results.p, (size_t)n_results * sizeof(ResultRec<D>), stream)) { release(out, stream); yr_set_error_oom("device allocation failed (results)"); return -1; }
     }
     if (n_nodes) {
         out->nodes = be::dev_alloc((size_t)n_nodes * sizeof(NodeRec<D>), stream);
-        if (!out->nodes || be::dev_copy(out->nodes, ws.nodes.p, (size_t)n_nodes * sizeof(NodeRec<D>), stream)) { release(out, stream); return fail("device allocation failed (nodes)"); }
+        if (!out->nodes || be::dev_copy(out->nodes, ws.nodes.p, (size_t)n_nodes * sizeof(NodeRec<D>), stream)) { release(out, stream); yr_set_error_oom("device allocation failed (nodes)"); return -1; }
     }
     out->n_results = n_results; out->n_nodes = n_nodes;
     out->rounds = f.rounds; out->launches = f.launches; out->slots = f.n_boxes;

@@ -129,16 +129,7 @@ __device__ __forceinline__ DeviceCtx make_ctx(double* red, uint64_t* mbar, int w
     return cx;
 }
 
-template <int D>
-__global__ void __launch_bounds__(256) level_kernel(const yr::LevelArgs<D> args, int ws_in_smem) {
-    extern __shared__ __align__(16) double dyn_ws[];
-    __shared__ yr::BoxShared<D> sh;
-    __shared__ double red[32];
-    __shared__ __align__(8) uint64_t mbar;
-    DeviceCtx cx = make_ctx(red, &mbar, ws_in_smem);
-    double* ws = ws_in_smem ? dyn_ws : args.gws + (size_t)blockIdx.x * args.gws_stride;
-    yr::level_worker<D>(cx, args, sh, ws);
-}
+__host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Warp-per-box variant of the execution context: one warp is a whole "CTA" of the pipeline.
 // Barriers become __syncwarp, block reductions one shuffle tree; a serial section (BILS, checks)
@@ -190,26 +181,6 @@ struct WarpCtx {
     }
     __device__ __forceinline__ double cospi_ratio(long long m, long long N) const { return cospi((double)m / (double)N); }
 };
-
-__host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
-// dynamic shared memory per warp: [BoxShared<D> | mbarrier (16 B) | workspace doubles]
-template <int D>
-__global__ void __launch_bounds__(512, 1) level_kernel_warp(const yr::LevelArgs<D> args, unsigned warp_stride_bytes, int lockstep) {
-    extern __shared__ __align__(16) unsigned char dyn_raw[];
-    const int w = threadIdx.x >> 5;
-    unsigned char* base = dyn_raw + (size_t)w * warp_stride_bytes;
-    yr::BoxShared<D>* sh = reinterpret_cast<yr::BoxShared<D>*>(base);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(base + align16(sizeof(yr::BoxShared<D>)));
-    double* ws = reinterpret_cast<double*>(base + align16(sizeof(yr::BoxShared<D>)) + 16);
-    WarpCtx cx;
-    cx.tid = cx.lane = threadIdx.x & 31; cx.nthreads = cx.lanes = 32; cx.warp = 0; cx.nwarps = 1;
-    cx.mbar = mbar; cx.phase = 0;
-    if (cx.lane == 0) { mbar_init(mbar, 1); fence_mbar_init(); }
-    __syncwarp();
-    if (lockstep) yr::lockstep_worker<D>(cx, args, *sh, ws);
-    else yr::level_worker<D>(cx, args, *sh, ws);
-}
 
 template <int D>
 __global__ void __launch_bounds__(256) init_kernel(const yr::InitArgs<D> args, int ws_in_smem) {
@@ -423,25 +394,6 @@ int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_pe
     return 0;
 }
 
-template <int D>
-int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void* stream) {
-    if (a.n_in == 0) return 0;
-    if (l.warp_per_box) {
-        if (!l.ws_in_smem) return yr_api::fail("warp-per-box mode needs the workspace in shared memory");
-        const size_t stride = align16(sizeof(yr::BoxShared<D>)) + 16 + align16((size_t)l.ws_doubles * 8);
-        const size_t smem = stride * (size_t)(l.threads / 32);
-        if (smem > 48 * 1024 && set_smem(level_kernel_warp<D>, smem)) return -1;
-        level_kernel_warp<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, (unsigned)stride, l.warp_per_box == 2);
-        cudaError_t e = cudaGetLastError();
-        return e == cudaSuccess ? 0 : cuda_fail(e, "level_kernel_warp launch");
-    }
-    const size_t smem = l.ws_in_smem ? (size_t)l.ws_doubles * 8 : 0;
-    if (!l.ws_in_smem && !l.gws) return yr_api::fail("global workspace missing");
-    if (smem > 48 * 1024 && set_smem(level_kernel<D>, smem)) return -1;
-    level_kernel<D><<<l.ctas, l.threads, smem, (cudaStream_t)stream>>>(a, l.ws_in_smem);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : cuda_fail(e, "level_kernel launch");
-}
 
 template <int D, class KC, class KW>
 int launch_box_step(const yr::PhaseArgs<D>& pa, const yr_launch& l, void* stream, KC cta_kernel, KW warp_kernel, const char* what) {

@@ -155,6 +155,11 @@ class CudaMemory:
     def stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
+    def free_bytes(self):
+        """Device memory a new solve can count on: free memory plus what the library's own pools hold but do not use."""
+        free, _ = self.torch.cuda.mem_get_info(self.device)
+        return free + self.torch.cuda.memory_reserved(self.device) - self.torch.cuda.memory_allocated(self.device)
+
     def synchronize(self):
         self.torch.cuda.current_stream(self.device).synchronize()
         self._staging.clear()
@@ -203,10 +208,9 @@ class SubdivisionEngine:
         self.warp_max_ws = int(os.environ.get("YR_WARP_MAX_WS", "28000"))     # doubles; larger boxes run CTA-per-box
         self.warp_min_items = int(os.environ.get("YR_WARP_MIN_ITEMS", "1024"))  # fewer boxes than this: CTA-per-box (latency)
         self.warp_teams = int(os.environ.get("YR_WARP_TEAMS", "16"))          # warp-teams per SM (register bound: 16 x 32 x 128)
-        self.warp_mode = int(os.environ.get("YR_WARP_MODE", "1"))             # 1: independent warp-teams, 2: lock-step CTA
-        # 2: round-based 2-D frontier pipeline (yr_frontier_solve) where it applies, else phase-split;
-        # 1: phase-split kernels per level; 0: one fused kernel per level
-        self.pipeline = int(os.environ.get("YR_PIPELINE", "2"))
+        # 2: the round-based frontier pipelines (yr_frontier_solve: dimension 2, 3, 4, plain arithmetic) where they apply,
+        #    the level pipeline elsewhere; 1: the level pipeline (phase-split kernels per level) for everything
+        self.pipeline = max(1, int(os.environ.get("YR_PIPELINE", "2")))
 
     def params(self, **kw):
         p = _lib.default_params(self.lib)
@@ -227,18 +231,12 @@ class SubdivisionEngine:
         static = int(self.lib.yr_static_smem_bytes(dim))
         per_warp = static + 16 + ((ws * 8 + 15) & ~15)
         if allow_warp and ws <= self.warp_max_ws and n_items >= self.warp_min_items and per_warp + 1024 <= self.max_smem_cta:
-            if self.warp_mode == 2:
-                # lock-step CTA of up to 16 warp-teams (512 threads x 128 registers fill an SM's register file)
-                warps = int(max(1, min(self.warp_teams, (self.max_smem_cta - 1024) // per_warp)))
-                per_cta = warps * per_warp + 1024
-                per_sm = max(1, min(16 // warps, self.smem_per_sm // per_cta))
-            else:
-                # independent warp-teams, 4 per CTA (fewer when a box is large)
-                warps = int(max(1, min(4, (self.max_smem_cta - 1024) // per_warp)))
-                per_cta = warps * per_warp + 1024
-                per_sm = max(1, min(self.warp_teams // warps, self.smem_per_sm // per_cta))
+            # independent warp-teams, 4 per CTA (fewer when a box is large)
+            warps = int(max(1, min(4, (self.max_smem_cta - 1024) // per_warp)))
+            per_cta = warps * per_warp + 1024
+            per_sm = max(1, min(self.warp_teams // warps, self.smem_per_sm // per_cta))
             ctas = int(max(1, min((n_items + warps - 1) // warps, self.sm_count * per_sm)))
-            return 32 * warps, ctas, True, ws, self.warp_mode
+            return 32 * warps, ctas, True, ws, 1
         threads = self.threads or (128 if total >= 768 else 64)
         in_smem = ws * 8 + static <= self.max_smem_cta
         if in_smem:
@@ -422,10 +420,8 @@ class SolveSession:
                 # the frontier's growth factor changes slowly from level to level: last factor + 30 %
                 cap_recs = min(worst_recs, max(4096, int(1.3 * growth[0] * n_in) + 1024))
                 cap_data = min(worst_data, max(1 << 16, int(1.3 * growth[1] * data_used) + (1 << 16)))
-            pipeline = min(eng.pipeline, 1)
-            if pipeline == 1 and warp == 2:
-                warp = 1                                                 # lock-step exists for the fused kernel only
-            work = m.empty(int(self.lib.yr_level_work_bytes(D, n_in))) if pipeline == 1 else None
+            pipeline = 1
+            work = m.empty(int(self.lib.yr_level_work_bytes(D, n_in)))
             first_c = None
             while True:
                 self._reserve("results", self.n_results + n_in)            # a box emits at most one record

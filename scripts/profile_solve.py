@@ -28,6 +28,9 @@ for rep in range(reps):
           f"({16*st.entry_coeffs/kms/1e6:.1f} GB/s algorithmic) retries {st.retries} "
           f"rounds {getattr(st, 'rounds', 0)} launches {st.launches} scalar {getattr(sess, 'scalar_ms', 0.0):.1f} ms "
           f"zooms {st.zooms} subdiv {st.subdivisions} discards c/q/z {st.discard_const}/{st.discard_quad}/{st.discard_zoom}")
+free, total = torch.cuda.mem_get_info()
+print(f"device memory in use after the solves (library pools keep their high-water mark): {(total - free) / 2**30:.2f} GiB "
+      f"= {(total - free) / max(B, 1) / 2**20:.1f} MiB per system; input coefficients {sum(m.size for Ms in systems for m in Ms) * 8 / 2**20 / B:.3f} MiB per system")
 for (lvl, k) in zip(st.per_level, sess.kernel_ms):
     print("  level: in %7d out %7d res %6d smem %s ctas %5d thr %3d ws %6d warp %s | %8.3f ms %8.1f GB/s %9.0f boxes/ms" %
           (lvl + (k[0], k[1] / k[0] / 1e6, k[2] / k[0])))

@@ -149,44 +149,6 @@ int device_limits(int32_t* sm_count, int64_t* max_smem_per_cta, int64_t* smem_pe
     return 0;
 }
 
-template <int D>
-int launch_level(const yr::LevelArgs<D>& a, const yr_launch& l, void*) {
-    const int lanes = env_int("YR_EMUL_LANES", 4);
-    if (l.warp_per_box) {
-        // one emulated CTA of W warp-teams walking the phases in lock step (lockstep_worker)
-        const int W = env_int("YR_EMUL_WARPS", 2);
-        CtaShared cta; cta.bar.n = W * lanes;
-        std::vector<Team> teams(W);
-        std::vector<std::vector<double>> wss(W);
-        std::vector<yr::BoxShared<D>*> shs(W);
-        for (int w = 0; w < W; ++w) {
-            teams[w].T = lanes; teams[w].lanes = lanes; teams[w].bar.n = lanes; teams[w].scratch.assign(lanes, 0.0);
-            wss[w].assign(l.ws_doubles + 8, 0.0);
-            shs[w] = new yr::BoxShared<D>();
-        }
-        std::vector<std::thread> th;
-        for (int w = 0; w < W; ++w)
-            for (int t = 0; t < lanes; ++t)
-                th.emplace_back([&, w, t]() {
-                    HostCtx cx; cx.tid = t; cx.nthreads = lanes; cx.lanes = lanes; cx.lane = t; cx.warp = 0; cx.nwarps = 1;
-                    cx.team = &teams[w]; cx.cta = &cta; cx.cta_tid = w * lanes + t;
-                    if (l.warp_per_box == 2) yr::lockstep_worker<D>(cx, a, *shs[w], wss[w].data());
-                    else yr::level_worker<D>(cx, a, *shs[w], wss[w].data());
-                });
-        for (auto& x : th) x.join();
-        for (auto p : shs) delete p;
-        return 0;
-    }
-    const int T = env_int("YR_EMUL_THREADS", 8);
-    std::vector<double> ws;
-    double* wsp;
-    if (l.ws_in_smem) { ws.assign(l.ws_doubles + 8, 0.0); wsp = ws.data(); } else wsp = l.gws;
-    yr::BoxShared<D>* sh = new yr::BoxShared<D>();
-    run_team(T, lanes, [&](HostCtx& cx) { yr::level_worker<D>(cx, a, *sh, wsp); });
-    delete sh;
-    return 0;
-}
-
 struct HostAtomics {
     unsigned long long add(unsigned long long* p, unsigned long long v) const { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 };

@@ -203,10 +203,9 @@ def test_argument_errors():
         S.solveChebyshevSubdivision([np.zeros((2, 2)), np.zeros((2, 2))], np.zeros(3))
 
 
-@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("dim,deg,N", [(1, 10, 2), (2, 10, 3), (3, 4, 2), (4, 2, 1)])
-def test_emulated_warp_per_box(emu, dim, deg, N, mode):
-    """The warp-per-box kernel paths (independent warp-teams / lock-step CTA) give the same search tree and roots."""
+def test_emulated_warp_per_box(emu, dim, deg, N):
+    """The level pipeline's warp-per-box kernels give the same search tree and roots."""
     systems = H.seeded_systems(dim, deg, N)
     errs = [np.full(dim, 2. ** -52)] * N
     old = emu.warp_min_items
@@ -214,13 +213,11 @@ def test_emulated_warp_per_box(emu, dim, deg, N, mode):
     try:
         emu.pipeline = 1
         emu.warp_min_items = 1                  # every level runs warp-per-box
-        emu.warp_mode = mode
         sess, boxes, worst = H.check_batch_against_oracle(S.solve_batch, systems, errs, engine=emu)
         assert sess.stats.boxes == boxes and worst < 1e-14
         assert all(lvl[7] for lvl in sess.stats.per_level)
     finally:
         emu.warp_min_items = old
-        emu.warp_mode = 1
         emu.pipeline = pipe
 
 
@@ -419,10 +416,12 @@ def test_batch_that_does_not_fit_is_solved_in_halves(monkeypatch):
         want = S.solve_batch(systems, errs, engine=eng)
     real, calls = eng.session, []
 
+    from rootfinding_b200._lib import DeviceOutOfMemory
+
     def limited(sy, er, **kw):
         calls.append(len(sy))
         if len(sy) > 2:
-            raise RuntimeError("CUDA out of memory. Tried to allocate 259.09 GiB")
+            raise DeviceOutOfMemory("yroots_b200: yr_frontier_solve failed: device allocation failed (frontier buffers)")
         return real(sy, er, **kw)
     monkeypatch.setattr(eng, "session", limited)
     with warnings.catch_warnings():
@@ -432,9 +431,32 @@ def test_batch_that_does_not_fit_is_solved_in_halves(monkeypatch):
     assert calls[:4] == [5, 2, 3, 1] and len(sess.chunk_sessions) == 3
     for a, b, c, bx in zip(want, got, got_b, boxes):
         assert np.array_equal(a, b) and np.array_equal(a, c) and len(bx) == len(a)
-    monkeypatch.setattr(eng, "session", lambda sy, er, **kw: (_ for _ in ()).throw(RuntimeError("CUDA out of memory")))
-    with pytest.raises(RuntimeError):
+    monkeypatch.setattr(eng, "session", lambda sy, er, **kw: (_ for _ in ()).throw(DeviceOutOfMemory("out of device memory")))
+    with pytest.raises(DeviceOutOfMemory):
         S.solve_batch(systems[:1], errs[:1], engine=eng)
+    # any other failure is not mistaken for a memory problem, whatever its text says
+    monkeypatch.setattr(eng, "session", lambda sy, er, **kw: (_ for _ in ()).throw(RuntimeError("kernel failed: out of memory?")))
+    with pytest.raises(RuntimeError):
+        S.solve_batch(systems, errs, engine=eng)
+
+
+def test_batches_are_pre_split_by_the_capacity_estimate(monkeypatch):
+    """solve_batch cuts a batch whose estimated peak frontier (input bytes x a measured factor per dimension) exceeds the
+    free device memory into consecutive sub-batches before launching anything."""
+    from emul.backend import emulated_engine
+    from rootfinding_b200 import ChebyshevSubdivisionSolver as S
+    from rootfinding_b200.workloads import random_systems
+    eng = emulated_engine()
+    systems, errs = random_systems(2, 6, 6, seed=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = S.solve_batch(systems, errs, engine=eng)
+        per_system = 2 * 49 * 8 * S._PEAK_FACTOR[2]
+        monkeypatch.setattr(eng.mem, "free_bytes", lambda: 2.5 * per_system / 0.6, raising=False)
+        got, sess = S.solve_batch(systems, errs, engine=eng, return_session=True)
+    assert [s.nsys for s in sess.chunk_sessions] == [2, 2, 2]
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
 
 
 def test_very_large_batches_are_pre_split(monkeypatch):
