@@ -50,15 +50,17 @@ def workload(batch, seed):
 
 
 def measured_traffic():
-    """DRAM bytes per tensor-kernel launch from the committed ncu launch list (profiles/r01_traffic.json: dram__bytes_read
-    + dram__bytes_write summed over every tensor launch of two solves of this workload / number of launches)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as fh:
-            t = json.load(fh)
-        return float(t["dram_bytes_per_launch"]), float(t["traffic_over_algorithmic"])
-    except Exception:
-        return None, None
+    """DRAM bytes per tensor-kernel launch from the committed ncu launch list of the newest round (profiles/rNN_traffic.json:
+    dram__bytes_read + dram__bytes_write summed over every tensor launch of two solves of this workload / number of launches)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            with open(path) as fh:
+                t = json.load(fh)
+            return float(t["dram_bytes_per_launch"]), float(t["traffic_over_algorithmic"]), os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None, None
 
 
 def measured_peak():
@@ -118,10 +120,16 @@ def run_reference(args, rank):
     if rank != 0:
         return
     base, wall, steps = cpu_arm(args.steps, min(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+    # the CPU arm solves a BOUNDED SAMPLE of the workload per step (one system of the same generator per host core, a few
+    # seconds of CPU work); boxes/s is a per-box rate, so it compares with the GPU arm's rate on the full batch
+    cfg = workload_config(args, args.batch)            # the workload definition of the GPU arm (what the ratio refers to)
+    line = {"impl": "reference", "systems_per_step": base["cores"] * 1,
+            "step_note": (f"a step of this arm solves {base['cores']} systems (one per host core) of the workload's generator, "
+                          f"not the {args.batch} systems per GPU of config: ms_per_step belongs to that smaller step; "
+                          "boxes/s is per box and compares directly"), "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.batch), "cpu_baseline": base, "gpu_launches": 0,
+            "config": cfg, "cpu_baseline": base, "gpu_launches": 0,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_line(line)
 
@@ -304,7 +312,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-        traffic, traffic_ratio = measured_traffic()
+        traffic, traffic_ratio, traffic_file = measured_traffic()
         line = {"metric": METRIC, "value": boxes_all / (total_ms_max * 1e-3), "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -314,7 +322,7 @@ def main():
                 "gpu_launches": launches_all,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_over_algorithmic": traffic_ratio,
-                             "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per tensor launch, same workload)",
+                             "traffic_source": f"{traffic_file} (ncu dram__bytes_read.sum + dram__bytes_write.sum per tensor launch, same workload)",
                              "algorithmic_bytes_per_launch": kernel_bytes / max(tensor_launches, 1),
                              "kernel": "f2_tensor_warp / f2_tensor_cta (restrict + subdivide launches of every round of the timed steps, rank 0)",
                              "fp64_frac_of_measured_dmul_dadd_peak": (2.0 * stats.restrict_macs / 1e12 / max(kernel_ms / args.steps * 1e-3, 1e-12)) / 18.56,

@@ -115,13 +115,16 @@ typedef struct yr_counters {
     uint64_t boxes, zooms, subdivisions, discard_const, discard_quad, discard_zoom;
     uint64_t entry_coeffs, restrict_macs, max_child_doubles, max_child_extent, max_level, overflow;
     uint64_t max_child_tensor;
-    uint64_t reserved[2];
+    uint64_t no_axis;            /* boxes whose subdivision had no axis left (point-sized box at level <= 5): the reference's
+                                  * getInverseOrder raises IndexError there (ChebyshevSubdivisionSolver.py:1010); the solve is void */
+    uint64_t reserved;
 } yr_counters;
 
 int         yr_abi_version(void);
 const char* yr_last_error(void);
 /* class of the last failure on this thread: 0 none, 1 generic, 2 the DEVICE ran out of memory (a caller may retry with a
- * smaller batch) */
+ * smaller batch), 3 a box had no axis left to subdivide along -- the input on which the reference raises IndexError
+ * (getInverseOrder, ChebyshevSubdivisionSolver.py:1010) */
 int         yr_last_error_code(void);
 const char* yr_build_info(void);                 /* "cuda sm_100a ..." */
 void        yr_default_params(yr_params* out);
@@ -206,6 +209,13 @@ int yr_frontier_fits_dim(int32_t dim, uint64_t max_extent, uint64_t max_tensor);
 int yr_frontier_release(yr_frontier_out* out, void* stream);
 /* the pipeline keeps its box tables, arenas and queues between solves (grow-only); this frees them */
 int yr_frontier_trim(void* stream);
+/* Compacts the records of SELECTED systems: every record of `table` (n records of rec_bytes bytes, the int32 system id at
+ * byte system_off: result or node records of a frontier solve) whose system has sys_flags[system] != 0 is appended to
+ * out_recs, its index in the table to out_index; *out_n (device counter, zeroed by the caller) counts them (records beyond
+ * `cap` are counted, not written).  All pointers are device pointers.  The host side of a large batch uses it to bring
+ * over full records only for the few systems that need the tree bookkeeping (collectors, merges). */
+int yr_gather_by_system(const void* table, uint64_t n, uint32_t rec_bytes, uint32_t system_off, const uint8_t* sys_flags, uint64_t nsys,
+                        uint32_t* out_index, void* out_recs, uint64_t cap, uint64_t* out_n, void* stream);
 /* device -> host copy of `bytes` bytes on `stream`, synchronous (host_dst is a HOST pointer) */
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void* stream);
 

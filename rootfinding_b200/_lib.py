@@ -52,7 +52,7 @@ class YrCounters(C.Structure):
     _fields_ = [(n, u64) for n in ("next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms",
                                    "subdivisions", "discard_const", "discard_quad", "discard_zoom", "entry_coeffs",
                                    "restrict_macs", "max_child_doubles", "max_child_extent", "max_level", "overflow",
-                                   "max_child_tensor", "reserved0", "reserved1")]
+                                   "max_child_tensor", "no_axis", "reserved1")]
 
 
 class YrFrontierDesc(C.Structure):
@@ -90,7 +90,7 @@ SORTED_DTYPE = sorted_dtype(2)
 COUNTER_FIELDS = ["next_box", "n_children", "data_used", "n_results", "n_nodes", "boxes", "zooms", "subdivisions",
                   "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "restrict_macs",
                   "max_child_doubles", "max_child_extent", "max_level", "overflow", "max_child_tensor",
-                  "reserved0", "reserved1"]
+                  "no_axis", "reserved1"]
 COUNTER_BYTES = 8 * len(COUNTER_FIELDS)
 
 # every symbol include/yroots_b200.h declares
@@ -99,7 +99,7 @@ EXPORTS = ["yr_abi_version", "yr_last_error", "yr_last_error_code", "yr_build_in
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
            "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch",
            "yr_frontier_begin", "yr_frontier_advance", "yr_frontier_export_bound", "yr_frontier_export",
-           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply", "yr_f2_tensor_ops", "yr_frontier_fits_dim"]
+           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply", "yr_f2_tensor_ops", "yr_frontier_fits_dim", "yr_gather_by_system"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -150,6 +150,8 @@ def bind(lib):
     lib.yr_frontier_fits.restype = C.c_int
     lib.yr_fetch.argtypes = [vp, vp, u64, vp]
     lib.yr_fetch.restype = C.c_int
+    lib.yr_gather_by_system.argtypes = [vp, u64, C.c_uint32, C.c_uint32, vp, u64, vp, vp, u64, vp, vp]
+    lib.yr_gather_by_system.restype = C.c_int
     lib.yr_frontier_fits_dim.argtypes = [i32, u64, u64]
     lib.yr_frontier_fits_dim.restype = C.c_int
     lib.yr_f2_tensor_ops.argtypes = [C.POINTER(YrF2OpsDesc), vp]
@@ -175,6 +177,15 @@ def bind(lib):
     return lib
 
 
+NO_AXIS_TEXT = ("a box has no axis left to subdivide along (point-sized box at level <= 5); the reference raises here: "
+                "IndexError in getInverseOrder, ChebyshevSubdivisionSolver.py:1010")
+
+
+class NoAxisLeft(IndexError):
+    """The input on which the reference's getInverseOrder raises IndexError (a zoom collapsed the box to a point before
+    level 6, then the final step asks for a subdivision: getSubdivisionDims :1036-1049 keeps no axis)."""
+
+
 class DeviceOutOfMemory(RuntimeError):
     """The device ran out of memory inside the library (yr_last_error_code() == 2): the batch can be retried in parts."""
 
@@ -182,7 +193,8 @@ class DeviceOutOfMemory(RuntimeError):
 def check(lib, rc, what):
     if rc != 0:
         msg = f"yroots_b200: {what} failed: {lib.yr_last_error().decode()}"
-        raise (DeviceOutOfMemory if lib.yr_last_error_code() == 2 else RuntimeError)(msg)
+        code = lib.yr_last_error_code()
+        raise (DeviceOutOfMemory if code == 2 else NoAxisLeft if code == 3 else RuntimeError)(msg)
 
 
 def default_params(lib):

@@ -199,6 +199,11 @@ int yr_abi_version(void) { return YR_ABI_VERSION; }
 const char* yr_last_error(void) { return yr_api::g_err; }
 void yr_set_error(const char* msg) { yr_api::fail(msg); }          /* used by the other translation units of the library */
 void yr_set_error_oom(const char* msg) { yr_api::fail(msg); yr_api::g_err_code = 2; }
+void yr_set_error_no_axis(void) {
+    yr_api::fail("a box has no axis left to subdivide along (point-sized box at level <= 5); the reference raises here: "
+                 "IndexError in getInverseOrder, ChebyshevSubdivisionSolver.py:1010");
+    yr_api::g_err_code = 3;
+}
 int yr_last_error_code(void) { return yr_api::g_err_code; }
 const char* yr_build_info(void) { return yr_backend::build_info(); }
 

@@ -654,6 +654,7 @@ YR_DEVN void subdivide_box(Ctx& cx, const LevelArgs<D>& args, BoxShared<D>& sh, 
     if (cx.tid == 0) {
         const int k = subdivision_axes<D>(sh.shape, sh.rec.st.iv, sh.level, sh.order);
         sh.nsplit = k;
+        if (k == 0) cx.atomic_add(&args.ctr->no_axis, 1ull);          // the reference raises here (:1010); the host reports it
         // ascending set of split axes; matrix 2j (lower half) and 2j+1 (upper half) of axis j
         bool used[D];
         for (int a = 0; a < D; ++a) used[a] = false;

@@ -166,7 +166,7 @@ struct Ctl {
     unsigned long long data_used;                   // doubles written to the current output arena
     unsigned long long cursor[kOps][kClasses];      // this round's tensor launches: next queue position to hand out
     unsigned long long n_boxes, n_results, n_nodes; // slots in use
-    unsigned long long overflow, bad_mid;
+    unsigned long long overflow, bad_mid, no_axis;
     unsigned long long boxes, zooms, subdivisions, dconst, dquad, dzoom, entry_coeffs, restrict_macs, max_level;
     unsigned long long reserved[4];
 };
@@ -1270,6 +1270,7 @@ YR_HDM void scalar_step_on(const Args& a, BoxRec<2>& rec, Work& wk, Decision& dc
             int shape[2][2] = {{rec.shape[0][0], rec.shape[0][1]}, {rec.shape[1][0], rec.shape[1][1]}};
             int order[2][2];
             const int k = subdivision_axes<2>(shape, st.iv, wk.node_level, order);
+            if (k == 0) { at.add(&a.ctl->no_axis, 1ull); break; }              // getInverseOrder of an empty order raises (:1010)
             wk.nsplit = k;
             for (int p = 0; p < 2; ++p) { wk.order[p][0] = order[p][0]; wk.order[p][1] = (k > 1) ? order[p][1] : order[p][0]; }
             wk.node_index = -1;

@@ -195,6 +195,23 @@ __global__ void __launch_bounds__(128) f2_import_kernel(const Args a, unsigned l
     commit_warp(a, (unsigned int)i, dc);
 }
 
+// ---- records of selected systems only (yr_gather_by_system) ----
+__global__ void gather_by_system_kernel(const unsigned char* table, unsigned long long n, unsigned rec_bytes, unsigned system_off,
+                                        const unsigned char* sys_flags, unsigned long long nsys, unsigned int* out_index,
+                                        unsigned char* out_recs, unsigned long long cap, unsigned long long* out_n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* rec = table + i * rec_bytes;
+    const int sys = *reinterpret_cast<const int*>(rec + system_off);
+    if (sys < 0 || (unsigned long long)sys >= nsys || !sys_flags[sys]) return;
+    const unsigned long long pos = atomicAdd(out_n, 1ull);
+    if (pos >= cap) return;
+    out_index[pos] = (unsigned int)i;
+    const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(rec);
+    unsigned long long* d8 = reinterpret_cast<unsigned long long*>(out_recs + pos * rec_bytes);
+    for (unsigned q = 0; q < rec_bytes / 8; ++q) d8[q] = s8[q];
+}
+
 // ---- moving queued boxes between frontiers (yr_frontier_export / _import) ----
 __global__ void __launch_bounds__(128) f2_export_kernel(const Args a, const yr_f2_host::XTake take, unsigned long long n, unsigned char* xbuf,
                                                         const double* __restrict__ data_in) {
@@ -546,6 +563,18 @@ int yr_frontier_fits_dim(int32_t dim, uint64_t max_extent, uint64_t max_tensor) 
     return yr_fd_fits(dim, max_extent, max_tensor);
 }
 int yr_frontier_trim(void* stream) { yr_fd_trim(stream); return yr_f2_host::trim_workspace(stream); }
+
+int yr_gather_by_system(const void* table, uint64_t n, uint32_t rec_bytes, uint32_t system_off, const uint8_t* sys_flags, uint64_t nsys,
+                        uint32_t* out_index, void* out_recs, uint64_t cap, uint64_t* out_n, void* stream) {
+    if (!n) return 0;
+    if (rec_bytes % 8) { yr_set_error("yr_gather_by_system: records must be a multiple of 8 bytes"); return -1; }
+    gather_by_system_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const unsigned char*>(table), n, rec_bytes, system_off, sys_flags, nsys, out_index, static_cast<unsigned char*>(out_recs), cap,
+        reinterpret_cast<unsigned long long*>(out_n));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { yr_set_error(cudaGetErrorString(e)); return -1; }
+    return 0;
+}
 
 int yr_fetch(void* host_dst, const void* dev_src, uint64_t bytes, void* stream) {
     if (!bytes) return 0;

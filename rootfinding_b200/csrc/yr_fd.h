@@ -779,6 +779,7 @@ YR_HDM void scalar_step(const Args<D>& a, unsigned int b, Decision& dc, At at) {
             int shape[D][D], order[D][D];
             for (int p = 0; p < D; ++p) for (int d = 0; d < D; ++d) shape[p][d] = rec.shape[p][d];
             const int k = subdivision_axes<D>(shape, st.iv, wk.node_level, order);
+            if (k == 0) { at.add(&a.ctl->no_axis, 1ull); break; }              // getInverseOrder of an empty order raises (:1010)
             wk.nsplit = k;
             for (int p = 0; p < D; ++p) for (int j = 0; j < D; ++j) wk.order[p][j] = order[p][j < k ? j : 0];
             wk.node_index = -1;

@@ -18,6 +18,7 @@ namespace yr_fd_host {
 using namespace yr;
 using namespace yr::f2;
 using yr_f2_host::fail;
+using yr_f2_host::fail_no_axis;
 using yr_f2_host::DevBuf;
 using yr_f2_host::release;
 
@@ -223,6 +224,7 @@ inline int advance(unsigned long long max_rounds, void* stream) {
         if (f.phases) { const double t_done = be::host_ms(); fprintf(stderr, " r%llu:%.2f+%.2f", f.rounds, t_issue - t_round0, t_done - t_issue); }
         if (h.overflow) { f.active = false; return fail("yr_frontier_solve: internal buffer overflow"); }
         if (h.bad_mid) { f.active = false; return fail("yr_frontier_solve: unexpected split point (nextTransformPoints)"); }
+        if (h.no_axis) { f.active = false; return fail_no_axis(); }
         f.n_boxes = h.n_boxes; f.n_results += h.n_results; f.n_nodes += h.n_nodes;
         f.data_in = a.data_out; f.own_input = true; f.in_arena = f.out_arena; f.in_used = h.data_used;
         f.out_arena ^= 1; f.cur ^= 1;

@@ -89,7 +89,8 @@ struct LevelCounters {
     unsigned long long max_level;
     unsigned long long overflow;        // non-zero: an output buffer was too small (host must retry)
     unsigned long long max_child_tensor;    // largest single tensor in the next level
-    unsigned long long reserved[2];
+    unsigned long long no_axis;             // subdivisions with no axis to halve along (the reference raises: :1010)
+    unsigned long long reserved;
 };
 
 template <int D>

@@ -31,6 +31,38 @@ class _Buf:
         self.ptr, self.nbytes, self.owner = ptr, nbytes, owner
 
 
+class _SparsePool:
+    """Keeps the big mostly-zero tables of SolveSession.sparse_records between solves: the first-touch page faults of a
+    fresh mapping cost more than the records written into it (15 000 records scattered over 140 MB: 15 ms, with or
+    without transparent huge pages).  A table is lent to one session at a time; what that session wrote is zeroed
+    again when the table is lent out next."""
+
+    def __init__(self):
+        self.slots = {}
+
+    def borrow(self, slot, count, dtype, who):
+        import weakref
+        ent = self.slots.get(slot)
+        if ent is not None:
+            prev = ent["owner"]() if ent["owner"] is not None else None
+            if prev is not None and prev is not who:
+                prev._detach_host(slot)                            # still in use: its records move to private memory
+            lease = ent["lease"]
+            arr = ent["arr"]
+            if arr.dtype != dtype or len(arr) < count:
+                ent = None
+            else:
+                rows = arr.view(np.uint8).reshape(len(arr), dtype.itemsize)      # (byte rows: far cheaper than record copies)
+                for idx in lease["idx"]:
+                    rows[idx] = 0
+                rows[lease["lo"]:lease["hi"]] = 0
+        if ent is None:
+            ent = self.slots[slot] = dict(arr=np.zeros(count + count // 2, dtype=dtype))
+        ent["owner"] = weakref.ref(who)
+        ent["lease"] = dict(idx=[], lo=0, hi=0)
+        return ent["arr"], ent["lease"]
+
+
 class _Growable:
     """Append-only structured host array on top of a byte buffer obtained from `alloc(nbytes, who)`."""
 
@@ -50,16 +82,29 @@ class _Growable:
             new = self.alloc(max(need + need // 8, 2 * self.buf.nbytes), self.who())
             new[:self.n * item] = self.buf[:self.n * item]
             self.buf = new
+            self.lease = None                                      # (a lent table was left behind: the pool zeroes what it knows)
         v = self.buf[self.n * item:need]
         self.n += k
+        if getattr(self, "lease", None) is not None:
+            self.lease["hi"] = self.n
         return v
 
     def view(self):
         return self.buf[:self.n * self.dtype.itemsize].view(self.dtype)
 
+    def adopt(self, table, n, lease=None):
+        """Replace the contents by the first n records of `table` (a structured array with spare room behind them).
+        `lease`: the pool's note of what this borrower writes (_SparsePool)."""
+        self.buf = table.view(np.uint8).reshape(-1)
+        self.n = n
+        self.lease = lease
+        if lease is not None:
+            lease["lo"] = lease["hi"] = n
+
     def detach(self):
         """Move to private memory (the lender wants its buffer back)."""
         self.buf = self.buf[:self.n * self.dtype.itemsize].copy()
+        self.lease = None
 
     def __len__(self):
         return self.n
@@ -110,10 +155,35 @@ class CudaMemory:
         pinned staging buffer, so the packed tensor data is written once on the host."""
         b = self.empty(total * 8)
         if total:
-            pinned = self.torch.empty(total * 8, dtype=self.torch.uint8, pin_memory=True)
-            np.concatenate(chunks, out=pinned.numpy().view(np.float64))
+            # one page-locked staging buffer is kept (grow-only): allocating 40 MB of pinned memory per call costs
+            # several milliseconds.  The event says when the previous copy out of it has finished.
+            stage = getattr(self, "_concat_stage", None)
+            if stage is None or stage[0].numel() < total * 8:
+                stage = self._concat_stage = (self.torch.empty(total * 8 + total, dtype=self.torch.uint8, pin_memory=True),
+                                              self.torch.cuda.Event())
+            else:
+                stage[1].synchronize()
+            pinned = stage[0][:total * 8]
+            dst = pinned.numpy().view(np.float64)
+            if total >= (1 << 21) and len(chunks) >= 64:
+                # a 40 MB gather runs at one core's copy rate (6 ms): four threads (numpy copies release the GIL)
+                pool = getattr(self, "_copy_pool", None)
+                if pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    pool = self._copy_pool = ThreadPoolExecutor(4)
+                ends = np.cumsum([c.size for c in chunks])
+                cuts = [0] + [int(np.searchsorted(ends, total * q / 4)) + 1 for q in (1, 2, 3)] + [len(chunks)]
+                jobs = []
+                for g0, g1 in zip(cuts[:-1], cuts[1:]):
+                    if g1 > g0:
+                        lo = int(ends[g0 - 1]) if g0 else 0
+                        jobs.append(pool.submit(np.concatenate, chunks[g0:g1], out=dst[lo:int(ends[g1 - 1])]))
+                for j in jobs:
+                    j.result()
+            else:
+                np.concatenate(chunks, out=dst)
             b.owner.view(self.torch.uint8)[:total * 8].copy_(pinned, non_blocking=True)
-            self._staging.append(pinned)
+            stage[1].record(self.torch.cuda.current_stream(self.device))
             self.h2d_bytes += total * 8
         return b
 
@@ -156,9 +226,14 @@ class CudaMemory:
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def free_bytes(self):
-        """Device memory a new solve can count on: free memory plus what the library's own pools hold but do not use."""
-        free, _ = self.torch.cuda.mem_get_info(self.device)
-        return free + self.torch.cuda.memory_reserved(self.device) - self.torch.cuda.memory_allocated(self.device)
+        """Device memory a new solve can count on: everything this process does not hold in live torch tensors.  (The
+        library's own grow-only pools are reused by the next solve, so they count as available.)  cudaMemGetInfo costs
+        3 - 40 ms per call on a busy device, so what OTHER owners hold (context, other processes) is measured once."""
+        if getattr(self, "_foreign_bytes", None) is None:
+            free, total = self.torch.cuda.mem_get_info(self.device)
+            self._total_bytes = total
+            self._foreign_bytes = max(0, total - free - self.torch.cuda.memory_reserved(self.device))
+        return self._total_bytes - self._foreign_bytes - self.torch.cuda.memory_allocated(self.device)
 
     def synchronize(self):
         self.torch.cuda.current_stream(self.device).synchronize()
@@ -211,6 +286,7 @@ class SubdivisionEngine:
         # 2: the round-based frontier pipelines (yr_frontier_solve: dimension 2, 3, 4, plain arithmetic) where they apply,
         #    the level pipeline elsewhere; 1: the level pipeline (phase-split kernels per level) for everything
         self.pipeline = max(1, int(os.environ.get("YR_PIPELINE", "2")))
+        self.sparse_pool = _SparsePool()
 
     def params(self, **kw):
         p = _lib.default_params(self.lib)
@@ -463,6 +539,8 @@ class SolveSession:
                     for k in ("boxes", "zooms", "discard_const", "discard_quad", "discard_zoom", "entry_coeffs", "max_level", "n_results"):
                         c[k] = first_c[k]
                     c["restrict_macs"] += first_c["restrict_macs"]
+                if c["no_axis"]:
+                    raise _lib.NoAxisLeft("yroots_b200: " + _lib.NO_AXIS_TEXT)
                 if not c["overflow"]:
                     break
                 self.stats.retries += 1                                      # optimistic buffers were too small
@@ -614,6 +692,57 @@ class SolveSession:
         self._order_raw = raw
         self._order_host, self._order_base = raw.view(self.sorted_dt), 0
         return self._order_host
+
+    def sparse_records(self, systems, n_results_hint=None):
+        """Bring the full result and node records of `systems` ONLY to the host (one device gather each:
+        yr_gather_by_system), as tables of the usual size and indexing whose other records read as zeros.  For a
+        session that slim_order() serves: a batch where a few systems need the tree bookkeeping of the host post-pass
+        (collectors, merges) no longer pays the device -> host copy of every record.  `n_results_hint`: how many result
+        records those systems have, when the caller knows.  Returns False, and fetches nothing, when the session is
+        not in that state; results() / nodes() then bring everything."""
+        if len(self._segments) != 1 or self._segments[0][0] != "frontier":
+            return False
+        _, r0, rn, n0, nn, out = self._segments[0]
+        if r0 != 0 or n0 != 0 or rn != self.n_results:
+            return False
+        m, lib = self.mem, self.lib
+        stream = m.stream()
+        mark = np.zeros(self.nsys, dtype=np.uint8)
+        mark[np.asarray(sorted(systems), dtype=np.int64)] = 1
+        d_mark = m.upload(mark)
+        d_n = m.zeros(16)
+        tables = ((out.results, rn, self.rdt, self._results_host, n_results_hint), (out.nodes, nn, self.ndt, self._nodes_host, None))
+        caps = [int(hint) if hint is not None else 4 * int(n_results_hint or 0) + 4096 for *_, hint in tables]
+        while True:
+            # one gather per table into [records | indices]; the counters tell whether the guessed capacity was enough
+            m.zero_(d_n)
+            bufs = []
+            for t, (ptr, n, dt, grow, _) in enumerate(tables):
+                item, cap = dt.itemsize, min(caps[t], n)
+                caps[t] = cap
+                buf = m.empty(cap * (item + 4))
+                bufs.append(buf)
+                _lib.check(lib, lib.yr_gather_by_system(ptr, n, item, dt.fields["system"][1], d_mark.ptr, self.nsys,
+                                                        buf.ptr + cap * item, buf.ptr, cap, d_n.ptr + 8 * t, stream),
+                           "yr_gather_by_system")
+            counts = [int(v) for v in m.download(d_n, 16).view(np.uint64)]
+            if all(c <= cap for c, cap in zip(counts, caps)):
+                break
+            caps = [max(c, cap) for c, cap in zip(counts, caps)]
+        for t, (ptr, n, dt, grow, _) in enumerate(tables):
+            item, cap, cnt = dt.itemsize, caps[t], counts[t]
+            table, lease = self.eng.sparse_pool.borrow(t, n + max(4096, n // 8), dt, self)      # (room for re-solved boxes)
+            if cnt:
+                raw = m.download(bufs[t], cap * (item + 4))
+                idx = raw[cap * item:cap * item + 4 * cnt].view(np.uint32).copy()
+                table.view(np.uint8).reshape(len(table), item)[idx] = raw[:cnt * item].reshape(cnt, item)
+                lease["idx"].append(idx)
+            grow.adopt(table, n, lease)
+        self._segments.clear()
+        self._pending.remove(out)
+        lib.yr_frontier_release(C.byref(out), stream)
+        self.sparse_systems = set(int(v) for v in systems)
+        return True
 
     def dfs_order(self):
         """(order, base, n): base + order["index"] puts records [base, base + n) in (system, depth-first path) order,

@@ -61,11 +61,17 @@ class ResultBox:
 
 
 def _path_order(res, idx):
-    return idx[np.lexsort((res["path_lo"][idx], res["path_hi"][idx], res["system"][idx]))]
+    """Records by (system, depth-first path).  Paths start at the level-0 job, so records of several re-solved merged
+    boxes of one system tie; the root coordinates break the tie (the record index would depend on the order in which
+    the device happened to emit them)."""
+    root = res["root"][idx]
+    keys = tuple(root[:, d] for d in range(root.shape[1] - 1, -1, -1))
+    return idx[np.lexsort(keys + (res["path_lo"][idx], res["path_hi"][idx], res["system"][idx]))]
 
 
-def resolve_collectors(res, start=0, stop=None):
-    """Step A on records [start, stop).  Record links (`collector`) are global indices into `res`.
+def resolve_collectors(res, start=0, stop=None, known=None):
+    """Step A on records [start, stop).  Record links (`collector`) are global indices into `res`.  `known` =
+    (collector records, member records) when the caller already has them (from the device-gathered entries).
 
     Returns (alive mask for that range, {global record index: list of roots}, set of extra-root records).
     """
@@ -73,9 +79,12 @@ def resolve_collectors(res, start=0, stop=None):
     alive = np.ones(stop - start, dtype=bool)
     dup = {}
     extra = set()
-    rng = np.arange(start, stop)
-    coll = rng[(res["flags"][start:stop] & RES_COLLECTOR) != 0]
-    member = rng[res["collector"][start:stop] >= 0]
+    if known is not None:
+        coll, member = known
+    else:
+        rng = np.arange(start, stop)
+        coll = rng[(res["flags"][start:stop] & RES_COLLECTOR) != 0]
+        member = rng[res["collector"][start:stop] >= 0]
     if len(coll) == 0 and len(member) == 0:
         return alive, dup, extra
     alive[member - start] = False              # everything below a collector is absorbed by it
@@ -277,24 +286,39 @@ def assemble(session, merge=True, need_records=False):
     if slim is not None:
         # one frontier solve produced every record: the device-gathered entries (reporting order) carry what the
         # common case needs; the full records come to the host only for bounding boxes, collectors or merges
-        fl = slim["flags"]
-        special = bool(np.any((fl & RES_COLLECTOR) != 0) or np.any(slim["collector"] >= 0))
+        fl = np.ascontiguousarray(slim["flags"])                  # (the entries are 32-byte records: strided fields)
+        sysv = np.ascontiguousarray(slim["system"])
+        is_coll, is_member = (fl & RES_COLLECTOR) != 0, slim["collector"] >= 0
+        special = bool(is_coll.any() or is_member.any())
         touch_pos = np.nonzero((fl & RES_TOUCH) != 0)[0]
-        touch_sys = slim["system"][touch_pos]
+        touch_sys = sysv[touch_pos]
         may_merge = merge and len(touch_pos) >= 2 and len(np.unique(touch_sys)) < len(touch_sys)
         keep = slim["index"]
-        session.sorted_fields = (slim["system"], np.ascontiguousarray(slim["root"]))
+        bounds = np.searchsorted(sysv, np.arange(session.nsys + 1))
+        session.sorted_fields = (sysv, np.ascontiguousarray(slim["root"]), bounds)
         session.late_by_system = {}
         if not special and not may_merge:
             return (session.results() if need_records else None), keep, {}, set()
+        known = None
+        if not need_records and hasattr(session, "sparse_records"):
+            # only the systems with a collector or with two candidates for a merge need their full records
+            need = set(np.unique(sysv[is_coll | is_member]).tolist())
+            if may_merge:
+                u, cnt = np.unique(touch_sys, return_counts=True)
+                need |= set(u[cnt >= 2].tolist())
+            hint = int(sum(bounds[s + 1] - bounds[s] for s in need))
+            if session.sparse_records(need, hint):
+                known = (np.sort(slim["index"][is_coll].astype(np.int64)), np.sort(slim["index"][is_member].astype(np.int64)))
         res = session.results()
         if special:
-            alive, dup, extra = resolve_collectors(res)
+            alive, dup, extra = resolve_collectors(res, known=known)
         else:
             alive, dup, extra = np.ones(len(res), dtype=bool), {}, set()
         n0 = len(res)
         if merge:
             cand = slim["index"][touch_pos].astype(np.int64)
+            if known is not None:                              # sparse tables: lone candidates of other systems read as zeros
+                cand = cand[np.isin(touch_sys, np.fromiter(need, dtype=np.int64, count=len(need)))]
             res, alive, dup, extra = merge_exterior(session, res, alive, dup, extra, cand=cand[alive[cand]])
         dead = np.nonzero(~alive[:n0])[0]
         late = np.nonzero(alive[n0:])[0] + n0
@@ -347,12 +371,15 @@ def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_
     (system, root) of the kept records in order, when the device already gathered them; `late_by_system` = live
     records that are not in `keep` (produced after the device sorted), merged into their systems by path;
     `redo_systems` = systems whose slice of `keep` contains dead records (`alive` says which)."""
+    bounds = None
     if sorted_fields is not None:
-        sysv, roots_all = sorted_fields
+        sysv, roots_all = sorted_fields[:2]
+        bounds = sorted_fields[2] if len(sorted_fields) > 2 else None
     else:
         sysv = np.take(res["system"], keep)
         roots_all = np.take(res["root"], keep, axis=0)
-    bounds = np.searchsorted(sysv, np.arange(nsys + 1))
+    if bounds is None:
+        bounds = np.searchsorted(sysv, np.arange(nsys + 1))
     late_by_system = late_by_system or {}
     redo_systems = redo_systems or set()
     out_roots, out_boxes, has_dup, has_extra = [], [], False, False

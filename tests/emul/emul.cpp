@@ -605,6 +605,19 @@ int yr_frontier_fits_dim(int32_t dim, uint64_t max_extent, uint64_t max_tensor) 
     return 0;
 }
 int yr_frontier_release(yr_frontier_out* out, void* stream) { return yr_f2_host::release(out, stream); }
+int yr_gather_by_system(const void* table, uint64_t n, uint32_t rec_bytes, uint32_t system_off, const uint8_t* sys_flags, uint64_t nsys,
+                        uint32_t* out_index, void* out_recs, uint64_t cap, uint64_t* out_n, void*) {
+    const unsigned char* t = static_cast<const unsigned char*>(table);
+    for (uint64_t i = 0; i < n; ++i) {
+        int sys; memcpy(&sys, t + i * rec_bytes + system_off, 4);
+        if (sys < 0 || (uint64_t)sys >= nsys || !sys_flags[sys]) continue;
+        const uint64_t pos = (*out_n)++;
+        if (pos >= cap) continue;
+        out_index[pos] = (uint32_t)i;
+        memcpy(static_cast<unsigned char*>(out_recs) + pos * rec_bytes, t + i * rec_bytes, rec_bytes);
+    }
+    return 0;
+}
 #include "../../rootfinding_b200/csrc/yr_f2_abi.inc"
 int yr_frontier_fits(uint64_t max_extent) { return yr_f2_host::fits(max_extent); }
 int yr_frontier_trim(void* stream) { yr_fd_host::trim_workspace<3>(stream); yr_fd_host::trim_workspace<4>(stream); return yr_f2_host::trim_workspace(stream); }

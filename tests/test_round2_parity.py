@@ -506,3 +506,102 @@ def test_fd_pipeline_gpu(gpu_yr, monkeypatch):
     monkeypatch.setenv("YR_F2_WARP_MAX_R", "64")
     monkeypatch.setenv("YR_F2_WARP_MAX_S", "64")
     _fd_vs_oracle_and_level(gpu_yr, get_engine(), [(3, 6, 2, {}), (4, 3, 1, {})])
+
+
+# ---- full records come to the host only for the systems whose tree bookkeeping needs them ---------
+def _tangent_system():
+    """y = 0.2 + (x - 0.1)^2 against y = 0.2: a double root.  The zooms collapse the box to a point at level 0, the final
+    step then asks for a subdivision and getSubdivisionDims (:1036-1049) keeps no axis: the reference raises IndexError
+    (getInverseOrder :1010, checked against the reference itself)."""
+    f = np.zeros((3, 2))
+    f[0, 0], f[1, 0], f[2, 0], f[0, 1] = -0.2 - 0.01 - 0.5, 0.2, -0.5, 1.0       # y - 0.2 - (x - 0.1)^2, x^2 = (T0 + T2) / 2
+    g = np.array([[-0.2, 1.0]])
+    return [f, g]
+
+
+def _sparse_records_match_full(yr, n_plain):
+    from rootfinding_b200.engine import SolveSession
+    from rootfinding_b200.workloads import random_systems
+    S = yr.ChebyshevSubdivisionSolver
+    systems, errors = random_systems(2, 6, n_plain, seed=5)
+    systems, errors = [list(s) for s in systems], list(errors)
+    e2 = np.full(2, 2.0 ** -52)
+    for pos, Ms in ((3, H.corner_system(7)), (6, H.corner_system(3)), (len(systems), H.corner_system(4))):
+        systems.insert(pos, Ms)
+        errors.insert(pos, e2)
+    special = {3, 6, n_plain}                         # (the tuple above was built before the inserts)
+    calls = []
+    orig = SolveSession.sparse_records
+
+    def spy(self, need, hint=None):
+        ok = orig(self, need, hint)
+        calls.append((set(need), ok, len(self.results()), int(np.count_nonzero(self.results()["level"]))))
+        return ok
+    SolveSession.sparse_records = spy
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            slim = S.solve_batch(systems, errors)
+            assert len(calls) == 1 and calls[0][0] == special and calls[0][1], calls
+            full, boxes = S.solve_batch(systems, errors, returnBoundingBoxes=True)      # needs every record: no gather
+            assert len(calls) == 1
+            # the big sparse tables are reused between solves: nothing of another batch may show through
+            other = S.solve_batch(systems[5:40][::-1], errors[5:40][::-1])
+            again = S.solve_batch(systems, errors)
+            assert len(calls) == 3 and calls[1][1] and calls[2][1]
+            for i, (a, b) in enumerate(zip(slim, again)):
+                assert np.array_equal(np.asarray(a), np.asarray(b)), i
+            for a, b in zip(other, list(slim[5:40])[::-1]):
+                assert np.array_equal(np.asarray(a), np.asarray(b))
+    finally:
+        SolveSession.sparse_records = orig
+    # only a fraction of the records was fetched ...
+    assert calls[0][3] < calls[0][2] * len(special) / max(1, n_plain) * 4 + 64, calls
+    # ... and the answer is the one of the full post-pass, bit for bit
+    for i, (a, b) in enumerate(zip(slim, full)):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), i
+    for i in (6, n_plain):
+        want, _ = H.oracle_solve(systems[i], e2)
+        assert len(slim[i]) == len(want), (i, len(slim[i]), len(want))
+        H.match_points(want, np.asarray(slim[i]).reshape(-1, 2), 1e-7)
+    want, _ = H.oracle_solve(systems[3], e2)
+    assert len(slim[3]) == len(want) and len(want) >= 1, (len(slim[3]), len(want))
+    H.match_points(want, np.asarray(slim[3]).reshape(-1, 2), 1e-6)
+
+
+def _no_axis_raises_like_the_reference(yr):
+    S = yr.ChebyshevSubdivisionSolver
+    e2 = np.full(2, 2.0 ** -52)
+    with pytest.raises(IndexError):
+        H.oracle_solve(_tangent_system(), e2)
+    for pipeline in (2, 1):
+        from rootfinding_b200.runtime import get_engine
+        eng = get_engine()
+        old, eng.pipeline = eng.pipeline, pipeline
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                with pytest.raises(IndexError, match="no axis left"):
+                    S.solve_batch([_tangent_system()], [e2])
+                got = S.solve_batch([H.corner_system(1)], [e2])          # the library is usable after the failure
+                assert len(got[0]) >= 1
+        finally:
+            eng.pipeline = old
+
+
+def test_no_axis_left_raises_emulated(emu_yr):
+    _no_axis_raises_like_the_reference(emu_yr)
+
+
+@pytest.mark.gpu
+def test_no_axis_left_raises_gpu(gpu_yr):
+    _no_axis_raises_like_the_reference(gpu_yr)
+
+
+def test_sparse_record_fetch_emulated(emu_yr):
+    _sparse_records_match_full(emu_yr, 24)
+
+
+@pytest.mark.gpu
+def test_sparse_record_fetch_gpu(gpu_yr):
+    _sparse_records_match_full(gpu_yr, 200)
