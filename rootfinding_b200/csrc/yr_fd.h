@@ -504,9 +504,21 @@ YR_HD void child_record(const Args<D>& a, const BoxRec<D>& rec, const Work<D>& w
 // The 2^k children are produced by a depth-first walk over the halvings (order[p][0], order[p][1], ...): at depth l the
 // lower half is written to region l + 1 and the upper half replaces the tensor where it stands, so the walk first
 // finishes everything below the lower half and then continues from the upper half with region l + 1 free again.
+// State of the depth-first walk, ONE copy per team in memory every lane of the team can read (shared memory on the
+// device).  As per-thread arrays indexed by the run-time depth they live in local memory: 400 bytes x every resident
+// thread does not fit L1 next to the shared-memory carve-out, and a third of the subdivide kernels' stall samples were
+// long-scoreboard waits on them (profiles/r02_fd.txt).  Every lane executes the walk and writes the SAME values; one
+// team barrier per step separates a step's reads from the next step's writes.
+template <int D>
+struct WalkState {
+    double sm[D + 1], er[D + 1], upper_sum[D + 1], child_err[D + 1];
+    int cur[D + 1], phase[D + 1], half[D];
+    int shp[D + 1][D], upper_shape[D + 1][D];
+};
+
 template <int D, bool FMA, class Team>
 YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* slice, const double* smat_lo, const double* smat_hi,
-                          int smat_nt, unsigned long long& macs) {
+                          int smat_nt, unsigned long long& macs, WalkState<D>* W) {
     const BoxRec<D>& rec = a.recs[b];
     const Work<D>& wk = a.work[b];
     const SolverParams& prm = a.prm;
@@ -537,12 +549,15 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
         int stride[D];
         strides_of<D>(wk.full[p], wk.ld[p], stride);
         // depth-first walk: level l holds the tensor in region cur[l] with view shp[l], sum|M| sm[l], error er[l]
-        int cur[D + 1], shp[D + 1][D], upper_shape[D + 1][D], phase[D + 1], half[D];
-        double sm[D + 1], er[D + 1], upper_sum[D + 1], child_err[D + 1];
+        int (&cur)[D + 1] = W->cur; int (&phase)[D + 1] = W->phase; int (&half)[D] = W->half;
+        int (&shp)[D + 1][D] = W->shp; int (&upper_shape)[D + 1][D] = W->upper_shape;
+        double (&sm)[D + 1] = W->sm; double (&er)[D + 1] = W->er; double (&upper_sum)[D + 1] = W->upper_sum; double (&child_err)[D + 1] = W->child_err;
         for (int d = 0; d < D; ++d) { shp[0][d] = rec.shape[p][d]; half[d] = 0; }
         cur[0] = 0; sm[0] = wk.sumabs[p]; er[0] = rec.err[p]; phase[0] = 0;
         int l = 0;
         while (l >= 0) {
+            const int ph = l < k ? phase[l] : -1;
+            tm.sync();                                              // every lane has read this step's phase; the previous step's writes are done
             if (l == k) {
                 // ---- a finished child tensor leaves for the arena
                 int c = 0;
@@ -575,7 +590,7 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
                 continue;
             }
             const int axis = wk.order[p][l];
-            if (phase[l] == 0) {
+            if (ph == 0) {
                 // ---- halve along `axis`: lower -> region l + 1, upper in place
                 const int n = shp[l][axis];
                 const int ms = midsel[axis];
@@ -610,7 +625,7 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
                 half[axis] = 0;
                 cur[l + 1] = l + 1; sm[l + 1] = sumL; er[l + 1] = child_err[l]; phase[l + 1] = 0;
                 ++l;
-            } else if (phase[l] == 1) {
+            } else if (ph == 1) {
                 phase[l] = 2;
                 half[axis] = 1;
                 cur[l + 1] = cur[l]; sm[l + 1] = upper_sum[l]; er[l + 1] = child_err[l]; phase[l + 1] = 0;

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(128, 4) fd_tensor_warp(const Args<D> a, const 
                                                          unsigned slice_doubles, int snt, unsigned long long* cursor) {
     extern __shared__ __align__(16) double dyn[];
     __shared__ uint64_t team_bars[4];
+    __shared__ WalkState<D> walk[OP == kTSubdivide ? 4 : 1];
     double* smat = dyn;
     int smat_doubles = 0;
     if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a.tab, smat, snt); }
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(128, 4) fd_tensor_warp(const Args<D> a, const 
     while (i < n) {
         const unsigned int b = list[i];
         if (OP == kTRestrict) restrict_box<D, FMA>(tm, a, b, slice, macs);
-        else subdivide_box<D, FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
+        else subdivide_box<D, FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs,
+                                   &walk[OP == kTSubdivide ? w : 0]);
         tm.sync();
         i = grab();
     }
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) fd_tensor_cta
                                                                                 unsigned long long n, int snt, unsigned long long* cursor) {
     extern __shared__ __align__(16) double dyn[];
     __shared__ CtaShared cta_sh;
+    __shared__ WalkState<D> walk;
     double* smat = dyn;
     int smat_doubles = 0;
     if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a.tab, smat, snt); }
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) fd_tensor_cta
         if (i >= n) break;
         const unsigned int b = list[i];
         if (OP == kTRestrict) restrict_box<D, FMA>(tm, a, b, slice, macs);
-        else subdivide_box<D, FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs);
+        else subdivide_box<D, FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs, &walk);
         __syncthreads();
     }
     if (tm.tid == 0 && macs) atomicAdd(&a.ctl->restrict_macs, macs);
@@ -173,7 +176,7 @@ const Dev& dev() {
     }
     return d;
 }
-constexpr size_t kStaticReserve = 1024;
+constexpr size_t kStaticReserve = 2048;          // team barriers, reduction scratch, the walk states of 4 teams (yr_fd.h: WalkState)
 template <class K>
 int ensure_smem(K kernel, size_t bytes) {
     static std::vector<const void*> done;

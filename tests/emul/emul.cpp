@@ -544,7 +544,7 @@ int launch_tensor(const yr::fd::Args<D>& a, int op, int cls, const unsigned int*
             const unsigned int b = list[i];
             const double* lo = smat.data(); const double* hi = smat.data() + yr::f2::panel_doubles(snt);
             if (op == yr::f2::kTRestrict) { if (fma) yr::fd::restrict_box<D, true>(tm, a, b, slice.data(), macs); else yr::fd::restrict_box<D, false>(tm, a, b, slice.data(), macs); }
-            else if (fma) yr::fd::subdivide_box<D, true>(tm, a, b, slice.data(), lo, hi, snt, macs); else yr::fd::subdivide_box<D, false>(tm, a, b, slice.data(), lo, hi, snt, macs);
+            else { yr::fd::WalkState<D> walk; if (fma) yr::fd::subdivide_box<D, true>(tm, a, b, slice.data(), lo, hi, snt, macs, &walk); else yr::fd::subdivide_box<D, false>(tm, a, b, slice.data(), lo, hi, snt, macs, &walk); }
             tm.sync();
         }
         if (tm.tid == 0) macs_total = macs;
