@@ -80,12 +80,22 @@ YR_HD int tensor_doubles(const int* full, int ld) {                // storage of
 template <int D>
 YR_HD int tight_doubles(const int* shape) { return tensor_doubles<D>(shape, odd_ld(shape[D - 1])); }
 
+// e / n for 0 <= e < 2^18, n >= 1: the element and fiber counts of one box.  On the device through a float reciprocal
+// (4 instructions instead of the ~20 of an integer division): (e + 0.5) / n is at least 0.5 / n away from an integer,
+// i.e. 0.5 / e >= 1.9e-6 relative, against the 2.4e-7 (2 ulp) of the fast division -- exact.
+YR_HD int small_div(int e, int n) {
+#ifdef __CUDA_ARCH__
+    return __float2int_rz(__fdividef((float)e + 0.5f, (float)n));
+#else
+    return e / n;
+#endif
+}
 // element e (row-major over `shape`) -> offset with `stride` (no division for the outermost axis)
 template <int D>
 YR_HD int view_offset(int e, const int* shape, const int* stride) {
     int off = 0;
 #pragma unroll
-    for (int a = D - 1; a >= 1; --a) { const int q = e / shape[a]; off += (e - q * shape[a]) * stride[a]; e = q; }
+    for (int a = D - 1; a >= 1; --a) { const int q = small_div(e, shape[a]); off += (e - q * shape[a]) * stride[a]; e = q; }
     return off + e * stride[0];
 }
 // fiber f along AXIS (row-major over the other axes) -> offset of its first element
@@ -96,7 +106,7 @@ YR_HD int fiber_offset_t(int f, const int* shape, const int* stride) {
 #pragma unroll
     for (int a = D - 1; a > kOuter; --a) {
         if (a == AXIS) continue;
-        const int q = f / shape[a];
+        const int q = small_div(f, shape[a]);
         off += (f - q * shape[a]) * stride[a];
         f = q;
     }
@@ -107,7 +117,7 @@ YR_HD int fiber_offset(int f, int axis, const int* shape, const int* stride) {
     int off = 0;
     for (int a = D - 1; a >= 0; --a) {
         if (a == axis) continue;
-        const int q = f / shape[a];
+        const int q = small_div(f, shape[a]);
         off += (f - q * shape[a]) * stride[a];
         f = q;
     }
@@ -238,7 +248,7 @@ YR_DEV double plane_abs_sum_rows(Team& tm, const double* M, const int* t, const 
         for (int a = D - 1; a >= 0; --a) {
             if (a == AXIS || a == INNER) continue;
             if (a == kOuter) off += rem * stride[a];
-            else { const int q = rem / t[a]; off += (rem - q * t[a]) * stride[a]; rem = q; }
+            else { const int q = small_div(rem, t[a]); off += (rem - q * t[a]) * stride[a]; rem = q; }
         }
         const double* row = plane + off;
         for (int i = 0; i < len; ++i) s += fabs(row[i * si]);
