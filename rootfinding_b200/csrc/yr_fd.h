@@ -522,7 +522,7 @@ YR_HD void child_record(const Args<D>& a, const BoxRec<D>& rec, const Work<D>& w
 template <int D>
 struct WalkState {
     double sm[D + 1], er[D + 1], upper_sum[D + 1], child_err[D + 1];
-    int cur[D + 1], phase[D + 1], half[D];
+    int cur[D + 1], phase[D + 1];
     int shp[D + 1][D], upper_shape[D + 1][D];
 };
 
@@ -539,6 +539,8 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
     int split_axes[D], midsel[D];
     { bool used[D]; for (int d = 0; d < D; ++d) used[d] = false; for (int j = 0; j < k; ++j) used[wk.order[0][j]] = true; int j = 0; for (int ax = 0; ax < D; ++ax) if (used[ax]) split_axes[j++] = ax; for (; j < D; ++j) split_axes[j] = split_axes[0]; }
     for (int ax = 0; ax < D; ++ax) midsel[ax] = (rec.st.next_mid[ax] == 0.0) ? 0 : 1;
+    int usedmask = 0;                                             // (registers: the walk indexes no per-thread array by depth)
+    for (int j = 0; j < k; ++j) usedmask |= 1 << wk.order[0][j];
     unsigned long long cbase = 0, dbase = 0;
     if (tm.tid == 0) {
         cbase = tm.atomic_add(&a.ctl->n_boxes, (unsigned long long)nchild);
@@ -556,22 +558,24 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
         if (p > 0) { tm.sync(); tm.copy_async(slice, a.data_in + wk.off[p], sz[p]); }
         tm.copy_wait();
         tm.sync();
-        int stride[D];
-        strides_of<D>(wk.full[p], wk.ld[p], stride);
+        int stride[D], fullp[D];
+        for (int d = 0; d < D; ++d) fullp[d] = wk.full[p][d];        // (registers: `wk` is global memory the stores below may alias)
+        strides_of<D>(fullp, wk.ld[p], stride);
         // depth-first walk: level l holds the tensor in region cur[l] with view shp[l], sum|M| sm[l], error er[l]
-        int (&cur)[D + 1] = W->cur; int (&phase)[D + 1] = W->phase; int (&half)[D] = W->half;
+        int (&cur)[D + 1] = W->cur; int (&phase)[D + 1] = W->phase;
         int (&shp)[D + 1][D] = W->shp; int (&upper_shape)[D + 1][D] = W->upper_shape;
         double (&sm)[D + 1] = W->sm; double (&er)[D + 1] = W->er; double (&upper_sum)[D + 1] = W->upper_sum; double (&child_err)[D + 1] = W->child_err;
-        for (int d = 0; d < D; ++d) { shp[0][d] = rec.shape[p][d]; half[d] = 0; }
+        for (int d = 0; d < D; ++d) shp[0][d] = rec.shape[p][d];
         cur[0] = 0; sm[0] = wk.sumabs[p]; er[0] = rec.err[p]; phase[0] = 0;
-        int l = 0;
+        int l = 0, halfmask = 0;
         while (l >= 0) {
             const int ph = l < k ? phase[l] : -1;
             tm.sync();                                              // every lane has read this step's phase; the previous step's writes are done
             if (l == k) {
                 // ---- a finished child tensor leaves for the arena
-                int c = 0;
-                for (int j = 0; j < k; ++j) c = (c << 1) | half[split_axes[j]];      // split axes ascending, smallest most significant
+                int c = 0;                                              // split axes ascending, smallest most significant
+#pragma unroll
+                for (int ax = 0; ax < D; ++ax) if ((usedmask >> ax) & 1) c = (c << 1) | ((halfmask >> ax) & 1);
                 const double* M = slice + (size_t)cur[l] * T;
                 const int ld_out = odd_ld(shp[l][D - 1]);
                 const unsigned long long off = dbase + per_child * c + poff;
@@ -582,7 +586,7 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
                 const bool is_dead = (dead >> c) & 1u;
                 if (!is_dead) {
                     tensor_epilogue<D>(tm, M, shp[l], stride, sm[l], er[l], prm, ep);
-                    copy_out<D>(tm, a.data_out + off, ld_out, M, shp[l], wk.full[p], stride);
+                    copy_out<D>(tm, a.data_out + off, ld_out, M, shp[l], fullp, stride);
                 } else {
                     for (int q = 0; q < kLow<D>; ++q) ep.low[q] = 0.0;
                     ep.low[0] = c0; ep.tsum = sm[l]; ep.terr = er[l];
@@ -632,12 +636,12 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
                 }
                 upper_sum[l] = sumU;
                 phase[l] = 1;
-                half[axis] = 0;
+                halfmask &= ~(1 << axis);
                 cur[l + 1] = l + 1; sm[l + 1] = sumL; er[l + 1] = child_err[l]; phase[l + 1] = 0;
                 ++l;
             } else if (ph == 1) {
                 phase[l] = 2;
-                half[axis] = 1;
+                halfmask |= 1 << axis;
                 cur[l + 1] = cur[l]; sm[l + 1] = upper_sum[l]; er[l + 1] = child_err[l]; phase[l + 1] = 0;
                 for (int d = 0; d < D; ++d) shp[l + 1][d] = upper_shape[l][d];
                 ++l;
