@@ -106,7 +106,7 @@ YR_HD int class_threads(int cls) { return cls < kLane16Classes ? 16 : (cls < kWa
 constexpr unsigned long long kWarp32Max = 4096ull;    // largest need a warp team can take
 constexpr unsigned long long kMaxNeed = 28800ull;     // doubles of dynamic shared memory a CTA may use (225 KiB of 227)
 
-// Launch-shape policy (host-tunable; defaults from profiles/r02_team_sweep.txt): the largest warp-team need per op
+// Launch-shape policy (host-tunable; defaults from the sweeps in profiles/r02_experiments.txt and profiles/r02_fd.txt): the largest warp-team need per op
 // (boxes above it run one CTA per box) and the largest 128-thread CTA need.
 struct TeamPolicy { unsigned long long warp_max[2]; unsigned long long cta128_max; };
 
