@@ -50,7 +50,9 @@ typedef struct yr_params {
     int32_t max_zoom_count;      /* SolverOptions.maxZoomCount = 25          (:39) */
     int32_t use_fma;             /* 0 = separately rounded mul/add: restrictions bit-identical to the reference */
     int32_t trim;                /* 1 = run trimMs (:1232) */
-    int32_t reserved;
+    int32_t trim_policy;         /* which trim: 0 = trimMs (:1131-1171); 1, 2, 3 = trimMsOptimized1/2/3 of the reference's experiment
+                                  * file tests/TrimMs optimization/ChebyshevSubdivisionSolverWithOptimizedTrimMs.py:1167-1271.
+                                  * Policies 1-3 are served by yr_process_level only (yr_frontier_begin refuses them). */
     double  trim_rel_tol;        /* trimMs relApproxTol = 1e-3 (:1131) */
     double  trim_abs_tol;        /* trimMs absApproxTol = 0 */
 } yr_params;

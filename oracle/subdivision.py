@@ -446,6 +446,69 @@ def trim_system(Ms, errors, relApproxTol=1e-3, absApproxTol=0):
             sel[axis] = slice(None)
 
 
+# ---- the alternative trim policies of the reference's experiment file ------------------------------------------------
+# /root/reference/tests/TrimMs optimization/ChebyshevSubdivisionSolverWithOptimizedTrimMs.py (cited below as T:line).  That
+# file is an older copy of the solver in which the experimenter swaps the function called at the trimMs call site by hand;
+# the three functions themselves are what is restated here (pinned bit for bit: tests/golden/trim_policies.npz), and
+# `trim_policy` plugs them into the CURRENT solver's call site (:1232).
+def trim_system_optimized1(Ms, errors, relApproxTol=1e-3, absApproxTol=0):
+    """trimMsOptimized1 T:1167-1197 -- one hyperplane per axis per sweep, while anything can be trimmed (extent > 2)."""
+    dim = Ms[0].ndim
+    for p in range(len(Ms)):
+        budget = absApproxTol + errors[p] * relApproxTol
+        again = True
+        while again:
+            again = False
+            swept = 0
+            for axis in range(dim):
+                last = np.sum(np.abs(np.take(Ms[p], indices=-1, axis=axis)))
+                if Ms[p].shape[axis] > 2 and last < budget:
+                    again = True
+                    Ms[p] = np.delete(Ms[p], -1, axis=axis)
+                    budget -= last
+                    swept += last
+            errors[p] += swept
+
+
+def trim_system_optimized2(Ms, errors, relApproxTol=1e-3, absApproxTol=0):
+    """trimMsOptimized2 T:1199-1235 -- always the axis whose last hyperplane is the smallest."""
+    dim = Ms[0].ndim
+    for p in range(len(Ms)):
+        budget = absApproxTol + errors[p] * relApproxTol
+        while True:
+            best, best_axis = float("inf"), None
+            for axis in range(dim):
+                last = np.sum(np.abs(np.take(Ms[p], indices=-1, axis=axis)))
+                if last < best and Ms[p].shape[axis] > 2:
+                    best, best_axis = last, axis
+            if best_axis is None or best >= budget:
+                break
+            Ms[p] = np.delete(Ms[p], -1, axis=best_axis)
+            budget -= best
+            errors[p] += best
+
+
+def trim_system_optimized3(Ms, errors, relApproxTol=1e-3, absApproxTol=0):
+    """trimMsOptimized3 T:1237-1271 -- axes by descending extent, each trimmed as far as it goes.  (The running total is
+    added to the error after EVERY axis, T:1271 sits inside the loop: the error grows by more than what was removed.)"""
+    for p in range(len(Ms)):
+        budget = absApproxTol + errors[p] * relApproxTol
+        total = 0
+        for axis in np.argsort(Ms[p].shape)[::-1]:
+            while True:
+                last = np.sum(np.abs(np.take(Ms[p], indices=-1, axis=axis)))
+                if last < budget and Ms[p].shape[axis] > 2:
+                    Ms[p] = np.delete(Ms[p], -1, axis=axis)
+                    budget -= last
+                    total += last
+                else:
+                    break
+            errors[p] += total
+
+
+TRIM_POLICIES = {0: trim_system, 1: trim_system_optimized1, 2: trim_system_optimized2, 3: trim_system_optimized3}
+
+
 def is_exterior(entry_box, box):
     """isExteriorInterval :1173-1175."""
     return np.any(box.getIntervalForCombining() == entry_box.getIntervalForCombining())
@@ -466,6 +529,7 @@ class Options:
         self.maxZoomCount = 25
         self.level = 0
         self.useFinalStep = True
+        self.trim_policy = 0           # 0: trimMs :1131; 1-3: trimMsOptimized1/2/3 of the reference's experiment file
 
 
 class Trace:
@@ -509,7 +573,7 @@ def solve_box(Ms, box, errors, opts, trace):
     entry_Ms = list(Ms)
     box = box.copy()
     errors = errors.copy()
-    trim_system(Ms, errors)
+    TRIM_POLICIES[getattr(opts, "trim_policy", 0)](Ms, errors)
 
     changed = True
     zoom_count = 0
@@ -640,8 +704,8 @@ def _child_options(opts, level):
 
 def solve_chebyshev_subdivision(Ms, errors, verbose=False, returnBoundingBoxes=False, exact=False,
                                 constant_check=True, low_dim_quadratic_check=True,
-                                all_dim_quadratic_check=False, trace=None):
-    """solveChebyshevSubdivision :1387-1464."""
+                                all_dim_quadratic_check=False, trace=None, trim_policy=0):
+    """solveChebyshevSubdivision :1387-1464.  (`trim_policy`: see TRIM_POLICIES; not a parameter of the reference.)"""
     if np.any([M.ndim != len(Ms) for M in Ms]):
         raise ValueError("Solver Takes in N polynomials of dimension N!")
     if len(Ms) != len(errors):
@@ -653,6 +717,7 @@ def solve_chebyshev_subdivision(Ms, errors, verbose=False, returnBoundingBoxes=F
     opts.constant_check = constant_check
     opts.low_dim_quadratic_check = low_dim_quadratic_check
     opts.all_dim_quadratic_check = all_dim_quadratic_check
+    opts.trim_policy = trim_policy
     if trace is None:
         trace = Trace()
     inner, outer = solve_box(Ms, top, errors, opts, trace)

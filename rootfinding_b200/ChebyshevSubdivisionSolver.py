@@ -133,19 +133,23 @@ def _batch_ranges_for_memory(sizes, dim, eng):
 
 
 def _solve_chunks(systems, errors, ranges, returnBoundingBoxes, exact, constant_check, low_dim_quadratic_check,
-                  all_dim_quadratic_check, use_fma, eng, return_session):
+                  all_dim_quadratic_check, use_fma, eng, return_session, trim_policy=0):
     """solve_batch over consecutive sub-batches, one after the other; the last session carries all of them in
     `chunk_sessions` (statistics)."""
     roots, boxes, sessions = [], [], []
     for lo, hi in ranges:
         out, sess = solve_batch(systems[lo:hi], errors[lo:hi], returnBoundingBoxes, exact, constant_check,
-                                low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, True)
+                                low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, True, trim_policy)
         if returnBoundingBoxes:
             roots += out[0]; boxes += out[1]
         else:
             roots += out
         if sess is not None:
-            sessions += getattr(sess, "chunk_sessions", [sess])
+            chunk = getattr(sess, "chunk_sessions", [sess])
+            if not return_session:
+                for c in chunk:                        # the next chunk needs the device memory this one still pins
+                    c.release_device()
+            sessions += chunk
         del sess
     last = sessions[-1] if sessions else None
     if last is not None:
@@ -156,12 +160,21 @@ def _solve_chunks(systems, errors, ranges, returnBoundingBoxes, exact, constant_
 
 def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constant_check=True,
                 low_dim_quadratic_check=True, all_dim_quadratic_check=False, use_fma=False, engine=None,
-                return_session=False):
+                return_session=False, trim_policy=0):
     """Solve many independent systems (each a list of `dim` tensors) in one device frontier.
 
-    Returns a list with one root array per system (and a list of box lists when
-    returnBoundingBoxes).  Root order within a system is depth-first, as in the reference.
+    `trim_policy` (not a parameter of the reference): 0 = the reference's trimMs (:1131-1171); 1, 2, 3 = trimMsOptimized1/2/3 of
+    its experiment file tests/TrimMs optimization/ChebyshevSubdivisionSolverWithOptimizedTrimMs.py:1167-1271, plugged into
+    the same call site (:1232).  Policies 1-3 run on the level pipeline.
+
+    Returns a list with one root array per system (and a list of box lists when returnBoundingBoxes).  Roots of a system
+    come in depth-first order of the boxes that produced them (re-solved merged boxes at their job's position).  The
+    reference appends a call's exterior results after its interior ones at every level of the recursion
+    (ChebyshevSubdivisionSolver.py:1318-1385), so its order differs; the root SET is the reference's and both test suites
+    compare sets (tests/test_Combined_Solver.py:12-29 of the reference).
     """
+    if trim_policy not in (0, 1, 2, 3):
+        raise ValueError("trim_policy must be 0 (trimMs) or 1, 2, 3 (trimMsOptimized1/2/3)")
     for Ms, e in zip(systems, errors):
         _check_system(Ms, e)
     if len(systems) == 0:                                  # an empty batch has an empty answer and needs no device
@@ -181,17 +194,18 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
             bounds = np.unique(np.clip(np.r_[0, edges, len(systems)], 0, len(systems)))
             if len(bounds) > 2:
                 return _solve_chunks(systems, errors, list(zip(bounds[:-1], bounds[1:])), returnBoundingBoxes, exact,
-                                     constant_check, low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, return_session)
+                                     constant_check, low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, return_session, trim_policy)
         ranges = _batch_ranges_for_memory(sizes, len(systems[0]), eng)
         if ranges is not None:
             return _solve_chunks(systems, errors, ranges, returnBoundingBoxes, exact, constant_check, low_dim_quadratic_check,
-                                 all_dim_quadratic_check, use_fma, eng, return_session)
+                                 all_dim_quadratic_check, use_fma, eng, return_session, trim_policy)
     sess = None
     try:
         sess = eng.session(systems, errors,
                            exact=int(bool(exact)), constant_check=int(bool(constant_check)),
                            low_dim_quad_check=int(bool(low_dim_quadratic_check)),
-                           all_dim_quad_check=int(bool(all_dim_quadratic_check)), use_fma=int(bool(use_fma)))
+                           all_dim_quad_check=int(bool(all_dim_quadratic_check)), use_fma=int(bool(use_fma)),
+                           trim_policy=int(trim_policy))
         sess.run_jobs(sess.unit_jobs())
     except RuntimeError as exc:
         if not _is_out_of_memory(exc) or len(systems) < 2:
@@ -204,7 +218,7 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
         eng.release_cached()
         half = len(systems) // 2
         return _solve_chunks(systems, errors, [(0, half), (half, len(systems))], returnBoundingBoxes, exact, constant_check,
-                             low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, return_session)
+                             low_dim_quadratic_check, all_dim_quadratic_check, use_fma, eng, return_session, trim_policy)
     res, keep, dup, extra = postpass.assemble(sess, need_records=returnBoundingBoxes)
     if sess.stats.max_level >= 25:
         warnings.warn("Extreme subdivision depth!\nSubdivision on the search interval has now reached"
@@ -223,13 +237,13 @@ def solve_batch(systems, errors, returnBoundingBoxes=False, exact=False, constan
 
 
 def solveChebyshevSubdivision(Ms, errors, verbose=False, returnBoundingBoxes=False, exact=False,
-                              constant_check=True, low_dim_quadratic_check=True, all_dim_quadratic_check=False):
-    """Roots (and optionally bounding boxes) of one Chebyshev system on [-1,1]^n (:1387-1464)."""
+                              constant_check=True, low_dim_quadratic_check=True, all_dim_quadratic_check=False, trim_policy=0):
+    """Roots (and optionally bounding boxes) of one Chebyshev system on [-1,1]^n (:1387-1464).  `trim_policy`: see solve_batch."""
     _check_system(Ms, errors)
     if verbose:
         print("Finding roots...", end=' ')
     out = solve_batch([Ms], [np.asarray(errors, dtype=np.float64)], True, exact, constant_check,
-                      low_dim_quadratic_check, all_dim_quadratic_check)
+                      low_dim_quadratic_check, all_dim_quadratic_check, trim_policy=trim_policy)
     roots, boxes = out[0][0], out[1][0]
     dim = len(Ms)
     roots = np.array(roots).reshape(-1, dim) if len(roots) else np.array([])

@@ -18,7 +18,7 @@ vp, dp = C.c_void_p, C.c_void_p          # device pointers travel as integers
 
 class YrParams(C.Structure):
     _fields_ = [("exact", i32), ("constant_check", i32), ("low_dim_quad_check", i32), ("all_dim_quad_check", i32),
-                ("max_zoom_count", i32), ("use_fma", i32), ("trim", i32), ("reserved", i32),
+                ("max_zoom_count", i32), ("use_fma", i32), ("trim", i32), ("trim_policy", i32),
                 ("trim_rel_tol", C.c_double), ("trim_abs_tol", C.c_double)]
 
 

@@ -516,8 +516,77 @@ YR_HD void compute_layout(BoxShared<D>& sh, bool exact, bool subdivide = true) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The alternative trim policies of the reference's experiment file (tests/TrimMs optimization/
+// ChebyshevSubdivisionSolverWithOptimizedTrimMs.py, "T:"): 1 = trimMsOptimized1 T:1167-1197 (one hyperplane per axis per
+// sweep), 2 = trimMsOptimized2 T:1199-1235 (always the axis with the smallest last hyperplane), 3 = trimMsOptimized3
+// T:1237-1271 (axes by descending extent, each as far as it goes; the running total is added to the error after EVERY
+// axis, as T:1271 does).  Extents stop at 2 (trimMs: 3).  Every thread carries the same extents / budget / error, the
+// plane sums are team-wide reductions.
+template <int D, class Ctx>
+YR_DEVN void trim_box_policy(Ctx& cx, BoxShared<D>& sh, double* ws, const SolverParams& prm) {
+    for (int p = 0; p < D; ++p) {
+        const double* base = ws + sh.lay.base[p];
+        int shape[D], stride[D];
+        for (int a = 0; a < D; ++a) { shape[a] = sh.shape[p][a]; stride[a] = sh.stride[p][a]; }
+        double err = sh.err[p];
+        double budget = prm.trim_abs_tol + err * prm.trim_rel_tol;
+        bool any = false;
+        auto last_sum = [&](int axis) {
+            int shp[D];
+            for (int a = 0; a < D; ++a) shp[a] = shape[a];
+            shp[axis] = 1;
+            return tensor_abs_sum<D>(cx, base + (long long)(shape[axis] - 1) * stride[axis], shp, stride);
+        };
+        if (prm.trim_policy == 1) {
+            bool again = true;
+            while (again) {
+                again = false;
+                double swept = 0;
+                for (int axis = 0; axis < D; ++axis) {
+                    const double s = last_sum(axis);
+                    if (shape[axis] > 2 && s < budget) { again = true; shape[axis] -= 1; budget -= s; swept += s; any = true; }
+                }
+                err += swept;
+            }
+        } else if (prm.trim_policy == 2) {
+            for (;;) {
+                double best = INFINITY; int best_axis = -1;
+                for (int axis = 0; axis < D; ++axis) {
+                    const double s = last_sum(axis);
+                    if (s < best && shape[axis] > 2) { best = s; best_axis = axis; }
+                }
+                if (best_axis < 0 || best >= budget) break;
+                shape[best_axis] -= 1; budget -= best; err += best; any = true;
+            }
+        } else {
+            // np.argsort(shape)[::-1]: ascending stable sort of the extents, reversed
+            int order[D];
+            for (int a = 0; a < D; ++a) order[a] = a;
+            for (int a = 1; a < D; ++a) { const int v = order[a]; int q = a - 1; while (q >= 0 && shape[order[q]] > shape[v]) { order[q + 1] = order[q]; --q; } order[q + 1] = v; }
+            double total = 0;
+            for (int j = D - 1; j >= 0; --j) {
+                const int axis = order[j];
+                for (;;) {
+                    const double s = last_sum(axis);
+                    if (s < budget && shape[axis] > 2) { shape[axis] -= 1; budget -= s; total += s; any = true; }
+                    else break;
+                }
+                err += total;
+            }
+        }
+        cx.sync();
+        if (cx.tid == 0) {
+            for (int a = 0; a < D; ++a) sh.shape[p][a] = shape[a];
+            sh.err[p] = err;
+            if (any) sh.trimmed_any = 1;
+        }
+        cx.sync();
+    }
+}
+
 template <int D, class Ctx>
 YR_DEVN void trim_box(Ctx& cx, BoxShared<D>& sh, double* ws, const SolverParams& prm) {
+    if (prm.trim_policy != 0) { trim_box_policy<D>(cx, sh, ws, prm); return; }
     for (int p = 0; p < D; ++p) {
         if (cx.tid == 0) sh.budget = prm.trim_abs_tol + sh.err[p] * prm.trim_rel_tol;
         cx.sync();

@@ -77,6 +77,7 @@ inline int begin(const yr_frontier_desc* d, void* stream) {
     if (f.active) return fail("yr_frontier_begin: a frontier solve is already in progress (one per process)");
     if (d->dim != D) return fail("yr_frontier_solve: dimension mismatch");
     if (d->prm.exact) return fail("yr_frontier_solve: exact mode is served by yr_process_level");
+    if (d->prm.trim_policy) return fail("yr_frontier_solve: the alternative trim policies are served by yr_process_level");
     const unsigned long long n0 = d->n_in;
     if (n0 > 0x3FFFFFFFull) return fail("yr_frontier_solve: too many level-0 boxes");
     const int nt = (int)(d->max_extent < 4 ? 4 : d->max_extent);

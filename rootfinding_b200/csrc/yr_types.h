@@ -19,7 +19,7 @@ struct SolverParams {
     int32_t max_zoom_count;        // 25
     int32_t use_fma;               // 0: separately rounded mul/add (bit-exact restriction); 1: fused
     int32_t trim;                  // 1: run trimMs (reference behaviour)
-    int32_t reserved;
+    int32_t trim_policy;           // 0: trimMs :1131-1171; 1-3: trimMsOptimized1/2/3 of the reference's experiment file (level pipeline)
     double  trim_rel_tol;          // 1e-3
     double  trim_abs_tol;          // 0
 };

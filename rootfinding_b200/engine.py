@@ -401,7 +401,7 @@ class SolveSession:
         self._reserve("nodes", max(256, 4 * self.nsys))
         # 2-D, plain arithmetic, tensors that fit shared memory: the round-based frontier pipeline serves the session
         # 2-D, 3-D and 4-D systems in plain arithmetic: the round-based frontier pipelines serve the session
-        self.use_frontier = bool(engine.pipeline == 2 and D in (2, 3, 4) and not prm.exact and self.nsys > 0)
+        self.use_frontier = bool(engine.pipeline == 2 and D in (2, 3, 4) and not prm.exact and not prm.trim_policy and self.nsys > 0)
         self.sorted_dt = _lib.sorted_dtype(D)
         self._segments = []               # record ranges in production order: ("level", start, count) / ("frontier", start, count, out)
         self.index_base = 0               # added to every record index the device links with (box-level multi-GPU: rank << 27)
@@ -653,6 +653,18 @@ class SolveSession:
             finally:
                 self._pending.remove(out)
                 lib.yr_frontier_release(C.byref(out), stream)
+
+    def release_device(self):
+        """Give back everything the session holds on the device: unfetched frontier outputs, the coefficient upload, the
+        record arrays.  Host copies and statistics stay.  (A chunked solve calls it after each chunk: the chunks exist
+        because the batch does not fit the device at once.)"""
+        stream = self.mem.stream()
+        for out in self._pending:
+            self.lib.yr_frontier_release(C.byref(out), stream)
+        self._pending = []
+        self._segments = []
+        self.d_coeffs = self.d_off = self.d_shapes = self.d_errs = self.d_results = self.d_nodes = None
+        self.cap_results = self.cap_nodes = 0
 
     def __del__(self):
         try:

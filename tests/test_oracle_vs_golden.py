@@ -236,3 +236,22 @@ def test_split_matrices_are_exact_mirror_images():
     rng = np.random.RandomState(1)
     c, v, x = rng.randn(1000), rng.randn(1000), rng.randn(1000)
     assert np.array_equal(x + (-c) * v, x - c * v)
+
+
+def test_trim_policies_match_reference(golden_dir):
+    """trimMs and trimMsOptimized1/2/3 of the reference's experiment file (tests/TrimMs optimization/...:1125-1271), run by
+    oracle/gen_golden_trim.py: the oracle's restatements leave the same extents and the same errors, bit for bit."""
+    z = _load(golden_dir, "trim_policies.npz")
+    trimmed = 0
+    for name in z["cases"]:
+        dim = int(str(name)[1])
+        Ms = [z[f"M_{name}_{p}"] for p in range(dim)]
+        for k, fn in osub.TRIM_POLICIES.items():
+            Mk, ek = [M.copy() for M in Ms], z[f"err_{name}"].copy()
+            fn(Mk, ek)
+            assert np.array_equal(np.array([M.shape for M in Mk]), z[f"shape_{name}_{k}"]), (name, k)
+            assert np.array_equal(ek, z[f"err_{name}_{k}"]), (name, k)
+            for p in range(dim):
+                assert np.array_equal(Mk[p], Ms[p][tuple(slice(0, e) for e in Mk[p].shape)])
+            trimmed += int(sum(M.size for M in Ms) - sum(M.size for M in Mk) > 0)
+    assert trimmed >= 20

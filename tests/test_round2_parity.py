@@ -605,3 +605,43 @@ def test_sparse_record_fetch_emulated(emu_yr):
 @pytest.mark.gpu
 def test_sparse_record_fetch_gpu(gpu_yr):
     _sparse_records_match_full(gpu_yr, 200)
+
+
+# ---- f4: the reference's alternative trim policies, plugged into the solver's trimMs call site -------------------------
+def _trim_policies(yr, plan):
+    S = yr.ChebyshevSubdivisionSolver
+    from rootfinding_b200.workloads import random_systems
+    differs = 0
+    for dim, deg, n, seed in plan:
+        systems, _ = random_systems(dim, deg, n, seed=seed)
+        errors = [np.full(dim, 1e-7)] * n                        # approximation errors of this size give the trims something to do
+        base_coeffs = None
+        for k in (0, 1, 2, 3):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                got, sess = S.solve_batch(systems, errors, trim_policy=k, return_session=True)
+            boxes = coeffs = 0
+            for Ms, e, g in zip(systems, errors, got):
+                want, trace = H.oracle_solve(Ms, e, trim_policy=k)
+                boxes += trace.boxes
+                coeffs += trace.entry_coeffs
+                assert len(g) == len(want), (dim, deg, k, len(g), len(want))
+                if len(want):
+                    H.match_points(want, np.asarray(g).reshape(-1, dim), 1e-10)
+            assert sess.stats.boxes == boxes, (dim, deg, k, sess.stats.boxes, boxes)      # same search tree as the oracle ...
+            assert sess.stats.entry_coeffs == coeffs, (dim, deg, k, sess.stats.entry_coeffs, coeffs)   # ... with the same trimmed extents
+            if k == 0:
+                base_coeffs = coeffs
+            differs += int(coeffs != base_coeffs)
+    assert differs >= 1                                       # the policies do trim differently (else the test is vacuous)
+    with pytest.raises(ValueError):
+        S.solve_batch(systems, errors, trim_policy=7)
+
+
+def test_trim_policies_emulated(emu_yr):
+    _trim_policies(emu_yr, [(2, 10, 2, 11), (3, 4, 2, 12)])
+
+
+@pytest.mark.gpu
+def test_trim_policies_gpu(gpu_yr):
+    _trim_policies(gpu_yr, [(2, 10, 2, 11), (2, 10, 6, 11), (2, 30, 2, 13), (3, 5, 3, 12), (4, 3, 2, 14)])
