@@ -295,7 +295,11 @@ def assemble(session, merge=True, need_records=False):
         may_merge = merge and len(touch_pos) >= 2 and len(np.unique(touch_sys)) < len(touch_sys)
         keep = slim["index"]
         bounds = np.searchsorted(sysv, np.arange(session.nsys + 1))
-        session.sorted_fields = (sysv, np.ascontiguousarray(slim["root"]), bounds)
+        # the roots handed to the caller: a pooled buffer (a fresh 11 MB array costs its first-touch page faults every call)
+        from .engine import result_pool
+        roots_all = result_pool.take(slim["root"].size * 8).view(np.float64).reshape(slim["root"].shape)
+        roots_all[...] = slim["root"]
+        session.sorted_fields = (sysv, roots_all, bounds)
         session.late_by_system = {}
         if not special and not may_merge:
             return (session.results() if need_records else None), keep, {}, set()
@@ -388,7 +392,8 @@ def per_system_roots(res, keep, dup, extra, nsys, dim, want_boxes=False, sorted_
     if not want_boxes:
         # ordinary systems are slices of the sorted roots: one split for all of them, then only the special ones
         # (lost records to a merge / collector, late records, duplicate or extra roots) are rebuilt record by record
-        out_roots = np.split(roots_all, bounds[1:-1]) if nsys else []
+        bl = bounds.tolist()
+        out_roots = [roots_all[bl[s]:bl[s + 1]] for s in range(nsys)]
         todo = sorted((set(redo_systems) | set(late_by_system) | special_systems) & set(range(nsys)))
     else:
         todo = range(nsys)
