@@ -514,11 +514,12 @@ YR_HD void child_record(const Args<D>& a, const BoxRec<D>& rec, const Work<D>& w
 // The 2^k children are produced by a depth-first walk over the halvings (order[p][0], order[p][1], ...): at depth l the
 // lower half is written to region l + 1 and the upper half replaces the tensor where it stands, so the walk first
 // finishes everything below the lower half and then continues from the upper half with region l + 1 free again.
-// State of the depth-first walk, ONE copy per team in memory every lane of the team can read (shared memory on the
-// device).  As per-thread arrays indexed by the run-time depth they live in local memory: 400 bytes x every resident
+// State of the depth-first walk, ONE copy per warp in memory every lane of the warp can read (shared memory on the
+// device; the warps of a 128-thread CTA team each keep their own identical copy, so a step costs a warp barrier, not a
+// CTA barrier; 256-thread CTAs share one copy: their static shared memory is tight against the largest box).  As per-thread arrays indexed by the run-time depth they live in local memory: 400 bytes x every resident
 // thread does not fit L1 next to the shared-memory carve-out, and a third of the subdivide kernels' stall samples were
 // long-scoreboard waits on them (profiles/r02_fd.txt).  Every lane executes the walk and writes the SAME values; one
-// team barrier per step separates a step's reads from the next step's writes.
+// warp barrier per step separates a step's reads from the next step's writes.
 template <int D>
 struct WalkState {
     double sm[D + 1], er[D + 1], upper_sum[D + 1], child_err[D + 1];
@@ -528,7 +529,7 @@ struct WalkState {
 
 template <int D, bool FMA, class Team>
 YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* slice, const double* smat_lo, const double* smat_hi,
-                          int smat_nt, unsigned long long& macs, WalkState<D>* W) {
+                          int smat_nt, unsigned long long& macs, WalkState<D>* W, bool state_per_warp = true) {
     const BoxRec<D>& rec = a.recs[b];
     const Work<D>& wk = a.work[b];
     const SolverParams& prm = a.prm;
@@ -570,7 +571,8 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
         int l = 0, halfmask = 0;
         while (l >= 0) {
             const int ph = l < k ? phase[l] : -1;
-            tm.sync();                                              // every lane has read this step's phase; the previous step's writes are done
+            // every lane sharing this copy of the state has read the step's phase, the previous step's writes are done
+            if (state_per_warp) tm.wsync(); else tm.sync();
             if (l == k) {
                 // ---- a finished child tensor leaves for the arena
                 int c = 0;                                              // split axes ascending, smallest most significant

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) fd_tensor_cta
                                                                                 unsigned long long n, int snt, unsigned long long* cursor) {
     extern __shared__ __align__(16) double dyn[];
     __shared__ CtaShared cta_sh;
-    __shared__ WalkState<D> walk;
+    constexpr bool kPerWarp = (THREADS == 128);
+    __shared__ WalkState<D> walk[(OP == kTSubdivide && kPerWarp) ? THREADS / 32 : 1];
     double* smat = dyn;
     int smat_doubles = 0;
     if (OP == kTSubdivide && snt > 0) { smat_doubles = 2 * panel_doubles(snt); stage_submats(a.tab, smat, snt); }
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) fd_tensor_cta
         if (i >= n) break;
         const unsigned int b = list[i];
         if (OP == kTRestrict) restrict_box<D, FMA>(tm, a, b, slice, macs);
-        else subdivide_box<D, FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs, &walk);
+        else subdivide_box<D, FMA>(tm, a, b, slice, snt > 0 ? smat : nullptr, snt > 0 ? smat + panel_doubles(snt) : nullptr, snt, macs,
+                                   &walk[(OP == kTSubdivide && kPerWarp) ? (threadIdx.x >> 5) : 0], kPerWarp);
         __syncthreads();
     }
     if (tm.tid == 0 && macs) atomicAdd(&a.ctl->restrict_macs, macs);
