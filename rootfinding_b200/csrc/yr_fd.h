@@ -391,20 +391,29 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
     Work<D>& wk = a.work[b];
     const SolverParams& prm = a.prm;
     const int copy_only = wk.copy_only;
-    int shp[D][D], full[D][D], ldg[D], lds[D], sz[D], nmax[D];
-    bool flat[D];
-    unsigned long long off_in[D];
+    // geometry of tensor p, straight from the records into registers.  (Kept in arrays indexed by the run-time p of the
+    // un-unrolled tensor loop below they lived in local memory: long-scoreboard waits, profiles/r02_fd.txt.  Thread 0
+    // rewrites the entries of tensor p only after every thread has read them.)
+    auto geom = [&](int p, int* shp_p, int* full_p, int& ldg_p, int& lds_p, unsigned long long& off_p, bool& flat_p) {
+#pragma unroll
+        for (int ax = 0; ax < D; ++ax) { shp_p[ax] = rec.shape[p][ax]; full_p[ax] = wk.full[p][ax]; }
+        ldg_p = wk.ld[p]; off_p = wk.off[p];
+        flat_p = (ldg_p & 1) && ldg_p >= full_p[D - 1] && (off_p & 1ull) == 0;
+        lds_p = flat_p ? ldg_p : odd_ld(full_p[D - 1]);
+    };
+    int nmax[D];
     int T = 0;
     for (int ax = 0; ax < D; ++ax) nmax[ax] = 0;
     unsigned long long out_total = 0;
+#pragma unroll
     for (int p = 0; p < D; ++p) {
-        for (int ax = 0; ax < D; ++ax) { shp[p][ax] = rec.shape[p][ax]; full[p][ax] = wk.full[p][ax]; if (shp[p][ax] > nmax[ax]) nmax[ax] = shp[p][ax]; }
-        ldg[p] = wk.ld[p]; off_in[p] = wk.off[p];
-        flat[p] = (ldg[p] & 1) && ldg[p] >= full[p][D - 1] && (off_in[p] & 1ull) == 0;
-        lds[p] = flat[p] ? ldg[p] : odd_ld(full[p][D - 1]);
-        sz[p] = tensor_doubles<D>(full[p], lds[p]);
-        if (sz[p] > T) T = sz[p];
-        out_total += (unsigned long long)tight_doubles<D>(shp[p]);
+        int shp_p[D], full_p[D], ldg_p, lds_p; unsigned long long off_p; bool flat_p;
+        geom(p, shp_p, full_p, ldg_p, lds_p, off_p, flat_p);
+#pragma unroll
+        for (int ax = 0; ax < D; ++ax) if (shp_p[ax] > nmax[ax]) nmax[ax] = shp_p[ax];
+        const int sz_p = tensor_doubles<D>(full_p, lds_p);
+        if (sz_p > T) T = sz_p;
+        out_total += (unsigned long long)tight_doubles<D>(shp_p);
     }
     double* A = slice;
     double* C[D]; int* rows[D];
@@ -416,14 +425,16 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
     }
     double al[D], be[D]; bool ident[D];
     for (int ax = 0; ax < D; ++ax) { al[ax] = wk.alpha[ax]; be[ax] = wk.beta[ax]; ident[ax] = copy_only || (al[ax] == 1.0 && be[ax] == 0.0); }
-    double sum_in[D], err_in[D];
-    for (int p = 0; p < D; ++p) { sum_in[p] = wk.sumabs[p]; err_in[p] = rec.err[p]; }
     unsigned long long base = 0;
     if (tm.tid == 0) base = tm.atomic_add(&a.ctl->data_used, out_total);
     base = tm.bcast(base);
     if (base + out_total > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
     tm.sync();                                                   // the previous box is done with the slice
-    fetch<D>(tm, A, full[0], lds[0], a.data_in + off_in[0], ldg[0], flat[0]);          // runs behind the matrix build
+    {
+        int shp_p[D], full_p[D], ldg_p, lds_p; unsigned long long off_p; bool flat_p;
+        geom(0, shp_p, full_p, ldg_p, lds_p, off_p, flat_p);
+        fetch<D>(tm, A, full_p, lds_p, a.data_in + off_p, ldg_p, flat_p);               // runs behind the matrix build
+    }
     for (int ax = 0; ax < D; ax += 2) {
         const int ax1 = ax + 1 < D ? ax + 1 : ax;
         PanelJob j0 = {C[ax], rows[ax], (!ident[ax] && nmax[ax] > 1) ? nmax[ax] : 0, al[ax], be[ax]};
@@ -433,14 +444,15 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
     unsigned long long out_off = base;
 #pragma unroll 1
     for (int p = 0; p < D; ++p) {
-        int stride[D], cur[D];
-        strides_of<D>(full[p], lds[p], stride);
-        for (int ax = 0; ax < D; ++ax) cur[ax] = shp[p][ax];
-        if (p > 0) fetch<D>(tm, A, full[p], lds[p], a.data_in + off_in[p], ldg[p], flat[p]);
+        int stride[D], cur[D], full_p[D], ldg_p, lds_p; unsigned long long off_p; bool flat_p;
+        geom(p, cur, full_p, ldg_p, lds_p, off_p, flat_p);
+        const double sum_in = wk.sumabs[p], err_in = rec.err[p];
+        strides_of<D>(full_p, lds_p, stride);
+        if (p > 0) fetch<D>(tm, A, full_p, lds_p, a.data_in + off_p, ldg_p, flat_p);
         tm.copy_wait();
         tm.sync();
-        double s = copy_only ? view_abs_sum<D>(tm, A, cur, stride) : sum_in[p];
-        double err = err_in[p];
+        double s = copy_only ? view_abs_sum<D>(tm, A, cur, stride) : sum_in;
+        double err = err_in;
 #pragma unroll
         for (int axis = 0; axis < D; ++axis) {                       // unrolled: the axis of every pass is a compile-time constant
             const int n = cur[axis];
@@ -462,7 +474,7 @@ YR_DEV void restrict_box(Team& tm, const Args<D>& a, unsigned int b, double* sli
                 wk.off[p] = out_off; wk.ld[p] = ld_out;
             }
         }
-        copy_out<D>(tm, a.data_out + out_off, ld_out, A, cur, full[p], stride);
+        copy_out<D>(tm, a.data_out + out_off, ld_out, A, cur, full_p, stride);
         out_off += (unsigned long long)osz;
         tm.sync();                                               // tensor p has left A before tensor p + 1 arrives
     }
