@@ -546,12 +546,13 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
     const Work<D>& wk = a.work[b];
     const SolverParams& prm = a.prm;
     const int k = wk.nsplit, nchild = 1 << k;
-    int T = 0, sz[D];
+    int T = 0;
     unsigned long long per_child = 0;
-    for (int p = 0; p < D; ++p) { sz[p] = tensor_doubles<D>(wk.full[p], wk.ld[p]); if (sz[p] > T) T = sz[p]; per_child += (unsigned long long)sz[p]; }
-    int split_axes[D], midsel[D];
+#pragma unroll
+    for (int p = 0; p < D; ++p) { const int s = tensor_doubles<D>(wk.full[p], wk.ld[p]); if (s > T) T = s; per_child += (unsigned long long)s; }
+    int split_axes[D], midmask = 0;
     { bool used[D]; for (int d = 0; d < D; ++d) used[d] = false; for (int j = 0; j < k; ++j) used[wk.order[0][j]] = true; int j = 0; for (int ax = 0; ax < D; ++ax) if (used[ax]) split_axes[j++] = ax; for (; j < D; ++j) split_axes[j] = split_axes[0]; }
-    for (int ax = 0; ax < D; ++ax) midsel[ax] = (rec.st.next_mid[ax] == 0.0) ? 0 : 1;
+    for (int ax = 0; ax < D; ++ax) midmask |= ((rec.st.next_mid[ax] == 0.0) ? 0 : 1) << ax;
     int usedmask = 0;                                             // (registers: the walk indexes no per-thread array by depth)
     for (int j = 0; j < k; ++j) usedmask |= 1 << wk.order[0][j];
     unsigned long long cbase = 0, dbase = 0;
@@ -563,12 +564,15 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
     cbase = tm.bcast(cbase); dbase = tm.bcast(dbase);
     if (cbase + nchild > a.cap_boxes || dbase + per_child * nchild > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
     tm.sync();
-    tm.copy_async(slice, a.data_in + wk.off[0], sz[0]);           // tensor 0 arrives while the child records are written
+    tm.copy_async(slice, a.data_in + wk.off[0], tensor_doubles<D>(wk.full[0], wk.ld[0]));   // tensor 0 arrives while the child records are written
     for (int c = tm.tid; c < nchild; c += tm.nthreads) child_record<D>(a, rec, wk, (unsigned int)(cbase + c), c, k, split_axes);
     unsigned dead = 0;                                            // children already known to fail the constant check
     unsigned long long poff = 0;
     for (int p = 0; p < D; ++p) {
-        if (p > 0) { tm.sync(); tm.copy_async(slice, a.data_in + wk.off[p], sz[p]); }
+        const int sz_p = tensor_doubles<D>(wk.full[p], wk.ld[p]);
+        int ordp = 0;                                               // the halving order of this tensor, 4 bits per depth
+        for (int j = 0; j < k; ++j) ordp |= wk.order[p][j] << (4 * j);
+        if (p > 0) { tm.sync(); tm.copy_async(slice, a.data_in + wk.off[p], sz_p); }
         tm.copy_wait();
         tm.sync();
         int stride[D], fullp[D];
@@ -617,11 +621,11 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
                 --l;
                 continue;
             }
-            const int axis = wk.order[p][l];
+            const int axis = (ordp >> (4 * l)) & 15;
             if (ph == 0) {
                 // ---- halve along `axis`: lower -> region l + 1, upper in place
                 const int n = shp[l][axis];
-                const int ms = midsel[axis];
+                const int ms = (midmask >> axis) & 1;
                 const bool smem = (ms == 0 && smat_lo != nullptr);
                 const double* mlo = smem ? smat_lo : a.tab.mat[ms][0];
                 const double* mhi = smem ? smat_hi : a.tab.mat[ms][1];
@@ -661,7 +665,7 @@ YR_DEV void subdivide_box(Team& tm, const Args<D>& a, unsigned int b, double* sl
                 ++l;
             } else --l;
         }
-        poff += (unsigned long long)sz[p];
+        poff += (unsigned long long)sz_p;
     }
     tm.sync();
 }
