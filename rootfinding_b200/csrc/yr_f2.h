@@ -250,11 +250,12 @@ YR_F2_BUILD void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb,
     const int b = i >> 2;
     double* ptr = j.Cp + panel_off(b, nt) + (i & 3);           // entry (i, k) lives at ptr[(k - 4b) * 4]
     const double alpha = j.alpha, beta = j.beta, beta2 = 2 * beta;
+    int* const rows_after = j.rows_after;                      // (a register copy: the job lives in local memory and the stores below may alias it)
     const bool live = i < B4 && nt > 0;
     double prev2 = (i == 0) ? 1.0 : 0.0;                       // column 0
     double prev = (i == 0) ? beta : (i == 1 ? alpha : 0.0);    // column 1
     if (live && b == 0) { ptr[0] = prev2; if (nt >= 2) ptr[4] = prev; }
-    if (i == 0 && nt > 0) { j.rows_after[0] = 1; if (nt >= 2) j.rows_after[1] = 2; }
+    if (i == 0 && nt > 0) { rows_after[0] = 1; if (nt >= 2) rows_after[1] = 2; }
     int rows = 2;
     const int segshift = (seg == 16 && w.lanes == 32) ? (lane & 16) : 0;
     for (int k = 2; k < kmax; ++k) {
@@ -273,7 +274,7 @@ YR_F2_BUILD void build_panels_warp(W& w, const PanelJob& ja, const PanelJob& jb,
             if (live && k >= 4 * b) ptr[(k - 4 * b) << 2] = val;
             prev2 = prev; prev = val;
             rows += grow;
-            if (i == (k & (seg - 1))) j.rows_after[k] = rows;
+            if (i == (k & (seg - 1))) rows_after[k] = rows;
         }
     }
     w.wsync();
@@ -293,6 +294,7 @@ YR_F2_BUILD void build_panels_pair(W& w, const PanelJob& ja, const PanelJob& jb)
     double* pb = jb.Cp + panel_off(b, ntb) + (i & 3);
     const bool livea = i < (((nta + 3) >> 2) << 2), liveb = i < (((ntb + 3) >> 2) << 2);
     const double ala = ja.alpha, be2a = 2 * ja.beta, alb = jb.alpha, be2b = 2 * jb.beta;
+    int* const ra = ja.rows_after; int* const rb = jb.rows_after;      // (register copies, see build_panels_warp)
     double p2a = (i == 0) ? 1.0 : 0.0, p2b = p2a;
     double p1a = (i == 0) ? ja.beta : (i == 1 ? ala : 0.0), p1b = (i == 0) ? jb.beta : (i == 1 ? alb : 0.0);
     if (b == 0) {
@@ -300,8 +302,8 @@ YR_F2_BUILD void build_panels_pair(W& w, const PanelJob& ja, const PanelJob& jb)
         if (liveb) { pb[0] = p2b; if (ntb >= 2) pb[4] = p1b; }
     }
     if (i == 0) {
-        ja.rows_after[0] = 1; if (nta >= 2) ja.rows_after[1] = 2;
-        jb.rows_after[0] = 1; if (ntb >= 2) jb.rows_after[1] = 2;
+        ra[0] = 1; if (nta >= 2) ra[1] = 2;
+        rb[0] = 1; if (ntb >= 2) rb[1] = 2;
     }
     int rowsa = 2, rowsb = 2;
     for (int k = 2; k < kmax; ++k) {
@@ -320,12 +322,12 @@ YR_F2_BUILD void build_panels_pair(W& w, const PanelJob& ja, const PanelJob& jb)
         if (k < nta) {
             if (livea && k >= 4 * b) pa[(k - 4 * b) << 2] = va;
             p2a = p1a; p1a = va; rowsa += growa;
-            if (i == (k & (seg - 1))) ja.rows_after[k] = rowsa;
+            if (i == (k & (seg - 1))) ra[k] = rowsa;
         }
         if (k < ntb) {
             if (liveb && k >= 4 * b) pb[(k - 4 * b) << 2] = vb;
             p2b = p1b; p1b = vb; rowsb += growb;
-            if (i == (k & (seg - 1))) jb.rows_after[k] = rowsb;
+            if (i == (k & (seg - 1))) rb[k] = rowsb;
         }
     }
     w.wsync();
@@ -913,31 +915,30 @@ YR_DEV void restrict_box_w(Team& tm, const Args& a, unsigned int b, double* slic
     Work& wk = a.work[b];
     const SolverParams& prm = a.prm;
     const int copy_only = wk.copy_only;
-    int shp[2][2], ldg[2], lds[2], sz[2];
-    bool flat[2];
-    unsigned long long off_in[2];
-    for (int p = 0; p < 2; ++p) {
-        shp[p][0] = rec.shape[p][0]; shp[p][1] = rec.shape[p][1]; ldg[p] = wk.ld[p]; off_in[p] = wk.off[p];
-        flat[p] = (ldg[p] & 1) && ldg[p] >= shp[p][1] && (off_in[p] & 1ull) == 0;
-        lds[p] = flat[p] ? ldg[p] : odd_ld(shp[p][1]);
-        sz[p] = tensor_doubles(shp[p][0], lds[p]);
-    }
-    const int T = sz[0] > sz[1] ? sz[0] : sz[1];
-    const int n0max = shp[0][0] > shp[1][0] ? shp[0][0] : shp[1][0];
-    const int n1max = shp[0][1] > shp[1][1] ? shp[0][1] : shp[1][1];
+    // per-tensor geometry in scalars, selected by p below: as arrays indexed by the loop variable of the (not unrolled)
+    // tensor loop they were kept in local memory (a 144-byte stack frame in the 16-lane RESTRICT kernel)
+    const int s00 = rec.shape[0][0], s01 = rec.shape[0][1], s10 = rec.shape[1][0], s11 = rec.shape[1][1];
+    const int ldg0 = wk.ld[0], ldg1 = wk.ld[1];
+    const unsigned long long off0 = wk.off[0], off1 = wk.off[1];
+    const bool flat0 = (ldg0 & 1) && ldg0 >= s01 && (off0 & 1ull) == 0, flat1 = (ldg1 & 1) && ldg1 >= s11 && (off1 & 1ull) == 0;
+    const int lds0 = flat0 ? ldg0 : odd_ld(s01), lds1 = flat1 ? ldg1 : odd_ld(s11);
+    const int sz0 = tensor_doubles(s00, lds0), sz1 = tensor_doubles(s10, lds1);
+    const int T = sz0 > sz1 ? sz0 : sz1;
+    const int n0max = s00 > s10 ? s00 : s10;
+    const int n1max = s01 > s11 ? s01 : s11;
     double* A = slice;
     double* C0 = slice + T; double* C1 = C0 + panel_doubles(n0max);
     int* rows0 = reinterpret_cast<int*>(C1 + panel_doubles(n1max)); int* rows1 = rows0 + n0max;
     const double al0 = wk.alpha[0], be0 = wk.beta[0], al1 = wk.alpha[1], be1 = wk.beta[1];
     const bool id0 = copy_only || (al0 == 1.0 && be0 == 0.0), id1 = copy_only || (al1 == 1.0 && be1 == 0.0);
-    const double sum_in[2] = {wk.sumabs[0], wk.sumabs[1]};
-    const double err_in[2] = {rec.err[0], rec.err[1]};
+    const double sum_in0 = wk.sumabs[0], sum_in1 = wk.sumabs[1];
+    const double err_in0 = rec.err[0], err_in1 = rec.err[1];
     unsigned long long base = 0;
-    if (tm.tid == 0) base = tm.atomic_add(&a.ctl->data_used, (unsigned long long)(sz[0] + sz[1]));
+    if (tm.tid == 0) base = tm.atomic_add(&a.ctl->data_used, (unsigned long long)(sz0 + sz1));
     base = tm.bcast(base);
-    if (base + (unsigned long long)(sz[0] + sz[1]) > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
+    if (base + (unsigned long long)(sz0 + sz1) > a.cap_data_out) { if (tm.tid == 0) tm.atomic_add(&a.ctl->overflow, 1ull); return; }
     tm.sync();                                                   // the previous box is done with the slice
-    fetch_tensor(tm, A, lds[0], a.data_in + off_in[0], ldg[0], shp[0][0], shp[0][1], flat[0]);   // runs behind the build
+    fetch_tensor(tm, A, lds0, a.data_in + off0, ldg0, s00, s01, flat0);   // runs behind the build
     {
         PanelJob j0 = {C0, rows0, (!id0 && n0max > 1) ? n0max : 0, al0, be0};
         PanelJob j1 = {C1, rows1, (!id1 && n1max > 1) ? n1max : 0, al1, be1};
@@ -945,12 +946,12 @@ YR_DEV void restrict_box_w(Team& tm, const Args& a, unsigned int b, double* slic
     }
     unsigned long long out_off = base;
     for (int p = 0; p < 2; ++p) {
-        const int n0 = shp[p][0], n1 = shp[p][1], ld = lds[p];
-        if (p == 1) fetch_tensor(tm, A, ld, a.data_in + off_in[1], ldg[1], n0, n1, flat[1]);
+        const int n0 = p ? s10 : s00, n1 = p ? s11 : s01, ld = p ? lds1 : lds0;
+        if (p == 1) fetch_tensor(tm, A, ld, a.data_in + off1, ldg1, n0, n1, flat1);
         tm.copy_wait();
         tm.sync();
-        double s = copy_only ? view_abs_sum(tm, A, n0, n1, ld) : sum_in[p];
-        double err = err_in[p];
+        double s = copy_only ? view_abs_sum(tm, A, n0, n1, ld) : (p ? sum_in1 : sum_in0);
+        double err = p ? err_in1 : err_in0;
         int r0 = n0, r1 = n1;
 #pragma unroll 1
         for (int axis = 0; axis < 2; ++axis) {                       // one copy of the pass in the instruction stream
