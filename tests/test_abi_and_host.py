@@ -475,3 +475,47 @@ def test_very_large_batches_are_pre_split(monkeypatch):
     assert sum(c.stats.boxes for c in sess.chunk_sessions) > 0
     for a, b in zip(want, got):
         assert np.array_equal(a, b)
+
+
+def test_host_pool_reuses_a_buffer_only_when_nothing_refers_to_it():
+    """engine.HostPool hands result arrays to callers: a buffer may come back only after every array and view made from it is
+    gone (its lifetime is tracked through the arrays' base object)."""
+    import gc
+    from rootfinding_b200.engine import HostPool
+    pool = HostPool()
+    a = pool.take(4000).view(np.float64).reshape(-1, 5)
+    a[...] = 7.0
+    parts = [a[:30], a[30:]]
+    addr = a.ctypes.data
+    del a
+    gc.collect()
+    assert pool.free == []                                   # the slices still refer to it
+    b = pool.take(4000)
+    assert b.ctypes.data != addr and np.all(parts[0] == 7.0)
+    del parts
+    gc.collect()
+    assert len(pool.free) == 1
+    c = pool.take(1000)
+    assert c.ctypes.data == addr and pool.free == []
+
+
+def test_chunked_solve_releases_each_chunk(emu, monkeypatch):
+    """a chunked solve must not keep every chunk's device buffers until the end."""
+    from rootfinding_b200 import ChebyshevSubdivisionSolver as S
+    from rootfinding_b200.engine import SolveSession
+    systems, errs = H.seeded_systems(2, 5, 6), [np.full(2, 2.0 ** -52)] * 6
+    released = []
+    orig = SolveSession.release_device
+
+    def spy(self):
+        orig(self)
+        released.append((self.d_coeffs, self.d_results, len(self._pending)))
+    monkeypatch.setattr(SolveSession, "release_device", spy)
+    whole = S.solve_batch(systems, errs, engine=emu)
+    parts = S._solve_chunks(systems, errs, [(0, 2), (2, 6)], False, False, True, True, False, False, emu, False)
+    assert released == [(None, None, 0), (None, None, 0)]
+    for a, b in zip(whole, parts):
+        assert np.array_equal(a, b)
+    released.clear()
+    out, last = S._solve_chunks(systems, errs, [(0, 2), (2, 6)], False, False, True, True, False, False, emu, True)
+    assert released == [] and len(last.chunk_sessions) == 2 and last.chunk_sessions[0].d_coeffs is not None
