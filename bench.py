@@ -255,6 +255,8 @@ def main():
         barrier()
         return sess, e0.elapsed_time(e1)
 
+    gather_ms = []                                             # host time of the final root all-gather per e2e step (this rank)
+
     def api_step():
         """Public API with host buffers: pack, pinned H2D, solve, D2H, post-pass, root all-gather."""
         flush.fill_(1)
@@ -262,10 +264,12 @@ def main():
         h0, d0 = eng.mem.h2d_bytes, eng.mem.d2h_bytes
         t0 = time.perf_counter()
         roots, sess = S.solve_batch(systems, errs, use_fma=bool(args.fma), return_session=True)
+        t1 = time.perf_counter()
         if world > 1:
             all_gather_roots(roots, np.arange(rank, world * len(systems), world), world * len(systems), DIM)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        gather_ms.append((time.perf_counter() - t1) * 1e3)
         barrier()
         # only numbers leave this function: a session that stays referenced keeps its page-locked record buffers
         return sess.stats.boxes, dt, eng.mem.h2d_bytes - h0, eng.mem.d2h_bytes - d0, sum(len(r) for r in roots)
@@ -318,7 +322,8 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, args.batch),
                 "e2e": {"value": e2e_boxes_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "solves_per_s": args.batch * world * args.steps / e2e_s_max, "roots_per_step_rank0": int(nroots)},
+                        "solves_per_s": args.batch * world * args.steps / e2e_s_max, "roots_per_step_rank0": int(nroots),
+                        "root_allgather_ms_per_step_rank0": (sum(gather_ms[1:]) / max(1, len(gather_ms) - 1)) if world > 1 else 0.0},
                 "gpu_launches": launches_all,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_over_algorithmic": traffic_ratio,
