@@ -14,14 +14,8 @@ def shard(n_items, rank, world):
     return np.arange(rank, n_items, world)
 
 
-_gather_stage = {}          # device index -> page-locked staging buffer of all_gather_roots (grow-only)
-_copy_pool = None
-
-
+_pinned_pool = None         # page-locked result buffers of all_gather_roots (engine.HostPool with a pinned allocator)
 from .engine import HostPool as _HostPool          # noqa: E402  (pooled result buffers)
-
-
-_result_pool = _HostPool()
 
 
 def all_gather_roots(local_roots, local_ids, n_systems, dim, group=None, device=None):
@@ -47,27 +41,17 @@ def all_gather_roots(local_roots, local_ids, n_systems, dim, group=None, device=
     big = torch.empty((world, max(cap, 1), dim), dtype=torch.float64, device=dev)
     dist.all_gather([big[r] for r in range(world)], mine, group=group)
     if big.is_cuda:
-        # device -> one cached page-locked buffer (allocating 90 MB of pinned memory per call costs more than the copy),
-        # then out of it into the caller's own array, four threads wide
+        # device -> a page-locked result buffer from the pool, directly: no staging copy, and no pinned allocation per call
+        # (a buffer returns to the pool when the caller has dropped every root array of an earlier call)
+        global _pinned_pool
+        if _pinned_pool is None:
+            def _pinned(nbytes):
+                return torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True).numpy()   # (the array keeps the tensor alive)
+            _pinned_pool = _HostPool(alloc=_pinned)
         nbytes = big.numel() * 8
-        stage = _gather_stage.get(big.device.index)
-        if stage is None or stage.numel() < big.numel():
-            stage = _gather_stage[big.device.index] = torch.empty(big.numel() + big.numel() // 4, dtype=torch.float64, pin_memory=True)
-        host = stage[:big.numel()].view(big.shape)
-        host.copy_(big, non_blocking=True)
+        blocks = _pinned_pool.take(nbytes).view(np.float64).reshape(tuple(big.shape))
+        torch.from_numpy(blocks).copy_(big, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        blocks = _result_pool.take(nbytes).view(np.float64).reshape(tuple(big.shape))
-        src, dst = host.numpy().reshape(-1), blocks.reshape(-1)
-        if nbytes >= (1 << 24):
-            from concurrent.futures import ThreadPoolExecutor
-            global _copy_pool
-            if _copy_pool is None:
-                _copy_pool = ThreadPoolExecutor(4)
-            cuts = np.linspace(0, len(src), 5).astype(np.int64)
-            for j in [_copy_pool.submit(np.copyto, dst[a:b], src[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]:
-                j.result()
-        else:
-            dst[:] = src
     else:
         blocks = big.numpy()
     out = [None] * n_systems

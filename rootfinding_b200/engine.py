@@ -44,11 +44,14 @@ class _Lease:
 
 
 class HostPool:
-    """Pageable host buffers for results handed to the caller.  A fresh 90 MB array costs ~20 ms of first-touch page
-    faults per call; a buffer whose previous result arrays have all been dropped is reused instead."""
+    """Host buffers for results handed to the caller.  A fresh 90 MB array costs ~20 ms of first-touch page faults per
+    call; a buffer whose previous result arrays have all been dropped is reused instead.  `alloc(nbytes)` returns the
+    uint8 storage array (default: pageable numpy memory; distributed.py passes a page-locked allocator so that device ->
+    host copies land in the result buffer directly)."""
 
-    def __init__(self, keep=3):
+    def __init__(self, keep=3, alloc=None):
         self.free, self.keep = [], keep
+        self.alloc = alloc or (lambda nbytes: np.empty(nbytes, dtype=np.uint8))
 
     def _give_back(self, storage):
         if len(self.free) < self.keep:
@@ -61,7 +64,7 @@ class HostPool:
                 self.free.pop(i)
                 break
         else:
-            st = np.empty(nbytes + nbytes // 4, dtype=np.uint8)
+            st = self.alloc(nbytes + nbytes // 4)
         lease = _Lease(st)
         weakref.finalize(lease, self._give_back, st)
         return np.asarray(lease)[:nbytes]
