@@ -208,6 +208,15 @@ int yr_frontier_finish(yr_frontier_out* out, void* stream);
 int yr_frontier_fits(uint64_t max_extent);
 /* the same for dim = 2, 3, 4 (0 for other dimensions): max_tensor = coefficients of the largest single tensor */
 int yr_frontier_fits_dim(int32_t dim, uint64_t max_extent, uint64_t max_tensor);
+/* Record tables of several processes' frontier solves (box-level multi-GPU), concatenated by the caller in rank order on the
+ * device, become ONE library-owned output as if a single solve had produced them: links (rank << rank_shift | local index)
+ * are remapped to positions in the concatenation (res_base[r] / node_base[r] = first position of rank r's records) and
+ * out->order is computed by the same device sort as yr_frontier_finish.  The inputs stay the caller's.  2-D records. */
+int yr_frontier_adopt(int32_t dim, const void* results, uint64_t n_results, const void* nodes, uint64_t n_nodes,
+                      const uint64_t* res_base, const uint64_t* node_base, int32_t nranks, int32_t rank_shift,
+                      yr_frontier_out* out, void* stream);
+/* device -> device copy on `stream` (asynchronous): lets a host move library-owned record arrays into buffers of its own */
+int yr_device_copy(void* dst, const void* src, uint64_t bytes, void* stream);
 int yr_frontier_release(yr_frontier_out* out, void* stream);
 /* the pipeline keeps its box tables, arenas and queues between solves (grow-only); this frees them */
 int yr_frontier_trim(void* stream);

@@ -99,7 +99,7 @@ EXPORTS = ["yr_abi_version", "yr_last_error", "yr_last_error_code", "yr_build_in
            "yr_quadcheck_batched", "yr_dct1_axis", "yr_poly_eval_axis", "yr_abs_axis_mean",
            "yr_frontier_solve", "yr_frontier_release", "yr_frontier_fits", "yr_frontier_trim", "yr_fetch",
            "yr_frontier_begin", "yr_frontier_advance", "yr_frontier_export_bound", "yr_frontier_export",
-           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply", "yr_f2_tensor_ops", "yr_frontier_fits_dim", "yr_gather_by_system"]
+           "yr_frontier_import", "yr_frontier_finish", "yr_decay_probe", "yr_upper_axis_apply", "yr_f2_tensor_ops", "yr_frontier_fits_dim", "yr_gather_by_system", "yr_frontier_adopt", "yr_device_copy"]
 
 _RESULT_FIELDS = ["root", "box", "comb_iv", "iv_lo", "cell_iv", "next_mid", "system", "parent_node", "collector",
                   "level", "flags", "path_hi", "path_lo"]
@@ -150,6 +150,11 @@ def bind(lib):
     lib.yr_frontier_fits.restype = C.c_int
     lib.yr_fetch.argtypes = [vp, vp, u64, vp]
     lib.yr_fetch.restype = C.c_int
+    lib.yr_frontier_adopt.argtypes = [C.c_int32, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64), C.c_int32, C.c_int32,
+                                      C.POINTER(YrFrontierOut), vp]
+    lib.yr_frontier_adopt.restype = C.c_int
+    lib.yr_device_copy.argtypes = [vp, vp, u64, vp]
+    lib.yr_device_copy.restype = C.c_int
     lib.yr_gather_by_system.argtypes = [vp, u64, C.c_uint32, C.c_uint32, vp, u64, vp, vp, u64, vp, vp]
     lib.yr_gather_by_system.restype = C.c_int
     lib.yr_frontier_fits_dim.argtypes = [i32, u64, u64]

@@ -36,6 +36,9 @@ void timer_mark(int which, int begin, void* stream);      // which: 0 tensor, 1 
 void timer_collect(double* tensor_ms, double* scalar_ms);
 // order[0..n) = record indices sorted by (system, path_hi, path_lo); returns a device buffer (or null)
 void* sort_results(const void* results, unsigned long long n, void* stream);
+// record links of several ranks' tables (rank << shift | local index) -> positions in their concatenation
+struct RankBases { unsigned long long res[16], node[16]; int shift; };
+int remap_links(void* results, unsigned long long n_results, void* nodes, unsigned long long n_nodes, const RankBases& rb, void* stream);
 double trace_sync_ms(void* stream);      // YR_F2_TRACE: synchronise and return host milliseconds since the previous call
 double host_ms();                        // host clock, milliseconds
 }  // namespace yr_f2_backend
@@ -88,6 +91,33 @@ inline int release(yr_frontier_out* out, void* stream) {
     if (out->nodes) yr_f2_backend::dev_free(out->nodes, stream);
     if (out->order) yr_f2_backend::dev_free(out->order, stream);
     out->results = nullptr; out->nodes = nullptr; out->order = nullptr;
+    return 0;
+}
+
+// Result / node records of several processes' frontiers, concatenated by the caller in rank order, become ONE library-owned
+// output as if a single solve had produced them: links remapped to positions in the concatenation, reporting order
+// computed by the same device sort.  (Box-level multi-GPU: rank 0 receives the other ranks' records over NCCL and goes on
+// with the ordinary single-solve post-pass; rootfinding_b200/distributed.py.)
+inline int adopt_records(const void* results, unsigned long long n_results, const void* nodes, unsigned long long n_nodes,
+                         const uint64_t* res_base, const uint64_t* node_base, int nranks, int rank_shift, yr_frontier_out* out, void* stream) {
+    namespace be = yr_f2_backend;
+    memset(out, 0, sizeof(*out));
+    if (nranks < 1 || nranks > 16) return fail("yr_frontier_adopt: 1..16 ranks");
+    be::RankBases rb;
+    for (int r = 0; r < 16; ++r) { rb.res[r] = r < nranks ? res_base[r] : 0ull; rb.node[r] = r < nranks ? node_base[r] : 0ull; }
+    rb.shift = rank_shift;
+    if (n_results) {
+        out->results = be::dev_alloc((size_t)n_results * sizeof(ResultRec<2>), stream);
+        if (!out->results || be::dev_copy(out->results, results, (size_t)n_results * sizeof(ResultRec<2>), stream)) { release(out, stream); yr_set_error_oom("device allocation failed (results)"); return -1; }
+    }
+    if (n_nodes) {
+        out->nodes = be::dev_alloc((size_t)n_nodes * sizeof(NodeRec<2>), stream);
+        if (!out->nodes || be::dev_copy(out->nodes, nodes, (size_t)n_nodes * sizeof(NodeRec<2>), stream)) { release(out, stream); yr_set_error_oom("device allocation failed (nodes)"); return -1; }
+    }
+    if (be::remap_links(out->results, n_results, out->nodes, n_nodes, rb, stream)) { release(out, stream); return -1; }
+    out->order = n_results ? be::sort_results(out->results, n_results, stream) : nullptr;
+    if (n_results && !out->order) { release(out, stream); yr_set_error_oom("device allocation failed (order)"); return -1; }
+    out->n_results = n_results; out->n_nodes = n_nodes;
     return 0;
 }
 

@@ -212,6 +212,21 @@ __global__ void gather_by_system_kernel(const unsigned char* table, unsigned lon
     for (unsigned q = 0; q < rec_bytes / 8; ++q) d8[q] = s8[q];
 }
 
+// ---- records of several ranks in one table (yr_frontier_adopt) ----
+__global__ void remap_links_kernel(ResultRec<2>* res, unsigned long long nr, NodeRec<2>* nodes, unsigned long long nn, const yr_f2_backend::RankBases rb) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int mask = (1 << rb.shift) - 1;
+    if (i < nr) {
+        const int p = res[i].parent_node, c = res[i].collector;
+        if (p >= 0) res[i].parent_node = (int)(rb.node[p >> rb.shift] + (unsigned long long)(p & mask));
+        if (c >= 0) res[i].collector = (int)(rb.res[c >> rb.shift] + (unsigned long long)(c & mask));
+    }
+    if (i < nn) {
+        const int p = nodes[i].parent_node;
+        if (p >= 0) nodes[i].parent_node = (int)(rb.node[p >> rb.shift] + (unsigned long long)(p & mask));
+    }
+}
+
 // ---- moving queued boxes between frontiers (yr_frontier_export / _import) ----
 __global__ void __launch_bounds__(128) f2_export_kernel(const Args a, const yr_f2_host::XTake take, unsigned long long n, unsigned char* xbuf,
                                                         const double* __restrict__ data_in) {
@@ -479,6 +494,15 @@ __global__ void f2_pack_sorted(const ResultRec<2>* res, const unsigned int* orde
     o.index = r; o.system = res[r].system; o.flags = res[r].flags; o.collector = res[r].collector;
     o.root[0] = res[r].root[0]; o.root[1] = res[r].root[1];
     out[i] = o;
+}
+
+int remap_links(void* results, unsigned long long n_results, void* nodes, unsigned long long n_nodes, const RankBases& rb, void* stream) {
+    const unsigned long long n = n_results > n_nodes ? n_results : n_nodes;
+    if (!n) return 0;
+    remap_links_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(static_cast<ResultRec<2>*>(results), n_results,
+                                                                                     static_cast<NodeRec<2>*>(nodes), n_nodes, rb);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : cuda_fail(e, "remap_links_kernel launch");
 }
 
 void* sort_results(const void* results, unsigned long long n, void* stream) {

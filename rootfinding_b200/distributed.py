@@ -6,6 +6,8 @@ followed by an all-gather of the (padded) roots, so that every rank returns the 
 NCCL over NVLink on GPUs, gloo in the CPU tests.  No floating-point reduction is involved, so the
 result does not depend on the number of ranks.
 """
+import ctypes as C
+
 import numpy as np
 
 
@@ -250,28 +252,87 @@ def solve_sharded(systems, errors, group=None, engine=None, every=2, min_move=25
     sess.run_jobs(sess.unit_jobs(mine))
     sess.mem.synchronize()
     t_solved = time.perf_counter()
-    # ---- records of every rank to rank 0 (a few hundred bytes per root / subdividing box) ----
-    res, nodes = sess.results(), sess.nodes()
-    sizes = sf._all_gather_ints([len(res), len(nodes)])
+    # ---- records of every rank to rank 0 ----
+    from . import _lib
+    lib, mem = sess.lib, sess.mem
     dev = sf._device()
     rdt, ndt = sess.rdt, sess.ndt
+    seg = sess._segments[0] if len(sess._segments) == 1 and sess._segments[0][0] == "frontier" and sess._segments[0][1] == 0 else None
+    on_device = bool(sf._all_gather_ints([int(seg is not None and hasattr(lib, "yr_frontier_adopt"))]).min())
+    if on_device:
+        # Every rank's records are still on its device (one frontier solve each): they travel device to device, rank 0
+        # concatenates them, has the links remapped and the reporting order computed there (yr_frontier_adopt) and goes on
+        # exactly like a single-GPU solve: device-sorted entries, full records only for the systems that need them.
+        _, _, rn, _, nn, out = seg
+        sizes = sf._all_gather_ints([rn, nn])
+        stream = mem.stream()
+        if rank == 0:
+            tot_r, tot_n = int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
+            res_base = np.r_[0, np.cumsum(sizes[:, 0])[:-1]].astype(np.uint64)
+            node_base = np.r_[0, np.cumsum(sizes[:, 1])[:-1]].astype(np.uint64)
+            bufs = []
+            for col, (ptr, dt, tot, base) in enumerate(((out.results, rdt, tot_r, res_base), (out.nodes, ndt, tot_n, node_base))):
+                t, tptr, keep = _bytes_tensor(mem, max(1, tot * dt.itemsize))
+                bufs.append((t, tptr, keep))
+                if int(sizes[0, col]):
+                    _lib.check(lib, lib.yr_device_copy(tptr, ptr, int(sizes[0, col]) * dt.itemsize, stream), "yr_device_copy")
+                mem.synchronize()
+                for r in range(1, world):
+                    n = int(sizes[r, col])
+                    if n:
+                        lo = int(base[r]) * dt.itemsize
+                        dist.recv(t[lo:lo + n * dt.itemsize], r, group=group)
+            if dev.type == "cuda":
+                torch.cuda.current_stream().synchronize()
+            merged = _lib.YrFrontierOut()
+            _lib.check(lib, lib.yr_frontier_adopt(2, bufs[0][1], tot_r, bufs[1][1], tot_n,
+                                                  res_base.ctypes.data_as(C.POINTER(C.c_uint64)), node_base.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                  world, RANK_SHIFT, C.byref(merged), stream), "yr_frontier_adopt")
+            mem.synchronize()
+            del bufs
+            sess._pending.remove(out)
+            lib.yr_frontier_release(C.byref(out), stream)
+            sess._pending.append(merged)
+            sess._segments = [("frontier", 0, tot_r, 0, tot_n, merged)]
+            sess.n_results, sess.n_nodes = tot_r, tot_n
+            sess._order_host = None
+        else:
+            for ptr, n, dt in ((out.results, rn, rdt), (out.nodes, nn, ndt)):
+                if n:
+                    t, tptr, keep = _bytes_tensor(mem, n * dt.itemsize)
+                    _lib.check(lib, lib.yr_device_copy(tptr, ptr, n * dt.itemsize, stream), "yr_device_copy")
+                    mem.synchronize()
+                    dist.send(t[:n * dt.itemsize], 0, group=group)
+                    del t, keep
+            sess._pending.remove(out)
+            lib.yr_frontier_release(C.byref(out), stream)
+            sess._segments = []
+    else:
+        res, nodes = sess.results(), sess.nodes()
+        sizes = sf._all_gather_ints([len(res), len(nodes)])
+        if rank == 0:
+            res_base = np.r_[0, np.cumsum(sizes[:, 0])[:-1]]
+            node_base = np.r_[0, np.cumsum(sizes[:, 1])[:-1]]
+            for r in range(1, world):
+                for which, n, dt in (("res", int(sizes[r, 0]), rdt), ("nodes", int(sizes[r, 1]), ndt)):
+                    if not n:
+                        continue
+                    t = torch.empty(n * dt.itemsize, dtype=torch.uint8, device=dev)
+                    dist.recv(t, r, group=group)
+                    grow = sess._results_host if which == "res" else sess._nodes_host
+                    grow.tail(n)[:] = t.cpu().numpy()
+            sess.n_results, sess.n_nodes = int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
+            sess._order_host = None                            # the device order covers rank 0's records only
+            res, nodes = sess._results_host.view(), sess._nodes_host.view()
+            res["parent_node"] = _remap(res["parent_node"], node_base, sizes[:, 1])
+            res["collector"] = _remap(res["collector"], res_base, sizes[:, 0])
+            nodes["parent_node"] = _remap(nodes["parent_node"], node_base, sizes[:, 1])
+        else:
+            for arr in (res, nodes):
+                if len(arr):
+                    t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).to(dev)
+                    dist.send(t, 0, group=group)
     if rank == 0:
-        res_base = np.r_[0, np.cumsum(sizes[:, 0])[:-1]]
-        node_base = np.r_[0, np.cumsum(sizes[:, 1])[:-1]]
-        for r in range(1, world):
-            for which, n, dt in (("res", int(sizes[r, 0]), rdt), ("nodes", int(sizes[r, 1]), ndt)):
-                if not n:
-                    continue
-                t = torch.empty(n * dt.itemsize, dtype=torch.uint8, device=dev)
-                dist.recv(t, r, group=group)
-                grow = sess._results_host if which == "res" else sess._nodes_host
-                grow.tail(n)[:] = t.cpu().numpy()
-        sess.n_results, sess.n_nodes = int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
-        sess._order_host = None                            # the device order covers rank 0's records only
-        res, nodes = sess._results_host.view(), sess._nodes_host.view()
-        res["parent_node"] = _remap(res["parent_node"], node_base, sizes[:, 1])
-        res["collector"] = _remap(res["collector"], res_base, sizes[:, 0])
-        nodes["parent_node"] = _remap(nodes["parent_node"], node_base, sizes[:, 1])
         sess.index_base, sess.frontier_runner = 0, None    # merge re-solves run on this rank alone
         res, keep, dup, extra = postpass.assemble(sess, need_records=returnBoundingBoxes)
         roots, boxes = postpass.per_system_roots(res, keep, dup, extra, sess.nsys, sess.dim, want_boxes=returnBoundingBoxes,
@@ -280,10 +341,6 @@ def solve_sharded(systems, errors, group=None, engine=None, every=2, min_move=25
                                                  redo_systems=getattr(sess, "redo_systems", None), alive=getattr(sess, "alive", None))
         payload = [roots, [[(b.finalInterval, b.possibleDuplicateRoots, b.possibleExtraRoot) for b in bs] for bs in boxes] if returnBoundingBoxes else None]
     else:
-        for arr in (res, nodes):
-            if len(arr):
-                t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).to(dev)
-                dist.send(t, 0, group=group)
         payload = [None, None]
     t_assembled = time.perf_counter()
     stats = sf._all_gather_ints([int(sess.stats.boxes), sf.boxes_moved, sf.bytes_moved, sf.rebalances,

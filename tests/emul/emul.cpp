@@ -481,6 +481,21 @@ int launch_scalar(const yr::f2::Args& a, const Segments& s, void*) {
     return 0;
 }
 
+int remap_links(void* results, unsigned long long nr, void* nodes, unsigned long long nn, const RankBases& rb, void*) {
+    yr::ResultRec<2>* res = static_cast<yr::ResultRec<2>*>(results);
+    yr::NodeRec<2>* nd = static_cast<yr::NodeRec<2>*>(nodes);
+    const int mask = (1 << rb.shift) - 1;
+    for (unsigned long long i = 0; i < nr; ++i) {
+        const int p = res[i].parent_node, c = res[i].collector;
+        if (p >= 0) res[i].parent_node = (int)(rb.node[p >> rb.shift] + (unsigned long long)(p & mask));
+        if (c >= 0) res[i].collector = (int)(rb.res[c >> rb.shift] + (unsigned long long)(c & mask));
+    }
+    for (unsigned long long i = 0; i < nn; ++i) {
+        const int p = nd[i].parent_node;
+        if (p >= 0) nd[i].parent_node = (int)(rb.node[p >> rb.shift] + (unsigned long long)(p & mask));
+    }
+    return 0;
+}
 void* sort_results(const void* results, unsigned long long n, void*) {
     const yr::ResultRec<2>* res = static_cast<const yr::ResultRec<2>*>(results);
     std::vector<unsigned int> v((size_t)n);
