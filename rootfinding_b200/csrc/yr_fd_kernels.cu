@@ -13,6 +13,13 @@
 #include <stdlib.h>
 #include <vector>
 
+// the per-box mathematics inline, so that its small arrays live in registers instead of a stack frame (as in yr_f2_kernels.cu)
+#ifndef YR_FD_INLINE_MATH
+#define YR_FD_INLINE_MATH 1
+#endif
+#if YR_FD_INLINE_MATH
+#define YR_HDM static __host__ __device__ __forceinline__     // see yr_math.h
+#endif
 #include "yr_fd_host.h"
 #include "yr_cuda_teams.cuh"
 

@@ -175,15 +175,19 @@ YR_HDM void jacobi_svd(const double A[D][D], double W[D][D], double V[D][D], dou
         for (int j = 0; j < D; ++j) { W[i][j] = A[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
     for (int sweep = 0; sweep < 30; ++sweep) {
         bool rotated = false;
+#pragma unroll
         for (int p = 0; p < D - 1; ++p)
-            for (int q = p + 1; q < D; ++q) {
+#pragma unroll
+            for (int q = p + 1; q < D; ++q) {                       // (unrolled: every W / V index is a compile-time constant)
                 double app = 0, aqq = 0, apq = 0;
+#pragma unroll
                 for (int i = 0; i < D; ++i) { app += W[i][p] * W[i][p]; aqq += W[i][q] * W[i][q]; apq += W[i][p] * W[i][q]; }
                 if (apq == 0.0 || fabs(apq) <= 4e-16 * yr_sqrt(app * aqq)) continue;   // columns orthogonal to ~2 ulp
                 rotated = true;
                 double zeta = yr_div(aqq - app, 2.0 * apq);
                 double t = yr_div(zeta >= 0 ? 1.0 : -1.0, fabs(zeta) + yr_sqrt(1.0 + zeta * zeta));
                 double c = yr_div(1.0, yr_sqrt(1.0 + t * t)), s = c * t;
+#pragma unroll
                 for (int i = 0; i < D; ++i) {
                     double wp = W[i][p], wq = W[i][q];
                     W[i][p] = c * wp - s * wq; W[i][q] = s * wp + c * wq;
@@ -369,51 +373,56 @@ YR_HDM BilsOut bounding_interval(const double lin[D][D], const double c0[D], con
 // order; returns k (identical for every polynomial).  shape[p][d] are the extents.
 template <int D>
 YR_HDM int subdivision_axes(const int shape[D][D], const double iv[D][2], int level, int order[D][D]) {
-    int cand[D]; int nc = 0;
-    for (int i = 0; i < D; ++i) cand[nc++] = i;
+    // The candidate list of the reference is always in ascending axis order, so a bit mask carries it; every loop below
+    // runs over compile-time axis indices (no array is indexed by a run-time value: the thread-per-box kernels keep
+    // everything in registers instead of a stack frame).
+    unsigned mask = (1u << D) - 1u;
+    int nc = D;
+#pragma unroll
     for (int i = 0; i < D; ++i) {
         const double a = iv[i][0], b = iv[i][1];
         const bool close = fabs(a - b) <= (1e-8 + 1e-5 * fabs(b));     // np.isclose defaults
-        if (close && nc != 1) {
-            int m = 0;
-            for (int j = 0; j < nc; ++j) if (cand[j] != i) cand[m++] = cand[j];
-            nc = m;
-        }
+        if (close && nc != 1) { mask &= ~(1u << i); nc -= 1; }
     }
     if (level <= 5) {
         double widest = -INFINITY;
-        for (int j = 0; j < nc; ++j) widest = fmax(widest, iv[cand[j]][1] - iv[cand[j]][0]);
-        int m = 0;
-        for (int j = 0; j < nc; ++j)
-            if ((iv[cand[j]][1] - iv[cand[j]][0]) > yr_div(widest, 5.0)) cand[m++] = cand[j];
-        nc = m;
+#pragma unroll
+        for (int i = 0; i < D; ++i) if ((mask >> i) & 1u) widest = fmax(widest, iv[i][1] - iv[i][0]);
+        const double bar = yr_div(widest, 5.0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) if (((mask >> i) & 1u) && !((iv[i][1] - iv[i][0]) > bar)) { mask &= ~(1u << i); nc -= 1; }
         if (nc > 1) {
             int per_axis[D]; int total = 0;
-            for (int d = 0; d < D; ++d) { per_axis[d] = 0; for (int p = 0; p < D; ++p) per_axis[d] += shape[p][d]; total += per_axis[d]; }
-            const int floor_share = total / (D + 1);
-            int snapshot[D]; const int ns = nc;
-            for (int j = 0; j < ns; ++j) snapshot[j] = cand[j];
-            for (int j = 0; j < ns; ++j) {
-                const int i = snapshot[j];
-                if (nc > 1 && per_axis[i] < floor_share) {
-                    int m2 = 0;
-                    for (int q = 0; q < nc; ++q) if (cand[q] != i) cand[m2++] = cand[q];
-                    nc = m2;
-                }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                per_axis[d] = 0;
+#pragma unroll
+                for (int p = 0; p < D; ++p) per_axis[d] += shape[p][d];
+                total += per_axis[d];
             }
+            const int floor_share = total / (D + 1);
+            const unsigned snapshot = mask;                            // :1046 iterates over a copy
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+                if (((snapshot >> i) & 1u) && nc > 1 && per_axis[i] < floor_share) { mask &= ~(1u << i); nc -= 1; }
         }
     }
-    // per polynomial: candidates by descending extent; np.argsort (quicksort == insertion
-    // sort for tiny arrays, stable) ascending, then reversed.
+    // per polynomial: candidates by descending extent.  np.argsort (insertion sort for tiny arrays: stable) ascending, then
+    // reversed: ties end up in DESCENDING axis order.  Slot j takes the candidate that j others precede.
+#pragma unroll
     for (int p = 0; p < D; ++p) {
-        int idx[D];
-        for (int j = 0; j < nc; ++j) idx[j] = j;
-        for (int j = 1; j < nc; ++j) {                     // stable insertion sort, ascending extent
-            int v = idx[j]; int q = j - 1;
-            while (q >= 0 && shape[p][cand[idx[q]]] > shape[p][cand[v]]) { idx[q + 1] = idx[q]; --q; }
-            idx[q + 1] = v;
+#pragma unroll
+        for (int j = 0; j < D; ++j) order[p][j] = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            int rank = 0;
+#pragma unroll
+            for (int q = 0; q < D; ++q)
+                if (q != i && ((mask >> q) & 1u) && (shape[p][q] > shape[p][i] || (shape[p][q] == shape[p][i] && q > i))) rank += 1;
+#pragma unroll
+            for (int j = 0; j < D; ++j) if (rank == j) order[p][j] = i;
         }
-        for (int j = 0; j < nc; ++j) order[p][j] = cand[idx[nc - 1 - j]];
     }
     return nc;
 }
