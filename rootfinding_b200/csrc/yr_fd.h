@@ -828,7 +828,10 @@ YR_HDM void scalar_step(const Args<D>& a, unsigned int b, Decision& dc, At at) {
             const int k = subdivision_axes<D>(shape, st.iv, wk.node_level, order);
             if (k == 0) { at.add(&a.ctl->no_axis, 1ull); break; }              // getInverseOrder of an empty order raises (:1010)
             wk.nsplit = k;
-            for (int p = 0; p < D; ++p) for (int j = 0; j < D; ++j) wk.order[p][j] = order[p][j < k ? j : 0];
+#pragma unroll
+            for (int p = 0; p < D; ++p)
+#pragma unroll
+                for (int j = 0; j < D; ++j) wk.order[p][j] = (j < k) ? order[p][j] : order[p][0];     // (value select: no run-time index)
             wk.node_index = -1;
             if (!wk.final_split) {
                 const unsigned long long ni = at.add(&a.ctl->n_nodes, 1ull);
