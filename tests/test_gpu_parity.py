@@ -399,7 +399,7 @@ def test_distributed_single_rank_nccl(yr):
     """world_size 1 over NCCL: the sharded entry point returns what solve_batch returns."""
     import torch
     import torch.distributed as dist
-    from rootfinding_b200.distributed import solve_batch_sharded
+    from rootfinding_b200.distributed import solve_batch_sharded, solve_sharded
     S = yr.ChebyshevSubdivisionSolver
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29517", rank=0, world_size=1,
                             device_id=torch.device("cuda", 0))
@@ -412,5 +412,16 @@ def test_distributed_single_rank_nccl(yr):
             want = S.solve_batch(systems, errs)
         for g, w in zip(got, want):
             assert np.array_equal(g, w)
+        # the box-level mode through the same group: resumable frontier (begin / advance / finish), records adopted on the
+        # device (yr_frontier_adopt), ordinary post-pass -- incl. systems that need a merge re-solve
+        systems = systems + [H.corner_system(3), H.corner_system(4)]
+        errs = errs + [np.full(2, 2. ** -52)] * 2
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got, info = solve_sharded(systems, errs, every=2, return_stats=True)
+            want, sess = S.solve_batch(systems, errs, return_session=True)
+        assert info["boxes"] == sess.stats.boxes
+        for g, w in zip(got, want):
+            assert np.array_equal(np.asarray(g).reshape(-1, 2), np.asarray(w).reshape(-1, 2))
     finally:
         dist.destroy_process_group()
