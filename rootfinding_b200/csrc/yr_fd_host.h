@@ -125,7 +125,7 @@ inline int begin(const yr_frontier_desc* d, void* stream) {
         // team policy: warp teams up to these needs (doubles), one CTA per box above; overridable for experiments
         auto env_ull = [](const char* name, unsigned long long dflt) { const char* v = getenv(name); return v ? strtoull(v, nullptr, 10) : dflt; };
         a.pol.warp_max[0] = env_ull("YR_F2_WARP_MAX_R", kWarp32Max);
-        a.pol.warp_max[1] = env_ull("YR_F2_WARP_MAX_S", kWarp32Max);
+        a.pol.warp_max[1] = env_ull("YR_F2_WARP_MAX_S", 2048ull);    // SUBDIVIDE: 64-thread CTA teams above (see launch_tensor_t)
         a.pol.cta128_max = env_ull("YR_F2_CTA128_MAX", 7168ull);
         for (int o = 0; o < 2; ++o) if (a.pol.warp_max[o] > kWarp32Max) a.pol.warp_max[o] = kWarp32Max;
         if (a.pol.cta128_max > 7168ull) a.pol.cta128_max = 7168ull;

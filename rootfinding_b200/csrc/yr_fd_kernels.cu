@@ -2,7 +2,7 @@
 //
 // Kernels:
 //   fd_tensor_warp<D,OP,FMA>        4 independent 32-lane teams per CTA, each with its own slice of dynamic shared memory
-//   fd_tensor_cta<D,OP,FMA,THREADS> one team of 128 / 256 threads per CTA (boxes that need more than a warp's slice)
+//   fd_tensor_cta<D,OP,FMA,THREADS> one team of 64 / 256 threads per CTA (boxes that need more than a warp's slice; 128 on request)
 //   fd_scalar_kernel<D>             thread per box
 //   fd_import_kernel<D>, fd_sort_keys<D>, fd_pack_sorted<D>
 // Grids are one resident wave; teams take boxes from a per-(op, class) cursor.  Compiled with -fmad=false.
@@ -81,11 +81,11 @@ __global__ void __launch_bounds__(128, 4) fd_tensor_warp(const Args<D> a, const 
 }
 
 template <int D, int OP, bool FMA, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 3 : 1) fd_tensor_cta(const Args<D> a, const unsigned int* __restrict__ list,
+__global__ void __launch_bounds__(THREADS, THREADS == 64 ? 6 : (THREADS == 128 ? 3 : 1)) fd_tensor_cta(const Args<D> a, const unsigned int* __restrict__ list,
                                                                                 unsigned long long n, int snt, unsigned long long* cursor) {
     extern __shared__ __align__(16) double dyn[];
     __shared__ CtaShared cta_sh;
-    constexpr bool kPerWarp = (THREADS == 128);
+    constexpr bool kPerWarp = (THREADS <= 128);
     __shared__ WalkState<D> walk[(OP == kTSubdivide && kPerWarp) ? THREADS / 32 : 1];
     double* smat = dyn;
     int smat_doubles = 0;
@@ -225,7 +225,15 @@ int launch_tensor_t(const Args<D>& a, int cls, const unsigned int* list, unsigne
         const int threads = class_threads(cls);
         const size_t smem = smat + slice * 8;
         if (smem > (size_t)d.smem_cta - kStaticReserve) { yr_set_error("fd: CTA-team launch exceeds shared memory"); return -1; }
-        if (threads == 128) {
+        // boxes beyond a warp's slice run on TWO warps (64 threads), not four: every phase outside the sweeps is serial per box
+        // and each pass costs a CTA barrier (measured: 3-D degree 10 139.6 -> 138.0 ms, 4-D degree 4 116.8 -> 110.2 ms together
+        // with the lower warp-team limit for SUBDIVIDE, profiles/r02_fd.txt).  YR_FD_CTA128=1 restores four warps.
+        static const bool cta64 = getenv("YR_FD_CTA128") == nullptr;
+        if (threads == 128 && cta64) {
+            if (ensure_smem(fd_tensor_cta<D, OP, FMA, 64>, smem)) return -1;
+            const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(fd_tensor_cta<D, OP, FMA, 64>, 64, smem);
+            fd_tensor_cta<D, OP, FMA, 64><<<(unsigned)(n < cap ? n : cap), 64, smem, st>>>(a, list, n, snt, cursor);
+        } else if (threads == 128) {
             if (ensure_smem(fd_tensor_cta<D, OP, FMA, 128>, smem)) return -1;
             const unsigned long long cap = (unsigned long long)d.sm * resident_ctas(fd_tensor_cta<D, OP, FMA, 128>, 128, smem);
             fd_tensor_cta<D, OP, FMA, 128><<<(unsigned)(n < cap ? n : cap), 128, smem, st>>>(a, list, n, snt, cursor);
